@@ -1,0 +1,101 @@
+// Voxel geometry shared by the scatter and geometric-target kernels.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+struct VoxGeom {
+  float lo[3];        // range min x,y,z
+  float vs[3][3];     // [scale: 0 top, 1 med, 2 low][x,y,z]
+  int grid[3][3];     // [scale][x,y,z]
+  int ratio[3][3];    // [scale][z,y,x]
+  int n_frames;
+};
+
+__device__ __forceinline__ int vox_coord(float p, float lo, float vs, int g) {
+  // fp32 subtract, IEEE divide (no fast-math, no reciprocal), floor, clamp — bit-exact with
+  // voxelization_cpu.cpp:22-31 / voxelization_cuda.cu:35-57.
+  int c = (int)floorf(__fdiv_rn(__fsub_rn(p, lo), vs));
+  return min(max(c, 0), g - 1);
+}
+
+struct PointKeys {
+  int b;
+  int c[3][3];  // [scale][x,y,z]
+};
+
+__device__ __forceinline__ void point_keys(const VoxGeom& g, const float* p, PointKeys& k) {
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) k.c[s][a] = vox_coord(p[a], g.lo[a], g.vs[s][a], g.grid[s][a]);
+}
+
+__device__ __forceinline__ int frame_of(const int32_t* __restrict__ off, int n_frames, int64_t idx) {
+  int lo = 0, hi = n_frames;  // find largest b with off[b] <= idx
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if ((int64_t)__ldg(off + mid) <= idx) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int64_t top_cell(const VoxGeom& g, int b, int y, int x) {
+  return ((int64_t)b * g.grid[0][1] + y) * g.grid[0][0] + x;
+}
+
+// parent BEV cell + slot of a sub-voxel (…_ssl.py:659-665): parent = (y//ry, x//rx), pillar z ignored.
+__device__ __forceinline__ void sub_parent(const VoxGeom& g, int s, const PointKeys& k, int64_t& cell, int& slot) {
+  const int rz = g.ratio[s][0], ry = g.ratio[s][1], rx = g.ratio[s][2];
+  const int cx = k.c[s][0], cy = k.c[s][1], cz = k.c[s][2];
+  cell = top_cell(g, k.b, min(cy / ry, g.grid[0][1] - 1), min(cx / rx, g.grid[0][0] - 1));
+  slot = (cz % rz) * (ry * rx) + (cy % ry) * rx + (cx % rx);
+}
+
+__device__ __forceinline__ int cell_rank(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
+                                         int64_t cell) {
+  const uint32_t w = __ldg(bitmap + (cell >> 5));
+  const uint32_t bit = 1u << (cell & 31);
+  if (!(w & bit)) return -1;
+  return __ldg(word_rank + (cell >> 5)) + __popc(w & (bit - 1));
+}
+
+__device__ __forceinline__ int rank128(const uint4 m, int slot) {
+  const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+  int r = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < (slot >> 5)) r += __popc(w[i]);
+    else if (i == (slot >> 5)) r += __popc(w[i] & ((1u << (slot & 31)) - 1u));
+  }
+  return r;
+}
+
+inline int gm_make_geom(const geomae_voxel_cfg* cfg, int n_frames, VoxGeom* g) {
+  const float* sizes[3] = {cfg->voxel_top, cfg->voxel_med, cfg->voxel_low};
+  for (int a = 0; a < 3; ++a) g->lo[a] = cfg->range_min[a];
+  for (int s = 0; s < 3; ++s) {
+    int32_t grid[3];
+    int rc = geomae_grid_size(cfg->range_min, cfg->range_max, sizes[s], grid);
+    if (rc) return rc;
+    for (int a = 0; a < 3; ++a) {
+      g->vs[s][a] = sizes[s][a];
+      g->grid[s][a] = grid[a];
+    }
+  }
+  for (int a = 0; a < 3; ++a) {
+    g->ratio[0][a] = 1;
+    g->ratio[1][a] = cfg->ratio_med[a];
+    g->ratio[2][a] = cfg->ratio_low[a];
+  }
+  g->n_frames = n_frames;
+  const int slots_med = cfg->ratio_med[0] * cfg->ratio_med[1] * cfg->ratio_med[2];
+  const int slots_low = cfg->ratio_low[0] * cfg->ratio_low[1] * cfg->ratio_low[2];
+  GM_REQUIRE(slots_med >= 1 && slots_med <= 32, "sub_voxel_ratio_med has %d slots, supported 1..32", slots_med);
+  GM_REQUIRE(slots_low >= 1 && slots_low <= 128, "sub_voxel_ratio_low has %d slots, supported 1..128", slots_low);
+  GM_REQUIRE(g->grid[0][2] == 1, "pillar grid must be one voxel deep (z grid = %d)", g->grid[0][2]);
+  return GEOMAE_OK;
+}
+
+
+}  // namespace

@@ -1,0 +1,94 @@
+"""ctypes binding of libgeomae_b200.so (the C ABI declared in include/geomae_b200.h).
+
+There is NO fallback: if the shared library is missing, or an entry point fails, a
+RuntimeError is raised.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgeomae_b200.so")
+
+_lib = None
+
+
+class VoxelCfg(C.Structure):
+    _fields_ = [("range_min", C.c_float * 3), ("range_max", C.c_float * 3),
+                ("voxel_top", C.c_float * 3), ("voxel_med", C.c_float * 3), ("voxel_low", C.c_float * 3),
+                ("ratio_med", C.c_int32 * 3), ("ratio_low", C.c_int32 * 3)]
+
+
+class ScatterIO(C.Structure):
+    _fields_ = [("points", C.c_void_p), ("frame_offsets", C.c_void_p),
+                ("n_points", C.c_int64), ("stride", C.c_int32), ("n_frames", C.c_int32), ("cap", C.c_int64),
+                ("bitmap", C.c_void_p), ("word_rank", C.c_void_p), ("scan_tmp", C.c_void_p),
+                ("counts", C.c_void_p), ("pillar_coors", C.c_void_p), ("pillar_mean", C.c_void_p),
+                ("point_pillar", C.c_void_p), ("med_mask", C.c_void_p), ("low_mask", C.c_void_p),
+                ("med_ptr", C.c_void_p), ("low_ptr", C.c_void_p), ("med_mean", C.c_void_p),
+                ("low_mean", C.c_void_p), ("coors_top", C.c_void_p), ("coors_med", C.c_void_p),
+                ("coors_low", C.c_void_p)]
+
+
+def build_if_missing():
+    if not os.path.exists(LIB_PATH):
+        import subprocess
+        subprocess.check_call(["bash", os.path.join(_HERE, "csrc", "build.sh")])
+
+
+def lib():
+    """The loaded library; raises if it cannot be loaded (no CPU/eager fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"geomae_b200: {LIB_PATH} is missing — build it with geomae_b200/csrc/build.sh "
+                "(or __graft_entry__.build()); there is no fallback path")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.geomae_last_error.restype = C.c_char_p
+        for name in dir(_Sigs):
+            if name.startswith("geomae_"):
+                fn = getattr(_lib, name)
+                fn.argtypes = getattr(_Sigs, name)
+                fn.restype = C.c_int
+    return _lib
+
+
+_p, _i64, _i32, _f3 = C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_float)
+
+
+class _Sigs:
+    geomae_grid_size = [_f3, _f3, _f3, C.POINTER(C.c_int32)]
+    geomae_dynamic_voxelize = [_p, _i64, _i32, _f3, _f3, _f3, _p, _p]
+    geomae_voxel_scatter = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), _p]
+    geomae_geom_targets = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), _i64, _p, _p, _p, _p, _p, _p]
+    geomae_dense_targets = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"geomae_b200.{what} failed ({rc}): {lib().geomae_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "geomae_b200 kernels need contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f3(vals):
+    return (C.c_float * 3)(*[float(v) for v in vals])
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"geomae_b200: {name} must be a CUDA tensor (no CPU path exists)")

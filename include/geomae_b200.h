@@ -1,0 +1,120 @@
+/* geomae_b200 — C ABI of the B200-native GeoMAE pretraining hot path.
+ *
+ * Every entry point takes plain device pointers + sizes + a CUDA stream (passed
+ * as void* so this header needs no CUDA include), never allocates, never
+ * synchronises the device, and returns 0 on success or a negative GEOMAE_ERR_*
+ * code; geomae_last_error() returns the message for the calling thread.  The
+ * caller owns every buffer including workspaces.  Nothing throws across the ABI.
+ *
+ * Paths in "replaces:" comments are relative to the reference tree
+ * (Tsinghua-MARS-Lab/GeoMAE); they name the interface each symbol stands in for.
+ */
+#ifndef GEOMAE_B200_H
+#define GEOMAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEOMAE_OK 0
+#define GEOMAE_ERR_INVALID (-1) /* bad argument (null pointer, size, alignment, config) */
+#define GEOMAE_ERR_CUDA (-2)    /* a CUDA runtime call / kernel launch failed           */
+#define GEOMAE_ERR_CAPACITY (-3)
+
+const char* geomae_last_error(void);
+int geomae_abi_version(void);
+
+/* ---------------------------------------------------------------- voxelise */
+
+/* Three-scale voxel geometry of one config (configs/mae_sst/…6x_1e-5.py:14-24). */
+typedef struct geomae_voxel_cfg {
+  float range_min[3];   /* x, y, z */
+  float range_max[3];   /* x, y, z */
+  float voxel_top[3];   /* pillar size x, y, z                    (voxel_size)          */
+  float voxel_med[3];   /* sub-voxel size, middle scale           (sub_voxel_size_med)  */
+  float voxel_low[3];   /* sub-voxel size, finest scale           (sub_voxel_size_low)  */
+  int32_t ratio_med[3]; /* z, y, x sub-voxels per pillar, middle  (sub_voxel_ratio_med) */
+  int32_t ratio_low[3]; /* z, y, x sub-voxels per pillar, finest  (sub_voxel_ratio_low) */
+} geomae_voxel_cfg;
+
+/* grid[x,y,z] = ceil((max-min)/size) in fp32.
+ * replaces: mmdet3d/ops/voxel/src/voxelization_cuda.cu:375-377 */
+int geomae_grid_size(const float range_min[3], const float range_max[3], const float voxel[3],
+                     int32_t grid_xyz[3]);
+
+/* coors[i] = (z,y,x) = clamp(floor((p - min)/size), 0, grid-1), fp32 IEEE divide.
+ * points: [n, stride] fp32 row-major (stride >= 3); coors: [n,3] int32, caller-allocated.
+ * replaces: voxel_layer.dynamic_voxelize  (mmdet3d/ops/voxel/src/voxelization.h:97-109,
+ *           kernel voxelization_cuda.cu:22-63) */
+int geomae_dynamic_voxelize(const float* points, int64_t n, int32_t stride,
+                            const float voxel_xyz[3], const float range_min[3],
+                            const float range_max[3], int32_t* coors, void* stream);
+
+/* Workspace/outputs of the fused three-scale voxelise + scatter stage.  All device
+ * pointers; "cap" = capacity in pillars (>= number of non-empty pillars; n_points is
+ * always enough).  Arrays marked [opt] may be NULL. */
+typedef struct geomae_scatter_io {
+  /* inputs */
+  const float* points;          /* [n_points, stride] fp32, frames concatenated            */
+  const int32_t* frame_offsets; /* [n_frames+1] first point of each frame                  */
+  int64_t n_points;
+  int32_t stride;
+  int32_t n_frames;
+  int64_t cap;
+  /* scratch (caller zeroing not required) */
+  uint32_t* bitmap;             /* [ceil(n_frames*gy*gx/32)] pillar occupancy              */
+  int32_t* word_rank;           /* [same] exclusive popcount prefix                        */
+  int32_t* scan_tmp;            /* [3*4096] block sums                                     */
+  /* outputs */
+  int32_t* counts;              /* [4] n_pillars, n_med, n_low, overflow flag              */
+  int32_t* pillar_coors;        /* [cap,4] (b,z,y,x), lexicographically sorted             */
+  float* pillar_mean;           /* [cap,4] mean x,y,z and point count (as float)           */
+  int32_t* point_pillar;        /* [n_points] pillar row of each point (unq_inv)           */
+  uint32_t* med_mask;           /* [cap]   bit s set = middle sub-voxel slot s occupied     */
+  uint32_t* low_mask;           /* [cap,4] 128 slot bits                                   */
+  int32_t* med_ptr;             /* [cap+1] CSR offsets into med_mean (slot order)          */
+  int32_t* low_ptr;             /* [cap+1]                                                 */
+  float* med_mean;              /* [n_points,4] mean x,y,z,count per middle sub-voxel      */
+  float* low_mean;              /* [n_points,4]                                            */
+  int32_t* coors_top;           /* [opt] [n_points,4] (b,z,y,x) per point, pillar scale    */
+  int32_t* coors_med;           /* [opt]                                                   */
+  int32_t* coors_low;           /* [opt]                                                   */
+} geomae_scatter_io;
+
+/* One pass structure over the raw points: voxelise at three scales, build the sorted
+ * pillar list without a sort (occupancy bitmap + popcount ranks), point->pillar map,
+ * and per-pillar / per-sub-voxel centroids.
+ * replaces: MultiSubVoxelDynamicVoxelNetSSL.voxelize / sub_voxelize_low / sub_voxelize_med
+ *           (detectors/multi_sub_voxel_dynamic_voxelnet_ssl.py:307-377), scatter_v2(mode='avg')
+ *           (ops/sst/sst_ops.py:8-39), get_centroid_per_voxel x3 (…_ssl.py:726-768) and the
+ *           slot bookkeeping of get_multi_voxel_id_to_tensor_id_* (…_ssl.py:643-722). */
+int geomae_voxel_scatter(const geomae_voxel_cfg* cfg, const geomae_scatter_io* io, void* stream);
+
+/* ------------------------------------------------------- geometric targets */
+
+/* Per pillar: 3x3 scatter matrix of the neighbourhood's middle-scale centroids about the
+ * pillar centroid, symmetric eigen-solve, unit normal (z,y,x; sign: first non-zero
+ * component positive), singular values (descending) and curvature (S+1e-9)/sum in f64.
+ * replaces: spconv get_indice_pairs_implicit_gemm (call …_ssl.py:192-207) +
+ *           cal_regular_voxel_nor_and_curv (…_ssl.py:575-610). */
+int geomae_geom_targets(const geomae_voxel_cfg* cfg, const geomae_scatter_io* io, int64_t n_pillars,
+                        float* normal /*[n,3]*/, double* curvature /*[n,3]*/,
+                        float* cov6 /*[opt][n,6] zz,zy,zx,yy,yx,xx*/,
+                        float* singular /*[opt][n,3]*/, int32_t* pair /*[opt][9,n]*/, void* stream);
+
+/* Dense targets of the selected (masked) pillars, the layout the reference's loss consumes.
+ * rows: [m] pillar rows.  Any output may be NULL.
+ * replaces: normalize_centroid_sub_voxel (…_ssl.py:626-641) +
+ *           get_multi_voxel_id_to_tensor_id_ori (…_ssl.py:673-722) +
+ *           get_multi_voxel_id_to_tensor_id_for_curv (…_ssl.py:643-671, raw=1). */
+int geomae_dense_targets(const geomae_voxel_cfg* cfg, const geomae_scatter_io* io, const int64_t* rows,
+                         int64_t m, int32_t raw, float* low /*[m,slots_low,3]*/,
+                         uint8_t* low_mask /*[m,slots_low]*/, float* med /*[m,slots_med,3]*/,
+                         uint8_t* med_mask /*[m,slots_med]*/, float* top /*[m,3]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOMAE_B200_H */

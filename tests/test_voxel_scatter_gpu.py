@@ -1,0 +1,156 @@
+"""GPU parity of the fused voxelise+scatter stage and the geometric targets against the oracle
+(rows a1-a3, a6-a11 of SURVEY.md §8).  Integer outputs are compared bit-exactly."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geomae_oracle as O
+from tests.golden_util import align_sign, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def geometry(cfg):
+    from geomae_b200.voxel import VoxelGeometry
+    return VoxelGeometry(cfg.pc_range, cfg.voxel_size, cfg.sub_voxel_size_med, cfg.sub_voxel_size_low,
+                         cfg.sub_voxel_ratio_med, cfg.sub_voxel_ratio_low)
+
+
+def run_gpu(cfg, frames, want_coors=True):
+    from geomae_b200.voxel import scatter_frames
+    dev = torch.device("cuda:0")
+    return scatter_frames(geometry(cfg), [torch.from_numpy(f).to(dev) for f in frames], want_coors=want_coors)
+
+
+def csr_to_rows(ptr, mask_words, mean, n_slots):
+    """(parent, slot) -> mean xyz dict-like arrays from the CSR representation."""
+    parents, slots = [], []
+    for v in range(mask_words.shape[0]):
+        bits = [s for s in range(n_slots) if (int(mask_words[v, s // 32]) >> (s % 32)) & 1]
+        parents += [v] * len(bits)
+        slots += bits
+        assert ptr[v + 1] - ptr[v] == len(bits)
+    return np.array(parents), np.array(slots), mean[: ptr[mask_words.shape[0]]]
+
+
+def check_against_oracle(cfg, frames, ids_mask=None, atol=3e-6):
+    pb = run_gpu(cfg, frames)
+    v, n_med, n_low = pb.sizes()
+    ids_mask = np.arange(0, v, 3) if ids_mask is None else ids_mask
+    tgt = O.geometric_targets(frames, cfg, ids_mask)
+    n = sum(f.shape[0] for f in frames)
+    # a1/a2: voxel coordinates, bit exact at all three scales
+    for name in ("coors_top", "coors_med", "coors_low"):
+        assert np.array_equal(getattr(pb, name)[:n].cpu().numpy(), tgt[name]), name
+    # a3/a5: sorted pillar list + inverse map, bit exact
+    assert v == tgt["pillar_coors"].shape[0]
+    assert np.array_equal(pb.pillar_coors[:v].cpu().numpy(), tgt["pillar_coors"])
+    _, inv, cnt = O.unique_rows(tgt["coors_top"])
+    assert np.array_equal(pb.point_pillar[:n].cpu().numpy(), inv)
+    pm = pb.pillar_mean[:v].cpu().numpy()
+    assert np.array_equal(pm[:, 3].astype(np.int64), cnt)
+    np.testing.assert_allclose(pm[:, [2, 1, 0]], tgt["centroid_top"], rtol=0, atol=atol)
+    # a6/a7: sub-voxel sets and centroids
+    assert n_med == tgt["rows_med"].shape[0] and n_low == tgt["rows_low"].shape[0]
+    med_words = pb.med_mask[:v].cpu().numpy().astype(np.uint32).reshape(-1, 1)
+    low_words = pb.low_mask[:v].cpu().numpy().astype(np.uint32)
+    par, slot, mean = csr_to_rows(pb.med_ptr[: v + 1].cpu().numpy(), med_words, pb.med_mean.cpu().numpy(), cfg.slots_med)
+    dense = np.zeros((v, cfg.slots_med, 3), np.float32)
+    dense[par, slot] = mean[:, [2, 1, 0]]
+    occ = np.zeros((v, cfg.slots_med), bool)
+    occ[par, slot] = True
+    assert np.array_equal(occ, tgt["med_mask"])
+    np.testing.assert_allclose(dense, tgt["med_raw"], rtol=0, atol=atol)
+    par, slot, mean = csr_to_rows(pb.low_ptr[: v + 1].cpu().numpy(), low_words, pb.low_mean.cpu().numpy(), cfg.slots_low)
+    occ = np.zeros((v, cfg.slots_low), bool)
+    occ[par, slot] = True
+    assert np.array_equal(occ, tgt["low_mask"])
+    # a8/a9: neighbour table (bit exact), scatter matrix, normal (up to sign), curvature
+    normal, curv, cov6, sing, pair = pb.geom_targets(want_debug=True)
+    assert np.array_equal(pair.cpu().numpy(), tgt["pair"])
+    c = cov6.cpu().numpy()
+    cov = np.stack([c[:, [0, 1, 2]], c[:, [1, 3, 4]], c[:, [2, 4, 5]]], axis=1)
+    scale = np.abs(tgt["cov"]).max(axis=(1, 2), keepdims=True) + 1e-12
+    assert (np.abs(cov - tgt["cov"]) / scale).max() < 2e-5
+    s_ref = tgt["singular"]
+    np.testing.assert_allclose(sing.cpu().numpy(), s_ref, rtol=1e-4, atol=2e-5 * s_ref.max())
+    np.testing.assert_allclose(curv.cpu().numpy(), tgt["curvature"], rtol=1e-4, atol=2e-5)
+    well = (s_ref[:, 1] - s_ref[:, 2]) > 1e-3 * np.maximum(s_ref[:, 0], 1e-12)
+    mine = align_sign(tgt["normal"], normal.cpu().numpy())
+    assert well.sum() > 0.5 * v or v < 50
+    assert np.abs(mine[well] - tgt["normal"][well]).max() < 2e-3
+    nn = normal.cpu().numpy()
+    np.testing.assert_allclose(np.linalg.norm(nn, axis=1), 1.0, atol=1e-5)
+    # residual check on ALL pillars incl. degenerate ones: C n = lambda_min n
+    res = np.einsum("vij,vj->vi", tgt["cov"].astype(np.float64), nn) - s_ref[:, 2:3] * nn
+    assert (np.abs(res).max(axis=1) <= 1e-4 * np.maximum(s_ref[:, 0], 1e-9) + 1e-9).all()
+    # a10/a11: dense normalised slot targets of the masked rows
+    rows = torch.from_numpy(ids_mask).cuda()
+    low, low_m, med, med_m, top = pb.dense_targets(rows)
+    assert np.array_equal(low_m.cpu().numpy(), tgt["tgt_low_mask"])
+    assert np.array_equal(med_m.cpu().numpy(), tgt["tgt_med_mask"])
+    np.testing.assert_allclose(low.cpu().numpy(), tgt["tgt_low"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(med.cpu().numpy(), tgt["tgt_med"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(top.cpu().numpy(), tgt["tgt_top"], rtol=0, atol=1e-4)
+    _, _, med_raw, med_raw_m, _ = pb.dense_targets(torch.arange(v).cuda(), raw=True)
+    assert np.array_equal(med_raw_m.cpu().numpy(), tgt["med_mask"])
+    np.testing.assert_allclose(med_raw.cpu().numpy(), tgt["med_raw"], rtol=0, atol=atol)
+    return pb, tgt
+
+
+def test_golden_small_case():
+    case, cfg, frames, g = load_case("small_b2")
+    pb, tgt = check_against_oracle(cfg, frames, g["ids_mask"])
+    # and directly against the vectors captured from the unmodified reference
+    v = pb.n_pillars
+    assert np.array_equal(pb.pillar_coors[:v].cpu().numpy(), g["pillar_coors"])
+    n = sum(f.shape[0] for f in frames)
+    for k in ("coors_top", "coors_med", "coors_low"):
+        assert np.array_equal(getattr(pb, k)[:n].cpu().numpy(), g[k])
+    np.testing.assert_allclose(pb.pillar_mean[:v, [2, 1, 0]].cpu().numpy(), g["centroid_top"], atol=3e-6)
+    normal, curv = pb.geom_targets()
+    np.testing.assert_allclose(curv.cpu().numpy(), g["curvature"], rtol=1e-4, atol=2e-5)
+
+
+def test_full_size_frames():
+    from geomae_b200.synthetic import make_frame
+    cfg = O.PathConfig()
+    check_against_oracle(cfg, [make_frame(101), make_frame(102), make_frame(103, sweeps=2)])
+
+
+def test_ragged_and_edge_inputs():
+    cfg = O.PathConfig()
+    rng = np.random.default_rng(0)
+    lo, hi = np.array(cfg.pc_range[:3], np.float32), np.array(cfg.pc_range[3:], np.float32)
+
+    def rand(n, scale=1.0):
+        p = rng.uniform(lo * scale, hi * scale, (n, 3)).astype(np.float32)
+        return np.concatenate([p, rng.uniform(0, 1, (n, 2)).astype(np.float32)], axis=1)
+    # out-of-range points clamp into the edge voxels; exact voxel-boundary values; one-point frame
+    edge = rand(257, 1.3)
+    edge[:40, 0] = (np.arange(40) * np.float32(0.256) + np.float32(-51.2)).astype(np.float32)
+    edge[40:60, 1] = np.nextafter((np.arange(20) * np.float32(0.064) - np.float32(51.2)).astype(np.float32),
+                                  np.float32(-100))
+    frames = [rand(1), edge, rand(1000), rand(5)]
+    check_against_oracle(cfg, frames)
+
+
+def test_voxelization_module_matches_oracle():
+    from geomae_b200.voxel import Voxelization
+    cfg = O.PathConfig()
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(-60, 60, (5000, 5)).astype(np.float32)
+    for vs in (cfg.voxel_size, cfg.sub_voxel_size_med, cfg.sub_voxel_size_low, (0.32, 0.32, 6), (0.1, 0.1, 8)):
+        vox = Voxelization(vs, list(cfg.pc_range), -1, (-1, -1))
+        got = vox(torch.from_numpy(pts).cuda()).cpu().numpy()
+        assert got.dtype == np.int32
+        assert np.array_equal(got, O.dynamic_voxelize(pts, vs, cfg.pc_range))
+    assert Voxelization(cfg.voxel_size, list(cfg.pc_range), -1, (-1, -1))(torch.zeros((0, 5)).cuda()).shape == (0, 3)
+
+
+def test_waymo_shaped_geometry():
+    from geomae_b200.synthetic import make_frame
+    cfg = O.PathConfig(pc_range=(-74.88, -74.88, -2.0, 74.88, 74.88, 4.0), voxel_size=(0.32, 0.32, 6),
+                       sub_voxel_size_med=(0.16, 0.16, 1.5), sub_voxel_size_low=(0.08, 0.08, 0.75),
+                       grid_size=(1, 468, 468))
+    check_against_oracle(cfg, [make_frame(7, preset="waymo", point_scale=0.3)])
