@@ -1,0 +1,8 @@
+"""geomae_b200 — B200-native implementation of GeoMAE's masked-pretraining hot path.
+
+Importing the package registers the reference's registry names (DETECTORS
+'MultiSubVoxelDynamicVoxelNetSSL', BACKBONES 'MultiMAESSTSPChoose', VOXEL_ENCODERS
+'DynamicScatterVFE', NORM_LAYERS 'naiveSyncBN1d', LOSSES 'SmoothL1Loss'/'CrossEntropyLoss')."""
+from . import backbone, detector, losses, norm, voxel_encoder  # noqa: F401  (registration side effects)
+from .registry import Config, build_detector, build_model  # noqa: F401
+from .voxel import Voxelization, VoxelGeometry, scatter_frames  # noqa: F401

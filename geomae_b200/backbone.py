@@ -1,0 +1,114 @@
+"""MultiMAESSTSPChoose — mirror of mmdet3d/models/backbones/multi_mae_sst_spearate_top_only.py
+(same registry key, ctor kwargs and state_dict keys).  Window bookkeeping is the CSR layout of
+``windows.py``; there is no padding, no drop (a 12x12 window never exceeds the largest bucket,
+SURVEY F9) and no host synchronisation inside the blocks."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .registry import BACKBONES
+from .sst import BasicShiftBlock, window_pos_embed
+from .voxel import PillarBatch, VoxelGeometry
+from .windows import WindowLayout, WindowSpec
+
+
+@BACKBONES.register_module()
+class MultiMAESSTSPChoose(nn.Module):
+    def __init__(self, window_shape, shifts_list, point_cloud_range, voxel_size, shuffle_voxels=False, d_model=[],
+                 nhead=[], sub_voxel_ratio_low=[], sub_voxel_ratio_med=[], cls_sub_voxel=False, encoder_num_blocks=6,
+                 decoder_num_blocks=2, dim_feedforward=[], dropout=0.0, activation="gelu", output_shape=None,
+                 low=True, med=True, top=True, debug=True, drop_info=None, normalize_pos=False, pos_temperature=10000,
+                 in_channel=None, conv_kwargs=None, checkpoint_blocks=[]):
+        super().__init__()
+        assert drop_info is not None
+        if shuffle_voxels or normalize_pos or in_channel is not None:
+            raise NotImplementedError("shuffle_voxels / normalize_pos / in_channel are off the GeoMAE path")
+        assert len(set(d_model)) == 1, "one d_model for every block (…top_only.py:378)"
+        self.window_shape, self.shifts_list = tuple(window_shape), list(shifts_list)
+        self.point_cloud_range, self.voxel_size = point_cloud_range, voxel_size
+        self.meta_drop_info, self.pos_temperature = drop_info, pos_temperature
+        self.d_model, self.nhead = d_model, nhead
+        self.cls_sub_voxel, self.low, self.med, self.top = cls_sub_voxel, low, med, top
+        self.output_shape, self.debug = output_shape, debug
+        max_tokens = max(v["max_tokens"] for v in (drop_info[0] if isinstance(drop_info, tuple) else drop_info).values())
+        if window_shape[0] * window_shape[1] > max_tokens:
+            raise NotImplementedError("token dropping (window larger than the largest bucket) is not on this path")
+        self.spec = WindowSpec(window_shape, shifts_list)
+        # sub-voxel sizes do not matter for window geometry; reuse the pillar size for all three scales
+        self.geom = VoxelGeometry(tuple(point_cloud_range), tuple(voxel_size), tuple(voxel_size), tuple(voxel_size),
+                                  (1, 1, 1), (1, 1, 1))
+
+        def blocks(n):
+            return nn.ModuleList([BasicShiftBlock(d_model[i], nhead[i], dim_feedforward[i], dropout, activation,
+                                                  batch_first=False, block_id=i) for i in range(n)])
+        self.encoder_blocks = blocks(encoder_num_blocks)
+        self.decoder_centroid_blocks = blocks(decoder_num_blocks)
+        self.decoder_density_blocks = blocks(decoder_num_blocks)
+        d = d_model[-1]
+        self.mask_token = nn.Parameter(torch.zeros(1, d))
+        self.per_sub_voxel_num_low = sub_voxel_ratio_low[0] * sub_voxel_ratio_low[1] * sub_voxel_ratio_low[2]
+        self.per_sub_voxel_num_med = sub_voxel_ratio_med[0] * sub_voxel_ratio_med[1] * sub_voxel_ratio_med[2]
+        self.decoder_pred_low = nn.Linear(d, self.per_sub_voxel_num_low * 3)
+        self.decoder_pred_med = nn.Linear(d, self.per_sub_voxel_num_med * 3)
+        self.decoder_pred_top = nn.Linear(d, 3)
+        if low:
+            self.decoder_pred_density_low = nn.Linear(d, self.per_sub_voxel_num_low * 3)
+        if med:
+            self.decoder_pred_density_med = nn.Linear(d, self.per_sub_voxel_num_med * 3)
+        if top:
+            self.decoder_pred_density_top = nn.Linear(d, 3)
+        if cls_sub_voxel:
+            self.cls_pred_low = nn.Linear(d, self.per_sub_voxel_num_low * 2)
+            self.cls_pred_med = nn.Linear(d, self.per_sub_voxel_num_med * 2)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for name, p in self.named_parameters():     # …top_only.py:318-321
+            if p.dim() > 1 and "scaler" not in name:
+                nn.init.xavier_uniform_(p)
+
+    def _layout(self, coors, batch_size, pillar_batch: PillarBatch | None, rows):
+        if pillar_batch is not None:
+            return WindowLayout.from_pillars(self.spec, pillar_batch, rows)
+        return WindowLayout.from_coors(self.spec, self.geom, coors, batch_size)
+
+    def forward(self, voxel_feat, coors, coors_mask, batch_size, pillar_batch=None, rows_keep=None, rows_mask=None):
+        """Reference call form ``backbone(voxel_feat, coors, coors_mask, batch_size)``; when the
+        caller also holds the scatter result it passes it (with the pillar rows) to reuse its bitmap."""
+        enc_layout = self._layout(coors, batch_size, pillar_batch, rows_keep)
+        x = self.forward_encoder(voxel_feat, enc_layout)
+        return self.forward_decoder(x, coors, coors_mask, batch_size, pillar_batch, rows_keep, rows_mask)
+
+    def forward_encoder(self, voxel_feat, layout):
+        pos = window_pos_embed(layout, self.d_model[0], self.pos_temperature)
+        out = voxel_feat
+        for block in self.encoder_blocks:
+            out = block(out, layout, pos)
+        return out
+
+    def forward_decoder(self, visible_voxel_feat, coors, coors_mask, batch_size, pillar_batch=None, rows_keep=None,
+                        rows_mask=None):
+        n_vis = coors.shape[0]
+        tokens = torch.cat([visible_voxel_feat, self.mask_token.repeat(coors_mask.shape[0], 1)], dim=0)
+        all_coors = torch.cat([coors, coors_mask], dim=0)
+        rows = torch.cat([rows_keep, rows_mask]) if pillar_batch is not None else None
+        layout = self._layout(all_coors, batch_size, pillar_batch, rows)
+        pos = window_pos_embed(layout, self.d_model[0], self.pos_temperature)
+        cen = den = tokens
+        for block in self.decoder_centroid_blocks:
+            cen = block(cen, layout, pos)
+        for block in self.decoder_density_blocks:
+            den = block(den, layout, pos)
+        cen, den = cen[n_vis:], den[n_vis:]
+        reg_low = self.decoder_pred_low(cen).view(-1, self.per_sub_voxel_num_low, 3)
+        reg_med = self.decoder_pred_med(cen).view(-1, self.per_sub_voxel_num_med, 3)
+        reg_top = self.decoder_pred_top(cen)
+        nor_low = self.decoder_pred_density_low(den).view(-1, self.per_sub_voxel_num_low, 3) if self.low else None
+        nor_med = self.decoder_pred_density_med(den).view(-1, self.per_sub_voxel_num_med, 3) if self.med else None
+        nor_top = self.decoder_pred_density_top(den) if self.top else None
+        if self.cls_sub_voxel:
+            cls_low = self.cls_pred_low(cen).view(-1, self.per_sub_voxel_num_low, 2)
+            cls_med = self.cls_pred_med(cen).view(-1, self.per_sub_voxel_num_med, 2)
+            return reg_low, reg_med, reg_top, nor_low, nor_med, nor_top, cls_low, cls_med
+        return reg_low, reg_med, reg_top, nor_low, nor_med, nor_top

@@ -137,10 +137,11 @@ __global__ void __launch_bounds__(TPB) k_bitmap_rank(VoxGeom g, const uint32_t* 
         const int64_t cell = ((int64_t)(w0 + i) << 5) + bit;
         const int b = (int)(cell / cells_per_frame);
         const int r = (int)(cell - (int64_t)b * cells_per_frame);
-        reinterpret_cast<int4*>(pillar_coors)[rank] = make_int4(b, 0, r / g.grid[0][0], r % g.grid[0][0]);
-        reinterpret_cast<float4*>(pillar_mean)[rank] = make_float4(0.f, 0.f, 0.f, 0.f);
-        med_mask[rank] = 0u;
-        reinterpret_cast<uint4*>(low_mask)[rank] = make_uint4(0u, 0u, 0u, 0u);
+        if (pillar_coors)
+          reinterpret_cast<int4*>(pillar_coors)[rank] = make_int4(b, 0, r / g.grid[0][0], r % g.grid[0][0]);
+        if (pillar_mean) reinterpret_cast<float4*>(pillar_mean)[rank] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (med_mask) med_mask[rank] = 0u;
+        if (low_mask) reinterpret_cast<uint4*>(low_mask)[rank] = make_uint4(0u, 0u, 0u, 0u);
       }
       ++rank;
     }
@@ -310,6 +311,25 @@ __global__ void __launch_bounds__(TPB) k_sub_finalize(const int32_t* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- occupancy from explicit (b,z,y,x) rows
+__global__ void __launch_bounds__(TPB) k_mark_coors(VoxGeom g, const int32_t* __restrict__ coors, int64_t n,
+                                                    uint32_t* bitmap) {
+  const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = __ldg(reinterpret_cast<const int4*>(coors) + i);
+  const int64_t cell = top_cell(g, c.x, c.z, c.w);
+  atomicOr(bitmap + (cell >> 5), 1u << (cell & 31));
+}
+
+__global__ void __launch_bounds__(TPB) k_token_of_cell(VoxGeom g, const int32_t* __restrict__ coors, int64_t n,
+                                                       const uint32_t* __restrict__ bitmap,
+                                                       const int32_t* __restrict__ word_rank, int32_t* tok_of_pillar) {
+  const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = __ldg(reinterpret_cast<const int4*>(coors) + i);
+  tok_of_pillar[cell_rank(bitmap, word_rank, top_cell(g, c.x, c.z, c.w))] = (int32_t)i;
+}
+
 // ---------------------------------------------------------------- standalone dynamic_voxelize (a1)
 __global__ void __launch_bounds__(TPB) k_dynamic_voxelize(const float* __restrict__ pts, int64_t n, int stride, float lx,
                                                           float ly, float lz, float vx, float vy, float vz, int gx,
@@ -396,6 +416,30 @@ extern "C" int geomae_voxel_scatter(const geomae_voxel_cfg* cfg, const geomae_sc
                                              io->med_ptr, io->low_ptr, io->med_mean, io->low_mean);
     k_sub_finalize<<<GM_NUM_SMS * 4, TPB, 0, stream>>>(io->counts, io->med_mean, io->low_mean, io->n_points);
   }
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
+
+extern "C" int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* coors, int64_t n, int32_t n_frames,
+                                   uint32_t* bitmap, int32_t* word_rank, int32_t* scan_tmp, int32_t* counts,
+                                   int32_t* tok_of_pillar, void* stream_) {
+  GM_REQUIRE(cfg && bitmap && word_rank && scan_tmp && counts && tok_of_pillar && (coors || n == 0),
+             "coors_bitmap: null argument");
+  GM_REQUIRE(n_frames >= 1 && n >= 0, "coors_bitmap: bad sizes");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VoxGeom g;
+  int rc = gm_make_geom(cfg, n_frames, &g);
+  if (rc) return rc;
+  const int64_t n_cells = (int64_t)n_frames * g.grid[0][0] * g.grid[0][1];
+  const int n_words = gm_div_up(n_cells, 32);
+  const int scan_blocks = gm_div_up(n_words, SCAN_CHUNK);
+  GM_REQUIRE(scan_blocks <= SCAN_MAX_BLOCKS, "coors_bitmap: grid too large (%d scan blocks)", scan_blocks);
+  GM_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)n_words * 4, stream));
+  if (n > 0) k_mark_coors<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap);
+  k_bitmap_sums<<<scan_blocks, TPB, 0, stream>>>(bitmap, n_words, scan_tmp);
+  k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, bitmap, n_words, scan_tmp, word_rank, counts, nullptr, nullptr,
+                                                 nullptr, nullptr, n > 0 ? n : 1);
+  if (n > 0) k_token_of_cell<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap, word_rank, tok_of_pillar);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
 }

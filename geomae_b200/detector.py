@@ -1,0 +1,132 @@
+"""MultiSubVoxelDynamicVoxelNetSSL — mirror of
+mmdet3d/models/detectors/multi_sub_voxel_dynamic_voxelnet_ssl.py (same registry key, ctor kwargs,
+loss keys), restricted to the branch the shipped configs take: normalize_sub_voxel=True,
+mse_loss=True, cls_sub_voxel=True, vanilla random masking."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import lib as L
+from .registry import DETECTORS, build_backbone, build_loss, build_voxel_encoder
+from .voxel import PillarBatch, VoxelGeometry, Voxelization, scatter_frames
+
+
+@DETECTORS.register_module()
+class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
+    def __init__(self, loss, loss_ratio_low, loss_ratio_med, loss_ratio_top, loss_ratio_low_nor, loss_ratio_med_nor,
+                 loss_ratio_top_nor, hard_sub_voxel_layer_low, hard_sub_voxel_layer_med, hard_sub_voxel_layer_top,
+                 random_mask_ratio, grid_size, sub_voxel_ratio_low, sub_voxel_ratio_med, voxel_layer,
+                 sub_voxel_layer_low, sub_voxel_layer_med, voxel_encoder, backbone, spatial_shape=[1, 468, 468],
+                 nor_usr_sml1=None, cls_loss_ratio_low=None, cls_loss_ratio_med=None, vis=False, cls_sub_voxel=False,
+                 normalize_sub_voxel=None, use_focal_mask=None, norm_curv=True, mse_loss=None, neck=None,
+                 bbox_head=None, train_cfg=None, test_cfg=None, pretrained=None, init_cfg=None):
+        super().__init__()
+        if neck is not None or bbox_head is not None:
+            raise NotImplementedError("neck / bbox_head are not part of the SSL pretraining path")
+        if use_focal_mask is not None or nor_usr_sml1 is not None or not mse_loss or not normalize_sub_voxel \
+                or not cls_sub_voxel or not norm_curv:
+            raise NotImplementedError("only the branch taken by configs/mae_sst/* is implemented "
+                                      "(mse_loss, normalize_sub_voxel, cls_sub_voxel, vanilla mask)")
+        self.backbone = build_backbone(backbone)
+        self.voxel_encoder = build_voxel_encoder(voxel_encoder)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.spatial_shape, self.grid_size = spatial_shape, grid_size
+        self.loss_ratio_low, self.loss_ratio_med, self.loss_ratio_top = loss_ratio_low, loss_ratio_med, loss_ratio_top
+        self.loss_ratio_low_nor, self.loss_ratio_med_nor, self.loss_ratio_top_nor = \
+            loss_ratio_low_nor, loss_ratio_med_nor, loss_ratio_top_nor
+        self.cls_loss_ratio_low, self.cls_loss_ratio_med = cls_loss_ratio_low, cls_loss_ratio_med
+        self.random_mask_ratio = random_mask_ratio
+        self.point_cloud_range, self.voxel_size = voxel_layer["point_cloud_range"], voxel_layer["voxel_size"]
+        self.sub_voxel_size_low, self.sub_voxel_size_med = sub_voxel_layer_low["voxel_size"], sub_voxel_layer_med["voxel_size"]
+        self.sub_voxel_ratio_low, self.sub_voxel_ratio_med = sub_voxel_ratio_low, sub_voxel_ratio_med
+        self.voxel_layer = Voxelization(**voxel_layer)
+        self.sub_voxel_layer_low = Voxelization(**sub_voxel_layer_low)
+        self.sub_voxel_layer_med = Voxelization(**sub_voxel_layer_med)
+        # hard_sub_voxel_layer_* are constructed but never called by the reference (…_ssl.py:100-102); accepted, unused
+        self.reg_loss = build_loss(loss)
+        self.cls_loss = build_loss(dict(type="CrossEntropyLoss", use_sigmoid=True, loss_weight=1.0))
+        self.geom = VoxelGeometry(tuple(self.point_cloud_range), tuple(self.voxel_size), tuple(self.sub_voxel_size_med),
+                                  tuple(self.sub_voxel_size_low), tuple(sub_voxel_ratio_med), tuple(sub_voxel_ratio_low))
+        gx, gy, gz = self.geom_grid_host()
+        if (gz, gy, gx) != tuple(grid_size):
+            raise ValueError(f"grid_size {tuple(grid_size)} does not match the voxel geometry {(gz, gy, gx)}")
+
+    def geom_grid_host(self):
+        import math
+        r, v = self.point_cloud_range, self.voxel_size
+        return [int(math.ceil(round((r[3 + i] - r[i]) / v[i], 4))) for i in range(3)]
+
+    # ------------------------------------------------------------------ reference-named pieces
+    def voxelize(self, points):
+        """…_ssl.py:355-377: per-sample coords with the batch index prepended."""
+        coors = [nn.functional.pad(self.voxel_layer(p), (1, 0), value=i) for i, p in enumerate(points)]
+        return torch.cat(points, dim=0), torch.cat(coors, dim=0)
+
+    def sub_voxelize_low(self, points):
+        return torch.cat([nn.functional.pad(self.sub_voxel_layer_low(p), (1, 0), value=i) for i, p in enumerate(points)])
+
+    def sub_voxelize_med(self, points):
+        return torch.cat([nn.functional.pad(self.sub_voxel_layer_med(p), (1, 0), value=i) for i, p in enumerate(points)])
+
+    @torch.no_grad()
+    def get_vanilla_mask_index(self, coors, batch_size):
+        """…_ssl.py:287-304: per sample randperm(L) on the device, keep int(L*(1-ratio))."""
+        counts = torch.bincount(coors[:, 0].long(), minlength=batch_size).tolist()
+        keep, mask, start = [], [], 0
+        for n in counts:
+            len_keep = int(n * (1 - self.random_mask_ratio))
+            perm = torch.randperm(n, device=coors.device) + start
+            keep.append(perm[:len_keep])
+            mask.append(perm[len_keep:])
+            start += n
+        return torch.cat(keep), torch.cat(mask)
+
+    # ------------------------------------------------------------------ hot path
+    def extract_feat(self, points, ids=None):
+        batch_size = len(points)
+        pb = scatter_frames(self.geom, points)
+        voxel_features, feature_coors = self.voxel_encoder(pb)
+        ids_keep, ids_mask = ids if ids is not None else self.get_vanilla_mask_index(feature_coors, batch_size)
+        with torch.no_grad():
+            normal, curv = pb.geom_targets()
+            low, low_mask, med, med_mask, top = pb.dense_targets(ids_mask)
+            normal_m = normal.index_select(0, ids_mask)
+        x = self.backbone(voxel_features.index_select(0, ids_keep), feature_coors.index_select(0, ids_keep),
+                          feature_coors.index_select(0, ids_mask), batch_size, pillar_batch=pb, rows_keep=ids_keep,
+                          rows_mask=ids_mask)
+        return x, low, low_mask, med, med_mask, top, normal_m, None, None
+
+    def forward_train(self, points, img_metas=None, gt_bboxes_3d=None, gt_labels_3d=None, gt_bboxes_ignore=None,
+                      ids=None):
+        for p in points:
+            L.require_cuda(p, "points")
+        x, c_low, m_low, c_med, m_med, c_top, n_low, n_med, n_top = self.extract_feat(points, ids)
+        reg_low, reg_med, reg_top, nor_low, nor_med, nor_top, cls_low, cls_med = x
+        return self.forward_loss(c_low, m_low, c_med, m_med, c_top, n_low, n_med, n_top, reg_low, reg_med, reg_top,
+                                 nor_low, nor_med, nor_top, cls_low, cls_med)
+
+    def forward(self, return_loss=True, **kwargs):
+        if return_loss:
+            return self.forward_train(**kwargs)
+        raise NotImplementedError("the SSL detector has no test path")
+
+    @staticmethod
+    def _mse(pred, target, weight):
+        per_row = ((pred - target) ** 2).mean(dim=-1)
+        return per_row.sum() / per_row.shape[0] * weight
+
+    def forward_loss(self, centroid_low, centroid_low_mask, centroid_med, centroid_med_mask, centroid_high,
+                     centroid_normal_low, centroid_normal_med, centroid_normal_high, reg_pred_low, reg_pred_med,
+                     reg_pred_high, nor_pred_low, nor_pred_med, nor_pred_high, cls_pred_low=None, cls_pred_med=None):
+        """…_ssl.py:837-902, mse_loss branch."""
+        lm, mm = centroid_low_mask.reshape(-1), centroid_med_mask.reshape(-1)
+        loss_low = self._mse(reg_pred_low.reshape(-1, 3)[lm], centroid_low.reshape(-1, 3)[lm], self.loss_ratio_low)
+        loss_med = self._mse(reg_pred_med.reshape(-1, 3)[mm], centroid_med.reshape(-1, 3)[mm], self.loss_ratio_med)
+        loss_top = self._mse(reg_pred_high, centroid_high, self.loss_ratio_top)
+        nor_pred = nor_pred_high if (nor_pred_low is None and nor_pred_med is None) else nor_pred_low
+        loss_nor = self._mse(nor_pred, centroid_normal_low, self.loss_ratio_low_nor)
+        loss_cls_low = self.cls_loss(cls_pred_low.reshape(-1, 2), lm.long()) * self.cls_loss_ratio_low
+        loss_cls_med = self.cls_loss(cls_pred_med.reshape(-1, 2), mm.long()) * self.cls_loss_ratio_med
+        return dict(loss_curv_around=loss_nor, loss_centroid_low=loss_low, loss_centroid_med=loss_med,
+                    loss_centroid_top=loss_top, loss_cls_low=loss_cls_low, loss_cls_med=loss_cls_med)

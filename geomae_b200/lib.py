@@ -33,6 +33,18 @@ class ScatterIO(C.Structure):
                 ("coors_low", C.c_void_p)]
 
 
+class WindowCfg(C.Structure):
+    _fields_ = [("win_x", C.c_int32), ("win_y", C.c_int32), ("n_shifts", C.c_int32),
+                ("shift_x", C.c_int32 * 2), ("shift_y", C.c_int32 * 2)]
+
+
+class WindowIO(C.Structure):
+    _fields_ = [("ptr_stride", C.c_int64), ("cand_count", C.c_void_p), ("cand_tok_off", C.c_void_p),
+                ("cand_win_idx", C.c_void_p), ("n_windows", C.c_void_p), ("win_ptr", C.c_void_p),
+                ("win_id", C.c_void_p), ("win_tok", C.c_void_p), ("tok_cell", C.c_void_p),
+                ("tok_win", C.c_void_p), ("tok_pos", C.c_void_p)]
+
+
 def build_if_missing():
     if not os.path.exists(LIB_PATH):
         import subprocess
@@ -66,6 +78,18 @@ class _Sigs:
     geomae_voxel_scatter = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), _p]
     geomae_geom_targets = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), _i64, _p, _p, _p, _p, _p, _p]
     geomae_dense_targets = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
+    geomae_window_candidates = [C.POINTER(VoxelCfg), C.POINTER(WindowCfg), _i32, C.POINTER(C.c_int32),
+                                C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    geomae_coors_bitmap = [C.POINTER(VoxelCfg), _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
+    geomae_token_map = [_p, _i64, _p, _i64, _p]
+    geomae_window_csr = [C.POINTER(VoxelCfg), C.POINTER(WindowCfg), C.POINTER(ScatterIO), _p, _i64,
+                         C.POINTER(WindowIO), _p]
+    geomae_pos_table = [_i32, _i32, _i32, C.c_float, _p, _p]
+    geomae_vfe_decorate = [_p, _i64, _i32, _p, _p, _p, _f3, _f3, _p, _p]
+    geomae_scatter_reduce_fwd = [_p, _i64, _i32, _p, _p, _i64, _i32, _p, _p, _p]
+    geomae_scatter_reduce_bwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
+    geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p]
+    geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
 
 
 def check(rc: int, what: str):

@@ -114,6 +114,105 @@ int geomae_dense_targets(const geomae_voxel_cfg* cfg, const geomae_scatter_io* i
                          uint8_t* low_mask /*[m,slots_low]*/, float* med /*[m,slots_med,3]*/,
                          uint8_t* med_mask /*[m,slots_med]*/, float* top /*[m,3]*/, void* stream);
 
+/* ------------------------------------------------------ window partition */
+
+/* window_shape / shifts_list of the backbone (configs/mae_sst/…6x_1e-5.py:15,57). */
+typedef struct geomae_window_cfg {
+  int32_t win_x, win_y;
+  int32_t n_shifts;       /* 1 or 2 */
+  int32_t shift_x[2], shift_y[2];
+} geomae_window_cfg;
+
+/* CSR window layout of one token set, both shifts.  Arrays are [n_shifts, stride] with the
+ * stride given next to each; all device pointers, caller-allocated.  n_cand comes from
+ * geomae_window_candidates(). */
+typedef struct geomae_window_io {
+  int64_t ptr_stride;    /* >= n_cand + 1                                                      */
+  int32_t* cand_count;   /* scratch [n_shifts, n_cand]                                          */
+  int32_t* cand_tok_off; /* scratch [n_shifts, n_cand]                                          */
+  int32_t* cand_win_idx; /* scratch [n_shifts, n_cand]                                          */
+  int32_t* n_windows;    /* [n_shifts] number of non-empty windows                              */
+  int32_t* win_ptr;      /* [n_shifts, ptr_stride] CSR offsets, first n_windows+1 valid         */
+  int32_t* win_id;       /* [n_shifts, ptr_stride] batch_win_inds value of each window (sorted) */
+  int32_t* win_tok;      /* [n_shifts, n_tokens] token index, grouped by window, cell order     */
+  int32_t* tok_cell;     /* [n_shifts, n_tokens] in-window cell cx*win_y+cy of each token (position-table row) */
+  int32_t* tok_win;      /* [n_shifts, n_tokens] window row of each token                       */
+  int32_t* tok_pos;      /* [n_shifts, n_tokens] CSR position of each token                     */
+} geomae_window_io;
+
+/* Number of candidate windows n_frames*nwx*nwy, nw = ceil(grid/win)+1.
+ * replaces: MultiMAESSTSPChoose.window_partition bookkeeping
+ *           (backbones/multi_mae_sst_spearate_top_only.py:637-642). */
+int geomae_window_candidates(const geomae_voxel_cfg* cfg, const geomae_window_cfg* wcfg, int32_t n_frames,
+                             int32_t* n_cand, int32_t* nwx, int32_t* nwy);
+
+/* Occupancy bitmap + ranks from explicit token rows coors [n,4] (b,z,y,x) (unique cells), and
+ * tok_of_pillar[rank(cell_i)] = i.  Lets geomae_window_csr serve callers that only hold coordinates,
+ * i.e. the reference signature backbone.forward(voxel_feat, coors, coors_mask, batch_size)
+ * (…top_only.py:136-141) and SSTInputLayer.forward (middle_encoders/sst_input_layer.py:51-103).
+ * bitmap/word_rank: [ceil(n_frames*gy*gx/32)], scan_tmp [3*4096], counts [4], tok_of_pillar [n]. */
+int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* coors, int64_t n, int32_t n_frames,
+                        uint32_t* bitmap, int32_t* word_rank, int32_t* scan_tmp, int32_t* counts,
+                        int32_t* tok_of_pillar, void* stream);
+
+/* tok_of_pillar[rows[i]] = i, every other pillar -1 (rows = ids_keep, or [ids_keep; ids_mask]). */
+int geomae_token_map(const int64_t* rows, int64_t n_tokens, int32_t* tok_of_pillar, int64_t n_pillars,
+                     void* stream);
+
+/* Window CSR for the token set described by tok_of_pillar, using the scatter stage's bitmap.
+ * replaces: window_partition (…top_only.py:628-659), drop_single_shift / get_voxel_keep_inds
+ *           (:519-541,562-626; no token is ever dropped when win_x*win_y <= the largest bucket),
+ *           get_flat2win_inds / make_continuous_inds / get_inner_win_inds (:413-507,661-681),
+ *           and the flat2window / window2flat padding round trips (ops/sst/sst_ops.py:98-135,225-251). */
+int geomae_window_csr(const geomae_voxel_cfg* cfg, const geomae_window_cfg* wcfg, const geomae_scatter_io* io,
+                      const int32_t* tok_of_pillar, int64_t n_tokens, const geomae_window_io* out, void* stream);
+
+/* [win_x*win_y, d_model] sinusoidal position table, row = cx*win_y + cy.
+ * replaces: MultiMAESSTSPChoose.get_pos_embed (…top_only.py:361-399). */
+int geomae_pos_table(int32_t win_x, int32_t win_y, int32_t d_model, float temperature, float* table, void* stream);
+
+/* ------------------------------------------------------ voxel feature encoder */
+
+/* out[p] = [point channels | xyz - pillar mean | xyz - pillar centre], width channels+6.
+ * centre_offset = voxel/2 + range_min evaluated in double then rounded (voxel_encoder.py:155-157).
+ * replaces: the decoration block of DynamicScatterVFE.forward (voxel_encoders/voxel_encoder.py:371-398). */
+int geomae_vfe_decorate(const float* points, int64_t n, int32_t channels, const int32_t* point_pillar,
+                        const float* pillar_mean, const int32_t* pillar_coors, const float voxel_xyz[3],
+                        const float centre_offset_xyz[3], float* out, void* stream);
+
+/* Point -> pillar reduction over the row map produced by geomae_voxel_scatter.
+ * mode: 0 sum, 1 mean, 2 max.  out: [n_pillars, channels]; arg (max only): [n_pillars, channels]
+ * int32 arg-max point (smallest index among ties).  pillar_mean supplies the counts for mode 1.
+ * replaces: voxel_layer.dynamic_point_to_voxel_forward (mmdet3d/ops/voxel/src/voxelization.h:122-134,
+ *           scatter_points_cuda.cu:80-103) and torch_scatter.scatter/scatter_max as called by
+ *           scatter_v2 (ops/sst/sst_ops.py:29-32). */
+int geomae_scatter_reduce_fwd(const float* feat, int64_t n_points, int32_t channels, const int32_t* point_pillar,
+                              const float* pillar_mean, int64_t n_pillars, int32_t mode, float* out, int32_t* arg,
+                              void* stream);
+
+/* d_feat[p] = d_out[pillar(p)] routed to the arg-max point (max), or spread (sum / mean).
+ * replaces: voxel_layer.dynamic_point_to_voxel_backward (voxelization.h:136-154). */
+int geomae_scatter_reduce_bwd(const float* d_out, int64_t n_points, int32_t channels, const int32_t* point_pillar,
+                              const float* pillar_mean, const int32_t* arg, int32_t mode, float* d_feat,
+                              void* stream);
+
+/* ------------------------------------------------- sparse regional attention */
+
+/* Multi-head attention inside CSR windows (no padding, no key_padding_mask needed).
+ * qkv: [n_tokens, 3*d_model] fp32, rows in flat token order: q | k | v, q NOT yet scaled.
+ * out: [n_tokens, d_model]; lse: [n_tokens, n_heads] log-sum-exp saved for backward.
+ * head_dim must be 16 (d_model = 16*n_heads).
+ * replaces: nn.MultiheadAttention core inside WindowAttention.forward
+ *           (models/sst/sst_basic_block.py:26-61) on padded [T,W,C] buckets. */
+int geomae_sra_attention_fwd(const float* qkv, int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
+                             const int32_t* win_tok, const int32_t* n_windows, int32_t max_windows,
+                             float* out, float* lse, void* stream);
+
+/* Backward of the above: d_qkv [n_tokens, 3*d_model] from d_out, recomputing the probabilities. */
+int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
+                             int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr, const int32_t* win_tok,
+                             const int32_t* n_windows, int32_t max_windows, float* d_qkv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

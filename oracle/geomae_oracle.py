@@ -536,9 +536,13 @@ def losses(pred, tgt, cfg: PathConfig):
         loss_cls_med=occupancy_bce(pred["cls_med"].reshape(-1, 2), mm) * cfg.cls_med)
 
 
-def forward_train(params, frames, cfg: PathConfig, ids_keep, ids_mask, trace=None):
-    """detectors/…_ssl.py:126-166 end to end.  ``params``: reference state_dict names -> tensors."""
+def forward_train(params, frames, cfg: PathConfig, ids_keep, ids_mask, trace=None, normal_override=None):
+    """detectors/…_ssl.py:126-166 end to end.  ``params``: reference state_dict names -> tensors.
+    ``normal_override`` ([V,3]) replaces the per-pillar normals before the loss — the parity harness
+    uses it to sign-align / substitute the SVD-backend-dependent normals."""
     tgt = geometric_targets(frames, cfg, ids_mask)
+    if normal_override is not None:
+        tgt["tgt_normal"] = np.asarray(normal_override, np.float32)[np.asarray(ids_mask)]
     pts = torch.from_numpy(np.concatenate(frames, axis=0).astype(np.float32))
     feats, rows, inv = vfe_forward(params, pts, tgt["coors_top"], cfg)
     if trace is not None:

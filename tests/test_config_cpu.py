@@ -1,0 +1,51 @@
+"""Config / registry surface: the reference's own config file builds the model unchanged."""
+import os
+
+import pytest
+import torch
+
+import geomae_b200  # noqa: F401
+from geomae_b200.registry import Config, build_model
+from oracle import geomae_oracle as O
+
+REF_CFG = "/root/reference/configs/mae_sst/m_sst_nus_singlestage_curv_07_ssl_dataset_wo_dbsampler_6x_1e-5.py"
+REF_CFG_8X = "/root/reference/configs/mae_sst/m_sst_nus_singlestage_curv_07_ssl_dataset_wo_dbsampler_8x_1e-5.py"
+OWN_CFG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs/mae_sst/geomae_nus_pretrain.py")
+
+
+def test_own_config_builds_with_reference_state_dict_keys():
+    model = build_model(Config.fromfile(OWN_CFG).model)
+    assert sum(p.numel() for p in model.parameters()) == 2760854
+    sd = model.state_dict()
+    ref = O.init_params(O.PathConfig(), 0)
+    assert not [k for k in ref if k not in sd]
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    # every parameter of the model is named in the oracle's (= the reference's) parameter tree
+    assert not [k for k, _ in model.named_parameters() if k not in ref]
+    # the reference xavier-initialises the [1,128] mask token too (…top_only.py:114,131,318-321)
+    assert torch.count_nonzero(sd["backbone.mask_token"]) > 0
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference tree not present")
+@pytest.mark.parametrize("path", [REF_CFG, REF_CFG_8X])
+def test_reference_config_loads_unchanged(path):
+    cfg = Config.fromfile(path)
+    model = build_model(cfg.model)
+    assert type(model).__name__ == "MultiSubVoxelDynamicVoxelNetSSL"
+    assert type(model.backbone).__name__ == "MultiMAESSTSPChoose"
+    assert type(model.voxel_encoder.vfe_layers[0].norm).__name__ == "NaiveSyncBatchNorm1d"
+    assert cfg.data["samples_per_gpu"] == 4
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference tree not present")
+def test_own_config_equals_reference_model_dict():
+    a, b = Config.fromfile(OWN_CFG).model, Config.fromfile(REF_CFG).model
+
+    def norm(x):
+        if isinstance(x, dict):
+            return {k: norm(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [norm(v) for v in x]
+        return x
+    assert norm(a) == norm(b)

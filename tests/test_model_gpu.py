@@ -1,0 +1,225 @@
+"""GPU parity of window CSR, SRA attention, VFE scatter and the full train-step forward/backward
+against the oracle.  All calls go through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geomae_oracle as O
+from tests.golden_util import load_case
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OWN_CFG = os.path.join(ROOT, "configs/mae_sst/geomae_nus_pretrain.py")
+DEV = "cuda:0"
+
+
+def geometry(cfg):
+    from geomae_b200.voxel import VoxelGeometry
+    return VoxelGeometry(cfg.pc_range, cfg.voxel_size, cfg.sub_voxel_size_med, cfg.sub_voxel_size_low,
+                         cfg.sub_voxel_ratio_med, cfg.sub_voxel_ratio_low)
+
+
+@pytest.fixture(scope="module")
+def small():
+    from geomae_b200.voxel import scatter_frames
+    case, cfg, frames, g = load_case("small_b2")
+    pb = scatter_frames(geometry(cfg), [torch.from_numpy(f).to(DEV) for f in frames])
+    return case, cfg, frames, g, pb
+
+
+def check_layout(layout, coors, cfg):
+    n = coors.shape[0]
+    for s in range(2):
+        win, ciw = O.window_partition(coors, cfg, s)
+        nw = int(layout.n_windows[s])
+        uniq = np.unique(win)
+        assert nw == uniq.size
+        assert np.array_equal(layout.win_id[s, :nw].cpu().numpy(), uniq)          # sorted window ids
+        tok_win = layout.tok_win[s, :n].cpu().numpy()
+        assert np.array_equal(uniq[tok_win], win)                                  # membership, bit exact
+        assert np.array_equal(layout.tok_cell[s, :n].cpu().numpy(), ciw[:, 0] * cfg.window_shape[1] + ciw[:, 1])
+        ptr = layout.win_ptr[s, :nw + 1].cpu().numpy()
+        assert ptr[0] == 0 and ptr[-1] == n
+        assert np.array_equal(np.diff(ptr), np.bincount(win)[uniq])               # tokens per window
+        win_tok = layout.win_tok[s, :n].cpu().numpy()
+        assert np.array_equal(np.sort(win_tok), np.arange(n))                      # a permutation
+        pos = layout.tok_pos[s, :n].cpu().numpy()
+        assert np.array_equal(win_tok[pos], np.arange(n))
+        seg = np.repeat(np.arange(nw), np.diff(ptr))
+        assert np.array_equal(tok_win[win_tok], seg)                               # CSR rows hold their window's tokens
+        # bucket levels are a pure function of the counts (…top_only.py:519-541)
+        lvl, cnt = O.window_levels(win, cfg)
+        assert np.array_equal(np.diff(ptr)[tok_win], cnt)
+
+
+def test_window_csr_both_constructors(small):
+    from geomae_b200.windows import WindowLayout, WindowSpec
+    _, cfg, _, g, pb = small
+    spec = WindowSpec(cfg.window_shape, cfg.shifts)
+    rows_all = np.concatenate([g["ids_keep"], g["ids_mask"]])
+    pillars = pb.pillar_coors[:pb.n_pillars].cpu().numpy()
+    for rows in (g["ids_keep"], rows_all):
+        coors = pillars[rows]
+        lay = WindowLayout.from_pillars(spec, pb, torch.from_numpy(rows).to(DEV))
+        check_layout(lay, coors, cfg)
+        lay2 = WindowLayout.from_coors(spec, pb.geom, torch.from_numpy(coors).to(DEV), 2)
+        check_layout(lay2, coors, cfg)
+        for name in ("win_tok", "tok_cell", "tok_win", "tok_pos"):
+            assert torch.equal(getattr(lay, name), getattr(lay2, name))
+    # reference's own bookkeeping captured in the golden file (decoder token set)
+    lay = WindowLayout.from_pillars(spec, pb, torch.from_numpy(rows_all).to(DEV))
+    for s in (0, 1):
+        nw = int(lay.n_windows[s])
+        ids = lay.win_id[s, :nw].cpu().numpy()
+        assert np.array_equal(ids[lay.tok_win[s].cpu().numpy()], g[f"dec_win_shift{s}"])
+        ciw = g[f"dec_ciw_shift{s}"]
+        assert np.array_equal(lay.tok_cell[s].cpu().numpy(), ciw[:, 0] * 12 + ciw[:, 1])
+
+
+def test_window_csr_empty_and_single():
+    from geomae_b200.windows import WindowLayout, WindowSpec
+    cfg = O.PathConfig()
+    spec = WindowSpec(cfg.window_shape, cfg.shifts)
+    geom = geometry(cfg)
+    one = torch.tensor([[1, 0, 399, 399]], dtype=torch.int32, device=DEV)
+    lay = WindowLayout.from_coors(spec, geom, one, 2)
+    check_layout(lay, one.cpu().numpy(), cfg)
+    corners = torch.tensor([[0, 0, 0, 0], [0, 0, 0, 399], [0, 0, 399, 0], [0, 0, 5, 6], [0, 0, 6, 5], [0, 0, 11, 12]],
+                           dtype=torch.int32, device=DEV)
+    check_layout(WindowLayout.from_coors(spec, geom, corners, 1), corners.cpu().numpy(), cfg)
+
+
+def test_pos_table_matches_oracle():
+    from geomae_b200.windows import pos_table
+    cfg = O.PathConfig()
+    got = pos_table(cfg.window_shape, cfg.d_model, cfg.pos_temperature, torch.device(DEV)).cpu()
+    np.testing.assert_allclose(got.numpy(), O.pos_embed_table(cfg).numpy(), rtol=0, atol=2e-6)
+
+
+def ref_attention(qkv, win_of_tok, n_heads):
+    n, d3 = qkv.shape
+    d = d3 // 3
+    q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]
+    out = torch.zeros(n, d, dtype=qkv.dtype)
+    for w in torch.unique(win_of_tok):
+        idx = torch.where(win_of_tok == w)[0]
+        qh = q[idx].view(-1, n_heads, 16).transpose(0, 1) * 0.25
+        kh = k[idx].view(-1, n_heads, 16).transpose(0, 1)
+        vh = v[idx].view(-1, n_heads, 16).transpose(0, 1)
+        p = torch.softmax(qh @ kh.transpose(1, 2), dim=-1)
+        out = out.index_put((idx,), (p @ vh).transpose(0, 1).reshape(-1, d))
+    return out
+
+
+def test_sra_attention_forward_backward(small):
+    from geomae_b200.sst import sra_attention
+    from geomae_b200.windows import WindowLayout, WindowSpec
+    _, cfg, _, g, pb = small
+    spec = WindowSpec(cfg.window_shape, cfg.shifts)
+    rows = np.concatenate([g["ids_keep"], g["ids_mask"]])[:2500]
+    lay = WindowLayout.from_pillars(spec, pb, torch.from_numpy(rows).to(DEV))
+    n = rows.shape[0]
+    gen = torch.Generator().manual_seed(0)
+    for s in (0, 1):
+        lens = np.diff(lay.win_ptr[s, :int(lay.n_windows[s]) + 1].cpu().numpy())
+        assert lens.max() > 32 or s == 0          # exercise the multi-chunk path
+        qkv = (torch.randn(n, 384, generator=gen) * 1.5).requires_grad_(True)
+        d_out = torch.randn(n, 128, generator=gen)
+        ref = ref_attention(qkv, lay.tok_win[s, :n].cpu().long(), 8)
+        ref.backward(d_out)
+        x = qkv.detach().to(DEV).requires_grad_(True)
+        out = sra_attention(x, lay.shift(s), 8)
+        out.backward(d_out.to(DEV))
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), qkv.grad.numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_scatter_reduce_modes(small):
+    from geomae_b200.voxel_encoder import scatter_reduce
+    _, _, frames, _, pb = small
+    n = sum(f.shape[0] for f in frames)
+    v = pb.n_pillars
+    inv = pb.point_pillar[:n].cpu().long()
+    gen = torch.Generator().manual_seed(1)
+    feat = torch.randn(n, 19, generator=gen)
+    feat[::7] = feat[::7].round()                 # create exact ties
+    d_out = torch.randn(v, 19, generator=gen)
+    for mode in ("max", "mean", "sum"):
+        x = feat.clone().requires_grad_(True)
+        if mode == "max":
+            ref = O._ScatterMaxFn.apply(x, inv, v)
+        else:
+            ref = torch.zeros(v, 19).index_add(0, inv, x)
+            if mode == "mean":
+                ref = ref / torch.bincount(inv, minlength=v).float().view(-1, 1)
+        ref.backward(d_out)
+        y = feat.clone().to(DEV).requires_grad_(True)
+        out = scatter_reduce(y, pb, mode)
+        out.backward(d_out.to(DEV))
+        tol = dict(rtol=0, atol=0) if mode == "max" else dict(rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), **tol)
+        np.testing.assert_allclose(y.grad.cpu().numpy(), x.grad.numpy(), **tol)
+
+
+def build_model(cfg, params):
+    import geomae_b200  # noqa: F401
+    from geomae_b200.registry import Config, build_model as build
+    mcfg = Config.fromfile(OWN_CFG).model
+    mcfg["backbone"] = dict(mcfg["backbone"], encoder_num_blocks=cfg.enc_blocks, decoder_num_blocks=cfg.dec_blocks)
+    model = build(mcfg)
+    sd = model.state_dict()
+    sd.update({k: v.detach().clone() for k, v in params.items()})
+    model.load_state_dict(sd)
+    return model.to(DEV).train()
+
+
+def run_parity(name, loss_tol=1e-4, grad_tol=2e-3):
+    case, cfg, frames, g = load_case(name)
+    params = O.init_params(cfg, case["param_seed"])
+    model = build_model(cfg, params)
+    ids = (torch.from_numpy(g["ids_keep"]).to(DEV), torch.from_numpy(g["ids_mask"]).to(DEV))
+    pts = [torch.from_numpy(f).to(DEV) for f in frames]
+    losses = model.forward_train(points=pts, img_metas=[{}] * len(pts), ids=ids)
+    sum(losses.values()).backward()
+    # oracle on the same inputs; normals: sign-aligned where well conditioned, ours substituted where the
+    # 3x3 problem is degenerate; the degenerate set's validity is tested in test_voxel_scatter_gpu
+    from geomae_b200.voxel import scatter_frames
+    normal = scatter_frames(model.geom, pts).geom_targets()[0].cpu().numpy()
+    tgt = O.geometric_targets(frames, cfg, g["ids_mask"])
+    s = tgt["singular"]
+    well = (s[:, 1] - s[:, 2]) > 1e-3 * np.maximum(s[:, 0], 1e-12)
+    sign = np.sign((tgt["normal"] * normal).sum(-1, keepdims=True))
+    aligned = np.where(well[:, None], tgt["normal"] * sign, normal)
+    oparams = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    olosses, _, _ = O.forward_train(oparams, frames, cfg, g["ids_keep"], g["ids_mask"], normal_override=aligned)
+    sum(olosses.values()).backward()
+    report = {}
+    for k, v in olosses.items():
+        got, ref = float(losses[k]), float(v)
+        report[k] = (got, ref, abs(got - ref) / abs(ref))
+        assert abs(got - ref) <= loss_tol * abs(ref), (k, got, ref)
+        if k != "loss_curv_around":   # the committed reference losses (LAPACK-sign normals excluded)
+            assert abs(got - float(g["loss/" + k])) <= loss_tol * abs(ref), (k, got, float(g["loss/" + k]))
+    bad = []
+    for k, p in model.named_parameters():
+        ref = oparams[k].grad
+        got = p.grad.cpu()
+        err = float((got - ref).norm() / (ref.norm() + 1e-12))
+        if err > grad_tol:
+            bad.append((k, err))
+    assert not bad, bad[:8]
+    return report
+
+
+def test_train_step_parity_small_case():
+    run_parity("small_b2")
+
+
+def test_train_step_parity_config0():
+    run_parity("config0_1frame_1block")
+
+
+def test_train_step_parity_full_config():
+    run_parity("full_b2", loss_tol=1e-4, grad_tol=5e-3)
