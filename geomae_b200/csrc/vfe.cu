@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(TPB) k_decorate(const float* __restrict__ pts,
 
 // order-preserving float <-> uint key so one atomicMax works for any sign
 __device__ __forceinline__ uint32_t f2key(float f) {
+  if (f == 0.f) f = 0.f;  // -0.0 and +0.0 compare equal in the reference: one key for both
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }

@@ -92,6 +92,9 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
             normal, curv = pb.geom_targets()
             low, low_mask, med, med_mask, top = pb.dense_targets(ids_mask)
             normal_m = normal.index_select(0, ids_mask)
+        if getattr(self, "keep_targets", False):   # parity harness: expose exactly what this step regressed against
+            self.last_targets = dict(pillar_batch=pb, normal=normal, curvature=curv, ids_keep=ids_keep,
+                                     ids_mask=ids_mask)
         x = self.backbone(voxel_features.index_select(0, ids_keep), feature_coors.index_select(0, ids_keep),
                           feature_coors.index_select(0, ids_mask), batch_size, pillar_batch=pb, rows_keep=ids_keep,
                           rows_mask=ids_mask)
