@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""Pre-training throughput of the GeoMAE hot path on B200 (frames/sec), one JSON line.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # CPU port of the reference path (oracle/), rank 0 only
+
+A "step" is one full training step of the mae_sst nuScenes config on `samples_per_gpu` synthetic
+nuScenes-shaped frames per GPU: 3-scale voxelise+scatter -> geometric targets -> VFE -> SRA encoder /
+decoders -> 6 losses -> backward -> gradient all-reduce -> grad-clip + AdamW.
+`value` times K steps with the frames already resident in HBM; `e2e` times the same K steps through
+FlatTrainer.train_step_from_host (pinned host frames, H2D inside the timed region, loss read back).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OWN_CFG = os.path.join(ROOT, "configs/mae_sst/geomae_nus_pretrain.py")
+METRIC = "pretrain frames/sec on nuScenes-shaped synthetic sweeps"
+WORKLOAD = "mae_sst nuScenes config, synthetic 30k-pt sweeps, 1xB200 (BASELINE.json configs[1])"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples-per-gpu", type=int, default=4)     # data.samples_per_gpu of the config
+    ap.add_argument("--sweeps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_batches(rank, n_batches, samples, sweeps):
+    from geomae_b200.synthetic import make_frame
+    return [[make_frame(1000 * rank + it * 16 + s + 1, sweeps=sweeps) for s in range(samples)] for it in range(n_batches)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def cpu_reference_step(samples, sweeps, threads, seed=1):
+    """One forward+backward of the oracle port on the host cores; returns (seconds, frames)."""
+    from geomae_b200.synthetic import make_frame
+    from oracle import geomae_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.PathConfig()
+    frames = [make_frame(seed + s, sweeps=sweeps) for s in range(samples)]
+    params = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, 0).items()}
+    rows, _, _ = O.unique_rows(O.batch_voxelize(frames, cfg.voxel_size, cfg.pc_range))
+    keep, mask = O.vanilla_mask_ids(rows, len(frames), cfg.mask_ratio, seed)
+    t0 = time.perf_counter()
+    losses, _, _ = O.forward_train(params, frames, cfg, keep, mask)
+    sum(losses.values()).backward()
+    return time.perf_counter() - t0, len(frames)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The reference is Python on mmcv/mmdet/spconv/
+    torch_scatter, none of which exist here, so the timed thing is the oracle port (kind "port"),
+    pinned against the unmodified reference by tests/golden.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    samples = 1                      # bounded sample: one frame per step keeps K+W steps within minutes
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(samples, args.sweeps, threads)
+    times = []
+    for i in range(max(1, min(args.steps, 5))):
+        t, n = cpu_reference_step(samples, args.sweeps, threads, seed=10 + i)
+        times.append(t / n)
+    sec_per_frame = float(np.mean(times))
+    v = 1.0 / sec_per_frame
+    sample = f"{len(times)} steps x {samples} frame (fwd+bwd, full 6+2+2-block model, no optimiser), {threads} threads"
+    print(json.dumps(dict(
+        metric=METRIC, value=v, unit="frames/s", n_gpus=args.gpus, steps=len(times), warmup=min(args.warmup, 1),
+        ms_per_step=1e3 * sec_per_frame * samples, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f32", data="synthetic", impl="reference",
+        config=dict(workload=WORKLOAD, samples_per_step=samples, sweeps=args.sweeps),
+        cpu_baseline=dict(value=v, unit="frames/s", cores=threads, kind="port", sample=sample),
+        e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False        # the reference trains fp32 with TF32 off (tools/train.py:24-25)
+    torch.backends.cudnn.allow_tf32 = False
+
+    import geomae_b200  # noqa: F401
+    from geomae_b200 import lib as L
+    from geomae_b200.registry import Config, build_model
+    from geomae_b200.train import FlatTrainer
+
+    cfg = Config.fromfile(OWN_CFG)
+    torch.manual_seed(0)
+    model = build_model(cfg.model).to(dev).train()
+    opt = cfg.optimizer
+    trainer = FlatTrainer(model, lr=opt["lr"], betas=opt["betas"], weight_decay=opt["weight_decay"],
+                          max_grad_norm=cfg.optimizer_config["grad_clip"]["max_norm"])
+    K, W, S = args.steps, args.warmup, args.samples_per_gpu
+    pool = make_batches(rank, min(K + W, 8), S, args.sweeps)
+    host = [[torch.from_numpy(f).pin_memory() for f in b] for b in pool]
+    resident = [[f.to(dev) for f in b] for b in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, n):
+        evs = []
+        for i in range(n):
+            flush.zero_()                                   # evict L2 between steps (outside the timed events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn(i)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    last = {}
+
+    def step_resident(i):
+        last["loss"] = trainer.train_step(resident[i % len(resident)])[0]
+
+    def step_host(i):
+        last["loss"] = trainer.train_step_from_host(host[i % len(host)])[0]
+        last["loss_host"] = float(last["loss"])             # D2H read of the step's loss, every step
+
+    for i in range(W):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.reset_call_counts()
+    L.start_timing()
+    ms = timed_loop(step_resident, K)
+    per_call = L.stop_timing()
+    launches = L.launch_count()
+    barrier()
+    for i in range(min(W, 2)):
+        step_host(i)
+    barrier()
+    ms_e2e = timed_loop(step_host, K)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames = K * S * world
+    h2d = sum(f.numel() * 4 for f in host[0])
+    # roofline of the dominant hand-written kernel: SRA attention backward (one kernel per C-ABI call)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured" if peaks else "fallback"
+    roof = None
+    name = "sra_attention_bwd"
+    if name in per_call:
+        tot_ms, n_calls = per_call[name]
+        # algorithmic flops of attention backward per launch: 5 LxLx16 products * 2 flop, summed over windows;
+        # counted from the CSR lengths of the last step (token-weighted), see DESIGN.md
+        flops = last.get("attn_bwd_flops")
+        roof = dict(kernel="k_sra_bwd", bound="tensor", achieved=None, peak=tens_peak, unit="TFLOP/s", frac=None,
+                    traffic=None, peak_source=peak_src, avg_launch_ms=tot_ms / n_calls, launches=n_calls,
+                    share_of_step=tot_ms / ms)
+        if flops:
+            ach = flops / (tot_ms / n_calls * 1e-3) / 1e12
+            roof.update(achieved=ach, frac=ach / tens_peak)
+    line = dict(
+        metric=METRIC, value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=K, warmup=W,
+        ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+        data="synthetic",
+        config=dict(workload=WORKLOAD, samples_per_gpu=S, sweeps=args.sweeps, points_per_frame=int(pool[0][0].shape[0]),
+                    parallelism=f"dp{world}", l2="flushed between steps (256 MiB write, outside the timed events)",
+                    precision="fp32 storage and accumulate, TF32 off (reference parity mode)"),
+        e2e=dict(value=frames / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                 ms_per_step=ms_e2e / K),
+        gpu_launches=launches, clocks=clocks, roofline=roof,
+        kernel_ms_per_step={k: round(v[0] / K, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
+        loss=last.get("loss_host"))
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sec, n = cpu_reference_step(1, args.sweeps, threads)
+        sec, n = cpu_reference_step(1, args.sweeps, threads, seed=2)
+        line["cpu_baseline"] = dict(value=n / sec, unit="frames/s", cores=threads, kind="port",
+                                    sample="1 frame fwd+bwd of the oracle port (full model), second of two runs")
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

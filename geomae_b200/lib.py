@@ -90,6 +90,58 @@ class _Sigs:
     geomae_scatter_reduce_bwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
     geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p]
     geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
+    geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                         C.c_float, C.c_float, _i64, _p, _p]
+
+
+_timing = None      # list of (name, start_event, end_event) while bench.py measures per-call device time
+_calls = {}         # name -> number of C-ABI calls (bench.py reports kernel launches from these)
+
+# kernels launched per C-ABI call (upper bound for the optional ones), for the gpu_launches claim
+LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=8, geom_targets=1, dense_targets=1, coors_bitmap=4,
+                         token_map=1, window_csr=3, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
+                         scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=1, adamw_step=2)
+
+
+def start_timing():
+    global _timing
+    _timing = []
+
+
+def stop_timing():
+    """-> {name: (total_ms, n_calls)}; synchronises the device."""
+    global _timing
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _timing or []:
+        t, n = out.get(name, (0.0, 0))
+        out[name] = (t + e0.elapsed_time(e1), n + 1)
+    _timing = None
+    return out
+
+
+def reset_call_counts():
+    _calls.clear()
+
+
+def launch_count():
+    return sum(LAUNCHES_PER_CALL.get(k, 1) * v for k, v in _calls.items())
+
+
+def run(what: str, *args):
+    """Call geomae_<what>(*args); raise RuntimeError on a non-zero status."""
+    fn = getattr(lib(), "geomae_" + what)
+    _calls[what] = _calls.get(what, 0) + 1
+    if _timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _timing.append((what, e0, e1))
+    else:
+        rc = fn(*args)
+    if rc != 0:
+        raise RuntimeError(f"geomae_b200.{what} failed ({rc}): {lib().geomae_last_error().decode()}")
 
 
 def check(rc: int, what: str):

@@ -22,9 +22,9 @@ class _SRAAttention(torch.autograd.Function):
         d = three_d // 3
         out = torch.empty((n, d), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((n, n_heads), dtype=torch.float32, device=qkv.device)
-        L.check(L.lib().geomae_sra_attention_fwd(L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]),
+        L.run("sra_attention_fwd", L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]),
                                                  L.ptr(win["n_windows"]), win["max_windows"], L.ptr(out), L.ptr(lse),
-                                                 L.stream_ptr(qkv.device)), "sra_attention_fwd")
+                                                 L.stream_ptr(qkv.device))
         ctx.save_for_backward(qkv, out, lse)
         ctx.win, ctx.n_heads = win, n_heads
         return out
@@ -35,10 +35,10 @@ class _SRAAttention(torch.autograd.Function):
         d_out = d_out.contiguous()
         d_qkv = torch.empty_like(qkv)
         win = ctx.win
-        L.check(L.lib().geomae_sra_attention_bwd(L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0],
+        L.run("sra_attention_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0],
                                                  ctx.n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]),
                                                  L.ptr(win["n_windows"]), win["max_windows"], L.ptr(d_qkv),
-                                                 L.stream_ptr(qkv.device)), "sra_attention_bwd")
+                                                 L.stream_ptr(qkv.device))
         return d_qkv, None, None
 
 

@@ -1,0 +1,68 @@
+"""One data-parallel pre-training step: forward_train -> backward -> gradient all-reduce ->
+grad-clip + AdamW.  Stands in for the mmcv runner pieces the reference uses around the hot path
+(EpochBasedRunner.run_iter / OptimizerHook / MMDistributedDataParallel): one
+process per GPU, all parameters and gradients live in ONE flat fp32 buffer each, so the DDP
+exchange is a single NCCL all-reduce over NVLink and the optimiser is a single fused kernel."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+
+
+class FlatTrainer:
+    def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, max_grad_norm=10.0,
+                 no_decay_keys=("norm",)):
+        self.model = model
+        named = list(model.named_parameters())
+        decay = [(k, p) for k, p in named if not any(s in k for s in no_decay_keys)]
+        no_decay = [(k, p) for k, p in named if any(s in k for s in no_decay_keys)]
+        self.order = decay + no_decay
+        self.n_decay = sum(p.numel() for _, p in decay)
+        self.n = sum(p.numel() for _, p in self.order)
+        dev = named[0][1].device
+        self.flat_param = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        off = 0
+        for _, p in self.order:
+            n = p.numel()
+            self.flat_param[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + n].view_as(p)
+            p.grad = self.flat_grad[off:off + n].view_as(p)
+            off += n
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self.partials = torch.zeros(1024, dtype=torch.float64, device=dev)
+        self.stats = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.step_count = 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def optimizer_step(self, lr=None):
+        self.step_count += 1
+        L.run("adamw_step", 
+            L.ptr(self.flat_param), L.ptr(self.flat_grad), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), self.n,
+            self.n_decay, L.ptr(self.partials), 1.0 / self.world, self.max_grad_norm, self.lr if lr is None else lr,
+            self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, L.ptr(self.stats),
+            L.stream_ptr(self.flat_param.device))
+
+    def train_step(self, points, ids=None, lr=None):
+        """points: list of [N_i, C] CUDA tensors (one rank's samples).  Returns (total loss, loss dict)."""
+        self.zero_grad()
+        losses = self.model.forward_train(points=points, img_metas=None, ids=ids)
+        total = sum(losses.values())
+        total.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad)          # the single gradient collective (sum; 1/world folded below)
+        self.optimizer_step(lr)
+        return total.detach(), losses
+
+    def train_step_from_host(self, host_points, ids=None, lr=None):
+        """host_points: list of pinned CPU tensors; H2D copies are issued on the compute stream."""
+        dev = self.flat_param.device
+        pts = [p.to(dev, non_blocking=True) for p in host_points]
+        return self.train_step(pts, ids=ids, lr=lr)

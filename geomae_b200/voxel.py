@@ -38,9 +38,9 @@ class Voxelization(nn.Module):
         points = points.contiguous()
         coors = torch.empty((points.shape[0], 3), dtype=torch.int32, device=points.device)
         rng = self.point_cloud_range
-        L.check(L.lib().geomae_dynamic_voxelize(L.ptr(points), points.shape[0], points.shape[1],
+        L.run("dynamic_voxelize", L.ptr(points), points.shape[0], points.shape[1],
                                                 L.f3(self.voxel_size), L.f3(rng[:3]), L.f3(rng[3:]),
-                                                L.ptr(coors), L.stream_ptr(points.device)), "dynamic_voxelize")
+                                                L.ptr(coors), L.stream_ptr(points.device))
         return coors
 
     def __repr__(self):
@@ -51,7 +51,7 @@ class Voxelization(nn.Module):
 def grid_size(voxel_size, pc_range):
     """[x, y, z] grid of one scale = ceil((max-min)/size) in fp32 (voxelization_cuda.cu:375-377)."""
     out = (C.c_int32 * 3)()
-    L.check(L.lib().geomae_grid_size(L.f3(pc_range[:3]), L.f3(pc_range[3:]), L.f3(voxel_size), out), "grid_size")
+    L.run("grid_size", L.f3(pc_range[:3]), L.f3(pc_range[3:]), L.f3(voxel_size), out)
     return list(out)
 
 
@@ -120,8 +120,8 @@ class PillarBatch:
         self._n = None
 
     def run(self):
-        L.check(L.lib().geomae_voxel_scatter(C.byref(self.geom.cstruct), C.byref(self.io),
-                                             L.stream_ptr(self.points.device)), "voxel_scatter")
+        L.run("voxel_scatter", C.byref(self.geom.cstruct), C.byref(self.io),
+                                             L.stream_ptr(self.points.device))
         self._n = None
         return self
 
@@ -149,9 +149,9 @@ class PillarBatch:
             cov6 = torch.empty((v, 6), dtype=torch.float32, device=dev)
             sing = torch.empty((v, 3), dtype=torch.float32, device=dev)
             pair = torch.empty((9, v), dtype=torch.int32, device=dev)
-        L.check(L.lib().geomae_geom_targets(C.byref(self.geom.cstruct), C.byref(self.io), v, L.ptr(normal),
+        L.run("geom_targets", C.byref(self.geom.cstruct), C.byref(self.io), v, L.ptr(normal),
                                             L.ptr(curv), L.ptr(cov6), L.ptr(sing), L.ptr(pair),
-                                            L.stream_ptr(dev)), "geom_targets")
+                                            L.stream_ptr(dev))
         return (normal, curv, cov6, sing, pair) if want_debug else (normal, curv)
 
     def dense_targets(self, rows: torch.Tensor, raw=False):
@@ -166,9 +166,9 @@ class PillarBatch:
         med = torch.empty((m, g.slots_med, 3), dtype=torch.float32, device=dev)
         med_m = torch.empty((m, g.slots_med), dtype=torch.uint8, device=dev)
         top = torch.empty((m, 3), dtype=torch.float32, device=dev)
-        L.check(L.lib().geomae_dense_targets(C.byref(g.cstruct), C.byref(self.io), L.ptr(rows), m, int(raw),
+        L.run("dense_targets", C.byref(g.cstruct), C.byref(self.io), L.ptr(rows), m, int(raw),
                                              L.ptr(low), L.ptr(low_m), L.ptr(med), L.ptr(med_m), L.ptr(top),
-                                             L.stream_ptr(dev)), "dense_targets")
+                                             L.stream_ptr(dev))
         return low, low_m.bool(), med, med_m.bool(), top
 
 

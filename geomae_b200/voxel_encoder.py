@@ -24,9 +24,9 @@ class _ScatterReduce(torch.autograd.Function):
         n, c = feat.shape
         out = torch.empty((n_pillars, c), dtype=torch.float32, device=feat.device)
         arg = torch.empty((n_pillars, c), dtype=torch.int32, device=feat.device) if mode == 2 else None
-        L.check(L.lib().geomae_scatter_reduce_fwd(L.ptr(feat), n, c, L.ptr(point_pillar), L.ptr(pillar_mean),
+        L.run("scatter_reduce_fwd", L.ptr(feat), n, c, L.ptr(point_pillar), L.ptr(pillar_mean),
                                                   n_pillars, mode, L.ptr(out), L.ptr(arg),
-                                                  L.stream_ptr(feat.device)), "scatter_reduce_fwd")
+                                                  L.stream_ptr(feat.device))
         ctx.mode, ctx.shape = mode, (n, c)
         ctx.save_for_backward(point_pillar, pillar_mean, arg)
         return out
@@ -37,9 +37,8 @@ class _ScatterReduce(torch.autograd.Function):
         n, c = ctx.shape
         d_out = d_out.contiguous()
         d_feat = torch.empty((n, c), dtype=torch.float32, device=d_out.device)
-        L.check(L.lib().geomae_scatter_reduce_bwd(L.ptr(d_out), n, c, L.ptr(point_pillar), L.ptr(pillar_mean),
-                                                  L.ptr(arg), ctx.mode, L.ptr(d_feat), L.stream_ptr(d_out.device)),
-                "scatter_reduce_bwd")
+        L.run("scatter_reduce_bwd", L.ptr(d_out), n, c, L.ptr(point_pillar), L.ptr(pillar_mean),
+                                                  L.ptr(arg), ctx.mode, L.ptr(d_feat), L.stream_ptr(d_out.device))
         return d_feat, None, None, None, None
 
 
@@ -95,10 +94,10 @@ class DynamicScatterVFE(nn.Module):
         if c != self.raw_channels:
             raise RuntimeError(f"points have {c} channels, encoder was built for {self.raw_channels}")
         out = torch.empty((n, c + 6), dtype=torch.float32, device=pts.device)
-        L.check(L.lib().geomae_vfe_decorate(L.ptr(pts), n, c, L.ptr(pb.point_pillar), L.ptr(pb.pillar_mean),
+        L.run("vfe_decorate", L.ptr(pts), n, c, L.ptr(pb.point_pillar), L.ptr(pb.pillar_mean),
                                             L.ptr(pb.pillar_coors), L.f3((self.vx, self.vy, self.vz)),
                                             L.f3((self.x_offset, self.y_offset, self.z_offset)), L.ptr(out),
-                                            L.stream_ptr(pts.device)), "vfe_decorate")
+                                            L.stream_ptr(pts.device))
         return out
 
     def forward(self, pb: PillarBatch, return_inv=False):

@@ -30,8 +30,8 @@ class WindowSpec:
 
     def candidates(self, geom: VoxelGeometry, n_frames: int) -> int:
         n = C.c_int32()
-        L.check(L.lib().geomae_window_candidates(C.byref(geom.cstruct), C.byref(self.cstruct), n_frames,
-                                                 C.byref(n), None, None), "window_candidates")
+        L.run("window_candidates", C.byref(geom.cstruct), C.byref(self.cstruct), n_frames,
+                                                 C.byref(n), None, None)
         return n.value
 
 
@@ -68,10 +68,9 @@ class WindowLayout:
         rows = rows.to(torch.int64).contiguous()
         tok_of_pillar = torch.empty(max(pb.n_pillars, 1), dtype=torch.int32, device=dev)
         s = L.stream_ptr(dev)
-        L.check(L.lib().geomae_token_map(L.ptr(rows), rows.shape[0], L.ptr(tok_of_pillar), pb.n_pillars, s),
-                "token_map")
-        L.check(L.lib().geomae_window_csr(C.byref(pb.geom.cstruct), C.byref(spec.cstruct), C.byref(pb.io),
-                                          L.ptr(tok_of_pillar), rows.shape[0], C.byref(self.io), s), "window_csr")
+        L.run("token_map", L.ptr(rows), rows.shape[0], L.ptr(tok_of_pillar), pb.n_pillars, s)
+        L.run("window_csr", C.byref(pb.geom.cstruct), C.byref(spec.cstruct), C.byref(pb.io),
+                                          L.ptr(tok_of_pillar), rows.shape[0], C.byref(self.io), s)
         self._keep = (tok_of_pillar, rows)
         return self
 
@@ -90,13 +89,13 @@ class WindowLayout:
         scan_tmp, counts = torch.empty(3 * 4096, **i32), torch.zeros(4, **i32)
         tok_of_pillar = torch.empty(max(n, 1), **i32)
         s = L.stream_ptr(dev)
-        L.check(L.lib().geomae_coors_bitmap(C.byref(geom.cstruct), L.ptr(coors), n, batch_size, L.ptr(bitmap),
+        L.run("coors_bitmap", C.byref(geom.cstruct), L.ptr(coors), n, batch_size, L.ptr(bitmap),
                                             L.ptr(word_rank), L.ptr(scan_tmp), L.ptr(counts),
-                                            L.ptr(tok_of_pillar), s), "coors_bitmap")
+                                            L.ptr(tok_of_pillar), s)
         io = L.ScatterIO()
         io.n_frames, io.bitmap, io.word_rank = batch_size, L.ptr(bitmap), L.ptr(word_rank)
-        L.check(L.lib().geomae_window_csr(C.byref(geom.cstruct), C.byref(spec.cstruct), C.byref(io),
-                                          L.ptr(tok_of_pillar), n, C.byref(self.io), s), "window_csr")
+        L.run("window_csr", C.byref(geom.cstruct), C.byref(spec.cstruct), C.byref(io),
+                                          L.ptr(tok_of_pillar), n, C.byref(self.io), s)
         self._keep = (bitmap, word_rank, scan_tmp, counts, tok_of_pillar, coors)
         return self
 
@@ -114,7 +113,7 @@ def pos_table(window_shape, d_model, temperature, device) -> torch.Tensor:
     key = (tuple(window_shape), d_model, float(temperature), str(device))
     if key not in _POS_TABLES:
         t = torch.empty((window_shape[0] * window_shape[1], d_model), dtype=torch.float32, device=device)
-        L.check(L.lib().geomae_pos_table(window_shape[0], window_shape[1], d_model, float(temperature), L.ptr(t),
-                                         L.stream_ptr(device)), "pos_table")
+        L.run("pos_table", window_shape[0], window_shape[1], d_model, float(temperature), L.ptr(t),
+                                         L.stream_ptr(device))
         _POS_TABLES[key] = t
     return _POS_TABLES[key]

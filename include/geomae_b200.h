@@ -213,6 +213,17 @@ int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* ls
                              int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr, const int32_t* win_tok,
                              const int32_t* n_windows, int32_t max_windows, float* d_qkv, void* stream);
 
+/* ---------------------------------------------------------------- optimiser */
+
+/* One fused step over flat fp32 buffers: g' = g*grad_scale (1/world_size), clip by global L2 norm
+ * to max_norm (<=0 disables), AdamW update (decoupled weight decay on the first n_decay elements
+ * only).  partials: [1024] f64 scratch.  stats [opt]: [2] = grad norm, clip coefficient.
+ * replaces: mmcv OptimizerHook(grad_clip) + torch.optim.AdamW as configured by
+ *           configs/_base_/schedules/cosine_2x.py:1-9 (paramwise 'norm' decay_mult=0). */
+int geomae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      int64_t n_decay, double* partials, float grad_scale, float max_norm, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int64_t step, float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
