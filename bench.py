@@ -175,6 +175,20 @@ def main():
         return sum(a.elapsed_time(b) for a, b in evs)
 
     last = {}
+    model.keep_targets = True
+
+    def attention_pair_counts():
+        """sum over windows of L^2 for the encoder / decoder token sets of the last step (both shifts)."""
+        from geomae_b200.windows import WindowLayout
+        tg = model.last_targets
+        out = {}
+        for name, rows in (("enc", tg["ids_keep"]), ("dec", torch.cat([tg["ids_keep"], tg["ids_mask"]]))):
+            lay = WindowLayout.from_pillars(model.backbone.spec, tg["pillar_batch"], rows)
+            for s in range(lay.spec.n_shifts):
+                nw = int(lay.n_windows[s])
+                ln = torch.diff(lay.win_ptr[s, :nw + 1]).double()
+                out[name, s] = float((ln * ln).sum())
+        return out
 
     def step_resident(i):
         last["loss"] = trainer.train_step(resident[i % len(resident)])[0]
@@ -225,7 +239,11 @@ def main():
         tot_ms, n_calls = per_call[name]
         # algorithmic flops of attention backward per launch: 5 LxLx16 products * 2 flop, summed over windows;
         # counted from the CSR lengths of the last step (token-weighted), see DESIGN.md
-        flops = last.get("attn_bwd_flops")
+        sq = attention_pair_counts()
+        bb = model.backbone
+        n_enc, n_dec = len(bb.encoder_blocks), len(bb.decoder_centroid_blocks) + len(bb.decoder_density_blocks)
+        pairs = n_enc * (sq["enc", 0] + sq["enc", 1]) + n_dec * (sq["dec", 0] + sq["dec", 1])   # per step, all layers
+        flops = pairs * bb.nhead[0] * 160.0 / (n_calls / K)        # per launch: 5 products x 16 x 2 flop per (i,j,head)
         roof = dict(kernel="k_sra_bwd", bound="tensor", achieved=None, peak=tens_peak, unit="TFLOP/s", frac=None,
                     traffic=None, peak_source=peak_src, avg_launch_ms=tot_ms / n_calls, launches=n_calls,
                     share_of_step=tot_ms / ms)
