@@ -1,0 +1,257 @@
+// Dense layers of the SRA block on the 5th-gen tensor cores:
+// token-tile GEMMs with fused prologues (position add, GELU) and epilogues (bias, residual +
+// LayerNorm, GELU-gradient), and the weight-gradient GEMM, all with tcgen05.mma accumulating in TMEM.
+//
+// One CTA = 128 tokens x NT outputs.  Operands are converted fp32 -> bf16 while being staged into the
+// swizzled shared-memory layout of tc_common.cuh; `precision 3` additionally stages the bf16 residuals
+// and issues hi*hi + hi*lo + lo*hi (fp32-equivalent to ~2^-16, the parity mode), `precision 1` is plain
+// bf16.  The accumulator row of a token lives in one TMEM lane = one thread of the epilogue, so the
+// LayerNorm statistics need no cross-thread reduction at all.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TM = 128;       // tokens per CTA
+constexpr int KC = 128;       // K elements staged per chunk
+constexpr int NTHREADS = 128;
+
+struct LinArgs {
+  const float* A; int lda; int n_rows; int K;
+  const float* pos_table; const int32_t* tok_cell; int pos_slabs;   // A += pos_table[tok_cell[row]] for slabs < pos_slabs
+  int a_gelu;                                                       // A = gelu(A)
+  const float* W; int ldw; int w_rows; int w_mn_major;              // 0: W[n][k] (y = x W^T), 1: W[k][n] (dX = dY W)
+  const float* bias; int N_total;
+  float* out; int ldo;
+  const float* add_src; int ld_add;                                 // out += add_src (residual / gradient sum)
+  const float* ln_gamma; const float* ln_beta; float ln_eps;        // EPI 1
+  float* ln_in; float* ln_stats;                                    // EPI 1: saved pre-LN rows [n,N] and (mean, rstd) [n,2]
+  const float* gelu_u; int ldu;                                     // EPI 2: out = acc * gelu'(u)
+  int precision;
+};
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+
+// Stage a [ROWS x COLS] fp32 tile (global rows row0.., columns col0..) as bf16 into swizzled 64-column blocks.
+template <int ROWS, int COLS>
+__device__ __forceinline__ void stage_tile(uint8_t* dst_hi, uint8_t* dst_lo, const float* __restrict__ src, int ld,
+                                           int row0, int row_end, int col0, const float* __restrict__ pos_table,
+                                           const int32_t* __restrict__ tok_cell, int pos_ld, bool do_gelu) {
+  constexpr int CPR = COLS / 8;                 // 16-byte chunks per row
+  constexpr int BLOCK_BYTES = ROWS * tc::LINE_BYTES;
+  for (int i = threadIdx.x; i < ROWS * CPR; i += NTHREADS) {
+    const int r = i / CPR, c8 = i % CPR;
+    const int grow = row0 + r;
+    float f[8];
+    if (grow < row_end) {
+      const float4* p = reinterpret_cast<const float4*>(src + (int64_t)grow * ld + col0 + c8 * 8);
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      if (pos_table) {
+        const float4* q = reinterpret_cast<const float4*>(pos_table + (int64_t)__ldg(tok_cell + grow) * pos_ld + col0 + c8 * 8);
+        const float4 c = __ldg(q), d = __ldg(q + 1);
+        f[0] += c.x; f[1] += c.y; f[2] += c.z; f[3] += c.w; f[4] += d.x; f[5] += d.y; f[6] += d.z; f[7] += d.w;
+      }
+      if (do_gelu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = gelu_f(f[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    }
+    uint4 lo;
+    const uint4 hi = tc::pack8(f, dst_lo ? &lo : nullptr);
+    const uint32_t off = (uint32_t)(c8 >> 3) * BLOCK_BYTES + tc::swz(r, c8 & 7);
+    *reinterpret_cast<uint4*>(dst_hi + off) = hi;
+    if (dst_lo) *reinterpret_cast<uint4*>(dst_lo + off) = lo;
+  }
+}
+
+// EPI: 0 = acc (+bias) (+add_src); 1 = LayerNorm(acc + bias + add_src); 2 = acc * gelu'(u)
+template <int NT, int EPI>
+__global__ void __launch_bounds__(NTHREADS) k_tc_linear(const LinArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = TM * KC * 2;          // 32 KB
+  constexpr int B_BYTES = NT * KC * 2;
+  const bool x3 = a.precision == 3;
+  uint8_t* sA = smem;
+  uint8_t* sAlo = sA + A_BYTES;
+  uint8_t* sB = sA + (x3 ? 2 : 1) * A_BYTES;
+  uint8_t* sBlo = sB + B_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * TM;
+  const int n0 = blockIdx.y * NT;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, NT);
+  if (threadIdx.x == 0) tc::mbar_init(&mbar, 1);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const bool use_pos = a.pos_table && (int)blockIdx.y < a.pos_slabs;
+  const int n_chunks = a.K / KC;
+  for (int kc = 0; kc < n_chunks; ++kc) {
+    const int k0 = kc * KC;
+    if (kc > 0) {                       // operands of the previous chunk must be consumed before overwriting
+      tc::mbar_wait(&mbar, (kc - 1) & 1);
+      tc::fence_after_sync();
+    }
+    stage_tile<TM, KC>(sA, x3 ? sAlo : nullptr, a.A, a.lda, row0, a.n_rows, k0, use_pos ? a.pos_table : nullptr,
+                       a.tok_cell, a.K, a.a_gelu != 0);
+    if (a.w_mn_major)   // rows = k, columns = n
+      stage_tile<KC, NT>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, k0, a.w_rows, n0, nullptr, nullptr, 0, false);
+    else                // rows = n, columns = k
+      stage_tile<NT, KC>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, n0, a.w_rows, k0, nullptr, nullptr, 0, false);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::make_idesc_bf16(TM, NT, 0, a.w_mn_major);
+      const uint32_t a_hi = tc::smem_u32(sA), a_lo = tc::smem_u32(sAlo), b_hi = tc::smem_u32(sB), b_lo = tc::smem_u32(sBlo);
+      bool acc = kc > 0;
+#pragma unroll
+      for (int j = 0; j < KC / 16; ++j) {
+        const uint32_t a_off = (uint32_t)(j >> 2) * (TM * tc::LINE_BYTES) + (uint32_t)(j & 3) * 32;
+        uint32_t b_off, b_lbo;
+        if (a.w_mn_major) { b_off = (uint32_t)j * 2 * tc::ATOM_BYTES; b_lbo = KC * tc::LINE_BYTES; }
+        else { b_off = (uint32_t)(j >> 2) * (NT * tc::LINE_BYTES) + (uint32_t)(j & 3) * 32; b_lbo = 16; }
+        const uint64_t da_hi = tc::make_desc(a_hi + a_off, 16, tc::ATOM_BYTES);
+        const uint64_t db_hi = tc::make_desc(b_hi + b_off, b_lbo, tc::ATOM_BYTES);
+        tc::mma_bf16(tmem, da_hi, db_hi, idesc, acc);
+        acc = true;
+        if (x3) {
+          const uint64_t da_lo = tc::make_desc(a_lo + a_off, 16, tc::ATOM_BYTES);
+          const uint64_t db_lo = tc::make_desc(b_lo + b_off, b_lbo, tc::ATOM_BYTES);
+          tc::mma_bf16(tmem, da_hi, db_lo, idesc, true);
+          tc::mma_bf16(tmem, da_lo, db_hi, idesc, true);
+        }
+      }
+      tc::mma_commit(&mbar);
+    }
+  }
+  tc::mbar_wait(&mbar, (n_chunks - 1) & 1);
+  tc::fence_after_sync();
+
+  // ---- epilogue: thread <-> one token row (TMEM lane)
+  const int row = row0 + warp * 32 + lane;
+  const bool valid = row < a.n_rows;
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  if constexpr (EPI == 1) {
+    static_assert(EPI != 1 || NT == 128, "LayerNorm epilogue needs the whole row in one CTA");
+    float v[NT];
+#pragma unroll
+    for (int c = 0; c < NT / 32; ++c) tc::tmem_ld32(t_lane + c * 32, v + c * 32);
+    tc::tmem_ld_wait();
+    float mean = 0.f;
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < NT; c += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+        const float4 r = __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add + c));
+        v[c] += b.x + r.x; v[c + 1] += b.y + r.y; v[c + 2] += b.z + r.z; v[c + 3] += b.w + r.w;
+        mean += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
+      }
+      mean *= (1.0f / NT);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < NT; ++c) { const float d = v[c] - mean; var = fmaf(d, d, var); }
+      const float rstd = rsqrtf(var * (1.0f / NT) + a.ln_eps);
+      if (a.ln_stats) { a.ln_stats[2 * (int64_t)row] = mean; a.ln_stats[2 * (int64_t)row + 1] = rstd; }
+      float* o = a.out + (int64_t)row * a.ldo;
+      float* s = a.ln_in ? a.ln_in + (int64_t)row * NT : nullptr;
+#pragma unroll
+      for (int c = 0; c < NT; c += 4) {
+        if (s) *reinterpret_cast<float4*>(s + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(a.ln_beta + c));
+        *reinterpret_cast<float4*>(o + c) =
+            make_float4((v[c] - mean) * rstd * g.x + b.x, (v[c + 1] - mean) * rstd * g.y + b.y,
+                        (v[c + 2] - mean) * rstd * g.z + b.z, (v[c + 3] - mean) * rstd * g.w + b.w);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(t_lane + c0, v);
+      tc::tmem_ld_wait();
+      if (valid) {
+        const int col = n0 + c0;
+        float* o = a.out + (int64_t)row * a.ldo + col;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          if constexpr (EPI == 2) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(a.gelu_u + (int64_t)row * a.ldu + col + c));
+            r.x *= gelu_grad_f(u.x); r.y *= gelu_grad_f(u.y); r.z *= gelu_grad_f(u.z); r.w *= gelu_grad_f(u.w);
+          } else {
+            if (a.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + c));
+              r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+            }
+            if (a.add_src) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add + col + c));
+              r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
+            }
+          }
+          *reinterpret_cast<float4*>(o + c) = r;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_free(tmem, NT);
+}
+
+template <int NT, int EPI>
+int launch_linear(const LinArgs& a, cudaStream_t stream) {
+  const int smem = (a.precision == 3 ? 2 : 1) * (TM * KC * 2 + NT * KC * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    GM_CUDA(cudaFuncSetAttribute(k_tc_linear<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TM * KC * 2 + NT * KC * 2) + 1024));
+    configured = true;
+  }
+  const dim3 grid(gm_div_up(a.n_rows, TM), a.N_total / NT);
+  k_tc_linear<NT, EPI><<<grid, NTHREADS, smem, stream>>>(a);
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
+
+}  // namespace
+
+extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
+  GM_REQUIRE(p && p->A && p->W && p->out, "tc_linear: null argument");
+  GM_REQUIRE(p->K > 0 && p->K % KC == 0, "tc_linear: K=%d must be a positive multiple of %d", p->K, KC);
+  GM_REQUIRE(p->N_total > 0 && p->N_total % 128 == 0, "tc_linear: N=%d must be a multiple of 128", p->N_total);
+  GM_REQUIRE(p->precision == 1 || p->precision == 3, "tc_linear: precision must be 1 (bf16) or 3 (bf16x3)");
+  GM_REQUIRE(p->epilogue >= 0 && p->epilogue <= 2, "tc_linear: unknown epilogue %d", p->epilogue);
+  GM_REQUIRE(p->lda % 4 == 0 && p->ldw % 4 == 0 && p->ldo % 4 == 0, "tc_linear: leading dimensions must be multiples of 4");
+  if (p->n_rows == 0) return GEOMAE_OK;
+  LinArgs a;
+  a.A = p->A; a.lda = p->lda; a.n_rows = p->n_rows; a.K = p->K;
+  a.pos_table = p->pos_table; a.tok_cell = p->tok_cell; a.pos_slabs = p->pos_slabs; a.a_gelu = p->a_gelu;
+  a.W = p->W; a.ldw = p->ldw; a.w_rows = p->w_rows; a.w_mn_major = p->w_mn_major;
+  a.bias = p->bias; a.N_total = p->N_total; a.out = p->out; a.ldo = p->ldo;
+  a.add_src = p->add_src; a.ld_add = p->ld_add;
+  a.ln_gamma = p->ln_gamma; a.ln_beta = p->ln_beta; a.ln_eps = p->ln_eps; a.ln_in = p->ln_in; a.ln_stats = p->ln_stats;
+  a.gelu_u = p->gelu_u; a.ldu = p->ldu; a.precision = p->precision;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (p->epilogue == 1) {
+    GM_REQUIRE(p->N_total == 128 && p->bias && p->add_src && p->ln_gamma && p->ln_beta,
+               "tc_linear: LayerNorm epilogue needs N=128, bias, residual, gamma, beta");
+    return launch_linear<128, 1>(a, stream);
+  }
+  if (p->epilogue == 2) {
+    GM_REQUIRE(p->gelu_u, "tc_linear: gelu-grad epilogue needs u");
+    return (p->N_total % 256 == 0) ? launch_linear<256, 2>(a, stream) : launch_linear<128, 2>(a, stream);
+  }
+  return (p->N_total % 256 == 0 && p->pos_slabs == 0) ? launch_linear<256, 0>(a, stream) : launch_linear<128, 0>(a, stream);
+}

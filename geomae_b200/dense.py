@@ -1,0 +1,47 @@
+"""Host wrappers of the tensor-core dense kernels (csrc/sra_layer.cu) used by the SRA block."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+
+def tc_linear(A, W, *, n_out, w_mn_major=False, bias=None, pos_table=None, tok_cell=None, pos_slabs=0, a_gelu=False,
+              add_src=None, ln=None, gelu_u=None, out=None, precision=3):
+    """out = prologue(A) @ (W^T | W) + epilogue on tcgen05 (see geomae_linear_args in include/geomae_b200.h).
+
+    ln = (gamma, beta, eps, want_saved) selects the LayerNorm epilogue and returns (out, ln_in, ln_stats)."""
+    L.require_cuda(A, "A")
+    n, K = A.shape
+    assert A.stride(1) == 1 and W.stride(1) == 1
+    if out is None:
+        out = torch.empty((n, n_out), dtype=torch.float32, device=A.device)
+    a = L.LinearArgs()
+    a.A, a.lda, a.n_rows, a.K = A.data_ptr(), A.stride(0), n, K
+    a.pos_table = pos_table.data_ptr() if pos_table is not None else None
+    a.tok_cell = tok_cell.data_ptr() if tok_cell is not None else None
+    a.pos_slabs, a.a_gelu = pos_slabs, int(a_gelu)
+    a.W, a.ldw, a.w_rows, a.w_mn_major = W.data_ptr(), W.stride(0), W.shape[0], int(w_mn_major)
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.N_total, a.out, a.ldo = n_out, out.data_ptr(), out.stride(0)
+    if add_src is not None:
+        a.add_src, a.ld_add = add_src.data_ptr(), add_src.stride(0)
+    ln_in = ln_stats = None
+    a.epilogue = 0
+    if ln is not None:
+        gamma, beta, eps, want_saved = ln
+        a.ln_gamma, a.ln_beta, a.ln_eps = gamma.data_ptr(), beta.data_ptr(), eps
+        if want_saved:
+            ln_in = torch.empty((n, n_out), dtype=torch.float32, device=A.device)
+            ln_stats = torch.empty((n, 2), dtype=torch.float32, device=A.device)
+            a.ln_in, a.ln_stats = ln_in.data_ptr(), ln_stats.data_ptr()
+        a.epilogue = 1
+    if gelu_u is not None:
+        a.gelu_u, a.ldu, a.epilogue = gelu_u.data_ptr(), gelu_u.stride(0), 2
+    a.precision = precision
+    L.run("tc_linear", C.byref(a), L.stream_ptr(A.device))
+    if ln is not None:
+        return out, ln_in, ln_stats
+    return out

@@ -45,6 +45,19 @@ class WindowIO(C.Structure):
                 ("tok_win", C.c_void_p), ("tok_pos", C.c_void_p)]
 
 
+class LinearArgs(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int32), ("n_rows", C.c_int32), ("K", C.c_int32),
+                ("pos_table", C.c_void_p), ("tok_cell", C.c_void_p), ("pos_slabs", C.c_int32), ("a_gelu", C.c_int32),
+                ("W", C.c_void_p), ("ldw", C.c_int32), ("w_rows", C.c_int32), ("w_mn_major", C.c_int32),
+                ("bias", C.c_void_p), ("N_total", C.c_int32),
+                ("out", C.c_void_p), ("ldo", C.c_int32),
+                ("add_src", C.c_void_p), ("ld_add", C.c_int32),
+                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("ln_in", C.c_void_p),
+                ("ln_stats", C.c_void_p),
+                ("gelu_u", C.c_void_p), ("ldu", C.c_int32),
+                ("epilogue", C.c_int32), ("precision", C.c_int32)]
+
+
 def build_if_missing():
     if not os.path.exists(LIB_PATH):
         import subprocess
@@ -90,6 +103,7 @@ class _Sigs:
     geomae_scatter_reduce_bwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
     geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p]
     geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
+    geomae_tc_linear = [C.POINTER(LinearArgs), _p]
     geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                          C.c_float, C.c_float, _i64, _p, _p]
 
@@ -100,7 +114,8 @@ _calls = {}         # name -> number of C-ABI calls (bench.py reports kernel lau
 # kernels launched per C-ABI call (upper bound for the optional ones), for the gpu_launches claim
 LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=8, geom_targets=1, dense_targets=1, coors_bitmap=4,
                          token_map=1, window_csr=3, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
-                         scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=1, adamw_step=2)
+                         scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=1, adamw_step=2,
+                         tc_linear=1)
 
 
 def start_timing():

@@ -213,6 +213,33 @@ int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* ls
                              int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr, const int32_t* win_tok,
                              const int32_t* n_windows, int32_t max_windows, float* d_qkv, void* stream);
 
+/* ------------------------------------------------ tensor-core dense layers */
+
+/* out[128-token tile, N] = prologue(A)[., K] x W + epilogue, on tcgen05 tensor cores (bf16 operands,
+ * fp32 accumulation in TMEM).  precision 1 = bf16, 3 = bf16x3 split (fp32-equivalent parity mode).
+ *   prologue : A += pos_table[tok_cell[row]] for the first pos_slabs 128-column slabs of the output
+ *              (q and k of the in-projection use x+pos, v uses x); a_gelu: A = gelu(A)
+ *   weights  : w_mn_major 0: W[n][k] row-major (y = x W^T, nn.Linear forward)
+ *              w_mn_major 1: W[k][n] row-major (dX = dY W, nn.Linear input gradient) — no transposed copy
+ *   epilogue : 0  out = acc (+ bias) (+ add_src)
+ *              1  out = LayerNorm(acc + bias + add_src) * gamma + beta; ln_in / ln_stats (mean, rstd) saved
+ *              2  out = acc * gelu'(gelu_u)
+ * replaces: the nn.MultiheadAttention in/out projections, EncoderLayer.linear1/linear2, norm1/norm2 and the
+ *           activation of models/sst/sst_basic_block.py:55,94-100 (library GEMM + 5-6 elementwise kernels). */
+typedef struct geomae_linear_args {
+  const float* A; int32_t lda; int32_t n_rows; int32_t K;
+  const float* pos_table; const int32_t* tok_cell; int32_t pos_slabs; int32_t a_gelu;
+  const float* W; int32_t ldw; int32_t w_rows; int32_t w_mn_major;
+  const float* bias; int32_t N_total;
+  float* out; int32_t ldo;
+  const float* add_src; int32_t ld_add;
+  const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_in; float* ln_stats;
+  const float* gelu_u; int32_t ldu;
+  int32_t epilogue; int32_t precision;
+} geomae_linear_args;
+
+int geomae_tc_linear(const geomae_linear_args* args, void* stream);
+
 /* ---------------------------------------------------------------- optimiser */
 
 /* One fused step over flat fp32 buffers: g' = g*grad_scale (1/world_size), clip by global L2 norm

@@ -1,0 +1,69 @@
+"""tcgen05 dense kernels against torch fp32 (float reference for a floating-point kernel)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = {3: dict(rtol=2e-4, atol=2e-4), 1: dict(rtol=3e-2, atol=3e-2)}
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("precision", [3, 1])
+@pytest.mark.parametrize("n", [128, 1000])
+def test_in_projection_with_position_prologue(precision, n):
+    from geomae_b200.dense import tc_linear
+    x, W, b = rnd(n, 128, seed=1), rnd(384, 128, scale=0.1, seed=2), rnd(384, seed=3)
+    table = rnd(144, 128, seed=4)
+    cell = torch.randint(0, 144, (n,), dtype=torch.int32, device="cuda")
+    got = tc_linear(x, W, n_out=384, bias=b, pos_table=table, tok_cell=cell, pos_slabs=2, precision=precision)
+    xp = x + table[cell.long()]
+    ref = torch.cat([F.linear(xp, W[:256], b[:256]), F.linear(x, W[256:], b[256:])], dim=1)
+    torch.testing.assert_close(got, ref, **TOL[precision])
+
+
+@pytest.mark.parametrize("precision", [3, 1])
+@pytest.mark.parametrize("K,gelu", [(128, False), (256, True)])
+def test_projection_residual_layernorm_epilogue(precision, K, gelu):
+    from geomae_b200.dense import tc_linear
+    n = 777
+    a, W, b, res = rnd(n, K, seed=5), rnd(128, K, scale=0.1, seed=6), rnd(128, seed=7), rnd(n, 128, seed=8)
+    gamma, beta = 1 + 0.1 * rnd(128, seed=9), 0.1 * rnd(128, seed=10)
+    out, ln_in, stats = tc_linear(a, W, n_out=128, bias=b, add_src=res, a_gelu=gelu, ln=(gamma, beta, 1e-5, True),
+                                  precision=precision)
+    s = F.linear(F.gelu(a) if gelu else a, W, b) + res
+    ref = F.layer_norm(s, (128,), gamma, beta, 1e-5)
+    torch.testing.assert_close(ln_in, s, **TOL[precision])
+    torch.testing.assert_close(out, ref, **TOL[precision])
+    torch.testing.assert_close(stats[:, 0], s.mean(dim=1), **TOL[precision])
+    torch.testing.assert_close(stats[:, 1], torch.rsqrt(s.var(dim=1, unbiased=False) + 1e-5), rtol=1e-2, atol=1e-3)
+
+
+@pytest.mark.parametrize("precision", [3, 1])
+def test_ffn1_plain_256(precision):
+    from geomae_b200.dense import tc_linear
+    y, W, b = rnd(515, 128, seed=11), rnd(256, 128, scale=0.1, seed=12), rnd(256, seed=13)
+    torch.testing.assert_close(tc_linear(y, W, n_out=256, bias=b, precision=precision), F.linear(y, W, b), **TOL[precision])
+
+
+@pytest.mark.parametrize("precision", [3, 1])
+def test_input_gradient_forms(precision):
+    from geomae_b200.dense import tc_linear
+    n = 900
+    # dh = ds2 @ W2, times gelu'(u)          (W2: [128 out, 256 in])
+    ds2, W2, u = rnd(n, 128, seed=14), rnd(128, 256, scale=0.1, seed=15), rnd(n, 256, seed=16)
+    got = tc_linear(ds2, W2, n_out=256, w_mn_major=True, gelu_u=u, precision=precision)
+    uu = u.clone().requires_grad_(True)
+    F.gelu(uu).backward(ds2 @ W2)
+    torch.testing.assert_close(got, uu.grad, **TOL[precision])
+    # dy = ds2 + du @ W1                      (W1: [256 out, 128 in], K = 256)
+    du, W1 = rnd(n, 256, seed=17), rnd(256, 128, scale=0.1, seed=18)
+    got = tc_linear(du, W1, n_out=128, w_mn_major=True, add_src=ds2, precision=precision)
+    torch.testing.assert_close(got, ds2 + du @ W1, **TOL[precision])
+    # dx = ds1 + dqkv @ Wqkv                  (Wqkv: [384 out, 128 in], K = 384)
+    dqkv, Wqkv = rnd(n, 384, seed=19), rnd(384, 128, scale=0.1, seed=20)
+    got = tc_linear(dqkv, Wqkv, n_out=128, w_mn_major=True, add_src=ds2, precision=precision)
+    torch.testing.assert_close(got, ds2 + dqkv @ Wqkv, **TOL[precision])
