@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--samples-per-gpu", type=int, default=4)     # data.samples_per_gpu of the config
     ap.add_argument("--sweeps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sra-impl", default="tc1", choices=["tc1", "tc3", "glue"],
+                    help="tc1: bf16 tensor-core SRA layers (BASELINE config 'bf16'); tc3: bf16x3 split (fp32 parity); "
+                         "glue: library GEMMs")
     return ap.parse_args()
 
 
@@ -148,6 +151,7 @@ def main():
     cfg = Config.fromfile(OWN_CFG)
     torch.manual_seed(0)
     model = build_model(cfg.model).to(dev).train()
+    model.backbone.set_sra_impl(args.sra_impl)
     opt = cfg.optimizer
     trainer = FlatTrainer(model, lr=opt["lr"], betas=opt["betas"], weight_decay=opt["weight_decay"],
                           max_grad_norm=cfg.optimizer_config["grad_clip"]["max_norm"])
@@ -252,11 +256,15 @@ def main():
             roof.update(achieved=ach, frac=ach / tens_peak)
     line = dict(
         metric=METRIC, value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=K, warmup=W,
-        ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+        ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype={"tc1": "bf16", "tc3": "bf16x3 (fp32-equivalent)", "glue": "f32"}[args.sra_impl],
         data="synthetic",
         config=dict(workload=WORKLOAD, samples_per_gpu=S, sweeps=args.sweeps, points_per_frame=int(pool[0][0].shape[0]),
                     parallelism=f"dp{world}", l2="flushed between steps (256 MiB write, outside the timed events)",
-                    precision="fp32 storage and accumulate, TF32 off (reference parity mode)"),
+                    sra_impl=args.sra_impl,
+                    precision={"tc1": "SRA GEMMs bf16 operands / fp32 TMEM accumulate; activations, LayerNorm, softmax, VFE, targets, losses fp32",
+                               "tc3": "SRA GEMMs bf16x3 split on tensor cores (fp32-equivalent, loss parity <=1e-4); rest fp32",
+                               "glue": "fp32 library GEMMs, TF32 off"}[args.sra_impl]),
         e2e=dict(value=frames / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / K),
         gpu_launches=launches, clocks=clocks, roofline=roof,

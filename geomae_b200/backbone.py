@@ -9,6 +9,7 @@ from torch import nn
 
 from .registry import BACKBONES
 from .sst import BasicShiftBlock, window_pos_embed
+from .windows import pos_table
 from .voxel import PillarBatch, VoxelGeometry
 from .windows import WindowLayout, WindowSpec
 
@@ -63,6 +64,21 @@ class MultiMAESSTSPChoose(nn.Module):
             self.cls_pred_med = nn.Linear(d, self.per_sub_voxel_num_med * 2)
         self._reset_parameters()
 
+    def set_sra_impl(self, impl: str):
+        """"tc3" (default, bf16x3 tensor-core, fp32 parity) | "tc1" (plain bf16 tensor-core) | "glue" (library GEMMs)."""
+        assert impl in ("tc3", "tc1", "glue")
+        for m in self.modules():
+            if hasattr(m, "impl") and hasattr(m, "win_attn"):
+                m.impl = impl
+        self.sra_impl = impl
+
+    def _pos(self, layout):
+        """(per-shift gathered position rows for the glue path | None, the [144,128] table for the fused path)."""
+        table = pos_table(self.window_shape, self.d_model[0], self.pos_temperature, layout.tok_cell.device)
+        if getattr(self, "sra_impl", "tc3") == "glue":
+            return window_pos_embed(layout, self.d_model[0], self.pos_temperature), table
+        return None, table
+
     def _reset_parameters(self):
         for name, p in self.named_parameters():     # …top_only.py:318-321
             if p.dim() > 1 and "scaler" not in name:
@@ -81,10 +97,10 @@ class MultiMAESSTSPChoose(nn.Module):
         return self.forward_decoder(x, coors, coors_mask, batch_size, pillar_batch, rows_keep, rows_mask)
 
     def forward_encoder(self, voxel_feat, layout):
-        pos = window_pos_embed(layout, self.d_model[0], self.pos_temperature)
+        pos, table = self._pos(layout)
         out = voxel_feat
         for block in self.encoder_blocks:
-            out = block(out, layout, pos)
+            out = block(out, layout, pos, table)
         return out
 
     def forward_decoder(self, visible_voxel_feat, coors, coors_mask, batch_size, pillar_batch=None, rows_keep=None,
@@ -94,12 +110,12 @@ class MultiMAESSTSPChoose(nn.Module):
         all_coors = torch.cat([coors, coors_mask], dim=0)
         rows = torch.cat([rows_keep, rows_mask]) if pillar_batch is not None else None
         layout = self._layout(all_coors, batch_size, pillar_batch, rows)
-        pos = window_pos_embed(layout, self.d_model[0], self.pos_temperature)
+        pos, table = self._pos(layout)
         cen = den = tokens
         for block in self.decoder_centroid_blocks:
-            cen = block(cen, layout, pos)
+            cen = block(cen, layout, pos, table)
         for block in self.decoder_density_blocks:
-            den = block(den, layout, pos)
+            den = block(den, layout, pos, table)
         cen, den = cen[n_vis:], den[n_vis:]
         reg_low = self.decoder_pred_low(cen).view(-1, self.per_sub_voxel_num_low, 3)
         reg_med = self.decoder_pred_med(cen).view(-1, self.per_sub_voxel_num_med, 3)

@@ -225,6 +225,181 @@ int launch_linear(const LinArgs& a, cudaStream_t stream) {
   return GEOMAE_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: dW[m, n] += sum_tok dY[tok, m] * X[tok, n]  (+ db[m] += sum_tok dY[tok, m]).
+// Both operands are MN-major views of token-major activations (K = tokens), so they are staged
+// exactly like a forward operand.  The bias gradient rides along as one extra N=16 MMA against a
+// constant block whose first column is 1.  A CTA accumulates its token range in TMEM and finishes
+// with vector reductions into the fp32 gradient buffer.
+struct WgradArgs {
+  const float* dY; int ldy; const float* X; int ldx; int n_rows;
+  const float* pos_table; const int32_t* tok_cell; int pos_slabs; int x_gelu;
+  float* dW; int ldw; float* db; int M_total; int N_total;
+  int tiles_per_cta; int precision;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NTHREADS) k_tc_wgrad(const WgradArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = TM * 128 * 2;             // dY tile: 128 tokens x 128 m-columns
+  constexpr int B_BYTES = TM * NT * 2;              // X tile : 128 tokens x NT n-columns
+  constexpr int ONES_BYTES = TM * tc::LINE_BYTES;   // one 64-column block
+  constexpr int TCOLS = NT == 256 ? 512 : 256;      // NT accumulator columns + 16 bias columns
+  const bool x3 = a.precision == 3;
+  uint8_t* sA = smem;
+  uint8_t* sAlo = sA + A_BYTES;
+  uint8_t* sB = sA + (x3 ? 2 : 1) * A_BYTES;
+  uint8_t* sBlo = sB + B_BYTES;
+  uint8_t* sOnes = sB + (x3 ? 2 : 1) * B_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.z * NT;
+  const int tile_begin = blockIdx.x * a.tiles_per_cta;
+  const int n_tiles_total = (a.n_rows + TM - 1) / TM;
+  const int tile_end = min(tile_begin + a.tiles_per_cta, n_tiles_total);
+  if (tile_begin >= tile_end) return;
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, TCOLS);
+  if (threadIdx.x == 0) tc::mbar_init(&mbar, 1);
+  const bool want_bias = a.db != nullptr && blockIdx.z == 0;
+  // constant "ones" block: element (row, col 0) = 1.0
+  for (int i = threadIdx.x; i < TM * 8; i += NTHREADS) {
+    const int r = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c == 0) v.x = 0x00003F80u;    // bf16(1.0) in the low half
+    *reinterpret_cast<uint4*>(sOnes + tc::swz(r, c)) = v;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const bool use_pos = a.pos_table && (int)blockIdx.y < a.pos_slabs;
+  int it = 0;
+  for (int tile = tile_begin; tile < tile_end; ++tile, ++it) {
+    const int row0 = tile * TM;
+    if (it > 0) {
+      tc::mbar_wait(&mbar, (it - 1) & 1);
+      tc::fence_after_sync();
+    }
+    stage_tile<TM, 128>(sA, x3 ? sAlo : nullptr, a.dY, a.ldy, row0, a.n_rows, m0, nullptr, nullptr, 0, false);
+    stage_tile<TM, NT>(sB, x3 ? sBlo : nullptr, a.X, a.ldx, row0, a.n_rows, n0, use_pos ? a.pos_table : nullptr,
+                       a.tok_cell, a.N_total, a.x_gelu != 0);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::make_idesc_bf16(128, NT, 1, 1);
+      const uint32_t idesc_b = tc::make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t lbo = TM * tc::LINE_BYTES;     // stride between 64-column blocks
+      bool acc = it > 0;
+#pragma unroll
+      for (int j = 0; j < TM / 16; ++j) {
+        const uint32_t off = (uint32_t)j * 2 * tc::ATOM_BYTES;
+        const uint64_t da_hi = tc::make_desc(tc::smem_u32(sA) + off, lbo, tc::ATOM_BYTES);
+        const uint64_t db_hi = tc::make_desc(tc::smem_u32(sB) + off, lbo, tc::ATOM_BYTES);
+        tc::mma_bf16(tmem, da_hi, db_hi, idesc, acc);
+        uint64_t da_lo = 0;
+        if (x3) {
+          da_lo = tc::make_desc(tc::smem_u32(sAlo) + off, lbo, tc::ATOM_BYTES);
+          const uint64_t db_lo = tc::make_desc(tc::smem_u32(sBlo) + off, lbo, tc::ATOM_BYTES);
+          tc::mma_bf16(tmem, da_hi, db_lo, idesc, true);
+          tc::mma_bf16(tmem, da_lo, db_hi, idesc, true);
+        }
+        if (want_bias) {
+          const uint64_t d1 = tc::make_desc(tc::smem_u32(sOnes) + off, lbo, tc::ATOM_BYTES);
+          tc::mma_bf16(tmem + NT, da_hi, d1, idesc_b, acc);
+          if (x3) tc::mma_bf16(tmem + NT, da_lo, d1, idesc_b, true);
+        }
+        acc = true;
+      }
+      tc::mma_commit(&mbar);
+    }
+  }
+  tc::mbar_wait(&mbar, (it - 1) & 1);
+  tc::fence_after_sync();
+  const int m = m0 + warp * 32 + lane;                 // this thread's dW row
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += 32) {
+    float v[32];
+    tc::tmem_ld32(t_lane + c0, v);
+    tc::tmem_ld_wait();
+    if (m < a.M_total) {
+      float* o = a.dW + (int64_t)m * a.ldw + n0 + c0;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c), "f"(v[c]), "f"(v[c + 1]),
+                     "f"(v[c + 2]), "f"(v[c + 3])
+                     : "memory");
+    }
+  }
+  if (want_bias) {
+    float v[32];
+    tc::tmem_ld32(t_lane + NT, v);
+    tc::tmem_ld_wait();
+    if (m < a.M_total) atomicAdd(a.db + m, v[0]);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_free(tmem, TCOLS);
+}
+
+template <int NT>
+int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
+  const int max_smem = 2 * (TM * 128 * 2 + TM * NT * 2) + TM * tc::LINE_BYTES + 1024;
+  const int smem = (a.precision == 3 ? 2 : 1) * (TM * 128 * 2 + TM * NT * 2) + TM * tc::LINE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    GM_CUDA(cudaFuncSetAttribute(k_tc_wgrad<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    configured = true;
+  }
+  const int n_tiles = gm_div_up(a.n_rows, TM);
+  const dim3 grid(gm_div_up(n_tiles, a.tiles_per_cta), a.M_total / 128, a.N_total / NT);
+  k_tc_wgrad<NT><<<grid, NTHREADS, smem, stream>>>(a);
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward over saved (pre-LN row, mean, rstd): one warp per row, float4 per lane (C = 128).
+__global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dz, const float* __restrict__ s,
+                                                const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                int n_rows, float* ds, float* dgamma, float* dbeta) {
+  __shared__ float sg[8][128], sb[8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+  float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg;
+  for (int row = blockIdx.x * 8 + warp; row < n_rows; row += gridDim.x * 8) {
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)row * 128) + lane);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(s + (int64_t)row * 128) + lane);
+    const float mean = __ldg(stats + 2 * (int64_t)row), rstd = __ldg(stats + 2 * (int64_t)row + 1);
+    const float4 xh = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+    const float4 g = make_float4(d.x * g4.x, d.y * g4.y, d.z * g4.z, d.w * g4.w);
+    float s1 = (g.x + g.y) + (g.z + g.w);
+    float s2 = (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
+    s1 = gm_warp_sum(s1) * (1.0f / 128.f);
+    s2 = gm_warp_sum(s2) * (1.0f / 128.f);
+    reinterpret_cast<float4*>(ds + (int64_t)row * 128)[lane] =
+        make_float4(rstd * (g.x - s1 - xh.x * s2), rstd * (g.y - s1 - xh.y * s2), rstd * (g.z - s1 - xh.z * s2),
+                    rstd * (g.w - s1 - xh.w * s2));
+    accg.x += d.x * xh.x; accg.y += d.y * xh.y; accg.z += d.z * xh.z; accg.w += d.w * xh.w;
+    accb.x += d.x; accb.y += d.y; accb.z += d.z; accb.w += d.w;
+  }
+  reinterpret_cast<float4*>(sg[warp])[lane] = accg;
+  reinterpret_cast<float4*>(sb[warp])[lane] = accb;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { tg += sg[w][threadIdx.x]; tb += sb[w][threadIdx.x]; }
+    atomicAdd(dgamma + threadIdx.x, tg);
+    atomicAdd(dbeta + threadIdx.x, tb);
+  }
+}
+
 }  // namespace
 
 extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
@@ -254,4 +429,37 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
     return (p->N_total % 256 == 0) ? launch_linear<256, 2>(a, stream) : launch_linear<128, 2>(a, stream);
   }
   return (p->N_total % 256 == 0 && p->pos_slabs == 0) ? launch_linear<256, 0>(a, stream) : launch_linear<128, 0>(a, stream);
+}
+
+extern "C" int geomae_tc_wgrad(const geomae_wgrad_args* p, void* stream_) {
+  GM_REQUIRE(p && p->dY && p->X && p->dW, "tc_wgrad: null argument");
+  GM_REQUIRE(p->M_total > 0 && p->M_total % 128 == 0 && p->N_total > 0 && p->N_total % 128 == 0,
+             "tc_wgrad: M=%d and N=%d must be multiples of 128", p->M_total, p->N_total);
+  GM_REQUIRE(p->precision == 1 || p->precision == 3, "tc_wgrad: precision must be 1 or 3");
+  GM_REQUIRE(p->ldy % 4 == 0 && p->ldx % 4 == 0 && p->ldw % 4 == 0, "tc_wgrad: leading dimensions must be multiples of 4");
+  if (p->n_rows == 0) return GEOMAE_OK;
+  WgradArgs a;
+  a.dY = p->dY; a.ldy = p->ldy; a.X = p->X; a.ldx = p->ldx; a.n_rows = p->n_rows;
+  a.pos_table = p->pos_table; a.tok_cell = p->tok_cell; a.pos_slabs = p->pos_slabs; a.x_gelu = p->x_gelu;
+  a.dW = p->dW; a.ldw = p->ldw; a.db = p->db; a.M_total = p->M_total; a.N_total = p->N_total;
+  a.precision = p->precision;
+  const int n_tiles = gm_div_up(p->n_rows, TM);
+  const int slabs = (p->M_total / 128) * (p->N_total % 256 == 0 ? p->N_total / 256 : p->N_total / 128);
+  int splits = (2 * GM_NUM_SMS + slabs - 1) / slabs;           // aim at ~2 CTAs per SM
+  if (splits > n_tiles) splits = n_tiles;
+  a.tiles_per_cta = gm_div_up(n_tiles, splits);
+  return (p->N_total % 256 == 0) ? launch_wgrad<256>(a, (cudaStream_t)stream_) : launch_wgrad<128>(a, (cudaStream_t)stream_);
+}
+
+extern "C" int geomae_layernorm_bwd(const float* d_out, const float* ln_in, const float* ln_stats, const float* gamma,
+                                    int64_t n_rows, int32_t channels, float* d_in, float* d_gamma, float* d_beta,
+                                    void* stream) {
+  GM_REQUIRE(channels == 128, "layernorm_bwd: specialised for 128 channels (got %d)", channels);
+  if (n_rows == 0) return GEOMAE_OK;
+  GM_REQUIRE(d_out && ln_in && ln_stats && gamma && d_in && d_gamma && d_beta, "layernorm_bwd: null argument");
+  int blocks = gm_div_up(n_rows, 8);
+  if (blocks > GM_NUM_SMS * 4) blocks = GM_NUM_SMS * 4;
+  k_ln_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, ln_in, ln_stats, gamma, (int)n_rows, d_in, d_gamma, d_beta);
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
 }

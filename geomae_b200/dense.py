@@ -45,3 +45,26 @@ def tc_linear(A, W, *, n_out, w_mn_major=False, bias=None, pos_table=None, tok_c
     if ln is not None:
         return out, ln_in, ln_stats
     return out
+
+
+def tc_wgrad(dY, X, dW, db=None, *, pos_table=None, tok_cell=None, pos_slabs=0, x_gelu=False, precision=3):
+    """dW += dY^T @ prologue(X); db += dY.sum(0).  dW/db are fp32 accumulators (e.g. views of the flat grad buffer)."""
+    n, m_total = dY.shape
+    a = L.WgradArgs()
+    a.dY, a.ldy, a.X, a.ldx, a.n_rows = dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0), n
+    a.pos_table = pos_table.data_ptr() if pos_table is not None else None
+    a.tok_cell = tok_cell.data_ptr() if tok_cell is not None else None
+    a.pos_slabs, a.x_gelu = pos_slabs, int(x_gelu)
+    a.dW, a.ldw = dW.data_ptr(), dW.stride(0)
+    a.db = db.data_ptr() if db is not None else None
+    a.M_total, a.N_total, a.precision = m_total, X.shape[1], precision
+    assert tuple(dW.shape) == (m_total, X.shape[1])
+    L.run("tc_wgrad", C.byref(a), L.stream_ptr(dY.device))
+
+
+def layernorm_bwd(d_out, ln_in, ln_stats, gamma, d_gamma, d_beta):
+    """-> d_in; d_gamma / d_beta are accumulated in place."""
+    d_in = torch.empty_like(d_out)
+    L.run("layernorm_bwd", L.ptr(d_out), L.ptr(ln_in), L.ptr(ln_stats), L.ptr(gamma), d_out.shape[0], d_out.shape[1],
+          L.ptr(d_in), L.ptr(d_gamma), L.ptr(d_beta), L.stream_ptr(d_out.device))
+    return d_in

@@ -58,6 +58,13 @@ class LinearArgs(C.Structure):
                 ("epilogue", C.c_int32), ("precision", C.c_int32)]
 
 
+class WgradArgs(C.Structure):
+    _fields_ = [("dY", C.c_void_p), ("ldy", C.c_int32), ("X", C.c_void_p), ("ldx", C.c_int32), ("n_rows", C.c_int32),
+                ("pos_table", C.c_void_p), ("tok_cell", C.c_void_p), ("pos_slabs", C.c_int32), ("x_gelu", C.c_int32),
+                ("dW", C.c_void_p), ("ldw", C.c_int32), ("db", C.c_void_p), ("M_total", C.c_int32),
+                ("N_total", C.c_int32), ("precision", C.c_int32)]
+
+
 def build_if_missing():
     if not os.path.exists(LIB_PATH):
         import subprocess
@@ -104,6 +111,8 @@ class _Sigs:
     geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p]
     geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
     geomae_tc_linear = [C.POINTER(LinearArgs), _p]
+    geomae_tc_wgrad = [C.POINTER(WgradArgs), _p]
+    geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]
     geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                          C.c_float, C.c_float, _i64, _p, _p]
 
@@ -115,7 +124,7 @@ _calls = {}         # name -> number of C-ABI calls (bench.py reports kernel lau
 LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=8, geom_targets=1, dense_targets=1, coors_bitmap=4,
                          token_map=1, window_csr=3, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
                          scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=1, adamw_step=2,
-                         tc_linear=1)
+                         tc_linear=1, tc_wgrad=1, layernorm_bwd=1)
 
 
 def start_timing():

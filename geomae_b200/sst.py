@@ -12,19 +12,30 @@ from . import lib as L
 from .windows import WindowLayout, pos_table
 
 
+def _attn_fwd(qkv, win, n_heads):
+    n, three_d = qkv.shape
+    out = torch.empty((n, three_d // 3), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((n, n_heads), dtype=torch.float32, device=qkv.device)
+    L.run("sra_attention_fwd", L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]),
+          L.ptr(win["n_windows"]), win["max_windows"], L.ptr(out), L.ptr(lse), L.stream_ptr(qkv.device))
+    return out, lse
+
+
+def _attn_bwd(qkv, out, lse, d_out, win, n_heads):
+    d_qkv = torch.empty_like(qkv)
+    L.run("sra_attention_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0], n_heads,
+          L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["n_windows"]), win["max_windows"], L.ptr(d_qkv),
+          L.stream_ptr(qkv.device))
+    return d_qkv
+
+
 class _SRAAttention(torch.autograd.Function):
     """out[i] = softmax_j(q_i.k_j / sqrt(hd)) v_j over the tokens j sharing i's window."""
 
     @staticmethod
     def forward(ctx, qkv, win, n_heads):
         qkv = qkv.contiguous()
-        n, three_d = qkv.shape
-        d = three_d // 3
-        out = torch.empty((n, d), dtype=qkv.dtype, device=qkv.device)
-        lse = torch.empty((n, n_heads), dtype=torch.float32, device=qkv.device)
-        L.run("sra_attention_fwd", L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]),
-                                                 L.ptr(win["n_windows"]), win["max_windows"], L.ptr(out), L.ptr(lse),
-                                                 L.stream_ptr(qkv.device))
+        out, lse = _attn_fwd(qkv, win, n_heads)
         ctx.save_for_backward(qkv, out, lse)
         ctx.win, ctx.n_heads = win, n_heads
         return out
@@ -32,14 +43,64 @@ class _SRAAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         qkv, out, lse = ctx.saved_tensors
-        d_out = d_out.contiguous()
-        d_qkv = torch.empty_like(qkv)
-        win = ctx.win
-        L.run("sra_attention_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0],
-                                                 ctx.n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]),
-                                                 L.ptr(win["n_windows"]), win["max_windows"], L.ptr(d_qkv),
-                                                 L.stream_ptr(qkv.device))
-        return d_qkv, None, None
+        return _attn_bwd(qkv, out, lse, d_out.contiguous(), ctx.win, ctx.n_heads), None, None
+
+
+def _grad_of(p):
+    """The accumulator the fused backward adds into (FlatTrainer pre-binds it to the flat gradient buffer)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+class _SRALayerFn(torch.autograd.Function):
+    """One whole EncoderLayer (sst_basic_block.py:85-102) as 5 forward / 11 backward kernels:
+    in-proj(+pos) -> window attention -> out-proj+residual+LN1 -> FFN1 -> GELU+FFN2+residual+LN2, every GEMM on
+    tcgen05.  Parameter gradients are accumulated straight into ``p.grad`` (no autograd bookkeeping for the 12
+    parameter tensors); only d(input) is returned to autograd."""
+
+    @staticmethod
+    def forward(ctx, x, layer, win, table, precision):
+        from .dense import tc_linear
+        x = x.contiguous()
+        mha = layer.win_attn.self_attn
+        d, nh = layer.win_attn.d_model, layer.win_attn.nhead
+        cell = win["tok_cell"]
+        qkv = tc_linear(x, mha.in_proj_weight, n_out=3 * d, bias=mha.in_proj_bias, pos_table=table, tok_cell=cell,
+                        pos_slabs=2, precision=precision)
+        a, lse = _attn_fwd(qkv, win, nh)
+        y, s1, st1 = tc_linear(a, mha.out_proj.weight, n_out=d, bias=mha.out_proj.bias, add_src=x,
+                               ln=(layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, True), precision=precision)
+        u = tc_linear(y, layer.linear1.weight, n_out=layer.linear1.out_features, bias=layer.linear1.bias,
+                      precision=precision)
+        z, s2, st2 = tc_linear(u, layer.linear2.weight, n_out=d, bias=layer.linear2.bias, add_src=y, a_gelu=True,
+                               ln=(layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, True), precision=precision)
+        ctx.save_for_backward(x, qkv, a, lse, s1, st1, y, u, s2, st2)
+        ctx.layer, ctx.win, ctx.table, ctx.precision = layer, win, table, precision
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        from .dense import layernorm_bwd, tc_linear, tc_wgrad
+        x, qkv, a, lse, s1, st1, y, u, s2, st2 = ctx.saved_tensors
+        layer, win, table, prec = ctx.layer, ctx.win, ctx.table, ctx.precision
+        mha = layer.win_attn.self_attn
+        d, nh = layer.win_attn.d_model, layer.win_attn.nhead
+        g = _grad_of
+        dz = dz.contiguous()
+        ds2 = layernorm_bwd(dz, s2, st2, layer.norm2.weight, g(layer.norm2.weight), g(layer.norm2.bias))
+        du = tc_linear(ds2, layer.linear2.weight, n_out=u.shape[1], w_mn_major=True, gelu_u=u, precision=prec)
+        tc_wgrad(ds2, u, g(layer.linear2.weight), g(layer.linear2.bias), x_gelu=True, precision=prec)
+        dy = tc_linear(du, layer.linear1.weight, n_out=d, w_mn_major=True, add_src=ds2, precision=prec)
+        tc_wgrad(du, y, g(layer.linear1.weight), g(layer.linear1.bias), precision=prec)
+        ds1 = layernorm_bwd(dy, s1, st1, layer.norm1.weight, g(layer.norm1.weight), g(layer.norm1.bias))
+        da = tc_linear(ds1, mha.out_proj.weight, n_out=d, w_mn_major=True, precision=prec)
+        tc_wgrad(ds1, a, g(mha.out_proj.weight), g(mha.out_proj.bias), precision=prec)
+        dqkv = _attn_bwd(qkv, a, lse, da, win, nh)
+        dx = tc_linear(dqkv, mha.in_proj_weight, n_out=d, w_mn_major=True, add_src=ds1, precision=prec)
+        tc_wgrad(dqkv, x, g(mha.in_proj_weight), g(mha.in_proj_bias), pos_table=table, tok_cell=win["tok_cell"],
+                 pos_slabs=2, precision=prec)
+        return dx, None, None, None, None
 
 
 def sra_attention(qkv, win, n_heads):
@@ -85,8 +146,16 @@ class EncoderLayer(nn.Module):
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
         self.activation = {"relu": F.relu, "gelu": F.gelu}[activation]
+        self.activation_name = activation
+        # "tc3": fused tcgen05 kernels, bf16x3 split (fp32-parity);  "tc1": same kernels, plain bf16;
+        # "glue": hand-written attention + library GEMM/LayerNorm under autograd (the round-1 v1 path)
+        self.impl = "tc3"
 
-    def forward(self, src, pos, win):
+    def forward(self, src, pos, win, table=None):
+        if self.impl in ("tc3", "tc1"):
+            if self.activation_name != "gelu":
+                raise NotImplementedError("the fused SRA layer implements the GELU feed-forward of the GeoMAE configs")
+            return _SRALayerFn.apply(src, self, win, table, 3 if self.impl == "tc3" else 1)
         src = self.norm1(src + self.win_attn(src, pos, win))
         src2 = self.linear2(self.activation(self.linear1(src)))
         return self.norm2(src + src2)
@@ -102,11 +171,11 @@ class BasicShiftBlock(nn.Module):
             EncoderLayer(d_model, nhead, dim_feedforward, dropout, activation, batch_first, layer_id=block_id * 2 + j)
             for j in range(2)])
 
-    def forward(self, src, layout: WindowLayout, pos_list):
+    def forward(self, src, layout: WindowLayout, pos_list, table=None):
         n_shifts = layout.spec.n_shifts
         for i, layer in enumerate(self.encoder_list):
             s = i % n_shifts
-            src = layer(src, pos_list[s], layout.shift(s))
+            src = layer(src, pos_list[s] if pos_list is not None else None, layout.shift(s), table)
         return src
 
 

@@ -240,6 +240,27 @@ typedef struct geomae_linear_args {
 
 int geomae_tc_linear(const geomae_linear_args* args, void* stream);
 
+/* dW[M_total, N_total] += dY^T X over the token rows, db[M_total] += column sums of dY (db may be NULL).
+ * X prologue: + pos_table[tok_cell] for the first pos_slabs 128-row slabs of dW (q,k rows of in_proj), gelu.
+ * Accumulates with fp32 vector reductions: the destination must hold the running gradient (or zeros).
+ * replaces: the weight/bias gradient GEMMs autograd runs for nn.Linear / MultiheadAttention in
+ *           models/sst/sst_basic_block.py (library sgemm + column-sum reductions). */
+typedef struct geomae_wgrad_args {
+  const float* dY; int32_t ldy; const float* X; int32_t ldx; int32_t n_rows;
+  const float* pos_table; const int32_t* tok_cell; int32_t pos_slabs; int32_t x_gelu;
+  float* dW; int32_t ldw; float* db; int32_t M_total; int32_t N_total;
+  int32_t precision;
+} geomae_wgrad_args;
+
+int geomae_tc_wgrad(const geomae_wgrad_args* args, void* stream);
+
+/* LayerNorm backward from the saved pre-LN rows and (mean, rstd): d_in, and d_gamma / d_beta accumulated
+ * (+=) into their buffers.  channels must be 128.
+ * replaces: ATen layer_norm backward (GammaBetaBackward + grad_input kernels) under nn.LayerNorm
+ *           (sst_basic_block.py:76-77,96,100). */
+int geomae_layernorm_bwd(const float* d_out, const float* ln_in, const float* ln_stats, const float* gamma,
+                         int64_t n_rows, int32_t channels, float* d_in, float* d_gamma, float* d_beta, void* stream);
+
 /* ---------------------------------------------------------------- optimiser */
 
 /* One fused step over flat fp32 buffers: g' = g*grad_scale (1/world_size), clip by global L2 norm

@@ -67,3 +67,50 @@ def test_input_gradient_forms(precision):
     dqkv, Wqkv = rnd(n, 384, seed=19), rnd(384, 128, scale=0.1, seed=20)
     got = tc_linear(dqkv, Wqkv, n_out=128, w_mn_major=True, add_src=ds2, precision=precision)
     torch.testing.assert_close(got, ds2 + dqkv @ Wqkv, **TOL[precision])
+
+
+@pytest.mark.parametrize("precision", [3, 1])
+def test_weight_gradient_forms(precision):
+    from geomae_b200.dense import tc_wgrad
+    for n in (100, 1000, 5000):
+        # bf16 rounding of ~n unit-variance products: error ~ 2^-9 * sqrt(n) * few sigma
+        tol = dict(rtol=1e-3, atol=2e-3) if precision == 3 else dict(rtol=5e-2, atol=0.02 * n ** 0.5)
+        # dW2 [128, 256] += ds2^T gelu(u), db2
+        ds2, u = rnd(n, 128, seed=21), rnd(n, 256, seed=22)
+        dW, db = torch.full((128, 256), 0.5, device="cuda"), torch.full((128,), 0.25, device="cuda")
+        tc_wgrad(ds2, u, dW, db, x_gelu=True, precision=precision)
+        torch.testing.assert_close(dW, 0.5 + ds2.t() @ F.gelu(u), **tol)
+        torch.testing.assert_close(db, 0.25 + ds2.sum(0), **tol)
+        # dW1 [256, 128] += du^T y
+        du, y = rnd(n, 256, seed=23), rnd(n, 128, seed=24)
+        dW, db = torch.zeros(256, 128, device="cuda"), torch.zeros(256, device="cuda")
+        tc_wgrad(du, y, dW, db, precision=precision)
+        torch.testing.assert_close(dW, du.t() @ y, **tol)
+        torch.testing.assert_close(db, du.sum(0), **tol)
+        # dWqkv [384, 128] += dqkv^T [x+pos | x+pos | x]
+        dqkv, x, table = rnd(n, 384, seed=25), rnd(n, 128, seed=26), rnd(144, 128, seed=27)
+        cell = torch.randint(0, 144, (n,), dtype=torch.int32, device="cuda")
+        dW, db = torch.zeros(384, 128, device="cuda"), torch.zeros(384, device="cuda")
+        tc_wgrad(dqkv, x, dW, db, pos_table=table, tok_cell=cell, pos_slabs=2, precision=precision)
+        xp = x + table[cell.long()]
+        ref = torch.cat([dqkv[:, :256].t() @ xp, dqkv[:, 256:].t() @ x], dim=0)
+        torch.testing.assert_close(dW, ref, **tol)
+        torch.testing.assert_close(db, dqkv.sum(0), **tol)
+
+
+def test_layernorm_backward():
+    from geomae_b200.dense import layernorm_bwd
+    n = 3001
+    s = rnd(n, 128, seed=30).requires_grad_(True)
+    gamma = (1 + 0.1 * rnd(128, seed=31)).requires_grad_(True)
+    beta = (0.1 * rnd(128, seed=32)).requires_grad_(True)
+    dz = rnd(n, 128, seed=33)
+    F.layer_norm(s, (128,), gamma, beta, 1e-5).backward(dz)
+    sd = s.detach()
+    mean = sd.mean(dim=1)
+    rstd = torch.rsqrt(sd.var(dim=1, unbiased=False) + 1e-5)
+    dg, db = torch.zeros(128, device="cuda"), torch.zeros(128, device="cuda")
+    ds = layernorm_bwd(dz, sd, torch.stack([mean, rstd], dim=1).contiguous(), gamma.detach(), dg, db)
+    torch.testing.assert_close(ds, s.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dg, gamma.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(db, beta.grad, rtol=1e-4, atol=1e-3)
