@@ -19,10 +19,15 @@ class FlatTrainer:
         decay = [(k, p) for k, p in named if not any(s in k for s in no_decay_keys)]
         no_decay = [(k, p) for k, p in named if any(s in k for s in no_decay_keys)]
         self.order = decay + no_decay
-        self.n_decay = sum(p.numel() for _, p in decay)
-        self.n = sum(p.numel() for _, p in self.order)
+        align = 64      # floats: every tensor starts 256-byte aligned (the kernels use 128-bit accesses)
+
+        def padded(p):
+            return (p.numel() + align - 1) // align * align
+        self.n_decay = sum(padded(p) for _, p in decay)
+        self.n = sum(padded(p) for _, p in self.order)
+        self.n_params = sum(p.numel() for _, p in self.order)
         dev = named[0][1].device
-        self.flat_param = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.flat_param = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
         off = 0
         for _, p in self.order:
@@ -30,7 +35,7 @@ class FlatTrainer:
             self.flat_param[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + n].view_as(p)
             p.grad = self.flat_grad[off:off + n].view_as(p)
-            off += n
+            off += padded(p)
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.partials = torch.zeros(1024, dtype=torch.float64, device=dev)
