@@ -8,7 +8,7 @@ import torch
 from torch import nn
 
 from .registry import BACKBONES
-from .sst import BasicShiftBlock, window_pos_embed
+from .sst import BasicShiftBlock, SRAStack, window_pos_embed
 from .windows import pos_table
 from .voxel import PillarBatch, VoxelGeometry
 from .windows import WindowLayout, WindowSpec
@@ -72,6 +72,19 @@ class MultiMAESSTSPChoose(nn.Module):
                 m.impl = impl
         self.sra_impl = impl
 
+    def _precision(self):
+        return 1 if getattr(self, "sra_impl", "tc3") == "tc1" else 3
+
+    def _stack(self, blocks):
+        """All EncoderLayers of a ModuleList of BasicShiftBlocks as one executor (layer j of a block uses shift j)."""
+        key = id(blocks)
+        cache = self.__dict__.setdefault("_stacks", {})
+        if key not in cache:
+            layers = [layer for block in blocks for layer in block.encoder_list]
+            shifts = [j % self.spec.n_shifts for block in blocks for j in range(len(block.encoder_list))]
+            cache[key] = SRAStack(layers, shifts)
+        return cache[key]
+
     def _pos(self, layout):
         """(per-shift gathered position rows for the glue path | None, the [144,128] table for the fused path)."""
         table = pos_table(self.window_shape, self.d_model[0], self.pos_temperature, layout.tok_cell.device)
@@ -98,6 +111,8 @@ class MultiMAESSTSPChoose(nn.Module):
 
     def forward_encoder(self, voxel_feat, layout):
         pos, table = self._pos(layout)
+        if pos is None:
+            return self._stack(self.encoder_blocks)(voxel_feat, layout, table, self._precision())
         out = voxel_feat
         for block in self.encoder_blocks:
             out = block(out, layout, pos, table)
@@ -112,10 +127,14 @@ class MultiMAESSTSPChoose(nn.Module):
         layout = self._layout(all_coors, batch_size, pillar_batch, rows)
         pos, table = self._pos(layout)
         cen = den = tokens
-        for block in self.decoder_centroid_blocks:
-            cen = block(cen, layout, pos, table)
-        for block in self.decoder_density_blocks:
-            den = block(den, layout, pos, table)
+        if pos is None:
+            cen = self._stack(self.decoder_centroid_blocks)(tokens, layout, table, self._precision())
+            den = self._stack(self.decoder_density_blocks)(tokens, layout, table, self._precision())
+        else:
+            for block in self.decoder_centroid_blocks:
+                cen = block(cen, layout, pos, table)
+            for block in self.decoder_density_blocks:
+                den = block(den, layout, pos, table)
         cen, den = cen[n_vis:], den[n_vis:]
         reg_low = self.decoder_pred_low(cen).view(-1, self.per_sub_voxel_num_low, 3)
         reg_med = self.decoder_pred_med(cen).view(-1, self.per_sub_voxel_num_med, 3)

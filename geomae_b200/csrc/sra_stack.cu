@@ -1,0 +1,109 @@
+// Host-side executor of a stack of SRA EncoderLayers (forward and hand-derived backward).
+// One C-ABI call runs every kernel of every layer of the stack on the given stream, so the Python
+// host pays one call per stack and direction instead of one per kernel (the v1 path was CPU-bound).
+// Layer math: models/sst/sst_basic_block.py:26-61,85-102 (post-norm EncoderLayer with window attention).
+#include "common.cuh"
+
+namespace {
+
+int lin(const float* A, int lda, int n, int K, const float* W, int ldw, int w_rows, int mn, const float* bias, int N,
+        float* out, int ldo, int prec, void* stream, geomae_linear_args* extra = nullptr) {
+  geomae_linear_args a = extra ? *extra : geomae_linear_args{};
+  a.A = A; a.lda = lda; a.n_rows = n; a.K = K; a.W = W; a.ldw = ldw; a.w_rows = w_rows; a.w_mn_major = mn;
+  a.bias = bias; a.N_total = N; a.out = out; a.ldo = ldo; a.precision = prec;
+  return geomae_tc_linear(&a, stream);
+}
+
+int wgrad(const float* dY, int ldy, const float* X, int ldx, int n, float* dW, int ldw, float* db, int M, int N,
+          int prec, void* stream, const float* pos = nullptr, const int32_t* cell = nullptr, int pos_slabs = 0,
+          int gelu = 0) {
+  geomae_wgrad_args a{};
+  a.dY = dY; a.ldy = ldy; a.X = X; a.ldx = ldx; a.n_rows = n; a.pos_table = pos; a.tok_cell = cell;
+  a.pos_slabs = pos_slabs; a.x_gelu = gelu; a.dW = dW; a.ldw = ldw; a.db = db; a.M_total = M; a.N_total = N;
+  a.precision = prec;
+  return geomae_tc_wgrad(&a, stream);
+}
+
+#define GM_TRY(call)            \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__) return rc__;      \
+  } while (0)
+
+}  // namespace
+
+extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers,
+                                        const geomae_sra_saved* saved, const float* x_in, void* stream) {
+  GM_REQUIRE(c && layers && saved && (x_in || c->n_tokens == 0), "sra_stack_forward: null argument");
+  GM_REQUIRE(c->d_model == 128 && c->n_heads == 8, "sra_stack: specialised for d_model 128 / 8 heads (got %d / %d)",
+             c->d_model, c->n_heads);
+  GM_REQUIRE(c->ffn % 128 == 0, "sra_stack: ffn width must be a multiple of 128");
+  const int n = (int)c->n_tokens, d = c->d_model, f = c->ffn, p = c->precision;
+  if (n == 0) return GEOMAE_OK;
+  const float* x = x_in;
+  for (int l = 0; l < n_layers; ++l) {
+    const geomae_sra_layer& L = layers[l];
+    const geomae_sra_saved& S = saved[l];
+    const geomae_sra_windows& w = c->shift[L.shift];
+    geomae_linear_args e{};
+    e.pos_table = c->pos_table; e.tok_cell = w.tok_cell; e.pos_slabs = 2;
+    GM_TRY(lin(x, d, n, d, L.in_proj_w, d, 3 * d, 0, L.in_proj_b, 3 * d, S.qkv, 3 * d, p, stream, &e));
+    GM_TRY(geomae_sra_attention_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.n_windows, w.max_windows, S.attn,
+                                    S.lse, stream));
+    geomae_linear_args e1{};
+    e1.add_src = x; e1.ld_add = d; e1.ln_gamma = L.norm1_w; e1.ln_beta = L.norm1_b; e1.ln_eps = L.ln_eps;
+    e1.ln_in = S.s1; e1.ln_stats = S.st1; e1.epilogue = 1;
+    GM_TRY(lin(S.attn, d, n, d, L.out_proj_w, d, d, 0, L.out_proj_b, d, S.y, d, p, stream, &e1));
+    GM_TRY(lin(S.y, d, n, d, L.lin1_w, d, f, 0, L.lin1_b, f, S.u, f, p, stream));
+    geomae_linear_args e2{};
+    e2.add_src = S.y; e2.ld_add = d; e2.ln_gamma = L.norm2_w; e2.ln_beta = L.norm2_b; e2.ln_eps = L.ln_eps;
+    e2.ln_in = S.s2; e2.ln_stats = S.st2; e2.epilogue = 1; e2.a_gelu = 1;
+    GM_TRY(lin(S.u, f, n, f, L.lin2_w, f, d, 0, L.lin2_b, d, S.z, d, p, stream, &e2));
+    x = S.z;
+  }
+  return GEOMAE_OK;
+}
+
+extern "C" int geomae_sra_stack_backward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers,
+                                         const geomae_sra_saved* saved, const float* x_in, const float* d_out,
+                                         float* d_in, float* scratch, void* stream) {
+  GM_REQUIRE(c && layers && saved && d_out && d_in && scratch, "sra_stack_backward: null argument");
+  const int n = (int)c->n_tokens, d = c->d_model, f = c->ffn, p = c->precision;
+  if (n == 0) return GEOMAE_OK;
+  // scratch: ds2 | du | dy | ds1 | da | dqkv | dx_a | dx_b   ([n, d] each except du [n, f], dqkv [n, 3d])
+  float* ds2 = scratch;
+  float* du = ds2 + (int64_t)n * d;
+  float* dy = du + (int64_t)n * f;
+  float* ds1 = dy + (int64_t)n * d;
+  float* da = ds1 + (int64_t)n * d;
+  float* dqkv = da + (int64_t)n * d;
+  float* dx_buf[2] = {dqkv + (int64_t)n * 3 * d, dqkv + (int64_t)n * 3 * d + (int64_t)n * d};
+  const float* dz = d_out;
+  for (int l = n_layers - 1; l >= 0; --l) {
+    const geomae_sra_layer& L = layers[l];
+    const geomae_sra_saved& S = saved[l];
+    const geomae_sra_windows& w = c->shift[L.shift];
+    const float* x = l == 0 ? x_in : saved[l - 1].z;
+    float* dx = l == 0 ? d_in : dx_buf[l & 1];
+    GM_TRY(geomae_layernorm_bwd(dz, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, stream));
+    geomae_linear_args e{};
+    e.gelu_u = S.u; e.ldu = f; e.epilogue = 2;
+    GM_TRY(lin(ds2, d, n, d, L.lin2_w, f, d, 1, nullptr, f, du, f, p, stream, &e));
+    GM_TRY(wgrad(ds2, d, S.u, f, n, L.g_lin2_w, f, L.g_lin2_b, d, f, p, stream, nullptr, nullptr, 0, 1));
+    geomae_linear_args e1{};
+    e1.add_src = ds2; e1.ld_add = d;
+    GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, dy, d, p, stream, &e1));
+    GM_TRY(wgrad(du, f, S.y, d, n, L.g_lin1_w, d, L.g_lin1_b, f, d, p, stream));
+    GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, stream));
+    GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, stream));
+    GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, L.g_out_proj_b, d, d, p, stream));
+    GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.n_windows,
+                                    w.max_windows, dqkv, stream));
+    geomae_linear_args e2{};
+    e2.add_src = ds1; e2.ld_add = d;
+    GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, dx, d, p, stream, &e2));
+    GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, stream, c->pos_table, w.tok_cell, 2, 0));
+    dz = dx;
+  }
+  return GEOMAE_OK;
+}

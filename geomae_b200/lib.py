@@ -65,6 +65,31 @@ class WgradArgs(C.Structure):
                 ("N_total", C.c_int32), ("precision", C.c_int32)]
 
 
+class SRAWindows(C.Structure):
+    _fields_ = [("win_ptr", C.c_void_p), ("win_tok", C.c_void_p), ("n_windows", C.c_void_p), ("tok_cell", C.c_void_p),
+                ("max_windows", C.c_int32)]
+
+
+class SRACtx(C.Structure):
+    _fields_ = [("n_tokens", C.c_int64), ("d_model", C.c_int32), ("n_heads", C.c_int32), ("ffn", C.c_int32),
+                ("precision", C.c_int32), ("pos_table", C.c_void_p), ("shift", SRAWindows * 2)]
+
+
+_LAYER_PARAMS = ["in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
+                 "norm1_w", "norm1_b", "norm2_w", "norm2_b"]
+_LAYER_GRADS = ["g_in_proj_w", "g_in_proj_b", "g_out_proj_w", "g_out_proj_b", "g_lin1_w", "g_lin1_b", "g_lin2_w",
+                "g_lin2_b", "g_norm1_w", "g_norm1_b", "g_norm2_w", "g_norm2_b"]
+
+
+class SRALayer(C.Structure):
+    _fields_ = ([("shift", C.c_int32), ("ln_eps", C.c_float)] + [(k, C.c_void_p) for k in _LAYER_PARAMS] +
+                [(k, C.c_void_p) for k in _LAYER_GRADS])
+
+
+class SRASaved(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("qkv", "attn", "lse", "s1", "st1", "y", "u", "s2", "st2", "z")]
+
+
 def build_if_missing():
     if not os.path.exists(LIB_PATH):
         import subprocess
@@ -112,6 +137,8 @@ class _Sigs:
     geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
     geomae_tc_linear = [C.POINTER(LinearArgs), _p]
     geomae_tc_wgrad = [C.POINTER(WgradArgs), _p]
+    geomae_sra_stack_forward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p]
+    geomae_sra_stack_backward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p]
     geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]
     geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                          C.c_float, C.c_float, _i64, _p, _p]
@@ -125,6 +152,7 @@ LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=8, geom_targets=1, de
                          token_map=1, window_csr=3, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
                          scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=1, adamw_step=2,
                          tc_linear=1, tc_wgrad=1, layernorm_bwd=1)
+# sra_stack_forward / _backward launch 5 / 11 kernels per layer: counted by the caller via add_launches()
 
 
 def start_timing():
@@ -148,8 +176,13 @@ def reset_call_counts():
     _calls.clear()
 
 
+def add_launches(n: int):
+    """Kernel launches issued inside a multi-kernel C-ABI call (the SRA stack executors)."""
+    _calls["__extra__"] = _calls.get("__extra__", 0) + n
+
+
 def launch_count():
-    return sum(LAUNCHES_PER_CALL.get(k, 1) * v for k, v in _calls.items())
+    return sum((1 if k == "__extra__" else LAUNCHES_PER_CALL.get(k, 1)) * v for k, v in _calls.items())
 
 
 def run(what: str, *args):

@@ -179,6 +179,95 @@ class BasicShiftBlock(nn.Module):
         return src
 
 
+class SRAStack:
+    """A sequence of EncoderLayers executed by ONE C-ABI call per direction
+    (geomae_sra_stack_forward / _backward, csrc/sra_stack.cu)."""
+
+    def __init__(self, layers, shifts):
+        self.layers, self.shifts = list(layers), list(shifts)
+
+    def _structs(self):
+        import ctypes as C
+        arr = (L.SRALayer * len(self.layers))()
+        for s, layer, shift in zip(arr, self.layers, self.shifts):
+            mha = layer.win_attn.self_attn
+            ps = [mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias, layer.linear1.weight,
+                  layer.linear1.bias, layer.linear2.weight, layer.linear2.bias, layer.norm1.weight, layer.norm1.bias,
+                  layer.norm2.weight, layer.norm2.bias]
+            s.shift, s.ln_eps = shift, layer.norm1.eps
+            for name, gname, p in zip(L._LAYER_PARAMS, L._LAYER_GRADS, ps):
+                setattr(s, name, p.data_ptr())
+                setattr(s, gname, _grad_of(p).data_ptr())
+        return arr
+
+    def ctx(self, layout: WindowLayout, table, n, precision):
+        first = self.layers[0]
+        c = L.SRACtx()
+        c.n_tokens, c.d_model, c.n_heads = n, first.win_attn.d_model, first.win_attn.nhead
+        c.ffn, c.precision, c.pos_table = first.linear1.out_features, precision, table.data_ptr()
+        for s in range(layout.spec.n_shifts):
+            w = layout.shift(s)
+            c.shift[s].win_ptr, c.shift[s].win_tok = w["win_ptr"].data_ptr(), w["win_tok"].data_ptr()
+            c.shift[s].n_windows, c.shift[s].tok_cell = w["n_windows"].data_ptr(), w["tok_cell"].data_ptr()
+            c.shift[s].max_windows = w["max_windows"]
+        return c
+
+    def __call__(self, x, layout, table, precision):
+        return _SRAStackFn.apply(x, self, layout, table, precision)
+
+
+def _carve(n, d, f, heads, n_layers, device):
+    """One arena for everything a stack saves for backward; returns (arena, SRASaved array, last z view)."""
+    sizes = [("qkv", 3 * d), ("attn", d), ("lse", heads), ("s1", d), ("st1", 2), ("y", d), ("u", f), ("s2", d),
+             ("st2", 2), ("z", d)]
+    pad = lambda k: (k + 63) // 64 * 64  # noqa: E731
+    per_layer = sum(pad(n * w) for _, w in sizes)
+    arena = torch.empty(max(per_layer * n_layers, 1), dtype=torch.float32, device=device)
+    saved = (L.SRASaved * n_layers)()
+    base = arena.data_ptr()
+    z_last = None
+    for l in range(n_layers):
+        off = l * per_layer
+        for name, w in sizes:
+            setattr(saved[l], name, base + 4 * off)
+            if name == "z" and l == n_layers - 1:
+                z_last = arena[off:off + n * d].view(n, d)
+            off += pad(n * w)
+    return arena, saved, z_last
+
+
+class _SRAStackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, stack: SRAStack, layout, table, precision):
+        import ctypes as C
+        x = x.contiguous()
+        n = x.shape[0]
+        first = stack.layers[0]
+        d, f, nh = first.win_attn.d_model, first.linear1.out_features, first.win_attn.nhead
+        arena, saved, z = _carve(n, d, f, nh, len(stack.layers), x.device)
+        layers = stack._structs()
+        c = stack.ctx(layout, table, n, precision)
+        L.run("sra_stack_forward", C.byref(c), len(stack.layers), layers, saved, L.ptr(x), L.stream_ptr(x.device))
+        L.add_launches(5 * len(stack.layers) - 1)
+        ctx.save_for_backward(x, arena)
+        ctx.stack, ctx.saved, ctx.layers, ctx.c, ctx.layout = stack, saved, layers, c, layout
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        import ctypes as C
+        x, arena = ctx.saved_tensors
+        n, d = x.shape
+        f = ctx.c.ffn
+        dz = dz.contiguous()
+        dx = torch.empty_like(x)
+        scratch = torch.empty(max(n * (9 * d + f), 1), dtype=torch.float32, device=x.device)
+        L.run("sra_stack_backward", C.byref(ctx.c), len(ctx.stack.layers), ctx.layers, ctx.saved, L.ptr(x), L.ptr(dz),
+              L.ptr(dx), L.ptr(scratch), L.stream_ptr(x.device))
+        L.add_launches(11 * len(ctx.stack.layers) - 1)
+        return dx, None, None, None, None
+
+
 def window_pos_embed(layout: WindowLayout, d_model, temperature):
     """Per-token position rows for each shift: table[tok_cell] (…top_only.py:361-399)."""
     table = pos_table(layout.spec.window_shape, d_model, temperature, layout.tok_cell.device)

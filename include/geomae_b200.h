@@ -261,6 +261,50 @@ int geomae_tc_wgrad(const geomae_wgrad_args* args, void* stream);
 int geomae_layernorm_bwd(const float* d_out, const float* ln_in, const float* ln_stats, const float* gamma,
                          int64_t n_rows, int32_t channels, float* d_in, float* d_gamma, float* d_beta, void* stream);
 
+/* ------------------------------------------------------- SRA layer stacks */
+
+typedef struct geomae_sra_windows {   /* one shift of a geomae_window_io */
+  const int32_t* win_ptr; const int32_t* win_tok; const int32_t* n_windows; const int32_t* tok_cell;
+  int32_t max_windows;
+} geomae_sra_windows;
+
+typedef struct geomae_sra_ctx {
+  int64_t n_tokens; int32_t d_model; int32_t n_heads; int32_t ffn; int32_t precision;   /* 1 bf16, 3 bf16x3 */
+  const float* pos_table;             /* [win_x*win_y, d_model] */
+  geomae_sra_windows shift[2];
+} geomae_sra_ctx;
+
+/* Parameters (and their fp32 gradient accumulators) of one EncoderLayer, reference names in comments. */
+typedef struct geomae_sra_layer {
+  int32_t shift; float ln_eps;
+  const float *in_proj_w, *in_proj_b;     /* win_attn.self_attn.in_proj_{weight,bias}  [3d,d],[3d] */
+  const float *out_proj_w, *out_proj_b;   /* win_attn.self_attn.out_proj.{weight,bias} [d,d],[d]   */
+  const float *lin1_w, *lin1_b;           /* linear1.{weight,bias} [f,d],[f] */
+  const float *lin2_w, *lin2_b;           /* linear2.{weight,bias} [d,f],[d] */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+  float *g_in_proj_w, *g_in_proj_b, *g_out_proj_w, *g_out_proj_b, *g_lin1_w, *g_lin1_b, *g_lin2_w, *g_lin2_b;
+  float *g_norm1_w, *g_norm1_b, *g_norm2_w, *g_norm2_b;
+} geomae_sra_layer;
+
+/* Activations one layer keeps for its backward (caller-allocated, n = n_tokens). */
+typedef struct geomae_sra_saved {
+  float* qkv;  /* [n,3d] */ float* attn; /* [n,d] */ float* lse; /* [n,heads] */
+  float* s1;   /* [n,d] pre-LN1 */ float* st1; /* [n,2] */ float* y; /* [n,d] */
+  float* u;    /* [n,f] pre-GELU */ float* s2; /* [n,d] pre-LN2 */ float* st2; /* [n,2] */ float* z; /* [n,d] output */
+} geomae_sra_saved;
+
+/* Forward of n_layers EncoderLayers: layer l reads layer l-1's z (layer 0 reads x_in); 5 kernels per layer.
+ * replaces: BasicShiftBlock / EncoderLayer / WindowAttention forward (models/sst/sst_basic_block.py:26-147)
+ *           as driven by forward_encoder / forward_decoder (backbones/…top_only.py:230-232,271-277). */
+int geomae_sra_stack_forward(const geomae_sra_ctx* ctx, int32_t n_layers, const geomae_sra_layer* layers,
+                             const geomae_sra_saved* saved, const float* x_in, void* stream);
+
+/* Backward: d_out = gradient w.r.t. the last layer's z, d_in receives the gradient w.r.t. x_in, parameter
+ * gradients are ACCUMULATED into the g_* buffers.  scratch: n_tokens * (9*d_model + ffn) floats. */
+int geomae_sra_stack_backward(const geomae_sra_ctx* ctx, int32_t n_layers, const geomae_sra_layer* layers,
+                              const geomae_sra_saved* saved, const float* x_in, const float* d_out, float* d_in,
+                              float* scratch, void* stream);
+
 /* ---------------------------------------------------------------- optimiser */
 
 /* One fused step over flat fp32 buffers: g' = g*grad_scale (1/world_size), clip by global L2 norm
