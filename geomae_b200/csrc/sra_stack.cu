@@ -48,8 +48,7 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
     geomae_linear_args e{};
     e.pos_table = c->pos_table; e.tok_cell = w.tok_cell; e.pos_slabs = 2;
     GM_TRY(lin(x, d, n, d, L.in_proj_w, d, 3 * d, 0, L.in_proj_b, 3 * d, S.qkv, 3 * d, p, stream, &e));
-    GM_TRY(geomae_sra_attention_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.n_windows, w.max_windows, S.attn,
-                                    S.lse, stream));
+    GM_TRY(geomae_sra_attention_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
     geomae_linear_args e1{};
     e1.add_src = x; e1.ld_add = d; e1.ln_gamma = L.norm1_w; e1.ln_beta = L.norm1_b; e1.ln_eps = L.ln_eps;
     e1.ln_in = S.s1; e1.ln_stats = S.st1; e1.epilogue = 1;
@@ -70,7 +69,7 @@ extern "C" int geomae_sra_stack_backward(const geomae_sra_ctx* c, int32_t n_laye
   GM_REQUIRE(c && layers && saved && d_out && d_in && scratch, "sra_stack_backward: null argument");
   const int n = (int)c->n_tokens, d = c->d_model, f = c->ffn, p = c->precision;
   if (n == 0) return GEOMAE_OK;
-  // scratch: ds2 | du | dy | ds1 | da | dqkv | dx_a | dx_b   ([n, d] each except du [n, f], dqkv [n, 3d])
+  // scratch: ds2 | du | dy | ds1 | da | dqkv | dx_a | dx_b | dd  ([n, d] each except du [n, f], dqkv [n, 3d], dd [n, heads])
   float* ds2 = scratch;
   float* du = ds2 + (int64_t)n * d;
   float* dy = du + (int64_t)n * f;
@@ -78,6 +77,7 @@ extern "C" int geomae_sra_stack_backward(const geomae_sra_ctx* c, int32_t n_laye
   float* da = ds1 + (int64_t)n * d;
   float* dqkv = da + (int64_t)n * d;
   float* dx_buf[2] = {dqkv + (int64_t)n * 3 * d, dqkv + (int64_t)n * 3 * d + (int64_t)n * d};
+  float* dd = dx_buf[1] + (int64_t)n * d;   // [n, heads] attention-backward scratch
   const float* dz = d_out;
   for (int l = n_layers - 1; l >= 0; --l) {
     const geomae_sra_layer& L = layers[l];
@@ -97,8 +97,8 @@ extern "C" int geomae_sra_stack_backward(const geomae_sra_ctx* c, int32_t n_laye
     GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, stream));
     GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, stream));
     GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, L.g_out_proj_b, d, d, p, stream));
-    GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.n_windows,
-                                    w.max_windows, dqkv, stream));
+    GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
+                                    dd, stream));
     geomae_linear_args e2{};
     e2.add_src = ds1; e2.ld_add = d;
     GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, dx, d, p, stream, &e2));

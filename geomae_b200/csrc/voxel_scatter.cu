@@ -148,6 +148,18 @@ __global__ void __launch_bounds__(TPB) k_bitmap_rank(VoxGeom g, const uint32_t* 
   }
 }
 
+// first pillar row of every frame: counts[4 + b] (b = 0..n_frames), so the host learns the per-sample pillar
+// counts (needed by the random mask split) from the same single read that returns the totals
+__global__ void k_frame_starts(VoxGeom g, const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
+                               int32_t* counts) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > g.n_frames) return;
+  if (b == g.n_frames) { counts[4 + b] = counts[0]; return; }
+  const int64_t cell = (int64_t)b * g.grid[0][0] * g.grid[0][1];
+  const uint32_t w = bitmap[cell >> 5];
+  counts[4 + b] = word_rank[cell >> 5] + __popc(w & ((1u << (cell & 31)) - 1u));
+}
+
 // ---------------------------------------------------------------- pass 3: point -> pillar, pillar sums, slot masks
 __global__ void __launch_bounds__(TPB) k_assign(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
                                                 const int32_t* __restrict__ frame_off,
@@ -403,6 +415,7 @@ extern "C" int geomae_voxel_scatter(const geomae_voxel_cfg* cfg, const geomae_sc
   k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, io->bitmap, n_words, io->scan_tmp, io->word_rank, io->counts,
                                                  io->pillar_coors, io->pillar_mean, io->med_mask, io->low_mask,
                                                  io->cap);
+  k_frame_starts<<<gm_div_up(io->n_frames + 1, 64), 64, 0, stream>>>(g, io->bitmap, io->word_rank, io->counts);
   if (n > 0)
     k_assign<<<pblocks, TPB, 0, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap, io->word_rank,
                                           io->cap, io->point_pillar, io->pillar_mean, io->med_mask, io->low_mask);

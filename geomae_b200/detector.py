@@ -12,6 +12,37 @@ from .registry import DETECTORS, build_backbone, build_loss, build_voxel_encoder
 from .voxel import PillarBatch, VoxelGeometry, Voxelization, scatter_frames
 
 
+class _GeomLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, reg_low, reg_med, reg_top, nor_top, cls_low, cls_med, pb, rows, normal, weights):
+        import ctypes as C
+        preds = [t.contiguous() for t in (reg_low, reg_med, reg_top, nor_top, cls_low, cls_med)]
+        rows = rows.to(torch.int64).contiguous()
+        dev = preds[0].device
+        a = L.LossArgs()
+        a.rows, a.m = rows.data_ptr(), rows.shape[0]
+        (a.reg_low, a.reg_med, a.reg_top, a.nor_top, a.cls_low, a.cls_med) = [p.data_ptr() for p in preds]
+        a.normal = normal.data_ptr()
+        a.w_low, a.w_med, a.w_top, a.w_nor, a.w_cls_low, a.w_cls_med = weights
+        counts = torch.empty(2, dtype=torch.int32, device=dev)
+        acc = torch.empty(6, dtype=torch.float64, device=dev)
+        out = torch.empty(6, dtype=torch.float32, device=dev)
+        L.run("geom_loss_fwd", C.byref(pb.geom.cstruct), C.byref(pb.io), C.byref(a), L.ptr(counts), L.ptr(acc), L.ptr(out),
+              L.stream_ptr(dev))
+        ctx.args, ctx.pb, ctx.keep = a, pb, (preds, rows, normal, counts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        preds, rows, normal, counts = ctx.keep
+        g = g.contiguous()
+        grads = [torch.empty_like(p) for p in preds]
+        L.run("geom_loss_bwd", C.byref(ctx.pb.geom.cstruct), C.byref(ctx.pb.io), C.byref(ctx.args), L.ptr(counts), L.ptr(g),
+              *[L.ptr(t) for t in grads], L.stream_ptr(g.device))
+        return (*grads, None, None, None, None)
+
+
 @DETECTORS.register_module()
 class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
     def __init__(self, loss, loss_ratio_low, loss_ratio_med, loss_ratio_top, loss_ratio_low_nor, loss_ratio_med_nor,
@@ -70,9 +101,11 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
         return torch.cat([nn.functional.pad(self.sub_voxel_layer_med(p), (1, 0), value=i) for i, p in enumerate(points)])
 
     @torch.no_grad()
-    def get_vanilla_mask_index(self, coors, batch_size):
-        """…_ssl.py:287-304: per sample randperm(L) on the device, keep int(L*(1-ratio))."""
-        counts = torch.bincount(coors[:, 0].long(), minlength=batch_size).tolist()
+    def get_vanilla_mask_index(self, coors, batch_size, counts=None):
+        """…_ssl.py:287-304: per sample randperm(L) on the device, keep int(L*(1-ratio)).
+        ``counts`` (per-sample pillar counts on the host) avoids a device->host sync when the caller has them."""
+        if counts is None:
+            counts = torch.bincount(coors[:, 0].long(), minlength=batch_size).tolist()
         keep, mask, start = [], [], 0
         for n in counts:
             len_keep = int(n * (1 - self.random_mask_ratio))
@@ -87,27 +120,51 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
         batch_size = len(points)
         pb = scatter_frames(self.geom, points)
         voxel_features, feature_coors = self.voxel_encoder(pb)
-        ids_keep, ids_mask = ids if ids is not None else self.get_vanilla_mask_index(feature_coors, batch_size)
+        ids_keep, ids_mask = ids if ids is not None else self.get_vanilla_mask_index(
+            feature_coors, batch_size, pb.pillars_per_frame())
+        fused = getattr(self, "fused_loss", True)
         with torch.no_grad():
             normal, curv = pb.geom_targets()
-            low, low_mask, med, med_mask, top = pb.dense_targets(ids_mask)
-            normal_m = normal.index_select(0, ids_mask)
+            if fused:       # the fused loss reads the CSR sub-voxel lists directly: no dense targets at all
+                low = low_mask = med = med_mask = top = None
+                normal_m = normal
+            else:
+                low, low_mask, med, med_mask, top = pb.dense_targets(ids_mask)
+                normal_m = normal.index_select(0, ids_mask)
         if getattr(self, "keep_targets", False):   # parity harness: expose exactly what this step regressed against
             self.last_targets = dict(pillar_batch=pb, normal=normal, curvature=curv, ids_keep=ids_keep,
                                      ids_mask=ids_mask)
         x = self.backbone(voxel_features.index_select(0, ids_keep), feature_coors.index_select(0, ids_keep),
                           feature_coors.index_select(0, ids_mask), batch_size, pillar_batch=pb, rows_keep=ids_keep,
                           rows_mask=ids_mask)
+        if fused:
+            return x, pb, ids_mask, normal_m
         return x, low, low_mask, med, med_mask, top, normal_m, None, None
 
     def forward_train(self, points, img_metas=None, gt_bboxes_3d=None, gt_labels_3d=None, gt_bboxes_ignore=None,
                       ids=None):
         for p in points:
             L.require_cuda(p, "points")
-        x, c_low, m_low, c_med, m_med, c_top, n_low, n_med, n_top = self.extract_feat(points, ids)
+        out = self.extract_feat(points, ids)
+        if len(out) == 4:
+            x, pb, ids_mask, normal = out
+            return self.fused_loss_from_csr(x, pb, ids_mask, normal)
+        x, c_low, m_low, c_med, m_med, c_top, n_low, n_med, n_top = out
         reg_low, reg_med, reg_top, nor_low, nor_med, nor_top, cls_low, cls_med = x
         return self.forward_loss(c_low, m_low, c_med, m_med, c_top, n_low, n_med, n_top, reg_low, reg_med, reg_top,
                                  nor_low, nor_med, nor_top, cls_low, cls_med)
+
+    LOSS_KEYS = ("loss_curv_around", "loss_centroid_low", "loss_centroid_med", "loss_centroid_top", "loss_cls_low",
+                 "loss_cls_med")
+
+    def fused_loss_from_csr(self, x, pb, ids_mask, normal):
+        """forward_loss (…_ssl.py:837-902) as one fused kernel over the CSR targets (csrc/loss.cu)."""
+        reg_low, reg_med, reg_top, nor_low, nor_med, nor_top, cls_low, cls_med = x
+        nor_pred = nor_top if (nor_low is None and nor_med is None) else nor_low
+        weights = (self.loss_ratio_low, self.loss_ratio_med, self.loss_ratio_top, self.loss_ratio_low_nor,
+                   self.cls_loss_ratio_low, self.cls_loss_ratio_med)
+        losses = _GeomLossFn.apply(reg_low, reg_med, reg_top, nor_pred, cls_low, cls_med, pb, ids_mask, normal, weights)
+        return {k: losses[i] for i, k in enumerate(self.LOSS_KEYS)}
 
     def forward(self, return_loss=True, **kwargs):
         if return_loss:

@@ -66,8 +66,7 @@ class WgradArgs(C.Structure):
 
 
 class SRAWindows(C.Structure):
-    _fields_ = [("win_ptr", C.c_void_p), ("win_tok", C.c_void_p), ("n_windows", C.c_void_p), ("tok_cell", C.c_void_p),
-                ("max_windows", C.c_int32)]
+    _fields_ = [("win_ptr", C.c_void_p), ("win_tok", C.c_void_p), ("tok_win", C.c_void_p), ("tok_cell", C.c_void_p)]
 
 
 class SRACtx(C.Structure):
@@ -88,6 +87,13 @@ class SRALayer(C.Structure):
 
 class SRASaved(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("qkv", "attn", "lse", "s1", "st1", "y", "u", "s2", "st2", "z")]
+
+
+class LossArgs(C.Structure):
+    _fields_ = [("rows", C.c_void_p), ("m", C.c_int64), ("reg_low", C.c_void_p), ("reg_med", C.c_void_p),
+                ("reg_top", C.c_void_p), ("nor_top", C.c_void_p), ("cls_low", C.c_void_p), ("cls_med", C.c_void_p),
+                ("normal", C.c_void_p), ("w_low", C.c_float), ("w_med", C.c_float), ("w_top", C.c_float),
+                ("w_nor", C.c_float), ("w_cls_low", C.c_float), ("w_cls_med", C.c_float)]
 
 
 def build_if_missing():
@@ -133,13 +139,16 @@ class _Sigs:
     geomae_vfe_decorate = [_p, _i64, _i32, _p, _p, _p, _f3, _f3, _p, _p]
     geomae_scatter_reduce_fwd = [_p, _i64, _i32, _p, _p, _i64, _i32, _p, _p, _p]
     geomae_scatter_reduce_bwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
-    geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p]
-    geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
+    geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]
+    geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
     geomae_tc_linear = [C.POINTER(LinearArgs), _p]
     geomae_tc_wgrad = [C.POINTER(WgradArgs), _p]
     geomae_sra_stack_forward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p]
     geomae_sra_stack_backward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p]
     geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]
+    geomae_geom_loss_fwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p]
+    geomae_geom_loss_bwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p, _p, _p, _p,
+                            _p, _p]
     geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                          C.c_float, C.c_float, _i64, _p, _p]
 
@@ -150,8 +159,8 @@ _calls = {}         # name -> number of C-ABI calls (bench.py reports kernel lau
 # kernels launched per C-ABI call (upper bound for the optional ones), for the gpu_launches claim
 LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=8, geom_targets=1, dense_targets=1, coors_bitmap=4,
                          token_map=1, window_csr=3, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
-                         scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=1, adamw_step=2,
-                         tc_linear=1, tc_wgrad=1, layernorm_bwd=1)
+                         scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=2, adamw_step=2,
+                         tc_linear=1, tc_wgrad=1, layernorm_bwd=1, geom_loss_fwd=3, geom_loss_bwd=1)
 # sra_stack_forward / _backward launch 5 / 11 kernels per layer: counted by the caller via add_launches()
 
 

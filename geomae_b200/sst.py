@@ -17,14 +17,15 @@ def _attn_fwd(qkv, win, n_heads):
     out = torch.empty((n, three_d // 3), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((n, n_heads), dtype=torch.float32, device=qkv.device)
     L.run("sra_attention_fwd", L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]),
-          L.ptr(win["n_windows"]), win["max_windows"], L.ptr(out), L.ptr(lse), L.stream_ptr(qkv.device))
+          L.ptr(win["tok_win"]), L.ptr(out), L.ptr(lse), L.stream_ptr(qkv.device))
     return out, lse
 
 
 def _attn_bwd(qkv, out, lse, d_out, win, n_heads):
     d_qkv = torch.empty_like(qkv)
+    scratch = torch.empty((qkv.shape[0], n_heads), dtype=torch.float32, device=qkv.device)
     L.run("sra_attention_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0], n_heads,
-          L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["n_windows"]), win["max_windows"], L.ptr(d_qkv),
+          L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(d_qkv), L.ptr(scratch),
           L.stream_ptr(qkv.device))
     return d_qkv
 
@@ -208,8 +209,7 @@ class SRAStack:
         for s in range(layout.spec.n_shifts):
             w = layout.shift(s)
             c.shift[s].win_ptr, c.shift[s].win_tok = w["win_ptr"].data_ptr(), w["win_tok"].data_ptr()
-            c.shift[s].n_windows, c.shift[s].tok_cell = w["n_windows"].data_ptr(), w["tok_cell"].data_ptr()
-            c.shift[s].max_windows = w["max_windows"]
+            c.shift[s].tok_win, c.shift[s].tok_cell = w["tok_win"].data_ptr(), w["tok_cell"].data_ptr()
         return c
 
     def __call__(self, x, layout, table, precision):
@@ -261,10 +261,10 @@ class _SRAStackFn(torch.autograd.Function):
         f = ctx.c.ffn
         dz = dz.contiguous()
         dx = torch.empty_like(x)
-        scratch = torch.empty(max(n * (9 * d + f), 1), dtype=torch.float32, device=x.device)
+        scratch = torch.empty(max(n * (9 * d + f + ctx.c.n_heads), 1), dtype=torch.float32, device=x.device)
         L.run("sra_stack_backward", C.byref(ctx.c), len(ctx.stack.layers), ctx.layers, ctx.saved, L.ptr(x), L.ptr(dz),
               L.ptr(dx), L.ptr(scratch), L.stream_ptr(x.device))
-        L.add_launches(11 * len(ctx.stack.layers) - 1)
+        L.add_launches(12 * len(ctx.stack.layers) - 1)
         return dx, None, None, None, None
 
 

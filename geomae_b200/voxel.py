@@ -96,7 +96,7 @@ class PillarBatch:
         self.bitmap = torch.empty(n_words, **i32)
         self.word_rank = torch.empty(n_words, **i32)
         self.scan_tmp = torch.empty(3 * 4096, **i32)
-        self.counts = torch.zeros(4, **i32)
+        self.counts = torch.zeros(4 + n_frames + 1, **i32)
         self.pillar_coors = torch.empty((cap, 4), **i32)
         self.pillar_mean = torch.empty((cap, 4), **f32)
         self.point_pillar = torch.empty(cap, **i32)
@@ -132,11 +132,18 @@ class PillarBatch:
             if c[3]:
                 raise RuntimeError("geomae_b200.voxel_scatter: pillar capacity exceeded")
             self._n = (c[0], c[1], c[2])
+            self.frame_starts = c[4:]
         return self._n
 
     @property
     def n_pillars(self):
         return self.sizes()[0]
+
+    def pillars_per_frame(self):
+        """Host list of per-sample pillar counts (comes with the same device->host read as sizes())."""
+        self.sizes()
+        fs = self.frame_starts
+        return [fs[b + 1] - fs[b] for b in range(self.n_frames)]
 
     def geom_targets(self, want_debug=False):
         """normal [V,3] f32 (z,y,x), curvature [V,3] f64 (+ cov6, singular, pair when want_debug)."""

@@ -68,7 +68,8 @@ typedef struct geomae_scatter_io {
   int32_t* word_rank;           /* [same] exclusive popcount prefix                        */
   int32_t* scan_tmp;            /* [3*4096] block sums                                     */
   /* outputs */
-  int32_t* counts;              /* [4] n_pillars, n_med, n_low, overflow flag              */
+  int32_t* counts;              /* [4+n_frames+1] n_pillars, n_med, n_low, overflow flag,  */
+                                /*   then the first pillar row of each frame (and V last)  */
   int32_t* pillar_coors;        /* [cap,4] (b,z,y,x), lexicographically sorted             */
   float* pillar_mean;           /* [cap,4] mean x,y,z and point count (as float)           */
   int32_t* point_pillar;        /* [n_points] pillar row of each point (unq_inv)           */
@@ -200,18 +201,19 @@ int geomae_scatter_reduce_bwd(const float* d_out, int64_t n_points, int32_t chan
 
 /* Multi-head attention inside CSR windows (no padding, no key_padding_mask needed).
  * qkv: [n_tokens, 3*d_model] fp32, rows in flat token order: q | k | v, q NOT yet scaled.
+ * win_ptr / win_tok / tok_win: one shift of a geomae_window_io.
  * out: [n_tokens, d_model]; lse: [n_tokens, n_heads] log-sum-exp saved for backward.
- * head_dim must be 16 (d_model = 16*n_heads).
+ * head_dim must be 16 (d_model = 16*n_heads), n_heads <= 8.
  * replaces: nn.MultiheadAttention core inside WindowAttention.forward
  *           (models/sst/sst_basic_block.py:26-61) on padded [T,W,C] buckets. */
 int geomae_sra_attention_fwd(const float* qkv, int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
-                             const int32_t* win_tok, const int32_t* n_windows, int32_t max_windows,
-                             float* out, float* lse, void* stream);
+                             const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse, void* stream);
 
-/* Backward of the above: d_qkv [n_tokens, 3*d_model] from d_out, recomputing the probabilities. */
+/* Backward of the above: d_qkv [n_tokens, 3*d_model] from d_out, recomputing the probabilities.
+ * scratch: [n_tokens * n_heads] floats. */
 int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
                              int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr, const int32_t* win_tok,
-                             const int32_t* n_windows, int32_t max_windows, float* d_qkv, void* stream);
+                             const int32_t* tok_win, float* d_qkv, float* scratch, void* stream);
 
 /* ------------------------------------------------ tensor-core dense layers */
 
@@ -264,8 +266,7 @@ int geomae_layernorm_bwd(const float* d_out, const float* ln_in, const float* ln
 /* ------------------------------------------------------- SRA layer stacks */
 
 typedef struct geomae_sra_windows {   /* one shift of a geomae_window_io */
-  const int32_t* win_ptr; const int32_t* win_tok; const int32_t* n_windows; const int32_t* tok_cell;
-  int32_t max_windows;
+  const int32_t* win_ptr; const int32_t* win_tok; const int32_t* tok_win; const int32_t* tok_cell;
 } geomae_sra_windows;
 
 typedef struct geomae_sra_ctx {
@@ -300,10 +301,35 @@ int geomae_sra_stack_forward(const geomae_sra_ctx* ctx, int32_t n_layers, const 
                              const geomae_sra_saved* saved, const float* x_in, void* stream);
 
 /* Backward: d_out = gradient w.r.t. the last layer's z, d_in receives the gradient w.r.t. x_in, parameter
- * gradients are ACCUMULATED into the g_* buffers.  scratch: n_tokens * (9*d_model + ffn) floats. */
+ * gradients are ACCUMULATED into the g_* buffers.  scratch: n_tokens * (9*d_model + ffn + n_heads) floats. */
 int geomae_sra_stack_backward(const geomae_sra_ctx* ctx, int32_t n_layers, const geomae_sra_layer* layers,
                               const geomae_sra_saved* saved, const float* x_in, const float* d_out, float* d_in,
                               float* scratch, void* stream);
+
+/* -------------------------------------------------------------------- losses */
+
+typedef struct geomae_loss_args {
+  const int64_t* rows; int64_t m;                 /* masked pillar rows (ids_mask) */
+  const float* reg_low;  /* [m,slots_low,3] */ const float* reg_med; /* [m,slots_med,3] */
+  const float* reg_top;  /* [m,3] */           const float* nor_top; /* [m,3] */
+  const float* cls_low;  /* [m,slots_low,2] */ const float* cls_med; /* [m,slots_med,2] */
+  const float* normal;   /* [V,3] per-pillar normal targets (geomae_geom_targets) */
+  float w_low, w_med, w_top, w_nor, w_cls_low, w_cls_med;   /* loss_ratio_* of the config */
+} geomae_loss_args;
+
+/* out[6] = loss_curv_around, loss_centroid_low, loss_centroid_med, loss_centroid_top, loss_cls_low, loss_cls_med.
+ * Masked MSE (mean over xyz, mean over occupied slots) and occupancy BCE-with-logits against the one-hot
+ * occupancy label, evaluated from the CSR sub-voxel lists.  counts [2] i32 and acc [6] f64 are scratch; counts is
+ * re-used by the backward.
+ * replaces: forward_loss (detectors/…_ssl.py:837-902) incl. mmdet CrossEntropyLoss(use_sigmoid=True), and the
+ *           dense-target construction it consumes. */
+int geomae_geom_loss_fwd(const geomae_voxel_cfg* cfg, const geomae_scatter_io* io, const geomae_loss_args* args,
+                         int32_t* counts, double* acc, float* out, void* stream);
+
+/* Gradients of the six prediction tensors given d_losses[6] (upstream gradient of each loss). */
+int geomae_geom_loss_bwd(const geomae_voxel_cfg* cfg, const geomae_scatter_io* io, const geomae_loss_args* args,
+                         const int32_t* counts, const float* d_losses, float* d_reg_low, float* d_reg_med,
+                         float* d_reg_top, float* d_nor_top, float* d_cls_low, float* d_cls_med, void* stream);
 
 /* ---------------------------------------------------------------- optimiser */
 
