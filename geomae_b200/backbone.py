@@ -128,8 +128,9 @@ class MultiMAESSTSPChoose(nn.Module):
         pos, table = self._pos(layout)
         cen = den = tokens
         if pos is None:
-            cen = self._stack(self.decoder_centroid_blocks)(tokens, layout, table, self._precision())
-            den = self._stack(self.decoder_density_blocks)(tokens, layout, table, self._precision())
+            from .sst import _SRADualStackFn
+            cen, den = _SRADualStackFn.apply(tokens, self._stack(self.decoder_centroid_blocks),
+                                             self._stack(self.decoder_density_blocks), layout, table, self._precision())
         else:
             for block in self.decoder_centroid_blocks:
                 cen = block(cen, layout, pos, table)

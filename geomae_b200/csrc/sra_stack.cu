@@ -63,47 +63,135 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
   return GEOMAE_OK;
 }
 
-extern "C" int geomae_sra_stack_backward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers,
-                                         const geomae_sra_saved* saved, const float* x_in, const float* d_out,
-                                         float* d_in, float* scratch, void* stream) {
-  GM_REQUIRE(c && layers && saved && d_out && d_in && scratch, "sra_stack_backward: null argument");
+namespace {
+
+// Internal side streams / events (created once).  Weight-gradient GEMMs run on a side stream so they overlap
+// the latency-bound dX chain; the two decoder stacks run on separate streams.
+struct Lanes {
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[64];
+  int next_ev = 0;
+  bool ready = false;
+  int init() {
+    if (ready) return GEOMAE_OK;
+    for (auto& st : side) GM_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& e : ev) GM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ready = true;
+    return GEOMAE_OK;
+  }
+  cudaEvent_t event() { cudaEvent_t e = ev[next_ev]; next_ev = (next_ev + 1) % 64; return e; }
+};
+Lanes g_lanes;
+
+// signal on `from`, wait on `to`
+int hand_off(cudaStream_t from, cudaStream_t to) {
+  cudaEvent_t e = g_lanes.event();
+  GM_CUDA(cudaEventRecord(e, from));
+  GM_CUDA(cudaStreamWaitEvent(to, e, 0));
+  return GEOMAE_OK;
+}
+
+int64_t scratch_floats(const geomae_sra_ctx* c) { return (int64_t)c->n_tokens * (9 * c->d_model + c->ffn + c->n_heads); }
+
+// backward of one stack: dX chain on `main`, weight gradients on `side`; scratch holds TWO sets (alternating per
+// layer) so the side stream may lag one layer behind.
+int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx* c, int32_t n_layers,
+                      const geomae_sra_layer* layers, const geomae_sra_saved* saved, const float* x_in,
+                      const float* d_out, float* d_in, float* scratch) {
   const int n = (int)c->n_tokens, d = c->d_model, f = c->ffn, p = c->precision;
-  if (n == 0) return GEOMAE_OK;
-  // scratch: ds2 | du | dy | ds1 | da | dqkv | dx_a | dx_b | dd  ([n, d] each except du [n, f], dqkv [n, 3d], dd [n, heads])
-  float* ds2 = scratch;
-  float* du = ds2 + (int64_t)n * d;
-  float* dy = du + (int64_t)n * f;
-  float* ds1 = dy + (int64_t)n * d;
-  float* da = ds1 + (int64_t)n * d;
-  float* dqkv = da + (int64_t)n * d;
-  float* dx_buf[2] = {dqkv + (int64_t)n * 3 * d, dqkv + (int64_t)n * 3 * d + (int64_t)n * d};
-  float* dd = dx_buf[1] + (int64_t)n * d;   // [n, heads] attention-backward scratch
+  const int64_t set = scratch_floats(c);
   const float* dz = d_out;
+  cudaEvent_t side_done[2] = {nullptr, nullptr};
   for (int l = n_layers - 1; l >= 0; --l) {
+    float* base = scratch + (int64_t)(l & 1) * set;
+    // ds2 | du | dy | ds1 | da | dqkv | dx | dd
+    float* ds2 = base;
+    float* du = ds2 + (int64_t)n * d;
+    float* dy = du + (int64_t)n * f;
+    float* ds1 = dy + (int64_t)n * d;
+    float* da = ds1 + (int64_t)n * d;
+    float* dqkv = da + (int64_t)n * d;
+    float* dxb = dqkv + (int64_t)n * 3 * d;
+    float* dd = dxb + (int64_t)n * d;
     const geomae_sra_layer& L = layers[l];
     const geomae_sra_saved& S = saved[l];
     const geomae_sra_windows& w = c->shift[L.shift];
     const float* x = l == 0 ? x_in : saved[l - 1].z;
-    float* dx = l == 0 ? d_in : dx_buf[l & 1];
-    GM_TRY(geomae_layernorm_bwd(dz, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, stream));
+    float* dx = l == 0 ? d_in : dxb;
+    if (side_done[l & 1]) GM_CUDA(cudaStreamWaitEvent(main, side_done[l & 1], 0));   // set (l&1) free again
+    GM_TRY(geomae_layernorm_bwd(dz, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, main));
+    GM_TRY(hand_off(main, side));
+    GM_TRY(wgrad(ds2, d, S.u, f, n, L.g_lin2_w, f, L.g_lin2_b, d, f, p, side, nullptr, nullptr, 0, 1));
     geomae_linear_args e{};
     e.gelu_u = S.u; e.ldu = f; e.epilogue = 2;
-    GM_TRY(lin(ds2, d, n, d, L.lin2_w, f, d, 1, nullptr, f, du, f, p, stream, &e));
-    GM_TRY(wgrad(ds2, d, S.u, f, n, L.g_lin2_w, f, L.g_lin2_b, d, f, p, stream, nullptr, nullptr, 0, 1));
+    GM_TRY(lin(ds2, d, n, d, L.lin2_w, f, d, 1, nullptr, f, du, f, p, main, &e));
+    GM_TRY(hand_off(main, side));
+    GM_TRY(wgrad(du, f, S.y, d, n, L.g_lin1_w, d, L.g_lin1_b, f, d, p, side));
     geomae_linear_args e1{};
     e1.add_src = ds2; e1.ld_add = d;
-    GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, dy, d, p, stream, &e1));
-    GM_TRY(wgrad(du, f, S.y, d, n, L.g_lin1_w, d, L.g_lin1_b, f, d, p, stream));
-    GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, stream));
-    GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, stream));
-    GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, L.g_out_proj_b, d, d, p, stream));
-    GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
-                                    dd, stream));
+    GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, dy, d, p, main, &e1));
+    GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, main));
+    GM_TRY(hand_off(main, side));
+    GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, L.g_out_proj_b, d, d, p, side));
+    GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main));
+    GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv, dd,
+                                    main));
+    GM_TRY(hand_off(main, side));
+    GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, side, c->pos_table, w.tok_cell, 2, 0));
+    side_done[l & 1] = g_lanes.event();
+    GM_CUDA(cudaEventRecord(side_done[l & 1], side));
     geomae_linear_args e2{};
     e2.add_src = ds1; e2.ld_add = d;
-    GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, dx, d, p, stream, &e2));
-    GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, stream, c->pos_table, w.tok_cell, 2, 0));
+    GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, dx, d, p, main, &e2));
     dz = dx;
   }
+  GM_TRY(hand_off(side, main));   // join
   return GEOMAE_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t geomae_sra_scratch_floats(const geomae_sra_ctx* c, int32_t n_stacks) {
+  return c ? 2 * n_stacks * scratch_floats(c) : 0;
+}
+
+extern "C" int geomae_sra_stack_backward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers,
+                                         const geomae_sra_saved* saved, const float* x_in, const float* d_out,
+                                         float* d_in, float* scratch, void* stream) {
+  GM_REQUIRE(c && layers && saved && d_out && d_in && scratch, "sra_stack_backward: null argument");
+  if (c->n_tokens == 0) return GEOMAE_OK;
+  GM_TRY(g_lanes.init());
+  cudaStream_t main = (cudaStream_t)stream;
+  GM_TRY(hand_off(main, g_lanes.side[0]));     // the side stream must see everything queued before this call
+  return stack_backward_on(main, g_lanes.side[0], c, n_layers, layers, saved, x_in, d_out, d_in, scratch);
+}
+
+// Two stacks that read the same input (the centroid and density decoders, backbones/…top_only.py:269-277)
+// executed concurrently on two streams.
+extern "C" int geomae_sra_stack2_forward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers_a,
+                                         const geomae_sra_saved* saved_a, const geomae_sra_layer* layers_b,
+                                         const geomae_sra_saved* saved_b, const float* x_in, void* stream) {
+  GM_TRY(g_lanes.init());
+  cudaStream_t main = (cudaStream_t)stream, other = g_lanes.side[1];
+  GM_TRY(hand_off(main, other));
+  GM_TRY(geomae_sra_stack_forward(c, n_layers, layers_a, saved_a, x_in, main));
+  GM_TRY(geomae_sra_stack_forward(c, n_layers, layers_b, saved_b, x_in, other));
+  return hand_off(other, main);
+}
+
+extern "C" int geomae_sra_stack2_backward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers_a,
+                                          const geomae_sra_saved* saved_a, const geomae_sra_layer* layers_b,
+                                          const geomae_sra_saved* saved_b, const float* x_in, const float* d_out_a,
+                                          const float* d_out_b, float* d_in_a, float* d_in_b, float* scratch,
+                                          void* stream) {
+  GM_REQUIRE(c && layers_a && layers_b && saved_a && saved_b && d_out_a && d_out_b && d_in_a && d_in_b && scratch,
+             "sra_stack2_backward: null argument");
+  if (c->n_tokens == 0) return GEOMAE_OK;
+  GM_TRY(g_lanes.init());
+  cudaStream_t main = (cudaStream_t)stream;
+  for (int i = 0; i < 3; ++i) GM_TRY(hand_off(main, g_lanes.side[i]));
+  GM_TRY(stack_backward_on(main, g_lanes.side[0], c, n_layers, layers_a, saved_a, x_in, d_out_a, d_in_a, scratch));
+  GM_TRY(stack_backward_on(g_lanes.side[1], g_lanes.side[2], c, n_layers, layers_b, saved_b, x_in, d_out_b, d_in_b,
+                           scratch + 2 * scratch_floats(c)));
+  return hand_off(g_lanes.side[1], main);
 }

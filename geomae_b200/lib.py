@@ -117,6 +117,8 @@ def lib():
                 fn = getattr(_lib, name)
                 fn.argtypes = getattr(_Sigs, name)
                 fn.restype = C.c_int
+        _lib.geomae_sra_scratch_floats.argtypes = [C.POINTER(SRACtx), C.c_int32]
+        _lib.geomae_sra_scratch_floats.restype = C.c_int64
     return _lib
 
 
@@ -145,6 +147,10 @@ class _Sigs:
     geomae_tc_wgrad = [C.POINTER(WgradArgs), _p]
     geomae_sra_stack_forward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p]
     geomae_sra_stack_backward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p]
+    geomae_sra_stack2_forward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), C.POINTER(SRALayer),
+                                 C.POINTER(SRASaved), _p, _p]
+    geomae_sra_stack2_backward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved),
+                                  C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p, _p, _p]
     geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]
     geomae_geom_loss_fwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p]
     geomae_geom_loss_bwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p, _p, _p, _p,

@@ -261,11 +261,49 @@ class _SRAStackFn(torch.autograd.Function):
         f = ctx.c.ffn
         dz = dz.contiguous()
         dx = torch.empty_like(x)
-        scratch = torch.empty(max(n * (9 * d + f + ctx.c.n_heads), 1), dtype=torch.float32, device=x.device)
+        scratch = torch.empty(max(L.lib().geomae_sra_scratch_floats(C.byref(ctx.c), 1), 1), dtype=torch.float32,
+                              device=x.device)
         L.run("sra_stack_backward", C.byref(ctx.c), len(ctx.stack.layers), ctx.layers, ctx.saved, L.ptr(x), L.ptr(dz),
               L.ptr(dx), L.ptr(scratch), L.stream_ptr(x.device))
         L.add_launches(12 * len(ctx.stack.layers) - 1)
         return dx, None, None, None, None
+
+
+class _SRADualStackFn(torch.autograd.Function):
+    """Two stacks over the same input (centroid / density decoders) executed concurrently."""
+
+    @staticmethod
+    def forward(ctx, x, stack_a: SRAStack, stack_b: SRAStack, layout, table, precision):
+        import ctypes as C
+        x = x.contiguous()
+        n = x.shape[0]
+        first = stack_a.layers[0]
+        nl = len(stack_a.layers)
+        assert nl == len(stack_b.layers) and stack_a.shifts == stack_b.shifts
+        d, f, nh = first.win_attn.d_model, first.linear1.out_features, first.win_attn.nhead
+        arena_a, saved_a, za = _carve(n, d, f, nh, nl, x.device)
+        arena_b, saved_b, zb = _carve(n, d, f, nh, nl, x.device)
+        la, lb = stack_a._structs(), stack_b._structs()
+        c = stack_a.ctx(layout, table, n, precision)
+        L.run("sra_stack2_forward", C.byref(c), nl, la, saved_a, lb, saved_b, L.ptr(x), L.stream_ptr(x.device))
+        L.add_launches(10 * nl - 1)
+        ctx.save_for_backward(x, arena_a, arena_b)
+        ctx.keep = (saved_a, saved_b, la, lb, c, layout, nl)
+        return za, zb
+
+    @staticmethod
+    def backward(ctx, dza, dzb):
+        import ctypes as C
+        x, _, _ = ctx.saved_tensors
+        saved_a, saved_b, la, lb, c, _, nl = ctx.keep
+        dza, dzb = dza.contiguous(), dzb.contiguous()
+        dxa, dxb = torch.empty_like(x), torch.empty_like(x)
+        scratch = torch.empty(max(L.lib().geomae_sra_scratch_floats(C.byref(c), 2), 1), dtype=torch.float32,
+                              device=x.device)
+        L.run("sra_stack2_backward", C.byref(c), nl, la, saved_a, lb, saved_b, L.ptr(x), L.ptr(dza), L.ptr(dzb), L.ptr(dxa),
+              L.ptr(dxb), L.ptr(scratch), L.stream_ptr(x.device))
+        L.add_launches(24 * nl - 1)
+        return dxa + dxb, None, None, None, None, None
 
 
 def window_pos_embed(layout: WindowLayout, d_model, temperature):

@@ -301,10 +301,23 @@ int geomae_sra_stack_forward(const geomae_sra_ctx* ctx, int32_t n_layers, const 
                              const geomae_sra_saved* saved, const float* x_in, void* stream);
 
 /* Backward: d_out = gradient w.r.t. the last layer's z, d_in receives the gradient w.r.t. x_in, parameter
- * gradients are ACCUMULATED into the g_* buffers.  scratch: n_tokens * (9*d_model + ffn + n_heads) floats. */
+ * gradients are ACCUMULATED into the g_* buffers.  scratch: geomae_sra_scratch_floats(ctx, 1) floats.
+ * The weight-gradient GEMMs run on an internal side stream overlapping the dX chain; the call returns with
+ * all work ordered after `stream`. */
 int geomae_sra_stack_backward(const geomae_sra_ctx* ctx, int32_t n_layers, const geomae_sra_layer* layers,
                               const geomae_sra_saved* saved, const float* x_in, const float* d_out, float* d_in,
                               float* scratch, void* stream);
+int64_t geomae_sra_scratch_floats(const geomae_sra_ctx* ctx, int32_t n_stacks);
+
+/* Two stacks reading the same input (decoder_centroid_blocks / decoder_density_blocks,
+ * backbones/…top_only.py:269-277), run concurrently on two streams.  scratch: geomae_sra_scratch_floats(ctx, 2). */
+int geomae_sra_stack2_forward(const geomae_sra_ctx* ctx, int32_t n_layers, const geomae_sra_layer* layers_a,
+                              const geomae_sra_saved* saved_a, const geomae_sra_layer* layers_b,
+                              const geomae_sra_saved* saved_b, const float* x_in, void* stream);
+int geomae_sra_stack2_backward(const geomae_sra_ctx* ctx, int32_t n_layers, const geomae_sra_layer* layers_a,
+                               const geomae_sra_saved* saved_a, const geomae_sra_layer* layers_b,
+                               const geomae_sra_saved* saved_b, const float* x_in, const float* d_out_a,
+                               const float* d_out_b, float* d_in_a, float* d_in_b, float* scratch, void* stream);
 
 /* -------------------------------------------------------------------- losses */
 
