@@ -132,7 +132,7 @@ def test_sra_attention_forward_backward(small):
         x = qkv.detach().to(DEV).requires_grad_(True)
         out = sra_attention(x, lay.shift(s), 8)
         out.backward(d_out.to(DEV))
-        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-4, atol=5e-6)
         np.testing.assert_allclose(x.grad.cpu().numpy(), qkv.grad.numpy(), rtol=2e-4, atol=2e-5)
 
 

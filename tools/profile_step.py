@@ -26,4 +26,4 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, to
     for _ in range(2):
         tr.train_step(frames)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+print(prof.key_averages().table(sort_by=(sys.argv[2] if len(sys.argv) > 2 else "cuda_time_total"), row_limit=45, max_name_column_width=70))
