@@ -86,6 +86,37 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm))
 
 
+def hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src, n_frames=256):
+    """HBM-bound stages on a batch large enough to leave L2 (256 frames ~ 7 M points, 140 MB of records):
+    achieved = algorithmic bytes (SURVEY.md §8d formulas, counted from the device-side totals) / CUDA-event time."""
+    from geomae_b200.voxel import scatter_frames
+    frames = [torch.from_numpy(pool[i % len(pool)][i % len(pool[0])]).to(dev) for i in range(n_frames)]
+    pb = scatter_frames(model.geom, frames)
+    v, vm, vl = pb.sizes()
+    p = pb.points.shape[0]
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    t_sc = timed(pb.run)
+    t_gt = timed(lambda: pb.geom_targets())
+    b_sc = 24.0 * p + 32.0 * v + 20.0 * (vm + vl)
+    b_gt = 20.0 * vm + 28.0 * v + 24.0 * v
+    out = []
+    for name, t, b in (("geomae_voxel_scatter (9 launches)", t_sc, b_sc), ("k_geom (geom_targets)", t_gt, b_gt)):
+        ach = b / (t * 1e-3) / 1e9
+        out.append(dict(kernel=name, bound="hbm", frames=n_frames, points=p, pillars=v, ms=t, algorithmic_bytes=b,
+                        achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src))
+    return out
+
+
 def cpu_reference_step(samples, sweeps, threads, seed=1):
     """One forward+backward of the oracle port on the host cores; returns (seconds, frames)."""
     from geomae_b200.synthetic import make_frame
@@ -151,7 +182,7 @@ def main():
     cfg = Config.fromfile(OWN_CFG)
     torch.manual_seed(0)
     model = build_model(cfg.model).to(dev).train()
-    model.backbone.set_sra_impl(args.sra_impl)
+    model.set_impl(args.sra_impl)
     opt = cfg.optimizer
     trainer = FlatTrainer(model, lr=opt["lr"], betas=opt["betas"], weight_decay=opt["weight_decay"],
                           max_grad_norm=cfg.optimizer_config["grad_clip"]["max_norm"])
@@ -207,11 +238,21 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    import ctypes as C
     L.reset_call_counts()
-    L.start_timing()
-    ms = timed_loop(step_resident, K)
-    per_call = L.stop_timing()
+    ms = timed_loop(step_resident, K)             # the headline number: no per-kernel instrumentation
     launches = L.launch_count()
+    barrier()
+    # same K steps again with CUDA events around every C-ABI call / stack kernel (roofline + kernel table);
+    # the events cost ~5-8 % so they are kept out of the headline loop
+    L.start_timing()
+    L.run("profile_enable", 1)
+    ms_prof = timed_loop(step_resident, K)
+    per_call = L.stop_timing()
+    prof_ms, prof_n, prof_fl = (C.c_double * 5)(), (C.c_int64 * 5)(), (C.c_double * 5)()
+    L.run("profile_read", prof_ms, prof_n, prof_fl)
+    L.run("profile_enable", 0)
+    prof_ms, prof_n, prof_fl = list(prof_ms), list(prof_n), list(prof_fl)
     barrier()
     for i in range(min(W, 2)):
         step_host(i)
@@ -229,31 +270,37 @@ def main():
         return
     frames = K * S * world
     h2d = sum(f.numel() * 4 for f in host[0])
-    # roofline of the dominant hand-written kernel: SRA attention backward (one kernel per C-ABI call)
+    # roofline of the dominant hand-written kernel family, timed live with CUDA events inside the stack executor
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured" if peaks else "fallback"
-    roof = None
-    name = "sra_attention_bwd"
-    if name in per_call:
-        tot_ms, n_calls = per_call[name]
-        # algorithmic flops of attention backward per launch: 5 LxLx16 products * 2 flop, summed over windows;
-        # counted from the CSR lengths of the last step (token-weighted), see DESIGN.md
+    fam_names = ["k_tc_linear", "k_tc_wgrad", "k_sra_fwd", "k_sra_bwd_q+k_sra_bwd_kv", "k_ln_bwd"]
+    roof, fam_table = None, {}
+    if prof_ms is not None and sum(prof_ms) > 0:
         sq = attention_pair_counts()
         bb = model.backbone
         n_enc, n_dec = len(bb.encoder_blocks), len(bb.decoder_centroid_blocks) + len(bb.decoder_density_blocks)
-        pairs = n_enc * (sq["enc", 0] + sq["enc", 1]) + n_dec * (sq["dec", 0] + sq["dec", 1])   # per step, all layers
-        flops = pairs * bb.nhead[0] * 160.0 / (n_calls / K)        # per launch: 5 products x 16 x 2 flop per (i,j,head)
-        roof = dict(kernel="k_sra_bwd", bound="tensor", achieved=None, peak=tens_peak, unit="TFLOP/s", frac=None,
-                    traffic=None, peak_source=peak_src, avg_launch_ms=tot_ms / n_calls, launches=n_calls,
-                    share_of_step=tot_ms / ms)
-        if flops:
-            ach = flops / (tot_ms / n_calls * 1e-3) / 1e12
-            roof.update(achieved=ach, frac=ach / tens_peak)
+        pairs = (n_enc * (sq["enc", 0] + sq["enc", 1]) + n_dec * (sq["dec", 0] + sq["dec", 1])) * K   # all layers, K steps
+        prof_fl[2] = pairs * bb.nhead[0] * 64.0     # fwd: QK^T + PV = 2 products x 16 x 2 flop per (i,j,head)
+        prof_fl[3] = pairs * bb.nhead[0] * 160.0    # bwd: 5 products
+        for f, nm in enumerate(fam_names):
+            if prof_n[f]:
+                fam_table[nm] = dict(ms_per_step=prof_ms[f] / K, launches_per_step=prof_n[f] / K,
+                                     tflops=prof_fl[f] / (prof_ms[f] * 1e-3) / 1e12 if prof_fl[f] else None)
+        top = max(range(5), key=lambda f: prof_ms[f])
+        ach = prof_fl[top] / (prof_ms[top] * 1e-3) / 1e12
+        roof = dict(kernel=fam_names[top], bound="tensor", achieved=ach, peak=tens_peak, unit="TFLOP/s",
+                    frac=ach / tens_peak, traffic=None, peak_source=peak_src,
+                    avg_launch_ms=prof_ms[top] / prof_n[top], launches=int(prof_n[top]),
+                    note="sum of per-launch device time of the family / timed wall time = share; kernels of different "
+                         "streams overlap, so shares can add up to more than 1",
+                    share_of_step=prof_ms[top] / ms_prof, instrumented_ms_per_step=ms_prof / K)
+    aux = hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src)
     line = dict(
         metric=METRIC, value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=K, warmup=W,
         ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -267,7 +314,7 @@ def main():
                                "glue": "fp32 library GEMMs, TF32 off"}[args.sra_impl]),
         e2e=dict(value=frames / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / K),
-        gpu_launches=launches, clocks=clocks, roofline=roof,
+        gpu_launches=launches, clocks=clocks, roofline=roof, kernel_families=fam_table, hbm_kernels=aux,
         kernel_ms_per_step={k: round(v[0] / K, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
         loss=last.get("loss_host"))
     if world == 1 and not args.no_cpu_baseline:

@@ -21,6 +21,7 @@ struct LinArgs {
   const float* pos_table; const int32_t* tok_cell; int pos_slabs;   // A += pos_table[tok_cell[row]] for slabs < pos_slabs
   int a_gelu;                                                       // A = gelu(A)
   const float* W; int ldw; int w_rows; int w_mn_major;              // 0: W[n][k] (y = x W^T), 1: W[k][n] (dX = dY W)
+  const uint8_t* Wp_hi; const uint8_t* Wp_lo; int wp_cols;          // optional pre-packed bf16 images of W (geomae_pack_weights)
   const float* bias; int N_total;
   float* out; int ldo;
   const float* add_src; int ld_add;                                 // out += add_src (residual / gradient sum)
@@ -96,11 +97,14 @@ template <int NT, int EPI>
 __global__ void __launch_bounds__(NTHREADS) k_tc_linear(const LinArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar_w;      // weight-image bulk copies
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = TM * KC * 2;          // 32 KB
   constexpr int B_BYTES = NT * KC * 2;
+  constexpr int BLOCK16K = 128 * tc::LINE_BYTES;   // one packed [128 x 64] bf16 block
   const bool x3 = a.precision == 3;
+  const bool packed = a.Wp_hi != nullptr;
   uint8_t* sA = smem;
   uint8_t* sAlo = sA + A_BYTES;
   uint8_t* sB = sA + (x3 ? 2 : 1) * A_BYTES;
@@ -109,48 +113,73 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_linear(const LinArgs a) {
   const int row0 = blockIdx.x * TM;
   const int n0 = blockIdx.y * NT;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, NT);
-  if (threadIdx.x == 0) tc::mbar_init(&mbar, 1);
+  if (threadIdx.x == 0) { tc::mbar_init(&mbar, 1); tc::mbar_init(&mbar_w, 1); }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const bool use_pos = a.pos_table && (int)blockIdx.y < a.pos_slabs;
   const int n_chunks = a.K / KC;
+  const int ncb = a.wp_cols / 64;       // 64-column blocks per 128-row band of the packed image
   for (int kc = 0; kc < n_chunks; ++kc) {
     const int k0 = kc * KC;
     if (kc > 0) {                       // operands of the previous chunk must be consumed before overwriting
       tc::mbar_wait(&mbar, (kc - 1) & 1);
       tc::fence_after_sync();
     }
+    if (packed && threadIdx.x == 0) {   // weights: bulk copies of the pre-swizzled bf16 image, no thread work
+      tc::mbar_expect_tx(&mbar_w, (uint32_t)((x3 ? 2 : 1) * B_BYTES));
+      for (int part = 0; part < (x3 ? 2 : 1); ++part) {
+        const uint8_t* img = part ? a.Wp_lo : a.Wp_hi;
+        uint8_t* dst = part ? sBlo : sB;
+        if (a.w_mn_major) {             // band k0/128, blocks n0/64 .. : contiguous
+          tc::bulk_g2s(dst, img + ((size_t)(k0 / 128) * ncb + n0 / 64) * BLOCK16K, B_BYTES, &mbar_w);
+        } else {                        // bands n0/128 + r, blocks k0/64, k0/64+1 : 32 KB each
+          for (int r = 0; r < NT / 128; ++r)
+            tc::bulk_g2s(dst + r * 2 * BLOCK16K, img + ((size_t)(n0 / 128 + r) * ncb + k0 / 64) * BLOCK16K,
+                         2 * BLOCK16K, &mbar_w);
+        }
+      }
+    }
     stage_tile<TM, KC>(sA, x3 ? sAlo : nullptr, a.A, a.lda, row0, a.n_rows, k0, use_pos ? a.pos_table : nullptr,
                        a.tok_cell, a.K, a.a_gelu != 0);
-    if (a.w_mn_major)   // rows = k, columns = n
-      stage_tile<KC, NT>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, k0, a.w_rows, n0, nullptr, nullptr, 0, false);
-    else                // rows = n, columns = k
-      stage_tile<NT, KC>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, n0, a.w_rows, k0, nullptr, nullptr, 0, false);
+    if (!packed) {
+      if (a.w_mn_major)   // rows = k, columns = n
+        stage_tile<KC, NT>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, k0, a.w_rows, n0, nullptr, nullptr, 0, false);
+      else                // rows = n, columns = k
+        stage_tile<NT, KC>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, n0, a.w_rows, k0, nullptr, nullptr, 0, false);
+    }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     if (threadIdx.x == 0) {
+      if (packed) tc::mbar_wait(&mbar_w, kc & 1);
       tc::fence_after_sync();
-      const uint32_t idesc = tc::make_idesc_bf16(TM, NT, 0, a.w_mn_major);
+      // packed K-major images are organised in 128-row bands: one N=128 MMA per band
+      const int n_sub = (packed && !a.w_mn_major) ? NT / 128 : 1;
+      const int n_mma = NT / n_sub;
+      const uint32_t idesc = tc::make_idesc_bf16(TM, n_mma, 0, a.w_mn_major);
       const uint32_t a_hi = tc::smem_u32(sA), a_lo = tc::smem_u32(sAlo), b_hi = tc::smem_u32(sB), b_lo = tc::smem_u32(sBlo);
-      bool acc = kc > 0;
+      const bool acc0 = kc > 0;
 #pragma unroll
       for (int j = 0; j < KC / 16; ++j) {
         const uint32_t a_off = (uint32_t)(j >> 2) * (TM * tc::LINE_BYTES) + (uint32_t)(j & 3) * 32;
-        uint32_t b_off, b_lbo;
-        if (a.w_mn_major) { b_off = (uint32_t)j * 2 * tc::ATOM_BYTES; b_lbo = KC * tc::LINE_BYTES; }
-        else { b_off = (uint32_t)(j >> 2) * (NT * tc::LINE_BYTES) + (uint32_t)(j & 3) * 32; b_lbo = 16; }
         const uint64_t da_hi = tc::make_desc(a_hi + a_off, 16, tc::ATOM_BYTES);
-        const uint64_t db_hi = tc::make_desc(b_hi + b_off, b_lbo, tc::ATOM_BYTES);
-        tc::mma_bf16(tmem, da_hi, db_hi, idesc, acc);
-        acc = true;
-        if (x3) {
-          const uint64_t da_lo = tc::make_desc(a_lo + a_off, 16, tc::ATOM_BYTES);
-          const uint64_t db_lo = tc::make_desc(b_lo + b_off, b_lbo, tc::ATOM_BYTES);
-          tc::mma_bf16(tmem, da_hi, db_lo, idesc, true);
-          tc::mma_bf16(tmem, da_lo, db_hi, idesc, true);
+        const uint64_t da_lo = tc::make_desc(a_lo + a_off, 16, tc::ATOM_BYTES);
+        for (int sub = 0; sub < n_sub; ++sub) {
+          uint32_t b_off, b_lbo;
+          if (a.w_mn_major) { b_off = (uint32_t)j * 2 * tc::ATOM_BYTES; b_lbo = KC * tc::LINE_BYTES; }
+          else if (packed) { b_off = (uint32_t)sub * 2 * BLOCK16K + (uint32_t)(j >> 2) * BLOCK16K + (uint32_t)(j & 3) * 32; b_lbo = 16; }
+          else { b_off = (uint32_t)(j >> 2) * (NT * tc::LINE_BYTES) + (uint32_t)(j & 3) * 32; b_lbo = 16; }
+          const uint64_t db_hi = tc::make_desc(b_hi + b_off, b_lbo, tc::ATOM_BYTES);
+          const uint32_t td = tmem + sub * 128;
+          const bool acc = acc0 || j > 0;
+          tc::mma_bf16(td, da_hi, db_hi, idesc, acc);
+          if (x3) {
+            const uint64_t db_lo = tc::make_desc(b_lo + b_off, b_lbo, tc::ATOM_BYTES);
+            tc::mma_bf16(td, da_hi, db_lo, idesc, true);
+            tc::mma_bf16(td, da_lo, db_hi, idesc, true);
+          }
         }
       }
       tc::mma_commit(&mbar);
@@ -420,6 +449,37 @@ __global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dz, co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Weight pre-packing: fp32 [rows, cols] -> bf16 hi (+ lo residual) images made of [128 x 64] swizzled blocks
+// (16 KB each, block index = band * (cols/64) + column block), i.e. exactly the bytes the tensor-core kernels
+// want in shared memory, so a CTA fetches its weight tile with one or two bulk copies and no thread work.
+struct PackItem { const float* W; int rows; int cols; uint8_t* hi; uint8_t* lo; };
+struct PackBatch { PackItem item[64]; int n; };
+
+__global__ void __launch_bounds__(256) k_pack_weights(const PackBatch b) {
+  const PackItem it = b.item[blockIdx.y];
+  const int bands = (it.rows + 127) / 128, cpr = it.cols / 8;
+  const int total = bands * 128 * cpr;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int r = i / cpr, c8 = i % cpr;
+    float f[8];
+    if (r < it.rows) {
+      const float4* p = reinterpret_cast<const float4*>(it.W + (int64_t)r * it.cols + c8 * 8);
+      const float4 x = __ldg(p), y = __ldg(p + 1);
+      f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; f[4] = y.x; f[5] = y.y; f[6] = y.z; f[7] = y.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    }
+    uint4 lo;
+    const uint4 hi = tc::pack8(f, &lo);
+    const size_t off = ((size_t)(r / 128) * (it.cols / 64) + (c8 >> 3)) * (128 * tc::LINE_BYTES) + tc::swz(r & 127, c8 & 7);
+    *reinterpret_cast<uint4*>(it.hi + off) = hi;
+    if (it.lo) *reinterpret_cast<uint4*>(it.lo + off) = lo;
+  }
+}
+
 }  // namespace
 
 extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
@@ -434,6 +494,9 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
   a.A = p->A; a.lda = p->lda; a.n_rows = p->n_rows; a.K = p->K;
   a.pos_table = p->pos_table; a.tok_cell = p->tok_cell; a.pos_slabs = p->pos_slabs; a.a_gelu = p->a_gelu;
   a.W = p->W; a.ldw = p->ldw; a.w_rows = p->w_rows; a.w_mn_major = p->w_mn_major;
+  a.Wp_hi = (const uint8_t*)p->Wp_hi; a.Wp_lo = (const uint8_t*)p->Wp_lo; a.wp_cols = p->ldw;
+  GM_REQUIRE(!p->Wp_hi || (p->precision == 1 || p->Wp_lo), "tc_linear: bf16x3 with packed weights needs the lo image");
+  GM_REQUIRE(!p->Wp_hi || p->ldw % 64 == 0, "tc_linear: packed weights need cols %% 64 == 0");
   a.bias = p->bias; a.N_total = p->N_total; a.out = p->out; a.ldo = p->ldo;
   a.add_src = p->add_src; a.ld_add = p->ld_add;
   a.ln_gamma = p->ln_gamma; a.ln_beta = p->ln_beta; a.ln_eps = p->ln_eps; a.ln_in = p->ln_in; a.ln_stats = p->ln_stats;
@@ -481,5 +544,30 @@ extern "C" int geomae_layernorm_bwd(const float* d_out, const float* ln_in, cons
   if (blocks > GM_NUM_SMS * 4) blocks = GM_NUM_SMS * 4;
   k_ln_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, ln_in, ln_stats, gamma, (int)n_rows, d_in, d_gamma, d_beta);
   GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
+
+extern "C" int geomae_pack_weights(int32_t n_items, const float* const* W, const int32_t* rows, const int32_t* cols,
+                                   void* const* hi, void* const* lo, void* stream) {
+  GM_REQUIRE(n_items >= 0 && (n_items == 0 || (W && rows && cols && hi)), "pack_weights: null argument");
+  int done = 0;
+  while (done < n_items) {
+    PackBatch b;
+    b.n = n_items - done < 64 ? n_items - done : 64;
+    int max_total = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const int k = done + i;
+      GM_REQUIRE(W[k] && hi[k] && rows[k] > 0 && cols[k] > 0 && cols[k] % 64 == 0,
+                 "pack_weights: item %d needs cols %% 64 == 0 and non-null buffers", k);
+      b.item[i] = PackItem{W[k], rows[k], cols[k], (uint8_t*)hi[k], lo ? (uint8_t*)lo[k] : nullptr};
+      const int total = (rows[k] + 127) / 128 * 128 * (cols[k] / 8);
+      if (total > max_total) max_total = total;
+    }
+    int gx = gm_div_up(max_total, 256 * 4);
+    if (gx < 1) gx = 1;
+    k_pack_weights<<<dim3(gx, b.n), 256, 0, (cudaStream_t)stream>>>(b);
+    GM_LAUNCH_CHECK();
+    done += b.n;
+  }
   return GEOMAE_OK;
 }

@@ -6,11 +6,45 @@
 
 namespace {
 
+// Optional per-kernel-family device timing (bench.py's roofline leg): CUDA events recorded on the launching
+// stream around every kernel of a family.  Off by default.
+struct Prof {
+  static constexpr int FAMILIES = 5;   // 0 tc_linear, 1 tc_wgrad, 2 attention fwd, 3 attention bwd, 4 layernorm bwd
+  static constexpr int MAX_SPANS = 8192;
+  bool on = false;
+  int n = 0;
+  cudaEvent_t start[MAX_SPANS], stop[MAX_SPANS];
+  int family[MAX_SPANS];
+  double flops[MAX_SPANS];
+  int created = 0;
+  cudaEvent_t* begin(int fam, double fl, cudaStream_t st) {
+    if (!on || n >= MAX_SPANS) return nullptr;
+    if (n >= created) {
+      if (cudaEventCreate(&start[n]) != cudaSuccess || cudaEventCreate(&stop[n]) != cudaSuccess) return nullptr;
+      created = n + 1;
+    }
+    family[n] = fam;
+    flops[n] = fl;
+    cudaEventRecord(start[n], st);
+    return &stop[n++];
+  }
+};
+Prof g_prof;
+
+struct Span {
+  cudaEvent_t* stop;
+  cudaStream_t st;
+  Span(int fam, double flops, void* stream) : st((cudaStream_t)stream) { stop = g_prof.begin(fam, flops, st); }
+  ~Span() { if (stop) cudaEventRecord(*stop, st); }
+};
+
 int lin(const float* A, int lda, int n, int K, const float* W, int ldw, int w_rows, int mn, const float* bias, int N,
-        float* out, int ldo, int prec, void* stream, geomae_linear_args* extra = nullptr) {
+        float* out, int ldo, int prec, void* stream, geomae_linear_args* extra = nullptr, void* const* packed = nullptr) {
   geomae_linear_args a = extra ? *extra : geomae_linear_args{};
   a.A = A; a.lda = lda; a.n_rows = n; a.K = K; a.W = W; a.ldw = ldw; a.w_rows = w_rows; a.w_mn_major = mn;
+  if (packed) { a.Wp_hi = packed[0]; a.Wp_lo = packed[1]; }
   a.bias = bias; a.N_total = N; a.out = out; a.ldo = ldo; a.precision = prec;
+  Span span(0, 2.0 * n * (double)K * N, stream);
   return geomae_tc_linear(&a, stream);
 }
 
@@ -21,6 +55,7 @@ int wgrad(const float* dY, int ldy, const float* X, int ldx, int n, float* dW, i
   a.dY = dY; a.ldy = ldy; a.X = X; a.ldx = ldx; a.n_rows = n; a.pos_table = pos; a.tok_cell = cell;
   a.pos_slabs = pos_slabs; a.x_gelu = gelu; a.dW = dW; a.ldw = ldw; a.db = db; a.M_total = M; a.N_total = N;
   a.precision = prec;
+  Span span(1, 2.0 * n * (double)M * N, stream);
   return geomae_tc_wgrad(&a, stream);
 }
 
@@ -41,23 +76,42 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
   const int n = (int)c->n_tokens, d = c->d_model, f = c->ffn, p = c->precision;
   if (n == 0) return GEOMAE_OK;
   const float* x = x_in;
+  {  // refresh the packed bf16 weight images of every layer (weights change every optimiser step): one launch
+    const float* W[64]; int32_t rows[64], cols[64]; void* hi[64]; void* lo[64];
+    int k = 0;
+    for (int l = 0; l < n_layers; ++l) {
+      const geomae_sra_layer& L = layers[l];
+      const float* ws[4] = {L.in_proj_w, L.out_proj_w, L.lin1_w, L.lin2_w};
+      void* const* ps[4] = {L.p_in_proj, L.p_out_proj, L.p_lin1, L.p_lin2};
+      const int r[4] = {3 * d, d, f, d}, cc[4] = {d, d, d, f};
+      for (int i = 0; i < 4; ++i) {
+        GM_REQUIRE(ps[i][0] && ps[i][1], "sra_stack_forward: layer %d has no packed-weight scratch", l);
+        W[k] = ws[i]; rows[k] = r[i]; cols[k] = cc[i]; hi[k] = ps[i][0]; lo[k] = ps[i][1];
+        if (++k == 64) { GM_TRY(geomae_pack_weights(k, W, rows, cols, hi, lo, stream)); k = 0; }
+      }
+    }
+    if (k) GM_TRY(geomae_pack_weights(k, W, rows, cols, hi, lo, stream));
+  }
   for (int l = 0; l < n_layers; ++l) {
     const geomae_sra_layer& L = layers[l];
     const geomae_sra_saved& S = saved[l];
     const geomae_sra_windows& w = c->shift[L.shift];
     geomae_linear_args e{};
     e.pos_table = c->pos_table; e.tok_cell = w.tok_cell; e.pos_slabs = 2;
-    GM_TRY(lin(x, d, n, d, L.in_proj_w, d, 3 * d, 0, L.in_proj_b, 3 * d, S.qkv, 3 * d, p, stream, &e));
-    GM_TRY(geomae_sra_attention_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
+    GM_TRY(lin(x, d, n, d, L.in_proj_w, d, 3 * d, 0, L.in_proj_b, 3 * d, S.qkv, 3 * d, p, stream, &e, L.p_in_proj));
+    {
+      Span span(2, 0.0, stream);
+      GM_TRY(geomae_sra_attention_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
+    }
     geomae_linear_args e1{};
     e1.add_src = x; e1.ld_add = d; e1.ln_gamma = L.norm1_w; e1.ln_beta = L.norm1_b; e1.ln_eps = L.ln_eps;
     e1.ln_in = S.s1; e1.ln_stats = S.st1; e1.epilogue = 1;
-    GM_TRY(lin(S.attn, d, n, d, L.out_proj_w, d, d, 0, L.out_proj_b, d, S.y, d, p, stream, &e1));
-    GM_TRY(lin(S.y, d, n, d, L.lin1_w, d, f, 0, L.lin1_b, f, S.u, f, p, stream));
+    GM_TRY(lin(S.attn, d, n, d, L.out_proj_w, d, d, 0, L.out_proj_b, d, S.y, d, p, stream, &e1, L.p_out_proj));
+    GM_TRY(lin(S.y, d, n, d, L.lin1_w, d, f, 0, L.lin1_b, f, S.u, f, p, stream, nullptr, L.p_lin1));
     geomae_linear_args e2{};
     e2.add_src = S.y; e2.ld_add = d; e2.ln_gamma = L.norm2_w; e2.ln_beta = L.norm2_b; e2.ln_eps = L.ln_eps;
     e2.ln_in = S.s2; e2.ln_stats = S.st2; e2.epilogue = 1; e2.a_gelu = 1;
-    GM_TRY(lin(S.u, f, n, f, L.lin2_w, f, d, 0, L.lin2_b, d, S.z, d, p, stream, &e2));
+    GM_TRY(lin(S.u, f, n, f, L.lin2_w, f, d, 0, L.lin2_b, d, S.z, d, p, stream, &e2, L.p_lin2));
     x = S.z;
   }
   return GEOMAE_OK;
@@ -119,30 +173,39 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     const float* x = l == 0 ? x_in : saved[l - 1].z;
     float* dx = l == 0 ? d_in : dxb;
     if (side_done[l & 1]) GM_CUDA(cudaStreamWaitEvent(main, side_done[l & 1], 0));   // set (l&1) free again
-    GM_TRY(geomae_layernorm_bwd(dz, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, main));
+    {
+      Span span(4, 0.0, main);
+      GM_TRY(geomae_layernorm_bwd(dz, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, main));
+    }
     GM_TRY(hand_off(main, side));
     GM_TRY(wgrad(ds2, d, S.u, f, n, L.g_lin2_w, f, L.g_lin2_b, d, f, p, side, nullptr, nullptr, 0, 1));
     geomae_linear_args e{};
     e.gelu_u = S.u; e.ldu = f; e.epilogue = 2;
-    GM_TRY(lin(ds2, d, n, d, L.lin2_w, f, d, 1, nullptr, f, du, f, p, main, &e));
+    GM_TRY(lin(ds2, d, n, d, L.lin2_w, f, d, 1, nullptr, f, du, f, p, main, &e, L.p_lin2));
     GM_TRY(hand_off(main, side));
     GM_TRY(wgrad(du, f, S.y, d, n, L.g_lin1_w, d, L.g_lin1_b, f, d, p, side));
     geomae_linear_args e1{};
     e1.add_src = ds2; e1.ld_add = d;
-    GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, dy, d, p, main, &e1));
-    GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, main));
+    GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, dy, d, p, main, &e1, L.p_lin1));
+    {
+      Span span(4, 0.0, main);
+      GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, main));
+    }
     GM_TRY(hand_off(main, side));
     GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, L.g_out_proj_b, d, d, p, side));
-    GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main));
-    GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv, dd,
-                                    main));
+    GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main, nullptr, L.p_out_proj));
+    {
+      Span span(3, 0.0, main);
+      GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
+                                      dd, main));
+    }
     GM_TRY(hand_off(main, side));
     GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, side, c->pos_table, w.tok_cell, 2, 0));
     side_done[l & 1] = g_lanes.event();
     GM_CUDA(cudaEventRecord(side_done[l & 1], side));
     geomae_linear_args e2{};
     e2.add_src = ds1; e2.ld_add = d;
-    GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, dx, d, p, main, &e2));
+    GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, dx, d, p, main, &e2, L.p_in_proj));
     dz = dx;
   }
   GM_TRY(hand_off(side, main));   // join
@@ -194,4 +257,27 @@ extern "C" int geomae_sra_stack2_backward(const geomae_sra_ctx* c, int32_t n_lay
   GM_TRY(stack_backward_on(g_lanes.side[1], g_lanes.side[2], c, n_layers, layers_b, saved_b, x_in, d_out_b, d_in_b,
                            scratch + 2 * scratch_floats(c)));
   return hand_off(g_lanes.side[1], main);
+}
+
+// ---- per-family timing of the stack kernels (bench.py roofline leg)
+extern "C" int geomae_profile_enable(int32_t on) {
+  g_prof.on = on != 0;
+  g_prof.n = 0;
+  return GEOMAE_OK;
+}
+
+// Synchronises the device; ms[f], launches[f], flops[f] for the 5 families (see Prof).
+extern "C" int geomae_profile_read(double* ms, int64_t* launches, double* flops) {
+  GM_REQUIRE(ms && launches && flops, "profile_read: null argument");
+  GM_CUDA(cudaDeviceSynchronize());
+  for (int f = 0; f < Prof::FAMILIES; ++f) { ms[f] = 0.0; launches[f] = 0; flops[f] = 0.0; }
+  for (int i = 0; i < g_prof.n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.start[i], g_prof.stop[i]) != cudaSuccess) continue;
+    ms[g_prof.family[i]] += t;
+    launches[g_prof.family[i]] += 1;
+    flops[g_prof.family[i]] += g_prof.flops[i];
+  }
+  g_prof.n = 0;
+  return GEOMAE_OK;
 }

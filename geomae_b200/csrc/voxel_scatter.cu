@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(TPB) k_mark(VoxGeom g, const float* __restrict
 // ---------------------------------------------------------------- pass 2: rank the bitmap
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_CHUNK = TPB * SCAN_ITEMS;
-constexpr int SCAN_MAX_BLOCKS = 4096;
+constexpr int SCAN_MAX_BLOCKS = 16384;
 
 __device__ __forceinline__ int block_base(const int32_t* __restrict__ sums, int* smem) {
   int v = 0;

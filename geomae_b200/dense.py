@@ -68,3 +68,34 @@ def layernorm_bwd(d_out, ln_in, ln_stats, gamma, d_gamma, d_beta):
     L.run("layernorm_bwd", L.ptr(d_out), L.ptr(ln_in), L.ptr(ln_stats), L.ptr(gamma), d_out.shape[0], d_out.shape[1],
           L.ptr(d_in), L.ptr(d_gamma), L.ptr(d_beta), L.stream_ptr(d_out.device))
     return d_in
+
+
+class _TCLinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) on tcgen05; backward = input gradient (MN-major weight view) + weight gradient accumulated
+    straight into ``weight.grad`` (and ``bias.grad``)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, precision):
+        x = x.contiguous()
+        y = tc_linear(x, weight, n_out=weight.shape[0], bias=bias, precision=precision)
+        ctx.save_for_backward(x)
+        ctx.weight, ctx.bias, ctx.precision = weight, bias, precision
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        w, b = ctx.weight, ctx.bias
+        dy = dy.contiguous()
+        for p in (w, b):
+            if p is not None and p.grad is None:
+                p.grad = torch.zeros_like(p)
+        tc_wgrad(dy, x, w.grad, b.grad if b is not None else None, precision=ctx.precision)
+        dx = tc_linear(dy, w, n_out=w.shape[1], w_mn_major=True, precision=ctx.precision) if ctx.needs_input_grad[0] \
+            else None
+        return dx, None, None, None
+
+
+def tc_linear_module(x, linear: torch.nn.Linear, precision):
+    """nn.Linear forward/backward on the tensor cores (in/out features must be multiples of 128)."""
+    return _TCLinearFn.apply(x, linear.weight, linear.bias, precision)

@@ -83,6 +83,13 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
         if (gz, gy, gx) != tuple(grid_size):
             raise ValueError(f"grid_size {tuple(grid_size)} does not match the voxel geometry {(gz, gy, gx)}")
 
+    def set_impl(self, impl: str):
+        """"tc3": tensor-core GEMMs in the bf16x3 split (fp32-equivalent, the parity mode; default);
+        "tc1": plain bf16 tensor-core GEMMs (the bf16 benchmark mode); "glue": library fp32 GEMMs."""
+        self.backbone.set_sra_impl(impl)
+        self.voxel_encoder.tc_precision = {"tc3": 3, "tc1": 1, "glue": 0}[impl]
+        return self
+
     def geom_grid_host(self):
         import math
         r, v = self.point_cloud_range, self.voxel_size

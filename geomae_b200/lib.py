@@ -55,7 +55,7 @@ class LinearArgs(C.Structure):
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("ln_in", C.c_void_p),
                 ("ln_stats", C.c_void_p),
                 ("gelu_u", C.c_void_p), ("ldu", C.c_int32),
-                ("epilogue", C.c_int32), ("precision", C.c_int32)]
+                ("epilogue", C.c_int32), ("precision", C.c_int32), ("Wp_hi", C.c_void_p), ("Wp_lo", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):
@@ -82,7 +82,8 @@ _LAYER_GRADS = ["g_in_proj_w", "g_in_proj_b", "g_out_proj_w", "g_out_proj_b", "g
 
 class SRALayer(C.Structure):
     _fields_ = ([("shift", C.c_int32), ("ln_eps", C.c_float)] + [(k, C.c_void_p) for k in _LAYER_PARAMS] +
-                [(k, C.c_void_p) for k in _LAYER_GRADS])
+                [(k, C.c_void_p) for k in _LAYER_GRADS] +
+                [(k, C.c_void_p * 2) for k in ("p_in_proj", "p_out_proj", "p_lin1", "p_lin2")])
 
 
 class SRASaved(C.Structure):
@@ -155,6 +156,9 @@ class _Sigs:
     geomae_geom_loss_fwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p]
     geomae_geom_loss_bwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p, _p, _p, _p,
                             _p, _p]
+    geomae_pack_weights = [_i32, _p, _p, _p, _p, _p, _p]
+    geomae_profile_enable = [_i32]
+    geomae_profile_read = [_p, _p, _p]
     geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                          C.c_float, C.c_float, _i64, _p, _p]
 

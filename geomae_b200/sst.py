@@ -186,6 +186,16 @@ class SRAStack:
 
     def __init__(self, layers, shifts):
         self.layers, self.shifts = list(layers), list(shifts)
+        self._packed = None     # bf16 weight images (hi, lo) per layer, refilled by the executor every forward
+
+    def _pack_arena(self, device):
+        if self._packed is None or self._packed.device != device:
+            first = self.layers[0]
+            d, f = first.win_attn.d_model, first.linear1.out_features
+            per_layer = 2 * 2 * (3 * d * d + d * d + f * d + d * f)       # bytes: (hi, lo) x bf16
+            self._per_layer = per_layer
+            self._packed = torch.empty(per_layer * len(self.layers), dtype=torch.uint8, device=device)
+        return self._packed
 
     def _structs(self):
         import ctypes as C
@@ -199,6 +209,15 @@ class SRAStack:
             for name, gname, p in zip(L._LAYER_PARAMS, L._LAYER_GRADS, ps):
                 setattr(s, name, p.data_ptr())
                 setattr(s, gname, _grad_of(p).data_ptr())
+        arena = self._pack_arena(self.layers[0].norm1.weight.device)
+        d, f = self.layers[0].win_attn.d_model, self.layers[0].linear1.out_features
+        sizes = [("p_in_proj", 3 * d * d), ("p_out_proj", d * d), ("p_lin1", f * d), ("p_lin2", d * f)]
+        for i, s in enumerate(arr):
+            off = arena.data_ptr() + i * self._per_layer
+            for name, elems in sizes:
+                getattr(s, name)[0] = off
+                getattr(s, name)[1] = off + 2 * elems
+                off += 4 * elems
         return arr
 
     def ctx(self, layout: WindowLayout, table, n, precision):

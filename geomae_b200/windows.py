@@ -86,7 +86,7 @@ class WindowLayout:
         n_words = (batch_size * gx * gy + 31) // 32
         i32 = dict(dtype=torch.int32, device=dev)
         bitmap, word_rank = torch.empty(n_words, **i32), torch.empty(n_words, **i32)
-        scan_tmp, counts = torch.empty(3 * 4096, **i32), torch.zeros(4, **i32)
+        scan_tmp, counts = torch.empty(3 * 16384, **i32), torch.zeros(4, **i32)
         tok_of_pillar = torch.empty(max(n, 1), **i32)
         s = L.stream_ptr(dev)
         L.run("coors_bitmap", C.byref(geom.cstruct), L.ptr(coors), n, batch_size, L.ptr(bitmap),

@@ -66,7 +66,7 @@ typedef struct geomae_scatter_io {
   /* scratch (caller zeroing not required) */
   uint32_t* bitmap;             /* [ceil(n_frames*gy*gx/32)] pillar occupancy              */
   int32_t* word_rank;           /* [same] exclusive popcount prefix                        */
-  int32_t* scan_tmp;            /* [3*4096] block sums                                     */
+  int32_t* scan_tmp;            /* [3*16384] block sums                                     */
   /* outputs */
   int32_t* counts;              /* [4+n_frames+1] n_pillars, n_med, n_low, overflow flag,  */
                                 /*   then the first pillar row of each frame (and V last)  */
@@ -151,7 +151,7 @@ int geomae_window_candidates(const geomae_voxel_cfg* cfg, const geomae_window_cf
  * tok_of_pillar[rank(cell_i)] = i.  Lets geomae_window_csr serve callers that only hold coordinates,
  * i.e. the reference signature backbone.forward(voxel_feat, coors, coors_mask, batch_size)
  * (…top_only.py:136-141) and SSTInputLayer.forward (middle_encoders/sst_input_layer.py:51-103).
- * bitmap/word_rank: [ceil(n_frames*gy*gx/32)], scan_tmp [3*4096], counts [4], tok_of_pillar [n]. */
+ * bitmap/word_rank: [ceil(n_frames*gy*gx/32)], scan_tmp [3*16384], counts [4], tok_of_pillar [n]. */
 int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* coors, int64_t n, int32_t n_frames,
                         uint32_t* bitmap, int32_t* word_rank, int32_t* scan_tmp, int32_t* counts,
                         int32_t* tok_of_pillar, void* stream);
@@ -238,9 +238,17 @@ typedef struct geomae_linear_args {
   const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_in; float* ln_stats;
   const float* gelu_u; int32_t ldu;
   int32_t epilogue; int32_t precision;
+  const void* Wp_hi; const void* Wp_lo;   /* optional: images of W from geomae_pack_weights (ldw = cols of W) */
 } geomae_linear_args;
 
 int geomae_tc_linear(const geomae_linear_args* args, void* stream);
+
+/* Pre-pack weights for the tensor-core kernels: fp32 W[k] [rows, cols] (row-major, cols % 64 == 0) ->
+ * bf16 "hi" image and bf16 residual "lo" image (lo may be NULL), each ceil(rows/128)*128*cols*2 bytes, laid
+ * out as [128 x 64] 128B-swizzled blocks so a CTA loads its weight tile with bulk copies.  One launch per
+ * 64 items. */
+int geomae_pack_weights(int32_t n_items, const float* const* W, const int32_t* rows, const int32_t* cols,
+                        void* const* hi, void* const* lo, void* stream);
 
 /* dW[M_total, N_total] += dY^T X over the token rows, db[M_total] += column sums of dY (db may be NULL).
  * X prologue: + pos_table[tok_cell] for the first pos_slabs 128-row slabs of dW (q,k rows of in_proj), gelu.
@@ -285,6 +293,9 @@ typedef struct geomae_sra_layer {
   const float *norm1_w, *norm1_b, *norm2_w, *norm2_b;
   float *g_in_proj_w, *g_in_proj_b, *g_out_proj_w, *g_out_proj_b, *g_lin1_w, *g_lin1_b, *g_lin2_w, *g_lin2_b;
   float *g_norm1_w, *g_norm1_b, *g_norm2_w, *g_norm2_b;
+  /* scratch for the packed bf16 images of the four weight matrices (hi, lo): in_proj 2*3d*d bytes each,
+   * out_proj 2*d*d, lin1 2*f*d, lin2 2*d*f.  (Re)filled by geomae_sra_stack_forward. */
+  void *p_in_proj[2], *p_out_proj[2], *p_lin1[2], *p_lin2[2];
 } geomae_sra_layer;
 
 /* Activations one layer keeps for its backward (caller-allocated, n = n_tokens). */
@@ -343,6 +354,12 @@ int geomae_geom_loss_fwd(const geomae_voxel_cfg* cfg, const geomae_scatter_io* i
 int geomae_geom_loss_bwd(const geomae_voxel_cfg* cfg, const geomae_scatter_io* io, const geomae_loss_args* args,
                          const int32_t* counts, const float* d_losses, float* d_reg_low, float* d_reg_med,
                          float* d_reg_top, float* d_nor_top, float* d_cls_low, float* d_cls_med, void* stream);
+
+/* Per-kernel-family device timing of the stack executors (CUDA events on the launching streams), used by
+ * bench.py for the roofline entry.  Families: 0 tc_linear, 1 tc_wgrad, 2 attention fwd, 3 attention bwd
+ * (2 kernels per span), 4 layernorm bwd.  geomae_profile_read synchronises the device and resets the log. */
+int geomae_profile_enable(int32_t on);
+int geomae_profile_read(double* ms /*[5]*/, int64_t* launches /*[5]*/, double* flops /*[5]*/);
 
 /* ---------------------------------------------------------------- optimiser */
 

@@ -172,7 +172,7 @@ def build_model(cfg, params, impl="tc3"):
     sd = model.state_dict()
     sd.update({k: v.detach().clone() for k, v in params.items()})
     model.load_state_dict(sd)
-    model.backbone.set_sra_impl(impl)
+    model.set_impl(impl)
     return model.to(DEV).train()
 
 

@@ -24,17 +24,17 @@ sets = {"dec": perm, "enc": perm[: int(v * 0.3)]}
 which = sys.argv[1:] or ["attn", "linear", "wgrad", "ln"]
 
 
-def timeit(fn, n=20):
+def timeit(fn, n=10):
+    """Mean device time (us) of the hand-written kernels launched by fn, from CUPTI kernel records."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n * 1e3
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+    tot = sum(e.device_time_total for e in prof.key_averages() if "k_" in e.key and "geomae" not in e.key)
+    return tot / n
 
 
 for name, rows in sets.items():

@@ -16,7 +16,7 @@ dev = torch.device("cuda:0")
 torch.backends.cuda.matmul.allow_tf32 = False
 cfg = Config.fromfile(os.path.join(ROOT, "configs/mae_sst/geomae_nus_pretrain.py"))
 model = build_model(cfg.model).to(dev).train()
-model.backbone.set_sra_impl(impl)
+model.set_impl(impl)
 tr = FlatTrainer(model)
 frames = [torch.from_numpy(make_frame(s + 1)).to(dev) for s in range(4)]
 for _ in range(3):
