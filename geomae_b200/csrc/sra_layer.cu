@@ -39,21 +39,22 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // Stage a [ROWS x COLS] fp32 tile (global rows row0.., columns col0..) as bf16 into swizzled 64-column blocks.
 // Loads are issued UNROLL items ahead of the conversions so one thread keeps 2*UNROLL 128-bit loads in
 // flight (the un-pipelined version spent ~20 us per tile waiting on one load at a time).
-template <int ROWS, int COLS>
+template <int ROWS, int COLS, int NTHR = NTHREADS, bool POS = true>
 __device__ __forceinline__ void stage_tile(uint8_t* dst_hi, uint8_t* dst_lo, const float* __restrict__ src, int ld,
-                                           int row0, int row_end, int col0, const float* __restrict__ pos_table,
+                                           int row0, int row_end, int col0, const float* __restrict__ pos_table_,
                                            const int32_t* __restrict__ tok_cell, int pos_ld, bool do_gelu) {
   constexpr int CPR = COLS / 8;                 // 16-byte chunks per row
   constexpr int BLOCK_BYTES = ROWS * tc::LINE_BYTES;
-  constexpr int ITEMS = ROWS * CPR / NTHREADS;  // per thread
+  constexpr int ITEMS = ROWS * CPR / NTHR;      // per thread
   constexpr int UNROLL = 8;
+  const float* pos_table = POS ? pos_table_ : nullptr;
   static_assert(ITEMS % UNROLL == 0, "tile size must be a multiple of the staging unroll");
 #pragma unroll 1
   for (int it = 0; it < ITEMS; it += UNROLL) {
     float4 a[UNROLL], b[UNROLL], c[UNROLL], d[UNROLL];
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k) {
-      const int i = (it + k) * NTHREADS + threadIdx.x;
+      const int i = (it + k) * NTHR + threadIdx.x;
       const int r = i / CPR, c8 = i % CPR;
       const int grow = row0 + r;
       if (grow < row_end) {
@@ -72,7 +73,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* dst_hi, uint8_t* dst_lo, con
     }
 #pragma unroll
     for (int k = 0; k < UNROLL; ++k) {
-      const int i = (it + k) * NTHREADS + threadIdx.x;
+      const int i = (it + k) * NTHR + threadIdx.x;
       const int r = i / CPR, c8 = i % CPR;
       float f[8] = {a[k].x, a[k].y, a[k].z, a[k].w, b[k].x, b[k].y, b[k].z, b[k].w};
       if (pos_table && row0 + r < row_end) {
@@ -92,9 +93,18 @@ __device__ __forceinline__ void stage_tile(uint8_t* dst_hi, uint8_t* dst_lo, con
   }
 }
 
+constexpr int LTHREADS = 256;  // k_tc_linear: 8 warps stage; warps w and w+4 share TMEM lane quarter w%4 and split the columns
+
+// fp32 accumulator tile in shared memory, [128 rows][C4 float4], XOR-swizzled so that both the row-per-thread
+// TMEM drain and the row-contiguous (coalesced) read-back are bank-conflict free
+template <int C4>
+__device__ __forceinline__ float4* ctile(float* base, int row, int c4) {
+  return reinterpret_cast<float4*>(base) + row * C4 + (c4 ^ (row & (C4 - 1)));
+}
+
 // EPI: 0 = acc (+bias) (+add_src); 1 = LayerNorm(acc + bias + add_src); 2 = acc * gelu'(u)
-template <int NT, int EPI>
-__global__ void __launch_bounds__(NTHREADS) k_tc_linear(const LinArgs a) {
+template <int NT, int EPI, bool POS>
+__global__ void __launch_bounds__(LTHREADS) k_tc_linear(const LinArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ __align__(8) uint64_t mbar_w;      // weight-image bulk copies
@@ -141,13 +151,13 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_linear(const LinArgs a) {
         }
       }
     }
-    stage_tile<TM, KC>(sA, x3 ? sAlo : nullptr, a.A, a.lda, row0, a.n_rows, k0, use_pos ? a.pos_table : nullptr,
-                       a.tok_cell, a.K, a.a_gelu != 0);
+    stage_tile<TM, KC, LTHREADS, POS>(sA, x3 ? sAlo : nullptr, a.A, a.lda, row0, a.n_rows, k0,
+                                      use_pos ? a.pos_table : nullptr, a.tok_cell, a.K, a.a_gelu != 0);
     if (!packed) {
       if (a.w_mn_major)   // rows = k, columns = n
-        stage_tile<KC, NT>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, k0, a.w_rows, n0, nullptr, nullptr, 0, false);
+        stage_tile<KC, NT, LTHREADS, false>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, k0, a.w_rows, n0, nullptr, nullptr, 0, false);
       else                // rows = n, columns = k
-        stage_tile<NT, KC>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, n0, a.w_rows, k0, nullptr, nullptr, 0, false);
+        stage_tile<NT, KC, LTHREADS, false>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, n0, a.w_rows, k0, nullptr, nullptr, 0, false);
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -188,70 +198,78 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_linear(const LinArgs a) {
   tc::mbar_wait(&mbar, (n_chunks - 1) & 1);
   tc::fence_after_sync();
 
-  // ---- epilogue: thread <-> one token row (TMEM lane)
-  const int row = row0 + warp * 32 + lane;
-  const bool valid = row < a.n_rows;
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  // ---- epilogue.  The accumulator row of a token is one TMEM lane; it is drained row-per-thread into a
+  // swizzled fp32 tile in (now free) operand shared memory and read back row-contiguously, so every global
+  // access of the epilogue (bias, residual, GELU input, outputs) is a coalesced 128-bit access.
+  float* sC = reinterpret_cast<float*>(smem);
+  const int q = warp & 3, hsel = warp >> 2;                    // TMEM lane quarter, column half
+  const int trow = q * 32 + lane;                              // tile row drained by this thread
+  const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
   if constexpr (EPI == 1) {
     static_assert(EPI != 1 || NT == 128, "LayerNorm epilogue needs the whole row in one CTA");
-    float v[NT];
+    constexpr int C4 = 32;                                     // 128 columns
 #pragma unroll
-    for (int c = 0; c < NT / 32; ++c) tc::tmem_ld32(t_lane + c * 32, v + c * 32);
-    tc::tmem_ld_wait();
-    float mean = 0.f;
-    if (valid) {
-#pragma unroll
-      for (int c = 0; c < NT; c += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-        const float4 r = __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add + c));
-        v[c] += b.x + r.x; v[c + 1] += b.y + r.y; v[c + 2] += b.z + r.z; v[c + 3] += b.w + r.w;
-        mean += (v[c] + v[c + 1]) + (v[c + 2] + v[c + 3]);
-      }
-      mean *= (1.0f / NT);
-      float var = 0.f;
-#pragma unroll
-      for (int c = 0; c < NT; ++c) { const float d = v[c] - mean; var = fmaf(d, d, var); }
-      const float rstd = rsqrtf(var * (1.0f / NT) + a.ln_eps);
-      if (a.ln_stats) { a.ln_stats[2 * (int64_t)row] = mean; a.ln_stats[2 * (int64_t)row + 1] = rstd; }
-      float* o = a.out + (int64_t)row * a.ldo;
-      float* s = a.ln_in ? a.ln_in + (int64_t)row * NT : nullptr;
-#pragma unroll
-      for (int c = 0; c < NT; c += 4) {
-        if (s) *reinterpret_cast<float4*>(s + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-        const float4 g = __ldg(reinterpret_cast<const float4*>(a.ln_gamma + c));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(a.ln_beta + c));
-        *reinterpret_cast<float4*>(o + c) =
-            make_float4((v[c] - mean) * rstd * g.x + b.x, (v[c + 1] - mean) * rstd * g.y + b.y,
-                        (v[c + 2] - mean) * rstd * g.z + b.z, (v[c + 3] - mean) * rstd * g.w + b.w);
-      }
-    }
-  } else {
-#pragma unroll 1
-    for (int c0 = 0; c0 < NT; c0 += 32) {
+    for (int half = 0; half < 2; ++half) {                     // this warp: columns hsel*64 + half*32 ..
       float v[32];
+      const int c0 = hsel * 64 + half * 32;
       tc::tmem_ld32(t_lane + c0, v);
       tc::tmem_ld_wait();
-      if (valid) {
-        const int col = n0 + c0;
-        float* o = a.out + (int64_t)row * a.ldo + col;
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          float4 r = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-          if constexpr (EPI == 2) {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(a.gelu_u + (int64_t)row * a.ldu + col + c));
-            r.x *= gelu_grad_f(u.x); r.y *= gelu_grad_f(u.y); r.z *= gelu_grad_f(u.z); r.w *= gelu_grad_f(u.w);
-          } else {
-            if (a.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + c));
-              r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
-            }
-            if (a.add_src) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add + col + c));
-              r.x += s.x; r.y += s.y; r.z += s.z; r.w += s.w;
-            }
+      for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (c0 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+    __syncthreads();
+    // one warp per row, one float4 per lane: s = acc + bias + residual; exact two-pass statistics; write s, LN(s)
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + lane);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma) + lane);
+    const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.ln_beta) + lane);
+    for (int r = warp; r < TM; r += LTHREADS / 32) {
+      const int row = row0 + r;
+      if (row >= a.n_rows) break;
+      float4 v = *ctile<C4>(sC, r, lane);
+      const float4 res = __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add) + lane);
+      v.x += b4.x + res.x; v.y += b4.y + res.y; v.z += b4.z + res.z; v.w += b4.w + res.w;
+      const float mean = gm_warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / NT);
+      const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+      const float var = gm_warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / NT);
+      const float rstd = rsqrtf(var + a.ln_eps);
+      if (a.ln_in) reinterpret_cast<float4*>(a.ln_in + (int64_t)row * NT)[lane] = v;
+      if (a.ln_stats && lane == 0) *reinterpret_cast<float2*>(a.ln_stats + 2 * (int64_t)row) = make_float2(mean, rstd);
+      reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[lane] =
+          make_float4(dx * rstd * g4.x + be4.x, dy * rstd * g4.y + be4.y, dz * rstd * g4.z + be4.z, dw * rstd * g4.w + be4.w);
+    }
+  } else {
+    constexpr int C4 = 16;                                     // 64-column panels
+#pragma unroll 1
+    for (int pc = 0; pc < NT / 64; ++pc) {
+      float v[32];
+      tc::tmem_ld32(t_lane + pc * 64 + hsel * 32, v);
+      tc::tmem_ld_wait();
+      if (pc > 0) __syncthreads();                             // previous panel fully read back
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (hsel * 32 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < TM * C4 / LTHREADS; ++k) {
+        const int i = k * LTHREADS + threadIdx.x;
+        const int r = i / C4, c4 = i % C4;
+        const int row = row0 + r;
+        if (row >= a.n_rows) continue;
+        const int col = n0 + pc * 64 + c4 * 4;
+        float4 o = *ctile<C4>(sC, r, c4);
+        if constexpr (EPI == 2) {
+          const float4 u = __ldg(reinterpret_cast<const float4*>(a.gelu_u + (int64_t)row * a.ldu + col));
+          o.x *= gelu_grad_f(u.x); o.y *= gelu_grad_f(u.y); o.z *= gelu_grad_f(u.z); o.w *= gelu_grad_f(u.w);
+        } else {
+          if (a.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-          *reinterpret_cast<float4*>(o + c) = r;
+          if (a.add_src) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add + col));
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+          }
         }
+        *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + col) = o;
       }
     }
   }
@@ -260,18 +278,24 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_linear(const LinArgs a) {
   if (warp == 0) tc::tmem_free(tmem, NT);
 }
 
-template <int NT, int EPI>
-int launch_linear(const LinArgs& a, cudaStream_t stream) {
-  const int smem = (a.precision == 3 ? 2 : 1) * (TM * KC * 2 + NT * KC * 2) + 1024;
+template <int NT, int EPI, bool POS>
+int launch_linear_impl(const LinArgs& a, cudaStream_t stream) {
+  const int smem = (a.precision == 3 ? 2 : 1) * (TM * KC * 2 + NT * KC * 2) + 1024;   // >= 64 KB: holds the epilogue tile
   static bool configured = false;
   if (!configured) {
-    GM_CUDA(cudaFuncSetAttribute(k_tc_linear<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TM * KC * 2 + NT * KC * 2) + 1024));
+    GM_CUDA(cudaFuncSetAttribute(k_tc_linear<NT, EPI, POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TM * KC * 2 + NT * KC * 2) + 1024));
     configured = true;
   }
   const dim3 grid(gm_div_up(a.n_rows, TM), a.N_total / NT);
-  k_tc_linear<NT, EPI><<<grid, NTHREADS, smem, stream>>>(a);
+  k_tc_linear<NT, EPI, POS><<<grid, LTHREADS, smem, stream>>>(a);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
+}
+
+template <int NT, int EPI>
+int launch_linear(const LinArgs& a, cudaStream_t stream) {
+  if (NT == 128 && EPI == 0 && a.pos_table && a.pos_slabs > 0) return launch_linear_impl<128, 0, true>(a, stream);
+  return launch_linear_impl<NT, EPI, false>(a, stream);
 }
 
 
