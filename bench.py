@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--samples-per-gpu", type=int, default=4)     # data.samples_per_gpu of the config
     ap.add_argument("--sweeps", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--list-only", action="store_true",
+                    help="profiler runs: W warm-up + K resident steps, then exit without the e2e / roofline / CPU legs")
     ap.add_argument("--sra-impl", default="tc1", choices=["tc1", "tc3", "glue"],
                     help="tc1: bf16 tensor-core SRA layers (BASELINE config 'bf16'); tc3: bf16x3 split (fp32 parity); "
                          "glue: library GEMMs")
@@ -243,6 +245,13 @@ def main():
     ms = timed_loop(step_resident, K)             # the headline number: no per-kernel instrumentation
     launches = L.launch_count()
     barrier()
+    if args.list_only:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps(dict(list_only=True, ms_per_step=ms / K, gpu_launches=launches)))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # same K steps again with CUDA events around every C-ABI call / stack kernel (roofline + kernel table);
     # the events cost ~5-8 % so they are kept out of the headline loop
     L.start_timing()

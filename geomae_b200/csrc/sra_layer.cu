@@ -46,7 +46,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* dst_hi, uint8_t* dst_lo, con
   constexpr int CPR = COLS / 8;                 // 16-byte chunks per row
   constexpr int BLOCK_BYTES = ROWS * tc::LINE_BYTES;
   constexpr int ITEMS = ROWS * CPR / NTHR;      // per thread
-  constexpr int UNROLL = 8;
+  constexpr int UNROLL = POS ? 4 : 8;           // the position prologue doubles the loads in flight per item
   const float* pos_table = POS ? pos_table_ : nullptr;
   static_assert(ITEMS % UNROLL == 0, "tile size must be a multiple of the staging unroll");
 #pragma unroll 1
@@ -104,7 +104,7 @@ __device__ __forceinline__ float4* ctile(float* base, int row, int c4) {
 
 // EPI: 0 = acc (+bias) (+add_src); 1 = LayerNorm(acc + bias + add_src); 2 = acc * gelu'(u)
 template <int NT, int EPI, bool POS>
-__global__ void __launch_bounds__(LTHREADS) k_tc_linear(const LinArgs a) {
+__global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ __align__(8) uint64_t mbar_w;      // weight-image bulk copies
@@ -195,12 +195,11 @@ __global__ void __launch_bounds__(LTHREADS) k_tc_linear(const LinArgs a) {
       tc::mma_commit(&mbar);
     }
   }
-  tc::mbar_wait(&mbar, (n_chunks - 1) & 1);
-  tc::fence_after_sync();
-
   // ---- epilogue.  The accumulator row of a token is one TMEM lane; it is drained row-per-thread into a
   // swizzled fp32 tile in (now free) operand shared memory and read back row-contiguously, so every global
-  // access of the epilogue (bias, residual, GELU input, outputs) is a coalesced 128-bit access.
+  // access of the epilogue (bias, residual, GELU input, outputs) is a coalesced 128-bit access.  The epilogue's
+  // global operands are PREFETCHED into registers before waiting on the MMA barrier (and panel p+1's while panel
+  // p is written), so their L2/DRAM latency overlaps the tensor-core work instead of serialising behind it.
   float* sC = reinterpret_cast<float*>(smem);
   const int q = warp & 3, hsel = warp >> 2;                    // TMEM lane quarter, column half
   const int trow = q * 32 + lane;                              // tile row drained by this thread
@@ -208,6 +207,22 @@ __global__ void __launch_bounds__(LTHREADS) k_tc_linear(const LinArgs a) {
   if constexpr (EPI == 1) {
     static_assert(EPI != 1 || NT == 128, "LayerNorm epilogue needs the whole row in one CTA");
     constexpr int C4 = 32;                                     // 128 columns
+    constexpr int RPW = TM / (LTHREADS / 32);                  // rows per warp (16), handled in two batches of 8
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + lane);
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma) + lane);
+    const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.ln_beta) + lane);
+    float4 res[RPW / 2];
+    auto fetch = [&](int batch) {
+#pragma unroll
+      for (int j = 0; j < RPW / 2; ++j) {
+        const int row = row0 + warp + (LTHREADS / 32) * (batch * (RPW / 2) + j);
+        res[j] = row < a.n_rows ? __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add) + lane)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    fetch(0);
+    tc::mbar_wait(&mbar, (n_chunks - 1) & 1);
+    tc::fence_after_sync();
 #pragma unroll
     for (int half = 0; half < 2; ++half) {                     // this warp: columns hsel*64 + half*32 ..
       float v[32];
@@ -219,28 +234,57 @@ __global__ void __launch_bounds__(LTHREADS) k_tc_linear(const LinArgs a) {
     }
     __syncthreads();
     // one warp per row, one float4 per lane: s = acc + bias + residual; exact two-pass statistics; write s, LN(s)
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + lane);
-    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma) + lane);
-    const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.ln_beta) + lane);
-    for (int r = warp; r < TM; r += LTHREADS / 32) {
-      const int row = row0 + r;
-      if (row >= a.n_rows) break;
-      float4 v = *ctile<C4>(sC, r, lane);
-      const float4 res = __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add) + lane);
-      v.x += b4.x + res.x; v.y += b4.y + res.y; v.z += b4.z + res.z; v.w += b4.w + res.w;
-      const float mean = gm_warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / NT);
-      const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-      const float var = gm_warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / NT);
-      const float rstd = rsqrtf(var + a.ln_eps);
-      if (a.ln_in) reinterpret_cast<float4*>(a.ln_in + (int64_t)row * NT)[lane] = v;
-      if (a.ln_stats && lane == 0) *reinterpret_cast<float2*>(a.ln_stats + 2 * (int64_t)row) = make_float2(mean, rstd);
-      reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[lane] =
-          make_float4(dx * rstd * g4.x + be4.x, dy * rstd * g4.y + be4.y, dz * rstd * g4.z + be4.z, dw * rstd * g4.w + be4.w);
+#pragma unroll
+    for (int batch = 0; batch < 2; ++batch) {
+      float4 cur[RPW / 2];
+#pragma unroll
+      for (int j = 0; j < RPW / 2; ++j) cur[j] = res[j];
+      if (batch == 0) fetch(1);
+#pragma unroll
+      for (int j = 0; j < RPW / 2; ++j) {
+        const int r = warp + (LTHREADS / 32) * (batch * (RPW / 2) + j);
+        const int row = row0 + r;
+        if (row < a.n_rows) {
+          float4 v = *ctile<C4>(sC, r, lane);
+          v.x += b4.x + cur[j].x; v.y += b4.y + cur[j].y; v.z += b4.z + cur[j].z; v.w += b4.w + cur[j].w;
+          const float mean = gm_warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / NT);
+          const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+          const float var = gm_warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / NT);
+          const float rstd = rsqrtf(var + a.ln_eps);
+          if (a.ln_in) reinterpret_cast<float4*>(a.ln_in + (int64_t)row * NT)[lane] = v;
+          if (a.ln_stats && lane == 0) *reinterpret_cast<float2*>(a.ln_stats + 2 * (int64_t)row) = make_float2(mean, rstd);
+          reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[lane] =
+              make_float4(dx * rstd * g4.x + be4.x, dy * rstd * g4.y + be4.y, dz * rstd * g4.z + be4.z, dw * rstd * g4.w + be4.w);
+        }
+      }
     }
   } else {
     constexpr int C4 = 16;                                     // 64-column panels
-#pragma unroll 1
-    for (int pc = 0; pc < NT / 64; ++pc) {
+    constexpr int NP = NT / 64;                                // panels
+    constexpr int RI = TM * C4 / LTHREADS;                     // rows per thread and panel (8)
+    const int c4 = threadIdx.x % C4, rbase = threadIdx.x / C4; // this thread: column quad c4 of rows rbase + 16 k
+    const float* esrc = EPI == 2 ? a.gelu_u : a.add_src;       // the per-element global operand (may be null for EPI 0)
+    const int eld = EPI == 2 ? a.ldu : a.ld_add;
+    float4 bias4[NP];
+#pragma unroll
+    for (int pc = 0; pc < NP; ++pc)
+      bias4[pc] = (EPI == 0 && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + pc * 64 + c4 * 4))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pre[RI];
+    auto fetch = [&](int pc) {
+#pragma unroll
+      for (int k = 0; k < RI; ++k) {
+        const int row = row0 + rbase + (LTHREADS / C4) * k;
+        pre[k] = (esrc && row < a.n_rows)
+                     ? __ldg(reinterpret_cast<const float4*>(esrc + (int64_t)row * eld + n0 + pc * 64 + c4 * 4))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    fetch(0);
+    tc::mbar_wait(&mbar, (n_chunks - 1) & 1);
+    tc::fence_after_sync();
+#pragma unroll
+    for (int pc = 0; pc < NP; ++pc) {
       float v[32];
       tc::tmem_ld32(t_lane + pc * 64 + hsel * 32, v);
       tc::tmem_ld_wait();
@@ -248,28 +292,25 @@ __global__ void __launch_bounds__(LTHREADS) k_tc_linear(const LinArgs a) {
 #pragma unroll
       for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (hsel * 32 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
       __syncthreads();
+      float4 cur[RI];
 #pragma unroll
-      for (int k = 0; k < TM * C4 / LTHREADS; ++k) {
-        const int i = k * LTHREADS + threadIdx.x;
-        const int r = i / C4, c4 = i % C4;
+      for (int k = 0; k < RI; ++k) cur[k] = pre[k];
+      if (pc + 1 < NP) fetch(pc + 1);
+#pragma unroll
+      for (int k = 0; k < RI; ++k) {
+        const int r = rbase + (LTHREADS / C4) * k;
         const int row = row0 + r;
-        if (row >= a.n_rows) continue;
-        const int col = n0 + pc * 64 + c4 * 4;
-        float4 o = *ctile<C4>(sC, r, c4);
-        if constexpr (EPI == 2) {
-          const float4 u = __ldg(reinterpret_cast<const float4*>(a.gelu_u + (int64_t)row * a.ldu + col));
-          o.x *= gelu_grad_f(u.x); o.y *= gelu_grad_f(u.y); o.z *= gelu_grad_f(u.z); o.w *= gelu_grad_f(u.w);
-        } else {
-          if (a.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        if (row < a.n_rows) {
+          float4 o = *ctile<C4>(sC, r, c4);
+          if constexpr (EPI == 2) {
+            const float4 u = cur[k];
+            o.x *= gelu_grad_f(u.x); o.y *= gelu_grad_f(u.y); o.z *= gelu_grad_f(u.z); o.w *= gelu_grad_f(u.w);
+          } else {
+            o.x += bias4[pc].x + cur[k].x; o.y += bias4[pc].y + cur[k].y;
+            o.z += bias4[pc].z + cur[k].z; o.w += bias4[pc].w + cur[k].w;
           }
-          if (a.add_src) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add + col));
-            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-          }
+          *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + n0 + pc * 64 + c4 * 4) = o;
         }
-        *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + col) = o;
       }
     }
   }

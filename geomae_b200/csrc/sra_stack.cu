@@ -101,7 +101,10 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
     GM_TRY(lin(x, d, n, d, L.in_proj_w, d, 3 * d, 0, L.in_proj_b, 3 * d, S.qkv, 3 * d, p, stream, &e, L.p_in_proj));
     {
       Span span(2, 0.0, stream);
-      GM_TRY(geomae_sra_attention_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
+      if (p == 1)    // bf16 mode: QK^T / PV tiles on the tensor cores (sra_attention_tc.cu)
+        GM_TRY(geomae_sra_attention_tc_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
+      else
+        GM_TRY(geomae_sra_attention_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
     }
     geomae_linear_args e1{};
     e1.add_src = x; e1.ld_add = d; e1.ln_gamma = L.norm1_w; e1.ln_beta = L.norm1_b; e1.ln_eps = L.ln_eps;
@@ -196,8 +199,12 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main, nullptr, L.p_out_proj));
     {
       Span span(3, 0.0, main);
-      GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
-                                      dd, main));
+      if (p == 1)
+        GM_TRY(geomae_sra_attention_tc_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
+                                           main));
+      else
+        GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
+                                        dd, main));
     }
     GM_TRY(hand_off(main, side));
     GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, side, c->pos_table, w.tok_cell, 2, 0));

@@ -144,6 +144,8 @@ class _Sigs:
     geomae_scatter_reduce_bwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
     geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]
     geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
+    geomae_sra_attention_tc_fwd = [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]
+    geomae_sra_attention_tc_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]
     geomae_tc_linear = [C.POINTER(LinearArgs), _p]
     geomae_tc_wgrad = [C.POINTER(WgradArgs), _p]
     geomae_sra_stack_forward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p]
@@ -169,7 +171,8 @@ _calls = {}         # name -> number of C-ABI calls (bench.py reports kernel lau
 # kernels launched per C-ABI call (upper bound for the optional ones), for the gpu_launches claim
 LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=8, geom_targets=1, dense_targets=1, coors_bitmap=4,
                          token_map=1, window_csr=3, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
-                         scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=2, adamw_step=2,
+                         scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=2, sra_attention_tc_fwd=1,
+                         sra_attention_tc_bwd=1, adamw_step=2,
                          tc_linear=1, tc_wgrad=1, layernorm_bwd=1, geom_loss_fwd=3, geom_loss_bwd=1)
 # sra_stack_forward / _backward launch 5 / 11 kernels per layer: counted by the caller via add_launches()
 

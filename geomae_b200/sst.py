@@ -12,17 +12,22 @@ from . import lib as L
 from .windows import WindowLayout, pos_table
 
 
-def _attn_fwd(qkv, win, n_heads):
+def _attn_fwd(qkv, win, n_heads, tc=False):
+    """tc=False: fp32 SIMT kernel (parity mode); tc=True: bf16 tensor-core kernel (csrc/sra_attention_tc.cu)."""
     n, three_d = qkv.shape
     out = torch.empty((n, three_d // 3), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((n, n_heads), dtype=torch.float32, device=qkv.device)
-    L.run("sra_attention_fwd", L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]),
-          L.ptr(win["tok_win"]), L.ptr(out), L.ptr(lse), L.stream_ptr(qkv.device))
+    L.run("sra_attention_tc_fwd" if tc else "sra_attention_fwd", L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]),
+          L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(out), L.ptr(lse), L.stream_ptr(qkv.device))
     return out, lse
 
 
-def _attn_bwd(qkv, out, lse, d_out, win, n_heads):
+def _attn_bwd(qkv, out, lse, d_out, win, n_heads, tc=False):
     d_qkv = torch.empty_like(qkv)
+    if tc:
+        L.run("sra_attention_tc_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0], n_heads,
+              L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(d_qkv), L.stream_ptr(qkv.device))
+        return d_qkv
     scratch = torch.empty((qkv.shape[0], n_heads), dtype=torch.float32, device=qkv.device)
     L.run("sra_attention_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0], n_heads,
           L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(d_qkv), L.ptr(scratch),
@@ -34,17 +39,17 @@ class _SRAAttention(torch.autograd.Function):
     """out[i] = softmax_j(q_i.k_j / sqrt(hd)) v_j over the tokens j sharing i's window."""
 
     @staticmethod
-    def forward(ctx, qkv, win, n_heads):
+    def forward(ctx, qkv, win, n_heads, tc=False):
         qkv = qkv.contiguous()
-        out, lse = _attn_fwd(qkv, win, n_heads)
+        out, lse = _attn_fwd(qkv, win, n_heads, tc)
         ctx.save_for_backward(qkv, out, lse)
-        ctx.win, ctx.n_heads = win, n_heads
+        ctx.win, ctx.n_heads, ctx.tc = win, n_heads, tc
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         qkv, out, lse = ctx.saved_tensors
-        return _attn_bwd(qkv, out, lse, d_out.contiguous(), ctx.win, ctx.n_heads), None, None
+        return _attn_bwd(qkv, out, lse, d_out.contiguous(), ctx.win, ctx.n_heads, ctx.tc), None, None, None
 
 
 def _grad_of(p):
@@ -69,7 +74,7 @@ class _SRALayerFn(torch.autograd.Function):
         cell = win["tok_cell"]
         qkv = tc_linear(x, mha.in_proj_weight, n_out=3 * d, bias=mha.in_proj_bias, pos_table=table, tok_cell=cell,
                         pos_slabs=2, precision=precision)
-        a, lse = _attn_fwd(qkv, win, nh)
+        a, lse = _attn_fwd(qkv, win, nh, precision == 1)
         y, s1, st1 = tc_linear(a, mha.out_proj.weight, n_out=d, bias=mha.out_proj.bias, add_src=x,
                                ln=(layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, True), precision=precision)
         u = tc_linear(y, layer.linear1.weight, n_out=layer.linear1.out_features, bias=layer.linear1.bias,
@@ -97,18 +102,18 @@ class _SRALayerFn(torch.autograd.Function):
         ds1 = layernorm_bwd(dy, s1, st1, layer.norm1.weight, g(layer.norm1.weight), g(layer.norm1.bias))
         da = tc_linear(ds1, mha.out_proj.weight, n_out=d, w_mn_major=True, precision=prec)
         tc_wgrad(ds1, a, g(mha.out_proj.weight), g(mha.out_proj.bias), precision=prec)
-        dqkv = _attn_bwd(qkv, a, lse, da, win, nh)
+        dqkv = _attn_bwd(qkv, a, lse, da, win, nh, prec == 1)
         dx = tc_linear(dqkv, mha.in_proj_weight, n_out=d, w_mn_major=True, add_src=ds1, precision=prec)
         tc_wgrad(dqkv, x, g(mha.in_proj_weight), g(mha.in_proj_bias), pos_table=table, tok_cell=win["tok_cell"],
                  pos_slabs=2, precision=prec)
         return dx, None, None, None, None
 
 
-def sra_attention(qkv, win, n_heads):
+def sra_attention(qkv, win, n_heads, tc=False):
     L.require_cuda(qkv, "qkv")
     if qkv.dtype != torch.float32:
         raise RuntimeError("sra_attention expects float32 q|k|v rows")
-    return _SRAAttention.apply(qkv, win, n_heads)
+    return _SRAAttention.apply(qkv, win, n_heads, tc)
 
 
 class WindowAttention(nn.Module):
@@ -284,7 +289,7 @@ class _SRAStackFn(torch.autograd.Function):
                               device=x.device)
         L.run("sra_stack_backward", C.byref(ctx.c), len(ctx.stack.layers), ctx.layers, ctx.saved, L.ptr(x), L.ptr(dz),
               L.ptr(dx), L.ptr(scratch), L.stream_ptr(x.device))
-        L.add_launches(12 * len(ctx.stack.layers) - 1)
+        L.add_launches((11 if ctx.c.precision == 1 else 12) * len(ctx.stack.layers) - 1)
         return dx, None, None, None, None
 
 
@@ -321,7 +326,7 @@ class _SRADualStackFn(torch.autograd.Function):
                               device=x.device)
         L.run("sra_stack2_backward", C.byref(c), nl, la, saved_a, lb, saved_b, L.ptr(x), L.ptr(dza), L.ptr(dzb), L.ptr(dxa),
               L.ptr(dxb), L.ptr(scratch), L.stream_ptr(x.device))
-        L.add_launches(24 * nl - 1)
+        L.add_launches((22 if c.precision == 1 else 24) * nl - 1)
         return dxa + dxb, None, None, None, None, None
 
 

@@ -215,6 +215,19 @@ int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* ls
                              int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr, const int32_t* win_tok,
                              const int32_t* tok_win, float* d_qkv, float* scratch, void* stream);
 
+/* The same attention with bf16 operands on the tensor cores (mma.sync m16n8k16, fp32 accumulate and softmax):
+ * windows are packed block-diagonally into 16-query x 16-key tiles; K|V of the contiguous CSR range a CTA can
+ * see are converted to bf16 while being staged into shared memory.  Same arguments and outputs as the fp32
+ * entry points above (no scratch: D = dO.O is recomputed from the staged rows).  Used by the SRA stack executor
+ * when precision == 1 (the bf16 benchmark mode); precision == 3 keeps the fp32 kernels.
+ * replaces: nn.MultiheadAttention core inside WindowAttention.forward
+ *           (models/sst/sst_basic_block.py:26-61) and its autograd backward. */
+int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
+                                const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse, void* stream);
+int geomae_sra_attention_tc_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
+                                int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr, const int32_t* win_tok,
+                                const int32_t* tok_win, float* d_qkv, void* stream);
+
 /* ------------------------------------------------ tensor-core dense layers */
 
 /* out[128-token tile, N] = prologue(A)[., K] x W + epilogue, on tcgen05 tensor cores (bf16 operands,

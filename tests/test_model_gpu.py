@@ -136,6 +136,34 @@ def test_sra_attention_forward_backward(small):
         np.testing.assert_allclose(x.grad.cpu().numpy(), qkv.grad.numpy(), rtol=2e-4, atol=2e-5)
 
 
+def test_sra_attention_tensor_core_kernel(small):
+    """bf16 tensor-core attention (precision-1 path) against the fp32 reference: bf16 operand rounding only."""
+    from geomae_b200.sst import sra_attention
+    from geomae_b200.windows import WindowLayout, WindowSpec
+    _, cfg, _, g, pb = small
+    spec = WindowSpec(cfg.window_shape, cfg.shifts)
+    all_rows = np.concatenate([g["ids_keep"], g["ids_mask"]])
+    gen = torch.Generator().manual_seed(1)
+    for n_rows in (2500, 37, len(all_rows)):          # 32-query and 64-query CTAs, ragged tails, one tiny set
+        rows = all_rows[:n_rows]
+        lay = WindowLayout.from_pillars(spec, pb, torch.from_numpy(rows).to(DEV))
+        n = rows.shape[0]
+        for s in (0, 1):
+            qkv = torch.randn(n, 384, generator=gen).requires_grad_(True)
+            d_out = torch.randn(n, 128, generator=gen)
+            ref = ref_attention(qkv, lay.tok_win[s, :n].cpu().long(), 8)
+            ref.backward(d_out)
+            x = qkv.detach().to(DEV).requires_grad_(True)
+            out = sra_attention(x, lay.shift(s), 8, tc=True)
+            out.backward(d_out.to(DEV))
+            torch.cuda.synchronize()
+            for got, want, name in ((out.detach().cpu(), ref.detach(), "out"), (x.grad.cpu(), qkv.grad, "d_qkv")):
+                assert torch.isfinite(got).all(), name
+                err = float((got - want).norm() / want.norm())
+                assert err < 1.5e-2, (name, n_rows, s, err)
+                assert float((got - want).abs().max()) < 0.15, (name, n_rows, s)
+
+
 def test_scatter_reduce_modes(small):
     from geomae_b200.voxel_encoder import scatter_reduce
     _, _, frames, _, pb = small
