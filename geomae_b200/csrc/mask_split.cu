@@ -107,7 +107,7 @@ extern "C" int geomae_mask_split(const int32_t* frame_starts, int32_t n_frames, 
                                  int64_t* ids_keep, int64_t* ids_mask, void* stream) {
   GM_REQUIRE(n_frames >= 0, "mask_split: negative frame count");
   if (n_frames == 0) return GEOMAE_OK;
-  GM_REQUIRE(frame_starts && ids_keep && ids_mask, "mask_split: null argument");
+  GM_REQUIRE(frame_starts, "mask_split: null frame_starts");   // ids_keep / ids_mask may be empty (null) lists
   GM_REQUIRE(keep_frac >= 0.0 && keep_frac <= 1.0, "mask_split: keep fraction %f not in [0,1]", keep_frac);
   k_mask_split<<<n_frames, 1024, 0, (cudaStream_t)stream>>>(frame_starts, n_frames, keep_frac, seed, ids_keep, ids_mask);
   GM_LAUNCH_CHECK();

@@ -14,7 +14,7 @@ namespace {
 
 constexpr int TM = 128;       // tokens per CTA
 constexpr int KC = 128;       // K elements staged per chunk
-constexpr int NTHREADS = 128;
+constexpr int NTHREADS = 256;    // k_tc_wgrad: 8 warps stage; warps w and w+4 share TMEM lane quarter w%4 and split the columns
 
 struct LinArgs {
   const float* A; int lda; int n_rows; int K;
@@ -31,9 +31,32 @@ struct LinArgs {
   int precision;
 };
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (F.gelu default, sst_basic_block.py:153-154) and its derivative, evaluated with the
+// Abramowitz-Stegun 7.1.26 rational form erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z)
+// (|error| <= 1.5e-7, i.e. fp32 rounding level): one MUFU.RCP + one MUFU.EX2 + 8 FMAs.  libdevice erff + expf
+// cost ~70 dependent instructions per element, which made the GELU prologue / GELU-gradient epilogue the
+// longest phase of three kernels (128 evaluations per thread at 8 warps per SM).  exp(-z^2) = exp(-x^2/2) is
+// shared between erf and the Gaussian density of the derivative.
+struct GeluParts { float cdf; float pdf_x; };    // Phi(x), x * phi(x)
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // argument in [1, inf): 1 ulp
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));  // 2 ulp; flushes to 0 below 2^-126
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  GeluParts r;
+  r.cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  r.pdf_x = x * e * 0.3989422804014327f;
+  return r;
+}
+__device__ __forceinline__ float gelu_f(float x) { return x * gelu_parts(x).cdf; }
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+  const GeluParts g = gelu_parts(x);
+  return g.cdf + g.pdf_x;
 }
 
 // Stage a [ROWS x COLS] fp32 tile (global rows row0.., columns col0..) as bf16 into swizzled 64-column blocks.
@@ -236,25 +259,43 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
     // one warp per row, one float4 per lane: s = acc + bias + residual; exact two-pass statistics; write s, LN(s)
 #pragma unroll
     for (int batch = 0; batch < 2; ++batch) {
-      float4 cur[RPW / 2];
+      // eight rows per batch, every step written for all eight at once so their shuffle reductions interleave
+      constexpr int RB = RPW / 2;
+      float4 v[RB];
+      float mean[RB], rstd[RB];
 #pragma unroll
-      for (int j = 0; j < RPW / 2; ++j) cur[j] = res[j];
+      for (int j = 0; j < RB; ++j) {
+        const int r = warp + (LTHREADS / 32) * (batch * RB + j);
+        v[j] = *ctile<C4>(sC, r, lane);
+        v[j].x += b4.x + res[j].x; v[j].y += b4.y + res[j].y; v[j].z += b4.z + res[j].z; v[j].w += b4.w + res[j].w;
+      }
       if (batch == 0) fetch(1);
 #pragma unroll
-      for (int j = 0; j < RPW / 2; ++j) {
-        const int r = warp + (LTHREADS / 32) * (batch * (RPW / 2) + j);
-        const int row = row0 + r;
+      for (int j = 0; j < RB; ++j) mean[j] = (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < RB; ++j) mean[j] += __shfl_xor_sync(0xffffffffu, mean[j], o);
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        mean[j] *= (1.0f / NT);
+        const float dx = v[j].x - mean[j], dy = v[j].y - mean[j], dz = v[j].z - mean[j], dw = v[j].w - mean[j];
+        rstd[j] = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < RB; ++j) rstd[j] += __shfl_xor_sync(0xffffffffu, rstd[j], o);
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int row = row0 + warp + (LTHREADS / 32) * (batch * RB + j);
         if (row < a.n_rows) {
-          float4 v = *ctile<C4>(sC, r, lane);
-          v.x += b4.x + cur[j].x; v.y += b4.y + cur[j].y; v.z += b4.z + cur[j].z; v.w += b4.w + cur[j].w;
-          const float mean = gm_warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / NT);
-          const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-          const float var = gm_warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / NT);
-          const float rstd = rsqrtf(var + a.ln_eps);
-          if (a.ln_in) reinterpret_cast<float4*>(a.ln_in + (int64_t)row * NT)[lane] = v;
-          if (a.ln_stats && lane == 0) *reinterpret_cast<float2*>(a.ln_stats + 2 * (int64_t)row) = make_float2(mean, rstd);
+          const float rs = rsqrtf(rstd[j] * (1.0f / NT) + a.ln_eps);
+          const float dx = v[j].x - mean[j], dy = v[j].y - mean[j], dz = v[j].z - mean[j], dw = v[j].w - mean[j];
+          if (a.ln_in) reinterpret_cast<float4*>(a.ln_in + (int64_t)row * NT)[lane] = v[j];
+          if (a.ln_stats && lane == 0) *reinterpret_cast<float2*>(a.ln_stats + 2 * (int64_t)row) = make_float2(mean[j], rs);
           reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[lane] =
-              make_float4(dx * rstd * g4.x + be4.x, dy * rstd * g4.y + be4.y, dz * rstd * g4.z + be4.z, dw * rstd * g4.w + be4.w);
+              make_float4(dx * rs * g4.x + be4.x, dy * rs * g4.y + be4.y, dz * rs * g4.z + be4.z, dw * rs * g4.w + be4.w);
         }
       }
     }
@@ -265,13 +306,10 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
     const int c4 = threadIdx.x % C4, rbase = threadIdx.x / C4; // this thread: column quad c4 of rows rbase + 16 k
     const float* esrc = EPI == 2 ? a.gelu_u : a.add_src;       // the per-element global operand (may be null for EPI 0)
     const int eld = EPI == 2 ? a.ldu : a.ld_add;
-    float4 bias4[NP];
-#pragma unroll
-    for (int pc = 0; pc < NP; ++pc)
-      bias4[pc] = (EPI == 0 && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + pc * 64 + c4 * 4))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 pre[RI];
+    float4 pre[RI], bias4;
     auto fetch = [&](int pc) {
+      bias4 = (EPI == 0 && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + pc * 64 + c4 * 4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < RI; ++k) {
         const int row = row0 + rbase + (LTHREADS / C4) * k;
@@ -283,7 +321,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
     fetch(0);
     tc::mbar_wait(&mbar, (n_chunks - 1) & 1);
     tc::fence_after_sync();
-#pragma unroll
+#pragma unroll 1
     for (int pc = 0; pc < NP; ++pc) {
       float v[32];
       tc::tmem_ld32(t_lane + pc * 64 + hsel * 32, v);
@@ -292,10 +330,6 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
 #pragma unroll
       for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (hsel * 32 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
       __syncthreads();
-      float4 cur[RI];
-#pragma unroll
-      for (int k = 0; k < RI; ++k) cur[k] = pre[k];
-      if (pc + 1 < NP) fetch(pc + 1);
 #pragma unroll
       for (int k = 0; k < RI; ++k) {
         const int r = rbase + (LTHREADS / C4) * k;
@@ -303,15 +337,16 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
         if (row < a.n_rows) {
           float4 o = *ctile<C4>(sC, r, c4);
           if constexpr (EPI == 2) {
-            const float4 u = cur[k];
+            const float4 u = pre[k];
             o.x *= gelu_grad_f(u.x); o.y *= gelu_grad_f(u.y); o.z *= gelu_grad_f(u.z); o.w *= gelu_grad_f(u.w);
           } else {
-            o.x += bias4[pc].x + cur[k].x; o.y += bias4[pc].y + cur[k].y;
-            o.z += bias4[pc].z + cur[k].z; o.w += bias4[pc].w + cur[k].w;
+            o.x += bias4.x + pre[k].x; o.y += bias4.y + pre[k].y;
+            o.z += bias4.z + pre[k].z; o.w += bias4.w + pre[k].w;
           }
           *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + n0 + pc * 64 + c4 * 4) = o;
         }
       }
+      if (pc + 1 < NP) fetch(pc + 1);          // in flight while the next panel is drained from TMEM
     }
   }
   tc::fence_before_sync();
@@ -354,7 +389,7 @@ struct WgradArgs {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(NTHREADS) k_tc_wgrad(const WgradArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 2) k_tc_wgrad(const WgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_slot;
@@ -362,7 +397,7 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_wgrad(const WgradArgs a) {
   constexpr int A_BYTES = TM * 128 * 2;             // dY tile: 128 tokens x 128 m-columns
   constexpr int B_BYTES = TM * NT * 2;              // X tile : 128 tokens x NT n-columns
   constexpr int ONES_BYTES = TM * tc::LINE_BYTES;   // one 64-column block
-  constexpr int TCOLS = NT == 256 ? 512 : 256;      // NT accumulator columns + 16 bias columns
+  constexpr int TCOLS = 256;                        // NT = 128: accumulator + 16 bias columns; NT = 256: accumulator only
   const bool x3 = a.precision == 3;
   uint8_t* sA = smem;
   uint8_t* sAlo = sA + A_BYTES;
@@ -377,7 +412,7 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_wgrad(const WgradArgs a) {
   if (tile_begin >= tile_end) return;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TCOLS);
   if (threadIdx.x == 0) tc::mbar_init(&mbar, 1);
-  const bool want_bias = a.db != nullptr && blockIdx.z == 0;
+  const bool want_bias = NT == 128 && a.db != nullptr && blockIdx.z == 0;
   // constant "ones" block: element (row, col 0) = 1.0
   for (int i = threadIdx.x; i < TM * 8; i += NTHREADS) {
     const int r = i >> 3, c = i & 7;
@@ -397,9 +432,13 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_wgrad(const WgradArgs a) {
       tc::mbar_wait(&mbar, (it - 1) & 1);
       tc::fence_after_sync();
     }
-    stage_tile<TM, 128>(sA, x3 ? sAlo : nullptr, a.dY, a.ldy, row0, a.n_rows, m0, nullptr, nullptr, 0, false);
-    stage_tile<TM, NT>(sB, x3 ? sBlo : nullptr, a.X, a.ldx, row0, a.n_rows, n0, use_pos ? a.pos_table : nullptr,
-                       a.tok_cell, a.N_total, a.x_gelu != 0);
+    stage_tile<TM, 128, NTHREADS, false>(sA, x3 ? sAlo : nullptr, a.dY, a.ldy, row0, a.n_rows, m0, nullptr, nullptr, 0, false);
+    if (use_pos)
+      stage_tile<TM, NT, NTHREADS, true>(sB, x3 ? sBlo : nullptr, a.X, a.ldx, row0, a.n_rows, n0, a.pos_table, a.tok_cell,
+                                         a.N_total, false);
+    else
+      stage_tile<TM, NT, NTHREADS, false>(sB, x3 ? sBlo : nullptr, a.X, a.ldx, row0, a.n_rows, n0, nullptr, nullptr, 0,
+                                          a.x_gelu != 0);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
@@ -434,10 +473,11 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_wgrad(const WgradArgs a) {
   }
   tc::mbar_wait(&mbar, (it - 1) & 1);
   tc::fence_after_sync();
-  const int m = m0 + warp * 32 + lane;                 // this thread's dW row
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const int qw = warp & 3, chalf = warp >> 2;          // TMEM lane quarter, column half
+  const int m = m0 + qw * 32 + lane;                   // this thread's dW row
+  const uint32_t t_lane = tmem + ((uint32_t)(qw * 32) << 16);
 #pragma unroll 1
-  for (int c0 = 0; c0 < NT; c0 += 32) {
+  for (int c0 = chalf * (NT / 2); c0 < (chalf + 1) * (NT / 2); c0 += 32) {
     float v[32];
     tc::tmem_ld32(t_lane + c0, v);
     tc::tmem_ld_wait();
@@ -450,7 +490,7 @@ __global__ void __launch_bounds__(NTHREADS) k_tc_wgrad(const WgradArgs a) {
                      : "memory");
     }
   }
-  if (want_bias) {
+  if (want_bias && chalf == 0) {
     float v[32];
     tc::tmem_ld32(t_lane + NT, v);
     tc::tmem_ld_wait();
@@ -481,11 +521,12 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
 // LayerNorm backward over saved (pre-LN row, mean, rstd): one warp per row, float4 per lane (C = 128).
 __global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dz, const float* __restrict__ s,
                                                 const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                int n_rows, float* ds, float* dgamma, float* dbeta) {
+                                                int n_rows, float* ds, float* dgamma, float* dbeta, float* dsum) {
   __shared__ float sg[8][128], sb[8][128];
+  __shared__ float ss[8][128];                  // column sums of ds (= bias gradient of the linear that produced the LN input)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
-  float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg;
+  float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg, accs = accg;
   for (int row = blockIdx.x * 8 + warp; row < n_rows; row += gridDim.x * 8) {
     const float4 d = __ldg(reinterpret_cast<const float4*>(dz + (int64_t)row * 128) + lane);
     const float4 x = __ldg(reinterpret_cast<const float4*>(s + (int64_t)row * 128) + lane);
@@ -496,21 +537,24 @@ __global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dz, co
     float s2 = (g.x * xh.x + g.y * xh.y) + (g.z * xh.z + g.w * xh.w);
     s1 = gm_warp_sum(s1) * (1.0f / 128.f);
     s2 = gm_warp_sum(s2) * (1.0f / 128.f);
-    reinterpret_cast<float4*>(ds + (int64_t)row * 128)[lane] =
-        make_float4(rstd * (g.x - s1 - xh.x * s2), rstd * (g.y - s1 - xh.y * s2), rstd * (g.z - s1 - xh.z * s2),
-                    rstd * (g.w - s1 - xh.w * s2));
+    const float4 o = make_float4(rstd * (g.x - s1 - xh.x * s2), rstd * (g.y - s1 - xh.y * s2), rstd * (g.z - s1 - xh.z * s2),
+                                 rstd * (g.w - s1 - xh.w * s2));
+    reinterpret_cast<float4*>(ds + (int64_t)row * 128)[lane] = o;
+    accs.x += o.x; accs.y += o.y; accs.z += o.z; accs.w += o.w;
     accg.x += d.x * xh.x; accg.y += d.y * xh.y; accg.z += d.z * xh.z; accg.w += d.w * xh.w;
     accb.x += d.x; accb.y += d.y; accb.z += d.z; accb.w += d.w;
   }
   reinterpret_cast<float4*>(sg[warp])[lane] = accg;
   reinterpret_cast<float4*>(sb[warp])[lane] = accb;
+  reinterpret_cast<float4*>(ss[warp])[lane] = accs;
   __syncthreads();
   if (threadIdx.x < 128) {
-    float tg = 0.f, tb = 0.f;
+    float tg = 0.f, tb = 0.f, ts = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { tg += sg[w][threadIdx.x]; tb += sb[w][threadIdx.x]; }
+    for (int w = 0; w < 8; ++w) { tg += sg[w][threadIdx.x]; tb += sb[w][threadIdx.x]; ts += ss[w][threadIdx.x]; }
     atomicAdd(dgamma + threadIdx.x, tg);
     atomicAdd(dbeta + threadIdx.x, tb);
+    if (dsum) atomicAdd(dsum + threadIdx.x, ts);
   }
 }
 
@@ -592,22 +636,25 @@ extern "C" int geomae_tc_wgrad(const geomae_wgrad_args* p, void* stream_) {
   a.dW = p->dW; a.ldw = p->ldw; a.db = p->db; a.M_total = p->M_total; a.N_total = p->N_total;
   a.precision = p->precision;
   const int n_tiles = gm_div_up(p->n_rows, TM);
-  const int slabs = (p->M_total / 128) * (p->N_total % 256 == 0 ? p->N_total / 256 : p->N_total / 128);
+  const int slabs = (p->M_total / 128) * ((p->N_total % 256 == 0 && !p->db) ? p->N_total / 256 : p->N_total / 128);
   int splits = (2 * GM_NUM_SMS + slabs - 1) / slabs;           // aim at ~2 CTAs per SM
   if (splits > n_tiles) splits = n_tiles;
   a.tiles_per_cta = gm_div_up(n_tiles, splits);
-  return (p->N_total % 256 == 0) ? launch_wgrad<256>(a, (cudaStream_t)stream_) : launch_wgrad<128>(a, (cudaStream_t)stream_);
+  // the 256-wide variant fills its TMEM allocation with the accumulator: no bias column there
+  return (p->N_total % 256 == 0 && !p->db) ? launch_wgrad<256>(a, (cudaStream_t)stream_)
+                                           : launch_wgrad<128>(a, (cudaStream_t)stream_);
 }
 
 extern "C" int geomae_layernorm_bwd(const float* d_out, const float* ln_in, const float* ln_stats, const float* gamma,
                                     int64_t n_rows, int32_t channels, float* d_in, float* d_gamma, float* d_beta,
-                                    void* stream) {
+                                    float* d_in_colsum, void* stream) {
   GM_REQUIRE(channels == 128, "layernorm_bwd: specialised for 128 channels (got %d)", channels);
   if (n_rows == 0) return GEOMAE_OK;
   GM_REQUIRE(d_out && ln_in && ln_stats && gamma && d_in && d_gamma && d_beta, "layernorm_bwd: null argument");
   int blocks = gm_div_up(n_rows, 8);
   if (blocks > GM_NUM_SMS * 4) blocks = GM_NUM_SMS * 4;
-  k_ln_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, ln_in, ln_stats, gamma, (int)n_rows, d_in, d_gamma, d_beta);
+  k_ln_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, ln_in, ln_stats, gamma, (int)n_rows, d_in, d_gamma, d_beta,
+                                                     d_in_colsum);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
 }

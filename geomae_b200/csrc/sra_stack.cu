@@ -178,10 +178,10 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     if (side_done[l & 1]) GM_CUDA(cudaStreamWaitEvent(main, side_done[l & 1], 0));   // set (l&1) free again
     {
       Span span(4, 0.0, main);
-      GM_TRY(geomae_layernorm_bwd(dz, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, main));
+      GM_TRY(geomae_layernorm_bwd(dz, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, L.g_lin2_b, main));
     }
     GM_TRY(hand_off(main, side));
-    GM_TRY(wgrad(ds2, d, S.u, f, n, L.g_lin2_w, f, L.g_lin2_b, d, f, p, side, nullptr, nullptr, 0, 1));
+    GM_TRY(wgrad(ds2, d, S.u, f, n, L.g_lin2_w, f, nullptr, d, f, p, side, nullptr, nullptr, 0, 1));   // bias: column sums of ds2 above
     geomae_linear_args e{};
     e.gelu_u = S.u; e.ldu = f; e.epilogue = 2;
     GM_TRY(lin(ds2, d, n, d, L.lin2_w, f, d, 1, nullptr, f, du, f, p, main, &e, L.p_lin2));
@@ -192,10 +192,10 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, dy, d, p, main, &e1, L.p_lin1));
     {
       Span span(4, 0.0, main);
-      GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, main));
+      GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, L.g_out_proj_b, main));
     }
     GM_TRY(hand_off(main, side));
-    GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, L.g_out_proj_b, d, d, p, side));
+    GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, nullptr, d, d, p, side));
     GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main, nullptr, L.p_out_proj));
     {
       Span span(3, 0.0, main);

@@ -62,11 +62,11 @@ def tc_wgrad(dY, X, dW, db=None, *, pos_table=None, tok_cell=None, pos_slabs=0, 
     L.run("tc_wgrad", C.byref(a), L.stream_ptr(dY.device))
 
 
-def layernorm_bwd(d_out, ln_in, ln_stats, gamma, d_gamma, d_beta):
-    """-> d_in; d_gamma / d_beta are accumulated in place."""
+def layernorm_bwd(d_out, ln_in, ln_stats, gamma, d_gamma, d_beta, d_in_colsum=None):
+    """-> d_in; d_gamma / d_beta (and, when given, the column sums of d_in) are accumulated in place."""
     d_in = torch.empty_like(d_out)
     L.run("layernorm_bwd", L.ptr(d_out), L.ptr(ln_in), L.ptr(ln_stats), L.ptr(gamma), d_out.shape[0], d_out.shape[1],
-          L.ptr(d_in), L.ptr(d_gamma), L.ptr(d_beta), L.stream_ptr(d_out.device))
+          L.ptr(d_in), L.ptr(d_gamma), L.ptr(d_beta), L.ptr(d_in_colsum), L.stream_ptr(d_out.device))
     return d_in
 
 

@@ -108,19 +108,29 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
         return torch.cat([nn.functional.pad(self.sub_voxel_layer_med(p), (1, 0), value=i) for i, p in enumerate(points)])
 
     @torch.no_grad()
-    def get_vanilla_mask_index(self, coors, batch_size, counts=None):
-        """…_ssl.py:287-304: per sample randperm(L) on the device, keep int(L*(1-ratio)).
-        ``counts`` (per-sample pillar counts on the host) avoids a device->host sync when the caller has them."""
+    def get_vanilla_mask_index(self, coors, batch_size, counts=None, frame_starts=None):
+        """…_ssl.py:287-304: per sample keep int(L*(1-ratio)) random pillars, mask the rest.
+
+        The reference draws torch.randperm(L) per sample; here ONE kernel (csrc/mask_split.cu) selects the same
+        number of pillars uniformly at random per frame (seeded from torch's CPU generator) and returns both index
+        lists in ascending pillar order — the model only depends on the subset.  ``counts`` (per-sample pillar
+        counts on the host) and ``frame_starts`` (device int32 [B+1]) come for free from the scatter stage."""
+        dev = coors.device
         if counts is None:
             counts = torch.bincount(coors[:, 0].long(), minlength=batch_size).tolist()
-        keep, mask, start = [], [], 0
-        for n in counts:
-            len_keep = int(n * (1 - self.random_mask_ratio))
-            perm = torch.randperm(n, device=coors.device) + start
-            keep.append(perm[:len_keep])
-            mask.append(perm[len_keep:])
-            start += n
-        return torch.cat(keep), torch.cat(mask)
+        if frame_starts is None:
+            starts = [0]
+            for n in counts:
+                starts.append(starts[-1] + n)
+            frame_starts = torch.tensor(starts, dtype=torch.int32, device=dev)
+        keep_frac = 1 - self.random_mask_ratio
+        n_keep = sum(int(n * keep_frac) for n in counts)
+        ids_keep = torch.empty(n_keep, dtype=torch.int64, device=dev)
+        ids_mask = torch.empty(sum(counts) - n_keep, dtype=torch.int64, device=dev)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # CPU generator: follows torch.manual_seed
+        L.run("mask_split", L.ptr(frame_starts), len(counts), float(keep_frac), seed, L.ptr(ids_keep), L.ptr(ids_mask),
+              L.stream_ptr(dev))
+        return ids_keep, ids_mask
 
     # ------------------------------------------------------------------ hot path
     def extract_feat(self, points, ids=None):
@@ -128,7 +138,7 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
         pb = scatter_frames(self.geom, points)
         voxel_features, feature_coors = self.voxel_encoder(pb)
         ids_keep, ids_mask = ids if ids is not None else self.get_vanilla_mask_index(
-            feature_coors, batch_size, pb.pillars_per_frame())
+            feature_coors, batch_size, pb.pillars_per_frame(), pb.counts[4:])
         fused = getattr(self, "fused_loss", True)
         with torch.no_grad():
             normal, curv = pb.geom_targets()

@@ -154,10 +154,11 @@ class _Sigs:
                                  C.POINTER(SRASaved), _p, _p]
     geomae_sra_stack2_backward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved),
                                   C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p, _p, _p]
-    geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p]
+    geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]
     geomae_geom_loss_fwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p]
     geomae_geom_loss_bwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p, _p, _p, _p,
                             _p, _p]
+    geomae_mask_split = [_p, _i32, C.c_double, C.c_uint64, _p, _p, _p]
     geomae_pack_weights = [_i32, _p, _p, _p, _p, _p, _p]
     geomae_profile_enable = [_i32]
     geomae_profile_read = [_p, _p, _p]

@@ -94,14 +94,16 @@ class _SRALayerFn(torch.autograd.Function):
         d, nh = layer.win_attn.d_model, layer.win_attn.nhead
         g = _grad_of
         dz = dz.contiguous()
-        ds2 = layernorm_bwd(dz, s2, st2, layer.norm2.weight, g(layer.norm2.weight), g(layer.norm2.bias))
+        ds2 = layernorm_bwd(dz, s2, st2, layer.norm2.weight, g(layer.norm2.weight), g(layer.norm2.bias),
+                            g(layer.linear2.bias))
         du = tc_linear(ds2, layer.linear2.weight, n_out=u.shape[1], w_mn_major=True, gelu_u=u, precision=prec)
-        tc_wgrad(ds2, u, g(layer.linear2.weight), g(layer.linear2.bias), x_gelu=True, precision=prec)
+        tc_wgrad(ds2, u, g(layer.linear2.weight), None, x_gelu=True, precision=prec)
         dy = tc_linear(du, layer.linear1.weight, n_out=d, w_mn_major=True, add_src=ds2, precision=prec)
         tc_wgrad(du, y, g(layer.linear1.weight), g(layer.linear1.bias), precision=prec)
-        ds1 = layernorm_bwd(dy, s1, st1, layer.norm1.weight, g(layer.norm1.weight), g(layer.norm1.bias))
+        ds1 = layernorm_bwd(dy, s1, st1, layer.norm1.weight, g(layer.norm1.weight), g(layer.norm1.bias),
+                            g(mha.out_proj.bias))
         da = tc_linear(ds1, mha.out_proj.weight, n_out=d, w_mn_major=True, precision=prec)
-        tc_wgrad(ds1, a, g(mha.out_proj.weight), g(mha.out_proj.bias), precision=prec)
+        tc_wgrad(ds1, a, g(mha.out_proj.weight), None, precision=prec)
         dqkv = _attn_bwd(qkv, a, lse, da, win, nh, prec == 1)
         dx = tc_linear(dqkv, mha.in_proj_weight, n_out=d, w_mn_major=True, add_src=ds1, precision=prec)
         tc_wgrad(dqkv, x, g(mha.in_proj_weight), g(mha.in_proj_bias), pos_table=table, tok_cell=win["tok_cell"],

@@ -156,6 +156,15 @@ int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* coors, int64
                         uint32_t* bitmap, int32_t* word_rank, int32_t* scan_tmp, int32_t* counts,
                         int32_t* tok_of_pillar, void* stream);
 
+/* Random visible / masked split of each frame's pillars: frame f (pillars frame_starts[f] .. frame_starts[f+1])
+ * keeps exactly k_f = (int)(L_f * keep_frac) pillars chosen uniformly at random (hash of (seed, f, index), k-th
+ * smallest found by radix select — no sort); ids_keep [sum k_f] and ids_mask [sum (L_f - k_f)] receive the pillar
+ * rows frame by frame, ascending inside a frame.  frame_starts: device int32 [n_frames + 1].
+ * replaces: MultiSubVoxelDynamicVoxelNetSSL.get_vanilla_mask_index
+ *           (detectors/multi_sub_voxel_dynamic_voxelnet_ssl.py:287-304; per-sample torch.randperm). */
+int geomae_mask_split(const int32_t* frame_starts, int32_t n_frames, double keep_frac, uint64_t seed,
+                      int64_t* ids_keep, int64_t* ids_mask, void* stream);
+
 /* tok_of_pillar[rows[i]] = i, every other pillar -1 (rows = ids_keep, or [ids_keep; ids_mask]). */
 int geomae_token_map(const int64_t* rows, int64_t n_tokens, int32_t* tok_of_pillar, int64_t n_pillars,
                      void* stream);
@@ -278,11 +287,14 @@ typedef struct geomae_wgrad_args {
 int geomae_tc_wgrad(const geomae_wgrad_args* args, void* stream);
 
 /* LayerNorm backward from the saved pre-LN rows and (mean, rstd): d_in, and d_gamma / d_beta accumulated
- * (+=) into their buffers.  channels must be 128.
+ * (+=) into their buffers.  channels must be 128.  d_in_colsum (optional, [channels], +=) receives the column
+ * sums of d_in, which are the bias gradient of the linear layer whose output (+ residual) was normalised
+ * (out_proj for norm1, linear2 for norm2) — that bias reduction then costs nothing extra.
  * replaces: ATen layer_norm backward (GammaBetaBackward + grad_input kernels) under nn.LayerNorm
- *           (sst_basic_block.py:76-77,96,100). */
+ *           (sst_basic_block.py:76-77,96,100) and the bias-gradient column reductions of linear2 / out_proj. */
 int geomae_layernorm_bwd(const float* d_out, const float* ln_in, const float* ln_stats, const float* gamma,
-                         int64_t n_rows, int32_t channels, float* d_in, float* d_gamma, float* d_beta, void* stream);
+                         int64_t n_rows, int32_t channels, float* d_in, float* d_gamma, float* d_beta,
+                         float* d_in_colsum, void* stream);
 
 /* ------------------------------------------------------- SRA layer stacks */
 

@@ -110,7 +110,9 @@ def test_layernorm_backward():
     mean = sd.mean(dim=1)
     rstd = torch.rsqrt(sd.var(dim=1, unbiased=False) + 1e-5)
     dg, db = torch.zeros(128, device="cuda"), torch.zeros(128, device="cuda")
-    ds = layernorm_bwd(dz, sd, torch.stack([mean, rstd], dim=1).contiguous(), gamma.detach(), dg, db)
+    colsum = torch.zeros(128, device="cuda")
+    ds = layernorm_bwd(dz, sd, torch.stack([mean, rstd], dim=1).contiguous(), gamma.detach(), dg, db, colsum)
     torch.testing.assert_close(ds, s.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(colsum, s.grad.sum(0), rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(dg, gamma.grad, rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(db, beta.grad, rtol=1e-4, atol=1e-3)

@@ -52,6 +52,7 @@ for name, rows in sets.items():
     if "attn" in which:
         out, lse = _attn_fwd(qkv, win, 8)
         print(f"  attn fwd {timeit(lambda: _attn_fwd(qkv, win, 8)):8.1f} us   bwd {timeit(lambda: _attn_bwd(qkv, out, lse, d128, win, 8)):8.1f} us")
+        print(f"  attn (bf16 mma) fwd {timeit(lambda: _attn_fwd(qkv, win, 8, True)):8.1f} us   bwd {timeit(lambda: _attn_bwd(qkv, out, lse, d128, win, 8, True)):8.1f} us")
     for prec in (1, 3):
         if "linear" in which:
             W384, b384 = torch.randn(384, 128, device=dev) * 0.1, torch.randn(384, device=dev)
@@ -70,7 +71,7 @@ for name, rows in sets.items():
             dW2, db2 = torch.zeros(128, 256, device=dev), torch.zeros(128, device=dev)
             dW3, db3 = torch.zeros(384, 128, device=dev), torch.zeros(384, device=dev)
             t = [timeit(lambda: tc_wgrad(d128, x, dW1, db1, precision=prec)),
-                 timeit(lambda: tc_wgrad(d128, u, dW2, db2, x_gelu=True, precision=prec)),
+                 timeit(lambda: tc_wgrad(d128, u, dW2, None, x_gelu=True, precision=prec)),
                  timeit(lambda: tc_wgrad(qkv, x, dW3, db3, pos_table=table, tok_cell=win["tok_cell"], pos_slabs=2, precision=prec))]
             print(f"  p{prec} wgrad 128x128 {t[0]:.1f} 128x256(gelu) {t[1]:.1f} 384x128(pos) {t[2]:.1f} us")
     if "ln" in which:
