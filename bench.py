@@ -62,28 +62,41 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
+
+    def wait_ready(self, timeout=5.0):
+        """Block until the first sample arrived, so nvidia-smi's initialisation is over before anything is timed."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Wall-clock bracket of a timed region: only samples taken inside brackets are reported."""
+        self.windows.append(time.time())
 
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        w = self.windows
+        inside = lambda t: any(w[i] <= t <= w[i + 1] for i in range(0, len(w) - 1, 2)) if len(w) >= 2 else True  # noqa: E731
+        rows = [r for r in self.rows if len(r) >= 10 and inside(r[-1])]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
                     reasons=reasons, samples=len(sm))
 
@@ -234,15 +247,18 @@ def main():
         last["loss"] = trainer.train_step_from_host(host[i % len(host)])[0]
         last["loss_host"] = float(last["loss"])             # D2H read of the step's loss, every step
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                           # before the warm-up: nvidia-smi's start-up (NVML init) stalls launches
+        sampler.wait_ready()
     for i in range(W):
         step_resident(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     import ctypes as C
     L.reset_call_counts()
+    sampler.mark()
     ms = timed_loop(step_resident, K)             # the headline number: no per-kernel instrumentation
+    sampler.mark()
     launches = L.launch_count()
     barrier()
     if args.list_only:
@@ -266,7 +282,9 @@ def main():
     for i in range(min(W, 2)):
         step_host(i)
     barrier()
+    sampler.mark()
     ms_e2e = timed_loop(step_host, K)
+    sampler.mark()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)

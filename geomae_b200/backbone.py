@@ -14,6 +14,78 @@ from .voxel import PillarBatch, VoxelGeometry
 from .windows import WindowLayout, WindowSpec
 
 
+class FusedHeads:
+    """The six prediction heads (…top_only.py:279-300) as TWO tensor-core GEMMs: the five heads that read the
+    centroid decoder share one [768, 128] weight (rows: low | cls_low | med | cls_med | top | zero pad), the normal
+    head of the density decoder is padded to 128 rows.  Outputs stay column slices of the fused result — the loss
+    kernel reads them with a row stride — and the backward is one dX GEMM + one weight-gradient GEMM per decoder."""
+
+    def __init__(self, bb):
+        self.heads_c = [bb.decoder_pred_low, bb.cls_pred_low, bb.decoder_pred_med, bb.cls_pred_med, bb.decoder_pred_top]
+        self.head_d = bb.decoder_pred_density_top
+        self.offsets, off = [], 0
+        for h in self.heads_c:
+            self.offsets.append(off)
+            off += h.out_features
+        self.n_c = off                                  # 723 for the GeoMAE config
+        self.width_c = (off + 127) // 128 * 128         # 768
+        self.width_d = 128
+
+    def cat_params(self, dev):
+        wc = torch.zeros((self.width_c, 128), dtype=torch.float32, device=dev)
+        bc = torch.zeros(self.width_c, dtype=torch.float32, device=dev)
+        torch.cat([h.weight.detach() for h in self.heads_c], out=wc[:self.n_c])
+        torch.cat([h.bias.detach() for h in self.heads_c], out=bc[:self.n_c])
+        wd = torch.zeros((self.width_d, 128), dtype=torch.float32, device=dev)
+        bd = torch.zeros(self.width_d, dtype=torch.float32, device=dev)
+        wd[:self.head_d.out_features].copy_(self.head_d.weight.detach())
+        bd[:self.head_d.out_features].copy_(self.head_d.bias.detach())
+        return wc, bc, wd, bd
+
+
+class _FusedHeadsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cen, den, n_vis, fh: FusedHeads, precision):
+        from .dense import pack_weight, tc_linear
+        cen, den = cen.contiguous(), den.contiguous()
+        wc, bc, wd, bd = fh.cat_params(cen.device)
+        pc, pd = pack_weight(wc, precision == 3), pack_weight(wd, precision == 3)
+        out_c = tc_linear(cen[n_vis:], wc, n_out=fh.width_c, bias=bc, precision=precision, packed=pc)
+        out_d = tc_linear(den[n_vis:], wd, n_out=fh.width_d, bias=bd, precision=precision, packed=pd)
+        ctx.save_for_backward(cen, den)
+        ctx.keep = (n_vis, fh, precision, wc, wd, pc, pd)
+        return out_c, out_d
+
+    @staticmethod
+    def backward(ctx, d_c, d_d):
+        from .dense import tc_linear, tc_wgrad
+        cen, den = ctx.saved_tensors
+        n_vis, fh, precision, wc, wd, pc, pd = ctx.keep
+        d_c, d_d = d_c.contiguous(), d_d.contiguous()
+        d_cen, d_den = torch.zeros_like(cen), torch.zeros_like(den)
+        tc_linear(d_c, wc, n_out=128, w_mn_major=True, out=d_cen[n_vis:], precision=precision, packed=pc)
+        tc_linear(d_d, wd, n_out=128, w_mn_major=True, out=d_den[n_vis:], precision=precision, packed=pd)
+        gw_c, gb_c = torch.zeros_like(wc), torch.zeros(fh.width_c, dtype=torch.float32, device=cen.device)
+        gw_d, gb_d = torch.zeros_like(wd), torch.zeros(fh.width_d, dtype=torch.float32, device=cen.device)
+        tc_wgrad(d_c, cen[n_vis:], gw_c, gb_c, precision=precision)
+        tc_wgrad(d_d, den[n_vis:], gw_d, gb_d, precision=precision)
+        dst, src = [], []
+        for h, off in zip(fh.heads_c, fh.offsets):
+            for p, g in ((h.weight, gw_c[off:off + h.out_features]), (h.bias, gb_c[off:off + h.out_features])):
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                dst.append(p.grad)
+                src.append(g)
+        k = fh.head_d.out_features
+        for p, g in ((fh.head_d.weight, gw_d[:k]), (fh.head_d.bias, gb_d[:k])):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            dst.append(p.grad)
+            src.append(g)
+        torch._foreach_add_(dst, src)
+        return d_cen, d_den, None, None, None
+
+
 @BACKBONES.register_module()
 class MultiMAESSTSPChoose(nn.Module):
     def __init__(self, window_shape, shifts_list, point_cloud_range, voxel_size, shuffle_voxels=False, d_model=[],
@@ -136,6 +208,17 @@ class MultiMAESSTSPChoose(nn.Module):
                 cen = block(cen, layout, pos, table)
             for block in self.decoder_density_blocks:
                 den = block(den, layout, pos, table)
+        self._fused_heads = None
+        if pos is None and self.cls_sub_voxel and self.top and not self.low and not self.med:
+            # the configuration of configs/mae_sst/*: all six heads as two tensor-core GEMMs
+            fh = self.__dict__.get("_fh") or self.__dict__.setdefault("_fh", FusedHeads(self))
+            out_c, out_d = _FusedHeadsFn.apply(cen, den, n_vis, fh, self._precision())
+            sl, sm = self.per_sub_voxel_num_low, self.per_sub_voxel_num_med
+            o = fh.offsets
+            self._fused_heads = (out_c, out_d, fh)
+            return (out_c[:, o[0]:o[0] + sl * 3].view(-1, sl, 3), out_c[:, o[2]:o[2] + sm * 3].view(-1, sm, 3),
+                    out_c[:, o[4]:o[4] + 3], None, None, out_d[:, :3],
+                    out_c[:, o[1]:o[1] + sl * 2].view(-1, sl, 2), out_c[:, o[3]:o[3] + sm * 2].view(-1, sm, 2))
         cen, den = cen[n_vis:], den[n_vis:]
         reg_low = self.decoder_pred_low(cen).view(-1, self.per_sub_voxel_num_low, 3)
         reg_med = self.decoder_pred_med(cen).view(-1, self.per_sub_voxel_num_med, 3)

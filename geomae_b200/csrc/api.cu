@@ -14,3 +14,7 @@ void gm_set_error(const char* fmt, ...) {
 
 extern "C" const char* geomae_last_error(void) { return g_err; }
 extern "C" int geomae_abi_version(void) { return 1; }
+
+static thread_local bool g_weights_stable = false;
+void gm_set_weights_stable(bool stable) { g_weights_stable = stable; }
+bool gm_weights_stable() { return g_weights_stable; }

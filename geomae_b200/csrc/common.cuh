@@ -30,6 +30,33 @@ void gm_set_error(const char* fmt, ...);
 
 static inline int gm_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL).  Kernels of the SRA chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may become resident and run their
+// prologue (barrier init, TMEM allocation, weight-image bulk copies) while the previous kernel drains.  Every such
+// kernel executes gm_pdl_wait() BEFORE it touches memory written by an earlier kernel and only then
+// gm_pdl_trigger() — so at most one successor is ever in flight and a successor's pre-wait work can only race with
+// its direct predecessor.
+__device__ __forceinline__ void gm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gm_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// true while the caller guarantees that the packed weight images a dense kernel reads were written before its
+// PREDECESSOR kernel started (the stack executor sets it for every kernel but the first after the packing launch);
+// only then may a kernel fetch weights ahead of gm_pdl_wait().
+void gm_set_weights_stable(bool stable);
+bool gm_weights_stable();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // B200: 148 SMs.  Grid-stride kernels are sized in multiples of this.
 constexpr int GM_NUM_SMS = 148;
 

@@ -14,6 +14,7 @@ struct LossIO {
   const float* cls_low; const float* cls_med;        // [m,S,3] / [m,3] / [m,S,2]
   const float* normal;                               // [V,3] targets (z,y,x)
   float w_low, w_med, w_top, w_nor, w_cls_low, w_cls_med;
+  int ld_low, ld_med, ld_top, ld_nor, ld_cls_low, ld_cls_med;   // row strides (floats) of the predictions / gradients
 };
 
 __device__ __forceinline__ float norm_coord(float c, int coor, float vs, float lo) {
@@ -68,23 +69,26 @@ __global__ void __launch_bounds__(256) k_loss(VoxGeom g, LossIO io, const int32_
       const float *reg, *cls;
       float *dreg, *dcls;
       float wreg, wcls, cnt;
+      int ldr, ldc;
       if (s == 1) {
         mask = make_uint4(__ldg(med_mask + v), 0u, 0u, 0u); base = __ldg(med_ptr + v); mean = med_mean;
         reg = io.reg_med; cls = io.cls_med; dreg = d_med; dcls = d_cls_med; wreg = io.w_med; wcls = io.w_cls_med; cnt = n_med;
+        ldr = io.ld_med; ldc = io.ld_cls_med;
       } else {
         mask = __ldg(reinterpret_cast<const uint4*>(low_mask) + v); base = __ldg(low_ptr + v); mean = low_mean;
         reg = io.reg_low; cls = io.cls_low; dreg = d_low; dcls = d_cls_low; wreg = io.w_low; wcls = io.w_cls_low; cnt = n_low;
+        ldr = io.ld_low; ldc = io.ld_cls_low;
       }
       const uint32_t w[4] = {mask.x, mask.y, mask.z, mask.w};
       const float greg = BWD ? gscale[s == 1 ? 2 : 1] * wreg * 2.0f / (3.0f * cnt) : 0.f;
       const float gcls = BWD ? gscale[s == 1 ? 5 : 4] * wcls / (mf * slots * 2.0f) : 0.f;
       for (int slot = lane; slot < slots; slot += 32) {
         const bool present = (w[slot >> 5] >> (slot & 31)) & 1u;
-        const int64_t e = i * slots + slot;
-        const float2 lg = __ldg(reinterpret_cast<const float2*>(cls) + e);
+        const int64_t er = i * ldr + slot * 3, ec = i * ldc + slot * 2;
+        const float2 lg = __ldg(reinterpret_cast<const float2*>(cls + ec));
         const float t0 = present ? 0.f : 1.f, t1 = present ? 1.f : 0.f;     // one-hot of the occupancy label
         if (BWD) {
-          reinterpret_cast<float2*>(dcls)[e] = make_float2((sigmoidf_(lg.x) - t0) * gcls, (sigmoidf_(lg.y) - t1) * gcls);
+          *reinterpret_cast<float2*>(dcls + ec) = make_float2((sigmoidf_(lg.x) - t0) * gcls, (sigmoidf_(lg.y) - t1) * gcls);
         } else {
           part[s == 1 ? 5 : 4] += bce_logit(lg.x, t0) + bce_logit(lg.y, t1);
         }
@@ -92,12 +96,12 @@ __global__ void __launch_bounds__(256) k_loss(VoxGeom g, LossIO io, const int32_
         if (present) {
           const float4 c = __ldg(reinterpret_cast<const float4*>(mean) + base + rank128(mask, slot));
           const int cz = slot / (ry * rx), cy = pc.z * ry + (slot / rx) % ry, cx = pc.w * rx + slot % rx;
-          dz = reg[e * 3 + 0] - norm_coord(c.z, cz, g.vs[s][2], g.lo[2]);
-          dy = reg[e * 3 + 1] - norm_coord(c.y, cy, g.vs[s][1], g.lo[1]);
-          dx = reg[e * 3 + 2] - norm_coord(c.x, cx, g.vs[s][0], g.lo[0]);
+          dz = reg[er + 0] - norm_coord(c.z, cz, g.vs[s][2], g.lo[2]);
+          dy = reg[er + 1] - norm_coord(c.y, cy, g.vs[s][1], g.lo[1]);
+          dx = reg[er + 2] - norm_coord(c.x, cx, g.vs[s][0], g.lo[0]);
           if (!BWD) part[s == 1 ? 2 : 1] += (dz * dz + dy * dy + dx * dx) * (1.0f / 3.0f);
         }
-        if (BWD) { dreg[e * 3 + 0] = dz * greg; dreg[e * 3 + 1] = dy * greg; dreg[e * 3 + 2] = dx * greg; }
+        if (BWD) { dreg[er + 0] = dz * greg; dreg[er + 1] = dy * greg; dreg[er + 2] = dx * greg; }
       }
     }
     if (lane < 3) {
@@ -105,11 +109,11 @@ __global__ void __launch_bounds__(256) k_loss(VoxGeom g, LossIO io, const int32_
       const float cen = lane == 0 ? norm_coord(c.z, pc.y, g.vs[0][2], g.lo[2])
                                   : (lane == 1 ? norm_coord(c.y, pc.z, g.vs[0][1], g.lo[1])
                                                : norm_coord(c.x, pc.w, g.vs[0][0], g.lo[0]));
-      const float dt = io.reg_top[i * 3 + lane] - cen;
-      const float dn = io.nor_top[i * 3 + lane] - __ldg(io.normal + v * 3 + lane);
+      const float dt = io.reg_top[i * io.ld_top + lane] - cen;
+      const float dn = io.nor_top[i * io.ld_nor + lane] - __ldg(io.normal + v * 3 + lane);
       if (BWD) {
-        d_top[i * 3 + lane] = dt * gscale[3] * io.w_top * 2.0f / (3.0f * mf);
-        d_nor[i * 3 + lane] = dn * gscale[0] * io.w_nor * 2.0f / (3.0f * mf);
+        d_top[i * io.ld_top + lane] = dt * gscale[3] * io.w_top * 2.0f / (3.0f * mf);
+        d_nor[i * io.ld_nor + lane] = dn * gscale[0] * io.w_nor * 2.0f / (3.0f * mf);
       } else {
         part[3] += dt * dt * (1.0f / 3.0f);
         part[0] += dn * dn * (1.0f / 3.0f);
@@ -140,7 +144,17 @@ __global__ void k_loss_finish(const double* __restrict__ acc, const int32_t* __r
   out[k] = (float)(acc[k] / denom[k] * w[k]);
 }
 
-int fill(LossIO* io, const geomae_loss_args* a) {
+int fill(LossIO* io, const geomae_loss_args* a, const geomae_voxel_cfg* cfg) {
+  const int sl = cfg->ratio_low[0] * cfg->ratio_low[1] * cfg->ratio_low[2];
+  const int sm = cfg->ratio_med[0] * cfg->ratio_med[1] * cfg->ratio_med[2];
+  const int dflt[6] = {sl * 3, sm * 3, 3, 3, sl * 2, sm * 2};
+  int ld[6];
+  for (int k = 0; k < 6; ++k) {
+    ld[k] = a->ld[k] ? a->ld[k] : dflt[k];
+    GM_REQUIRE(ld[k] >= dflt[k], "geom_loss: row stride %d of prediction %d is smaller than its row (%d)", ld[k], k, dflt[k]);
+  }
+  GM_REQUIRE(ld[4] % 2 == 0 && ld[5] % 2 == 0, "geom_loss: occupancy-logit row strides must be even");
+  io->ld_low = ld[0]; io->ld_med = ld[1]; io->ld_top = ld[2]; io->ld_nor = ld[3]; io->ld_cls_low = ld[4]; io->ld_cls_med = ld[5];
   GM_REQUIRE(a->rows && a->reg_low && a->reg_med && a->reg_top && a->nor_top && a->cls_low && a->cls_med && a->normal,
              "geom_loss: null prediction / target pointer");
   io->rows = a->rows; io->m = a->m;
@@ -164,7 +178,7 @@ extern "C" int geomae_geom_loss_fwd(const geomae_voxel_cfg* cfg, const geomae_sc
   int rc = gm_make_geom(cfg, sc->n_frames, &g);
   if (rc) return rc;
   LossIO io;
-  rc = fill(&io, a);
+  rc = fill(&io, a, cfg);
   if (rc) return rc;
   GM_CUDA(cudaMemsetAsync(counts, 0, 8, stream));
   GM_CUDA(cudaMemsetAsync(acc, 0, 48, stream));
@@ -192,7 +206,7 @@ extern "C" int geomae_geom_loss_bwd(const geomae_voxel_cfg* cfg, const geomae_sc
   int rc = gm_make_geom(cfg, sc->n_frames, &g);
   if (rc) return rc;
   LossIO io;
-  rc = fill(&io, a);
+  rc = fill(&io, a, cfg);
   if (rc) return rc;
   int blocks = gm_div_up(a->m, 8);
   if (blocks > GM_NUM_SMS * 8) blocks = GM_NUM_SMS * 8;

@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int p0 = blockIdx.x * TQ;
   const int nq = min(TQ, n - p0);
+  gm_pdl_wait();
+  gm_pdl_trigger();
   locate_rows<TQ>(meta, p0, n, win_ptr, win_tok, tok_win);
   stage_rows_bf16<1>(sQ, qkv, 3 * DM, 0, QSCALE, nullptr, nullptr, 0, 0, win_tok, p0, nq, TQ);
   __syncthreads();
@@ -300,6 +302,8 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int p0 = blockIdx.x * TQ;
   const int nq = min(TQ, n - p0);
+  gm_pdl_wait();
+  gm_pdl_trigger();
   locate_rows<TQ>(meta, p0, n, win_ptr, win_tok, tok_win);
   if (!AS_KEYS) {
     stage_rows_bf16<2>(sA, qkv, 3 * DM, 0, QSCALE, sB, d_out, DM, 0, win_tok, p0, nq, TQ);
@@ -441,8 +445,8 @@ int launch_fwd(const float* qkv, int n, const int32_t* win_ptr, const int32_t* w
     GM_CUDA(cudaFuncSetAttribute(k_sra_tc_fwd<TQ, KC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd<TQ>()));
     configured = true;
   }
-  k_sra_tc_fwd<TQ, KC_FWD><<<gm_div_up(n, TQ), 256, smem_fwd<TQ>(), st>>>(qkv, n, win_ptr, win_tok, tok_win, out, lse);
-  GM_LAUNCH_CHECK();
+  GM_CUDA(gm_launch_pdl(k_sra_tc_fwd<TQ, KC_FWD>, dim3(gm_div_up(n, TQ)), dim3(256), (size_t)smem_fwd<TQ>(), st, qkv, n,
+                        win_ptr, win_tok, tok_win, out, lse));
   return GEOMAE_OK;
 }
 
@@ -454,9 +458,8 @@ int launch_bwd(const float* qkv, const float* out, const float* lse, const float
     GM_CUDA(cudaFuncSetAttribute(k_sra_tc_bwd<TQ, KC_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd<TQ>()));
     configured = true;
   }
-  k_sra_tc_bwd<TQ, KC_BWD><<<dim3(gm_div_up(n, TQ), 2), 256, smem_bwd<TQ>(), st>>>(qkv, out, lse, d_out, n, win_ptr,
-                                                                                 win_tok, tok_win, d_qkv);
-  GM_LAUNCH_CHECK();
+  GM_CUDA(gm_launch_pdl(k_sra_tc_bwd<TQ, KC_BWD>, dim3(gm_div_up(n, TQ), 2), dim3(256), (size_t)smem_bwd<TQ>(), st, qkv, out,
+                        lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv));
   return GEOMAE_OK;
 }
 

@@ -7,6 +7,8 @@
 // and issues hi*hi + hi*lo + lo*hi (fp32-equivalent to ~2^-16, the parity mode), `precision 1` is plain
 // bf16.  The accumulator row of a token lives in one TMEM lane = one thread of the epilogue, so the
 // LayerNorm statistics need no cross-thread reduction at all.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -29,6 +31,7 @@ struct LinArgs {
   float* ln_in; float* ln_stats;                                    // EPI 1: saved pre-LN rows [n,N] and (mean, rstd) [n,2]
   const float* gelu_u; int ldu;                                     // EPI 2: out = acc * gelu'(u)
   int precision;
+  int w_early;      // packed weights may be fetched before gm_pdl_wait() (see common.cuh)
 };
 
 // Exact-erf GELU (F.gelu default, sst_basic_block.py:153-154) and its derivative, evaluated with the
@@ -69,7 +72,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* dst_hi, uint8_t* dst_lo, con
   constexpr int CPR = COLS / 8;                 // 16-byte chunks per row
   constexpr int BLOCK_BYTES = ROWS * tc::LINE_BYTES;
   constexpr int ITEMS = ROWS * CPR / NTHR;      // per thread
-  constexpr int UNROLL = POS ? 4 : 8;           // the position prologue doubles the loads in flight per item
+  constexpr int UNROLL = ITEMS < (POS ? 4 : 8) ? ITEMS : (POS ? 4 : 8);   // the position prologue doubles the loads per item
   const float* pos_table = POS ? pos_table_ : nullptr;
   static_assert(ITEMS % UNROLL == 0, "tile size must be a multiple of the staging unroll");
 #pragma unroll 1
@@ -126,14 +129,18 @@ __device__ __forceinline__ float4* ctile(float* base, int row, int c4) {
 }
 
 // EPI: 0 = acc (+bias) (+add_src); 1 = LayerNorm(acc + bias + add_src); 2 = acc * gelu'(u)
-template <int NT, int EPI, bool POS>
+// TMR = token rows per CTA = the M of the MMA.  128: accumulator row r lives in TMEM lane r.  64: the accumulator uses
+// 16 lanes of each 32-lane quarter (row r -> lane 32*(r/16) + r%16), so twice as many, half as long CTAs cover the
+// token set — these kernels are latency-bound per CTA, and the encoder has only 57 tiles of 128 tokens for 148 SMs.
+template <int NT, int EPI, bool POS, int TMR>
 __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mbar;
   __shared__ __align__(8) uint64_t mbar_w;      // weight-image bulk copies
   __shared__ uint32_t tmem_slot;
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int A_BYTES = TM * KC * 2;          // 32 KB
+  constexpr int TM = TMR;                       // shadows the file-level 128 inside this kernel
+  constexpr int A_BYTES = TM * KC * 2;          // 32 KB (16 KB for 64-row tiles)
   constexpr int B_BYTES = NT * KC * 2;
   constexpr int BLOCK16K = 128 * tc::LINE_BYTES;   // one packed [128 x 64] bf16 block
   const bool x3 = a.precision == 3;
@@ -147,33 +154,40 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
   const int n0 = blockIdx.y * NT;
   if (warp == 0) tc::tmem_alloc(&tmem_slot, NT);
   if (threadIdx.x == 0) { tc::mbar_init(&mbar, 1); tc::mbar_init(&mbar_w, 1); }
+  const bool use_pos = a.pos_table && (int)blockIdx.y < a.pos_slabs;
+  const int n_chunks = a.K / KC;
+  const int ncb = a.wp_cols / 64;       // 64-column blocks per 128-row band of the packed image
+  // weights: bulk copies of the pre-swizzled bf16 image of K-chunk kc, no thread work
+  auto fetch_weights = [&](int kc) {
+    const int k0 = kc * KC;
+    tc::mbar_expect_tx(&mbar_w, (uint32_t)((x3 ? 2 : 1) * B_BYTES));
+    for (int part = 0; part < (x3 ? 2 : 1); ++part) {
+      const uint8_t* img = part ? a.Wp_lo : a.Wp_hi;
+      uint8_t* dst = part ? sBlo : sB;
+      if (a.w_mn_major) {             // band k0/128, blocks n0/64 .. : contiguous
+        tc::bulk_g2s(dst, img + ((size_t)(k0 / 128) * ncb + n0 / 64) * BLOCK16K, B_BYTES, &mbar_w);
+      } else {                        // bands n0/128 + r, blocks k0/64, k0/64+1 : 32 KB each
+        for (int r = 0; r < NT / 128; ++r)
+          tc::bulk_g2s(dst + r * 2 * BLOCK16K, img + ((size_t)(n0 / 128 + r) * ncb + k0 / 64) * BLOCK16K,
+                       2 * BLOCK16K, &mbar_w);
+      }
+    }
+  };
+  const bool w_early = packed && a.w_early;
+  if (w_early && threadIdx.x == 0) fetch_weights(0);   // overlaps the predecessor kernel's tail (PDL)
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const bool use_pos = a.pos_table && (int)blockIdx.y < a.pos_slabs;
-  const int n_chunks = a.K / KC;
-  const int ncb = a.wp_cols / 64;       // 64-column blocks per 128-row band of the packed image
+  gm_pdl_wait();                        // everything below reads what earlier kernels wrote
+  gm_pdl_trigger();
   for (int kc = 0; kc < n_chunks; ++kc) {
     const int k0 = kc * KC;
     if (kc > 0) {                       // operands of the previous chunk must be consumed before overwriting
       tc::mbar_wait(&mbar, (kc - 1) & 1);
       tc::fence_after_sync();
     }
-    if (packed && threadIdx.x == 0) {   // weights: bulk copies of the pre-swizzled bf16 image, no thread work
-      tc::mbar_expect_tx(&mbar_w, (uint32_t)((x3 ? 2 : 1) * B_BYTES));
-      for (int part = 0; part < (x3 ? 2 : 1); ++part) {
-        const uint8_t* img = part ? a.Wp_lo : a.Wp_hi;
-        uint8_t* dst = part ? sBlo : sB;
-        if (a.w_mn_major) {             // band k0/128, blocks n0/64 .. : contiguous
-          tc::bulk_g2s(dst, img + ((size_t)(k0 / 128) * ncb + n0 / 64) * BLOCK16K, B_BYTES, &mbar_w);
-        } else {                        // bands n0/128 + r, blocks k0/64, k0/64+1 : 32 KB each
-          for (int r = 0; r < NT / 128; ++r)
-            tc::bulk_g2s(dst + r * 2 * BLOCK16K, img + ((size_t)(n0 / 128 + r) * ncb + k0 / 64) * BLOCK16K,
-                         2 * BLOCK16K, &mbar_w);
-        }
-      }
-    }
+    if (packed && threadIdx.x == 0 && !(w_early && kc == 0)) fetch_weights(kc);
     stage_tile<TM, KC, LTHREADS, POS>(sA, x3 ? sAlo : nullptr, a.A, a.lda, row0, a.n_rows, k0,
                                       use_pos ? a.pos_table : nullptr, a.tok_cell, a.K, a.a_gelu != 0);
     if (!packed) {
@@ -225,20 +239,23 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
   // p is written), so their L2/DRAM latency overlaps the tensor-core work instead of serialising behind it.
   float* sC = reinterpret_cast<float*>(smem);
   const int q = warp & 3, hsel = warp >> 2;                    // TMEM lane quarter, column half
-  const int trow = q * 32 + lane;                              // tile row drained by this thread
+  constexpr int LPQ = TM / 4;                                  // accumulator lanes in use per quarter (32 or 16)
+  const int trow = q * LPQ + lane;                             // tile row drained by this thread (if lane < LPQ)
+  const bool drains = lane < LPQ;
   const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
   if constexpr (EPI == 1) {
     static_assert(EPI != 1 || NT == 128, "LayerNorm epilogue needs the whole row in one CTA");
     constexpr int C4 = 32;                                     // 128 columns
-    constexpr int RPW = TM / (LTHREADS / 32);                  // rows per warp (16), handled in two batches of 8
+    constexpr int RPW = TM / (LTHREADS / 32);                  // rows per warp (16 or 8), handled in batches of 8
+    constexpr int NB = RPW / 8;
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + lane);
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma) + lane);
     const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.ln_beta) + lane);
-    float4 res[RPW / 2];
+    float4 res[8];
     auto fetch = [&](int batch) {
 #pragma unroll
-      for (int j = 0; j < RPW / 2; ++j) {
-        const int row = row0 + warp + (LTHREADS / 32) * (batch * (RPW / 2) + j);
+      for (int j = 0; j < 8; ++j) {
+        const int row = row0 + warp + (LTHREADS / 32) * (batch * 8 + j);
         res[j] = row < a.n_rows ? __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add) + lane)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -252,15 +269,17 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
       const int c0 = hsel * 64 + half * 32;
       tc::tmem_ld32(t_lane + c0, v);
       tc::tmem_ld_wait();
+      if (drains) {
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (c0 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (c0 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
     }
     __syncthreads();
     // one warp per row, one float4 per lane: s = acc + bias + residual; exact two-pass statistics; write s, LN(s)
 #pragma unroll
-    for (int batch = 0; batch < 2; ++batch) {
+    for (int batch = 0; batch < NB; ++batch) {
       // eight rows per batch, every step written for all eight at once so their shuffle reductions interleave
-      constexpr int RB = RPW / 2;
+      constexpr int RB = 8;
       float4 v[RB];
       float mean[RB], rstd[RB];
 #pragma unroll
@@ -269,7 +288,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
         v[j] = *ctile<C4>(sC, r, lane);
         v[j].x += b4.x + res[j].x; v[j].y += b4.y + res[j].y; v[j].z += b4.z + res[j].z; v[j].w += b4.w + res[j].w;
       }
-      if (batch == 0) fetch(1);
+      if (batch + 1 < NB) fetch(batch + 1);
 #pragma unroll
       for (int j = 0; j < RB; ++j) mean[j] = (v[j].x + v[j].y) + (v[j].z + v[j].w);
 #pragma unroll
@@ -327,8 +346,10 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
       tc::tmem_ld32(t_lane + pc * 64 + hsel * 32, v);
       tc::tmem_ld_wait();
       if (pc > 0) __syncthreads();                             // previous panel fully read back
+      if (drains) {
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (hsel * 32 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (hsel * 32 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < RI; ++k) {
@@ -354,24 +375,45 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
   if (warp == 0) tc::tmem_free(tmem, NT);
 }
 
-template <int NT, int EPI, bool POS>
+template <int NT, int EPI, bool POS, int TMR>
 int launch_linear_impl(const LinArgs& a, cudaStream_t stream) {
-  const int smem = (a.precision == 3 ? 2 : 1) * (TM * KC * 2 + NT * KC * 2) + 1024;   // >= 64 KB: holds the epilogue tile
+  constexpr int per_prec = TMR * KC * 2 + NT * KC * 2;
+  constexpr int epi_bytes = TMR * (EPI == 1 ? 128 : 64) * 4;          // fp32 staging tile of the epilogue
+  const int operands = (a.precision == 3 ? 2 : 1) * per_prec;
+  const int smem = (operands > epi_bytes ? operands : epi_bytes) + 1024;
   static bool configured = false;
   if (!configured) {
-    GM_CUDA(cudaFuncSetAttribute(k_tc_linear<NT, EPI, POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TM * KC * 2 + NT * KC * 2) + 1024));
+    GM_CUDA(cudaFuncSetAttribute(k_tc_linear<NT, EPI, POS, TMR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (2 * per_prec > epi_bytes ? 2 * per_prec : epi_bytes) + 1024));
     configured = true;
   }
-  const dim3 grid(gm_div_up(a.n_rows, TM), a.N_total / NT);
-  k_tc_linear<NT, EPI, POS><<<grid, LTHREADS, smem, stream>>>(a);
-  GM_LAUNCH_CHECK();
+  const dim3 grid(gm_div_up(a.n_rows, TMR), a.N_total / NT);
+  GM_CUDA(gm_launch_pdl(k_tc_linear<NT, EPI, POS, TMR>, grid, dim3(LTHREADS), (size_t)smem, stream, a));
   return GEOMAE_OK;
+}
+
+// Rows per CTA.  Token sets that give fewer 128-row tiles than SMs (the encoder: 57 tiles) run 64-row tiles — twice
+// the CTAs, each half as long (measured: 25-35 % faster per kernel there); large sets keep 128 rows (fewer weight
+// fetches; measured 10-30 % faster at 190+ tiles).  GEOMAE_TC_TILE_M=64|128 forces one (read once).
+inline int tile_rows(int n_rows) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("GEOMAE_TC_TILE_M");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 64 || forced == 128) return forced;
+  return gm_div_up(n_rows, 128) < GM_NUM_SMS ? 64 : 128;
 }
 
 template <int NT, int EPI>
 int launch_linear(const LinArgs& a, cudaStream_t stream) {
-  if (NT == 128 && EPI == 0 && a.pos_table && a.pos_slabs > 0) return launch_linear_impl<128, 0, true>(a, stream);
-  return launch_linear_impl<NT, EPI, false>(a, stream);
+  const bool pos = NT == 128 && EPI == 0 && a.pos_table && a.pos_slabs > 0;
+  if (tile_rows(a.n_rows) == 64) {
+    if (pos) return launch_linear_impl<128, 0, true, 64>(a, stream);
+    return launch_linear_impl<NT, EPI, false, 64>(a, stream);
+  }
+  if (pos) return launch_linear_impl<128, 0, true, 128>(a, stream);
+  return launch_linear_impl<NT, EPI, false, 128>(a, stream);
 }
 
 
@@ -410,6 +452,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_tc_wgrad(const WgradArgs a) {
   const int n_tiles_total = (a.n_rows + TM - 1) / TM;
   const int tile_end = min(tile_begin + a.tiles_per_cta, n_tiles_total);
   if (tile_begin >= tile_end) return;
+  gm_pdl_wait();
+  gm_pdl_trigger();
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TCOLS);
   if (threadIdx.x == 0) tc::mbar_init(&mbar, 1);
   const bool want_bias = NT == 128 && a.db != nullptr && blockIdx.z == 0;
@@ -512,8 +556,7 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t stream) {
   }
   const int n_tiles = gm_div_up(a.n_rows, TM);
   const dim3 grid(gm_div_up(n_tiles, a.tiles_per_cta), a.M_total / 128, a.N_total / NT);
-  k_tc_wgrad<NT><<<grid, NTHREADS, smem, stream>>>(a);
-  GM_LAUNCH_CHECK();
+  GM_CUDA(gm_launch_pdl(k_tc_wgrad<NT>, grid, dim3(NTHREADS), (size_t)smem, stream, a));
   return GEOMAE_OK;
 }
 
@@ -525,6 +568,8 @@ __global__ void __launch_bounds__(256) k_ln_bwd(const float* __restrict__ dz, co
   __shared__ float sg[8][128], sb[8][128];
   __shared__ float ss[8][128];                  // column sums of ds (= bias gradient of the linear that produced the LN input)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  gm_pdl_wait();
+  gm_pdl_trigger();
   const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
   float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg, accs = accg;
   for (int row = blockIdx.x * 8 + warp; row < n_rows; row += gridDim.x * 8) {
@@ -610,6 +655,7 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
   a.add_src = p->add_src; a.ld_add = p->ld_add;
   a.ln_gamma = p->ln_gamma; a.ln_beta = p->ln_beta; a.ln_eps = p->ln_eps; a.ln_in = p->ln_in; a.ln_stats = p->ln_stats;
   a.gelu_u = p->gelu_u; a.ldu = p->ldu; a.precision = p->precision;
+  a.w_early = gm_weights_stable() ? 1 : 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (p->epilogue == 1) {
     GM_REQUIRE(p->N_total == 128 && p->bias && p->add_src && p->ln_gamma && p->ln_beta,
@@ -653,9 +699,8 @@ extern "C" int geomae_layernorm_bwd(const float* d_out, const float* ln_in, cons
   GM_REQUIRE(d_out && ln_in && ln_stats && gamma && d_in && d_gamma && d_beta, "layernorm_bwd: null argument");
   int blocks = gm_div_up(n_rows, 8);
   if (blocks > GM_NUM_SMS * 4) blocks = GM_NUM_SMS * 4;
-  k_ln_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, ln_in, ln_stats, gamma, (int)n_rows, d_in, d_gamma, d_beta,
-                                                     d_in_colsum);
-  GM_LAUNCH_CHECK();
+  GM_CUDA(gm_launch_pdl(k_ln_bwd, dim3(blocks), dim3(256), (size_t)0, (cudaStream_t)stream, d_out, ln_in, ln_stats, gamma,
+                        (int)n_rows, d_in, d_gamma, d_beta, d_in_colsum));
   return GEOMAE_OK;
 }
 

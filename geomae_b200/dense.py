@@ -8,8 +8,23 @@ import torch
 from . import lib as L
 
 
+def pack_weight(W, want_lo=True):
+    """bf16 tensor-core image(s) of a [rows, cols] fp32 weight (cols % 64 == 0): (hi, lo | None) uint8 tensors made of
+    swizzled [128 x 64] blocks, ready for bulk copies into shared memory (geomae_pack_weights)."""
+    rows, cols = W.shape
+    assert W.is_contiguous() and cols % 64 == 0
+    nbytes = (rows + 127) // 128 * 128 * cols * 2
+    hi = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+    lo = torch.empty(nbytes, dtype=torch.uint8, device=W.device) if want_lo else None
+    Wp, r, c = (C.c_void_p * 1)(W.data_ptr()), (C.c_int32 * 1)(rows), (C.c_int32 * 1)(cols)
+    hp = (C.c_void_p * 1)(hi.data_ptr())
+    lp = (C.c_void_p * 1)(lo.data_ptr()) if want_lo else None
+    L.run("pack_weights", 1, Wp, r, c, hp, lp, L.stream_ptr(W.device))
+    return hi, lo
+
+
 def tc_linear(A, W, *, n_out, w_mn_major=False, bias=None, pos_table=None, tok_cell=None, pos_slabs=0, a_gelu=False,
-              add_src=None, ln=None, gelu_u=None, out=None, precision=3):
+              add_src=None, ln=None, gelu_u=None, out=None, precision=3, packed=None):
     """out = prologue(A) @ (W^T | W) + epilogue on tcgen05 (see geomae_linear_args in include/geomae_b200.h).
 
     ln = (gamma, beta, eps, want_saved) selects the LayerNorm epilogue and returns (out, ln_in, ln_stats)."""
@@ -41,6 +56,9 @@ def tc_linear(A, W, *, n_out, w_mn_major=False, bias=None, pos_table=None, tok_c
     if gelu_u is not None:
         a.gelu_u, a.ldu, a.epilogue = gelu_u.data_ptr(), gelu_u.stride(0), 2
     a.precision = precision
+    if packed is not None:
+        a.Wp_hi = packed[0].data_ptr()
+        a.Wp_lo = packed[1].data_ptr() if packed[1] is not None else None
     L.run("tc_linear", C.byref(a), L.stream_ptr(A.device))
     if ln is not None:
         return out, ln_in, ln_stats

@@ -43,6 +43,46 @@ class _GeomLossFn(torch.autograd.Function):
         return (*grads, None, None, None, None)
 
 
+class _GeomLossFusedFn(torch.autograd.Function):
+    """The same fused loss reading the predictions as column slices of the fused head outputs (row stride 768 / 128)."""
+
+    @staticmethod
+    def forward(ctx, out_c, out_d, fh, pb, rows, normal, weights):
+        import ctypes as C
+        rows = rows.to(torch.int64).contiguous()
+        dev = out_c.device
+        o = fh.offsets
+        a = L.LossArgs()
+        a.rows, a.m = rows.data_ptr(), rows.shape[0]
+        base = out_c.data_ptr()
+        a.reg_low, a.cls_low, a.reg_med, a.cls_med, a.reg_top = [base + 4 * k for k in o]
+        a.nor_top = out_d.data_ptr()
+        a.normal = normal.data_ptr()
+        a.w_low, a.w_med, a.w_top, a.w_nor, a.w_cls_low, a.w_cls_med = weights
+        wc, wd = out_c.shape[1], out_d.shape[1]
+        for k, v in enumerate((wc, wc, wc, wd, wc, wc)):       # reg_low, reg_med, reg_top, nor_top, cls_low, cls_med
+            a.ld[k] = v
+        counts = torch.empty(2, dtype=torch.int32, device=dev)
+        acc = torch.empty(6, dtype=torch.float64, device=dev)
+        out = torch.empty(6, dtype=torch.float32, device=dev)
+        L.run("geom_loss_fwd", C.byref(pb.geom.cstruct), C.byref(pb.io), C.byref(a), L.ptr(counts), L.ptr(acc), L.ptr(out),
+              L.stream_ptr(dev))
+        ctx.args, ctx.pb, ctx.keep = a, pb, (out_c, out_d, rows, normal, counts, o)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        out_c, out_d, rows, normal, counts, o = ctx.keep
+        g = g.contiguous()
+        d_c, d_d = torch.zeros_like(out_c), torch.zeros_like(out_d)     # pad columns must carry zero gradient
+        b = d_c.data_ptr()
+        d_low, d_cls_low, d_med, d_cls_med, d_top = [b + 4 * k for k in o]
+        L.run("geom_loss_bwd", C.byref(ctx.pb.geom.cstruct), C.byref(ctx.pb.io), C.byref(ctx.args), L.ptr(counts), L.ptr(g),
+              d_low, d_med, d_top, d_d.data_ptr(), d_cls_low, d_cls_med, L.stream_ptr(g.device))
+        return d_c, d_d, None, None, None, None, None
+
+
 @DETECTORS.register_module()
 class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
     def __init__(self, loss, loss_ratio_low, loss_ratio_med, loss_ratio_top, loss_ratio_low_nor, loss_ratio_med_nor,
@@ -180,7 +220,14 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
         nor_pred = nor_top if (nor_low is None and nor_med is None) else nor_low
         weights = (self.loss_ratio_low, self.loss_ratio_med, self.loss_ratio_top, self.loss_ratio_low_nor,
                    self.cls_loss_ratio_low, self.cls_loss_ratio_med)
-        losses = _GeomLossFn.apply(reg_low, reg_med, reg_top, nor_pred, cls_low, cls_med, pb, ids_mask, normal, weights)
+        fused = getattr(self.backbone, "_fused_heads", None)
+        if fused is not None:       # predictions are column slices of the fused head GEMMs: no copies
+            out_c, out_d, fh = fused
+            self.backbone._fused_heads = None
+            losses = _GeomLossFusedFn.apply(out_c, out_d, fh, pb, ids_mask, normal, weights)
+        else:
+            losses = _GeomLossFn.apply(reg_low, reg_med, reg_top, nor_pred, cls_low, cls_med, pb, ids_mask, normal, weights)
+        self.last_loss_vector = losses          # [6]; FlatTrainer sums this instead of six 0-dim views
         return {k: losses[i] for i, k in enumerate(self.LOSS_KEYS)}
 
     def forward(self, return_loss=True, **kwargs):

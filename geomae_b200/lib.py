@@ -94,7 +94,7 @@ class LossArgs(C.Structure):
     _fields_ = [("rows", C.c_void_p), ("m", C.c_int64), ("reg_low", C.c_void_p), ("reg_med", C.c_void_p),
                 ("reg_top", C.c_void_p), ("nor_top", C.c_void_p), ("cls_low", C.c_void_p), ("cls_med", C.c_void_p),
                 ("normal", C.c_void_p), ("w_low", C.c_float), ("w_med", C.c_float), ("w_top", C.c_float),
-                ("w_nor", C.c_float), ("w_cls_low", C.c_float), ("w_cls_med", C.c_float)]
+                ("w_nor", C.c_float), ("w_cls_low", C.c_float), ("w_cls_med", C.c_float), ("ld", C.c_int32 * 6)]
 
 
 def build_if_missing():

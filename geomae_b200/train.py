@@ -58,8 +58,10 @@ class FlatTrainer:
     def train_step(self, points, ids=None, lr=None):
         """points: list of [N_i, C] CUDA tensors (one rank's samples).  Returns (total loss, loss dict)."""
         self.zero_grad()
+        self.model.last_loss_vector = None
         losses = self.model.forward_train(points=points, img_metas=None, ids=ids)
-        total = sum(losses.values())
+        vec = getattr(self.model, "last_loss_vector", None)
+        total = vec.sum() if vec is not None else sum(losses.values())     # one reduction instead of six adds
         total.backward()
         if self.world > 1:
             dist.all_reduce(self.flat_grad)          # the single gradient collective (sum; 1/world folded below)

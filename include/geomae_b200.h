@@ -364,6 +364,10 @@ typedef struct geomae_loss_args {
   const float* cls_low;  /* [m,slots_low,2] */ const float* cls_med; /* [m,slots_med,2] */
   const float* normal;   /* [V,3] per-pillar normal targets (geomae_geom_targets) */
   float w_low, w_med, w_top, w_nor, w_cls_low, w_cls_med;   /* loss_ratio_* of the config */
+  /* row strides (floats) of reg_low, reg_med, reg_top, nor_top, cls_low, cls_med and of their gradients; 0 = the
+   * dense default (slots*3, slots*3, 3, 3, slots*2, slots*2).  Non-default strides let the six predictions be
+   * column slices of ONE fused head GEMM output [m, 768] (backbone heads, …top_only.py:279-300). */
+  int32_t ld[6];
 } geomae_loss_args;
 
 /* out[6] = loss_curv_around, loss_centroid_low, loss_centroid_med, loss_centroid_top, loss_cls_low, loss_cls_med.
