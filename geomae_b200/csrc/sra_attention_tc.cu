@@ -120,10 +120,16 @@ __device__ __forceinline__ void stage_rows_bf16(uint8_t* dst0, const float* __re
 // per-(row, head) D = dO . O (fp32, from global) and log2-domain LSE for `rows` CSR positions starting at p_start
 __device__ __forceinline__ void stage_lse_d(float* sL, float* sD, const float* __restrict__ lse,
                                             const float* __restrict__ d_out, const float* __restrict__ out,
-                                            const int32_t* __restrict__ win_tok, int p_start, int rows) {
+                                            const float* __restrict__ dd, const int32_t* __restrict__ win_tok,
+                                            int p_start, int rows) {
   for (int idx = threadIdx.x; idx < rows * NH; idx += 256) {
     const int r = idx >> 3, hh = idx & 7;
     const int64_t tok = __ldg(win_tok + p_start + r);
+    if (dd) {                             // D was produced by the GEMM that wrote d_out (geomae_linear_args.dot_out)
+      sD[idx] = __ldg(dd + tok * NH + hh);
+      sL[idx] = __ldg(lse + tok * NH + hh) * LOG2E;
+      continue;
+    }
     const float4* g4 = reinterpret_cast<const float4*>(d_out + tok * DM + hh * 16);
     const float4* o4 = reinterpret_cast<const float4*>(out + tok * DM + hh * 16);
     float d = 0.f;
@@ -290,7 +296,7 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
                                              const float* __restrict__ out, const float* __restrict__ lse,
                                              const float* __restrict__ d_out, int n, const int32_t* __restrict__ win_ptr,
                                              const int32_t* __restrict__ win_tok, const int32_t* __restrict__ tok_win,
-                                             float* d_qkv) {
+                                             float* d_qkv, const float* __restrict__ dd) {
   constexpr int MT = TQ / 16;
   uint8_t* sA = smem;                       // own rows, operand 1: Q*scale (queries) | K*scale (keys)
   uint8_t* sB = sA + TQ * RSB;              // own rows, operand 2: dO       (queries) | V       (keys)
@@ -307,7 +313,7 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
   locate_rows<TQ>(meta, p0, n, win_ptr, win_tok, tok_win);
   if (!AS_KEYS) {
     stage_rows_bf16<2>(sA, qkv, 3 * DM, 0, QSCALE, sB, d_out, DM, 0, win_tok, p0, nq, TQ);
-    stage_lse_d(sL, sDd, lse, d_out, out, win_tok, p0, nq);
+    stage_lse_d(sL, sDd, lse, d_out, out, dd, win_tok, p0, nq);
   } else {
     stage_rows_bf16<2>(sA, qkv, 3 * DM, DM, QSCALE, sB, qkv, 3 * DM, 2 * DM, win_tok, p0, nq, TQ);
   }
@@ -330,7 +336,7 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
       stage_rows_bf16<2>(sC, qkv, 3 * DM, DM, 1.0f, sD, qkv, 3 * DM, 2 * DM, win_tok, c0, rows, rows_pad);
     } else {
       stage_rows_bf16<2>(sC, qkv, 3 * DM, 0, 1.0f, sD, d_out, DM, 0, win_tok, c0, rows, rows_pad);
-      stage_lse_d(sL, sDd, lse, d_out, out, win_tok, c0, rows);
+      stage_lse_d(sL, sDd, lse, d_out, out, dd, win_tok, c0, rows);
     }
     __syncthreads();
 #pragma unroll
@@ -423,13 +429,14 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_bwd(const float* __restrict__
                                                        const float* __restrict__ lse, const float* __restrict__ d_out,
                                                        int n, const int32_t* __restrict__ win_ptr,
                                                        const int32_t* __restrict__ win_tok,
-                                                       const int32_t* __restrict__ tok_win, float* d_qkv) {
+                                                       const int32_t* __restrict__ tok_win, float* d_qkv,
+                                                       const float* __restrict__ dd) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ RowMeta meta;
   if (blockIdx.y == 0)
-    sra_bwd_body<TQ, KC, false>(smem, meta, qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv);
+    sra_bwd_body<TQ, KC, false>(smem, meta, qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd);
   else
-    sra_bwd_body<TQ, KC, true>(smem, meta, qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv);
+    sra_bwd_body<TQ, KC, true>(smem, meta, qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd);
 }
 
 constexpr int KC_FWD = 128, KC_BWD = 112;
@@ -452,14 +459,14 @@ int launch_fwd(const float* qkv, int n, const int32_t* win_ptr, const int32_t* w
 
 template <int TQ>
 int launch_bwd(const float* qkv, const float* out, const float* lse, const float* d_out, int n, const int32_t* win_ptr,
-               const int32_t* win_tok, const int32_t* tok_win, float* d_qkv, cudaStream_t st) {
+               const int32_t* win_tok, const int32_t* tok_win, float* d_qkv, const float* dd, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     GM_CUDA(cudaFuncSetAttribute(k_sra_tc_bwd<TQ, KC_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd<TQ>()));
     configured = true;
   }
   GM_CUDA(gm_launch_pdl(k_sra_tc_bwd<TQ, KC_BWD>, dim3(gm_div_up(n, TQ), 2), dim3(256), (size_t)smem_bwd<TQ>(), st, qkv, out,
-                        lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv));
+                        lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd));
   return GEOMAE_OK;
 }
 
@@ -481,13 +488,14 @@ extern "C" int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, i
 
 extern "C" int geomae_sra_attention_tc_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
                                            int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
-                                           const int32_t* win_tok, const int32_t* tok_win, float* d_qkv, void* stream) {
+                                           const int32_t* win_tok, const int32_t* tok_win, float* d_qkv, const float* dd,
+                                           void* stream) {
   GM_REQUIRE(n_heads == NH, "sra_attention_tc: built for %d heads of 16 channels (got %d)", NH, n_heads);
   if (n_tokens == 0) return GEOMAE_OK;
   GM_REQUIRE(qkv && out && lse && d_out && win_ptr && win_tok && tok_win && d_qkv, "sra_attention_tc_bwd: null argument");
   GM_REQUIRE(n_tokens < (int64_t)1 << 31, "sra_attention_tc: too many tokens");
   const int n = (int)n_tokens;
   if (gm_div_up(n, 64) < GM_NUM_SMS)
-    return launch_bwd<32>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, (cudaStream_t)stream);
-  return launch_bwd<64>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, (cudaStream_t)stream);
+    return launch_bwd<32>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, (cudaStream_t)stream);
+  return launch_bwd<64>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, (cudaStream_t)stream);
 }

@@ -32,6 +32,7 @@ struct LinArgs {
   const float* gelu_u; int ldu;                                     // EPI 2: out = acc * gelu'(u)
   int precision;
   int w_early;      // packed weights may be fetched before gm_pdl_wait() (see common.cuh)
+  const float* dot_src; int ld_dot; float* dot_out;   // EPI 0, N = 128: dot_out[row, h] = sum_head out * dot_src
 };
 
 // Exact-erf GELU (F.gelu default, sst_basic_block.py:153-154) and its derivative, evaluated with the
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
     fetch(0);
     tc::mbar_wait(&mbar, (n_chunks - 1) & 1);
     tc::fence_after_sync();
+    float4 dotv[(EPI == 0 && NT == 128 && !POS) ? RI : 1];
 #pragma unroll 1
     for (int pc = 0; pc < NP; ++pc) {
       float v[32];
@@ -365,6 +367,23 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
             o.z += bias4.z + pre[k].z; o.w += bias4.w + pre[k].w;
           }
           *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + n0 + pc * 64 + c4 * 4) = o;
+          if constexpr (EPI == 0 && NT == 128 && !POS) dotv[k] = o;
+        }
+      }
+      if constexpr (EPI == 0 && NT == 128 && !POS) {
+        if (a.dot_src) {                 // per-(row, head) dot with dot_src: 4 adjacent lanes hold one head's 16 columns
+#pragma unroll
+          for (int k = 0; k < RI; ++k) {
+            const int row = row0 + rbase + (LTHREADS / C4) * k;
+            float part = 0.f;
+            if (row < a.n_rows) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.dot_src + (int64_t)row * a.ld_dot + n0 + pc * 64 + c4 * 4));
+              part = (dotv[k].x * s4.x + dotv[k].y * s4.y) + (dotv[k].z * s4.z + dotv[k].w * s4.w);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (row < a.n_rows && (c4 & 3) == 0) a.dot_out[(int64_t)row * 8 + ((n0 + pc * 64) >> 4) + (c4 >> 2)] = part;
+          }
         }
       }
       if (pc + 1 < NP) fetch(pc + 1);          // in flight while the next panel is drained from TMEM
@@ -656,6 +675,9 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
   a.ln_gamma = p->ln_gamma; a.ln_beta = p->ln_beta; a.ln_eps = p->ln_eps; a.ln_in = p->ln_in; a.ln_stats = p->ln_stats;
   a.gelu_u = p->gelu_u; a.ldu = p->ldu; a.precision = p->precision;
   a.w_early = gm_weights_stable() ? 1 : 0;
+  a.dot_src = p->dot_src; a.ld_dot = p->ld_dot; a.dot_out = p->dot_out;
+  GM_REQUIRE(!p->dot_src || (p->dot_out && p->epilogue == 0 && p->N_total == 128 && p->pos_slabs == 0 && p->ld_dot % 4 == 0),
+             "tc_linear: the per-head dot side output needs epilogue 0, N = 128, no position prologue");
   cudaStream_t stream = (cudaStream_t)stream_;
   if (p->epilogue == 1) {
     GM_REQUIRE(p->N_total == 128 && p->bias && p->add_src && p->ln_gamma && p->ln_beta,

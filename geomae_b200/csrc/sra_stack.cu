@@ -197,12 +197,14 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
       Span span(4, 0.0, main);
       GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, L.g_out_proj_b, main));
     }
-    GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main, nullptr, L.p_out_proj));
+    geomae_linear_args ed{};          // bf16 mode: D = dO . O per (token, head) leaves this GEMM's epilogue
+    if (p == 1) { ed.dot_src = S.attn; ed.ld_dot = d; ed.dot_out = dd; }
+    GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main, &ed, L.p_out_proj));
     {
       Span span(3, 0.0, main);
       if (p == 1)
         GM_TRY(geomae_sra_attention_tc_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
-                                           main));
+                                           dd, main));
       else
         GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
                                         dd, main));

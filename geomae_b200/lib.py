@@ -55,7 +55,8 @@ class LinearArgs(C.Structure):
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float), ("ln_in", C.c_void_p),
                 ("ln_stats", C.c_void_p),
                 ("gelu_u", C.c_void_p), ("ldu", C.c_int32),
-                ("epilogue", C.c_int32), ("precision", C.c_int32), ("Wp_hi", C.c_void_p), ("Wp_lo", C.c_void_p)]
+                ("epilogue", C.c_int32), ("precision", C.c_int32), ("Wp_hi", C.c_void_p), ("Wp_lo", C.c_void_p),
+                ("dot_src", C.c_void_p), ("ld_dot", C.c_int32), ("dot_out", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):
@@ -145,7 +146,7 @@ class _Sigs:
     geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]
     geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
     geomae_sra_attention_tc_fwd = [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]
-    geomae_sra_attention_tc_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]
+    geomae_sra_attention_tc_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
     geomae_tc_linear = [C.POINTER(LinearArgs), _p]
     geomae_tc_wgrad = [C.POINTER(WgradArgs), _p]
     geomae_sra_stack_forward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p]

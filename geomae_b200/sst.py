@@ -22,11 +22,12 @@ def _attn_fwd(qkv, win, n_heads, tc=False):
     return out, lse
 
 
-def _attn_bwd(qkv, out, lse, d_out, win, n_heads, tc=False):
+def _attn_bwd(qkv, out, lse, d_out, win, n_heads, tc=False, dd=None):
     d_qkv = torch.empty_like(qkv)
     if tc:
         L.run("sra_attention_tc_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0], n_heads,
-              L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(d_qkv), L.stream_ptr(qkv.device))
+              L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(d_qkv), L.ptr(dd),
+              L.stream_ptr(qkv.device))
         return d_qkv
     scratch = torch.empty((qkv.shape[0], n_heads), dtype=torch.float32, device=qkv.device)
     L.run("sra_attention_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0], n_heads,

@@ -227,7 +227,7 @@ int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* ls
 /* The same attention with bf16 operands on the tensor cores (mma.sync m16n8k16, fp32 accumulate and softmax):
  * windows are packed block-diagonally into 16-query x 16-key tiles; K|V of the contiguous CSR range a CTA can
  * see are converted to bf16 while being staged into shared memory.  Same arguments and outputs as the fp32
- * entry points above (no scratch: D = dO.O is recomputed from the staged rows).  Used by the SRA stack executor
+ * entry points above (no scratch: D = dO.O is read from `dd` when given, else recomputed from the staged rows).  Used by the SRA stack executor
  * when precision == 1 (the bf16 benchmark mode); precision == 3 keeps the fp32 kernels.
  * replaces: nn.MultiheadAttention core inside WindowAttention.forward
  *           (models/sst/sst_basic_block.py:26-61) and its autograd backward. */
@@ -235,7 +235,8 @@ int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, int32_t n_he
                                 const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse, void* stream);
 int geomae_sra_attention_tc_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
                                 int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr, const int32_t* win_tok,
-                                const int32_t* tok_win, float* d_qkv, void* stream);
+                                const int32_t* tok_win, float* d_qkv, const float* dd /* [n_tokens, n_heads] D = dO.O, or NULL */,
+                                void* stream);
 
 /* ------------------------------------------------ tensor-core dense layers */
 
@@ -261,6 +262,10 @@ typedef struct geomae_linear_args {
   const float* gelu_u; int32_t ldu;
   int32_t epilogue; int32_t precision;
   const void* Wp_hi; const void* Wp_lo;   /* optional: images of W from geomae_pack_weights (ldw = cols of W) */
+  /* optional side output of epilogue 0 with N_total == 128: dot_out[row, h] = sum over the 16 columns of head h of
+   * out[row, .] * dot_src[row, .]  (h = 0..7).  The attention backward needs D = dO . O per (token, head); the
+   * GEMM that produces dO computes it on the way out instead of both attention passes re-reading dO and O. */
+  const float* dot_src; int32_t ld_dot; float* dot_out;
 } geomae_linear_args;
 
 int geomae_tc_linear(const geomae_linear_args* args, void* stream);
