@@ -160,6 +160,16 @@ class _Sigs:
     geomae_geom_loss_bwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p, _p, _p, _p,
                             _p, _p]
     geomae_mask_split = [_p, _i32, C.c_double, C.c_uint64, _p, _p, _p]
+    geomae_vfe0_forward = [_p, _i64, _i32, _p, _p, _p, _f3, _f3, _p, _p, _p, _p]
+    geomae_colstats = [_p, _i64, _i32, _p, _p]
+    geomae_vfe_bn_relu_max = [_p, _i64, _i32, _p, _p, _p, _p, C.c_float, _p, _p, C.c_float, C.c_float, _p, _i64, _p]
+    geomae_vfe_cat = [_p, _i64, _p, _p, _p, _p, C.c_float, _p, _p, _p]
+    geomae_vmax_decode = [_p, _i64, _p, _p]
+    geomae_vfe1_backward = [_i32, _p, _i64, _p, _p, _p, _p, C.c_float, _p, _p, _p, _p, C.c_float, _p, _p]
+    geomae_bn_backward_coeffs = [_i32, _p, _p, _p, C.c_float, _p, _p, _p, _p]
+    geomae_vfe_gather_backward = [_p, _i64, _p, _p, _i64, _p]
+    geomae_vfe0_backward = [_i32, _p, _i64, _i32, _p, _p, _p, _f3, _f3, _p, _p, _p, _p, C.c_float, _p, _p, _p, _p, _p,
+                            C.c_float, _p, _p]
     geomae_pack_weights = [_i32, _p, _p, _p, _p, _p, _p]
     geomae_profile_enable = [_i32]
     geomae_profile_read = [_p, _p, _p]

@@ -8,9 +8,11 @@ from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
+from torch import distributed as dist
 from torch import nn
 
 from . import lib as L
+from .norm import NaiveSyncBatchNorm1d
 from .registry import VOXEL_ENCODERS, build_norm_layer
 from .voxel import PillarBatch
 
@@ -46,6 +48,117 @@ def scatter_reduce(feat, pb: PillarBatch, mode: str):
     """Reduce per-point rows into per-pillar rows (lexicographic pillar order)."""
     L.require_cuda(feat, "feat")
     return _ScatterReduce.apply(feat, pb.point_pillar, pb.pillar_mean, pb.n_pillars, _ScatterReduce.MODES[mode])
+
+
+def _bn_moments(stats, n, world):
+    """[sum | sum of squares] (fp64) of this rank's n rows -> [E x | E x^2] averaged over ranks with EQUAL weight per
+    rank (the rule of naiveSyncBN1d, mmdet3d/ops/norm.py:66-73): one 2C-double all-reduce."""
+    mom = stats / float(max(n, 1))
+    if world > 1:
+        dist.all_reduce(mom)
+        mom /= world
+    return mom
+
+
+class _FusedVFEFn(torch.autograd.Function):
+    """The whole two-layer DynamicScatterVFE (max mode, BatchNorm in training mode) on the fused kernels of
+    csrc/vfe_fused.cu + one tcgen05 GEMM.  Parameter gradients are accumulated straight into ``p.grad``; the only
+    autograd input is a parameter used as an anchor (raw points carry no gradient)."""
+
+    @staticmethod
+    def forward(ctx, anchor, vfe, pb, precision):
+        from .dense import tc_linear
+        l0, l1 = vfe.vfe_layers
+        dev = pb.points.device
+        n, v = pb.points.shape[0], pb.n_pillars
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        sync = world > 1 and isinstance(l0.norm, NaiveSyncBatchNorm1d)
+        world = world if sync else 1
+        s = L.stream_ptr(dev)
+        f32, f64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.float64, device=dev)
+        vox, off = L.f3((vfe.vx, vfe.vy, vfe.vz)), L.f3((vfe.x_offset, vfe.y_offset, vfe.z_offset))
+        unbias = 1.0 if sync else n / max(n - 1, 1)
+
+        def bn_args(layer):
+            nm = layer.norm
+            return L.ptr(nm.weight), L.ptr(nm.bias), float(nm.eps)
+
+        w0, w1 = l0.linear.weight, l1.linear.weight
+        x1, stats0 = torch.empty((n, 64), **f32), torch.empty(128, **f64)
+        L.run("vfe0_forward", L.ptr(pb.points), n, pb.points.shape[1], L.ptr(pb.point_pillar), L.ptr(pb.pillar_mean),
+              L.ptr(pb.pillar_coors), vox, off, L.ptr(w0), L.ptr(x1), L.ptr(stats0), s)
+        mom0 = _bn_moments(stats0, n, world)
+        vmax1 = torch.empty((max(v, 1), 64), dtype=torch.int64, device=dev)
+        L.run("vfe_bn_relu_max", L.ptr(x1), n, 64, L.ptr(pb.point_pillar), L.ptr(mom0), *bn_args(l0),
+              L.ptr(l0.norm.running_mean), L.ptr(l0.norm.running_var), float(l0.norm.momentum), unbias, L.ptr(vmax1), v, s)
+        feat1 = torch.empty((n, 128), **f32)
+        L.run("vfe_cat", L.ptr(x1), n, L.ptr(pb.point_pillar), L.ptr(mom0), *bn_args(l0), L.ptr(vmax1), L.ptr(feat1), s)
+        x2 = tc_linear(feat1, w1, n_out=128, precision=precision)
+        stats1 = torch.empty(256, **f64)
+        L.run("colstats", L.ptr(x2), n, 128, L.ptr(stats1), s)
+        mom1 = _bn_moments(stats1, n, world)
+        vmax2 = torch.empty((max(v, 1), 128), dtype=torch.int64, device=dev)
+        L.run("vfe_bn_relu_max", L.ptr(x2), n, 128, L.ptr(pb.point_pillar), L.ptr(mom1), *bn_args(l1),
+              L.ptr(l1.norm.running_mean), L.ptr(l1.norm.running_var), float(l1.norm.momentum), unbias, L.ptr(vmax2), v, s)
+        out = torch.empty((v, 128), **f32)
+        L.run("vmax_decode", L.ptr(vmax2), v * 128, L.ptr(out), s)
+        if not sync:
+            for layer in (l0, l1):
+                layer.norm.num_batches_tracked += 1
+        ctx.keep = (vfe, pb, precision, world, x1, feat1, x2, mom0, mom1, vmax1, vmax2, vox, off)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_vox):
+        from .dense import tc_linear, tc_wgrad
+        vfe, pb, precision, world, x1, feat1, x2, mom0, mom1, vmax1, vmax2, vox, off = ctx.keep
+        l0, l1 = vfe.vfe_layers
+        dev = d_vox.device
+        n, v = pb.points.shape[0], pb.n_pillars
+        s = L.stream_ptr(dev)
+        f32, f64 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.float64, device=dev)
+        d_vox = d_vox.contiguous()
+        inv_wn = 1.0 / (world * max(n, 1))
+
+        def grad(p):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            return p.grad
+
+        def bn_args(layer):
+            nm = layer.norm
+            return L.ptr(nm.weight), L.ptr(nm.bias), float(nm.eps)
+
+        def coeffs(layer, c, sums, mom):
+            ab = torch.empty(2 * c, **f64)
+            nm = layer.norm
+            L.run("bn_backward_coeffs", c, L.ptr(sums), L.ptr(mom), L.ptr(nm.weight), float(nm.eps), L.ptr(ab),
+                  L.ptr(grad(nm.weight)), L.ptr(grad(nm.bias)), s)
+            if world > 1:
+                dist.all_reduce(ab)
+            return ab
+
+        # ---- layer 1
+        sums1 = torch.empty(256, **f64)
+        common1 = (L.ptr(x2), n, L.ptr(pb.point_pillar), L.ptr(mom1), *bn_args(l1), L.ptr(vmax2), L.ptr(d_vox))
+        L.run("vfe1_backward", 0, *common1, L.ptr(sums1), None, 0.0, None, s)
+        ab1 = coeffs(l1, 128, sums1, mom1)
+        dx2 = torch.empty((n, 128), **f32)
+        L.run("vfe1_backward", 1, *common1, None, L.ptr(ab1), inv_wn, L.ptr(dx2), s)
+        w1 = l1.linear.weight
+        tc_wgrad(dx2, feat1, grad(w1), None, precision=precision)
+        dfeat1 = tc_linear(dx2, w1, n_out=128, w_mn_major=True, precision=precision)
+        # ---- pillar-max gather of layer 1's operand, then layer 0
+        d_vmax1 = torch.empty((max(v, 1), 64), **f32)
+        L.run("vfe_gather_backward", L.ptr(dfeat1), n, L.ptr(pb.point_pillar), L.ptr(d_vmax1), v, s)
+        sums0 = torch.empty(128, **f64)
+        common0 = (L.ptr(pb.points), n, pb.points.shape[1], L.ptr(pb.point_pillar), L.ptr(pb.pillar_mean),
+                   L.ptr(pb.pillar_coors), vox, off, L.ptr(x1), L.ptr(mom0), *bn_args(l0), L.ptr(vmax1), L.ptr(d_vmax1),
+                   L.ptr(dfeat1))
+        L.run("vfe0_backward", 0, *common0, L.ptr(sums0), None, 0.0, None, s)
+        ab0 = coeffs(l0, 64, sums0, mom0)
+        L.run("vfe0_backward", 1, *common0, None, L.ptr(ab0), inv_wn, L.ptr(grad(l0.linear.weight)), s)
+        return None, None, None, None
 
 
 class DynamicVFELayer(nn.Module):
@@ -107,8 +220,21 @@ class DynamicScatterVFE(nn.Module):
                                             L.stream_ptr(pts.device))
         return out
 
+    def _can_fuse(self, pb):
+        l = self.vfe_layers
+        return (self.tc_precision in (1, 3) and self.training and self.mode == "max" and self.num_vfe == 2
+                and self.raw_channels == 5 and pb.points.shape[1] == 5 and pb.points.shape[0] > 1
+                and l[0].linear.out_features == 64 and l[1].linear.in_features == 128 and l[1].linear.out_features == 128
+                and all(isinstance(x.norm, nn.BatchNorm1d) and x.norm.affine and x.norm.track_running_stats
+                        and x.norm.momentum is not None for x in l)
+                and getattr(self, "fused", True))
+
     def forward(self, pb: PillarBatch, return_inv=False):
         """-> voxel_feats [V, C_out], voxel_coors [V,4] int32 (b,z,y,x) sorted (, point->pillar map)."""
+        if self._can_fuse(pb):       # the GeoMAE configuration in training: fused kernels (csrc/vfe_fused.cu)
+            voxel_feats = _FusedVFEFn.apply(self.vfe_layers[0].linear.weight, self, pb, self.tc_precision)
+            coors = pb.pillar_coors[:pb.n_pillars]
+            return (voxel_feats, coors, pb.point_pillar) if return_inv else (voxel_feats, coors)
         features = self.decorate(pb)
         voxel_feats = None
         for i, vfe in enumerate(self.vfe_layers):

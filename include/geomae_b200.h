@@ -206,6 +206,51 @@ int geomae_scatter_reduce_bwd(const float* d_out, int64_t n_points, int32_t chan
                               const float* pillar_mean, const int32_t* arg, int32_t mode, float* d_feat,
                               void* stream);
 
+/* ---- DynamicScatterVFE of the GeoMAE configs as fused kernels (csrc/vfe_fused.cu): 5 raw channels -> 11 decorated
+ * -> Linear(11->64, no bias) -> BN -> ReLU -> scatter-max -> [point | pillar max] -> Linear(128->128) -> BN -> ReLU ->
+ * scatter-max.  BatchNorm moments `mom` = [E x (C) | E x^2 (C)] are fp64 and already averaged over ranks (equal
+ * weight per rank, mmdet3d/ops/norm.py:66-73); `vmax` holds per (pillar, channel) one uint64 =
+ * (order-preserving key of the post-ReLU max << 32 | ~index of the arg-max point, smallest index on ties).
+ * replaces: DynamicScatterVFE.forward (voxel_encoders/voxel_encoder.py:358-419), DynamicVFELayer (utils.py:129-144),
+ *           scatter_v2(mode='max') (ops/sst/sst_ops.py:8-39), naiveSyncBN1d (ops/norm.py:55-86) and their autograd. */
+
+/* x1[n,64] = decorate(points) W0^T; stats[128] (fp64, zeroed here) = column sums and sums of squares of x1. */
+int geomae_vfe0_forward(const float* points, int64_t n, int32_t channels, const int32_t* point_pillar,
+                        const float* pillar_mean, const int32_t* pillar_coors, const float voxel_xyz[3],
+                        const float centre_offset_xyz[3], const float* W0, float* x1, double* stats, void* stream);
+/* stats[2*128] (fp64, zeroed here) of x [n,128]. */
+int geomae_colstats(const float* x, int64_t n, int32_t channels, double* stats, void* stream);
+/* vmax[n_pillars, C] (zeroed here) = scatter-max of relu(bn(x)); also the running-statistics update of the layer
+ * (running_* may be NULL; unbias = N/(N-1) for the single-rank nn.BatchNorm1d rule, 1 for the synchronised one). */
+int geomae_vfe_bn_relu_max(const float* x, int64_t n, int32_t channels, const int32_t* point_pillar, const double* mom,
+                           const float* gamma, const float* beta, float eps, float* running_mean, float* running_var,
+                           float momentum, float unbias, uint64_t* vmax, int64_t n_pillars, void* stream);
+/* feat1[n,128] = [relu(bn0(x1)) | max of the point's pillar]. */
+int geomae_vfe_cat(const float* x1, int64_t n, const int32_t* point_pillar, const double* mom, const float* gamma,
+                   const float* beta, float eps, const uint64_t* vmax1, float* feat1, void* stream);
+/* out[i] = value part of vmax[i]. */
+int geomae_vmax_decode(const uint64_t* vmax, int64_t total, float* out, void* stream);
+/* Layer-1 backward.  mode 0: sums[256] (zeroed here) = [sum g | sum g (x - mean)] with g the gradient reaching the
+ * BN output (arg-max routing of d_vox, ReLU mask).  mode 1: dx2 = scale g + (ab[c] + 2 ab[128+c] x) * inv_wn, where
+ * ab = geomae_bn_backward_coeffs summed over ranks and inv_wn = 1 / (world_size * n). */
+int geomae_vfe1_backward(int32_t mode, const float* x2, int64_t n, const int32_t* point_pillar, const double* mom,
+                         const float* gamma, const float* beta, float eps, const uint64_t* vmax2, const float* d_vox,
+                         double* sums, const double* ab, float inv_wn, float* dx2, void* stream);
+/* Per-channel BatchNorm backward terms from `sums`: d_gamma += sum g xhat, d_beta += sum g,
+ * ab = [dL/d(mean) | dL/d(mean of squares)] of this rank. */
+int geomae_bn_backward_coeffs(int32_t channels, const double* sums, const double* mom, const float* gamma, float eps,
+                              double* ab, float* d_gamma, float* d_beta, void* stream);
+/* d_vmax1[n_pillars,64] (zeroed here) += dfeat1[p, 64:128] of the pillar's points. */
+int geomae_vfe_gather_backward(const float* dfeat1, int64_t n, const int32_t* point_pillar, float* d_vmax1,
+                               int64_t n_pillars, void* stream);
+/* Layer-0 backward.  mode 0: the two BatchNorm sums[128] (zeroed here).  mode 1: dW0[64,11] += dx1^T decorate(points)
+ * (dx1 is formed on the fly and never stored: raw points carry no gradient). */
+int geomae_vfe0_backward(int32_t mode, const float* points, int64_t n, int32_t channels, const int32_t* point_pillar,
+                         const float* pillar_mean, const int32_t* pillar_coors, const float voxel_xyz[3],
+                         const float centre_offset_xyz[3], const float* x1, const double* mom, const float* gamma,
+                         const float* beta, float eps, const uint64_t* vmax1, const float* d_vmax1,
+                         const float* dfeat1, double* sums, const double* ab, float inv_wn, float* dW0, void* stream);
+
 /* ------------------------------------------------- sparse regional attention */
 
 /* Multi-head attention inside CSR windows (no padding, no key_padding_mask needed).
