@@ -33,6 +33,7 @@ struct LinArgs {
   int precision;
   int w_early;      // packed weights may be fetched before gm_pdl_wait() (see common.cuh)
   const float* dot_src; int ld_dot; float* dot_out;   // EPI 0, N = 128: dot_out[row, h] = sum_head out * dot_src
+  float* ln_dgamma; float* ln_dbeta; float* ln_dcolsum;   // EPI 3 accumulators (+=)
 };
 
 // Exact-erf GELU (F.gelu default, sst_basic_block.py:153-154) and its derivative, evaluated with the
@@ -319,6 +320,100 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
         }
       }
     }
+  } else if constexpr (EPI == 3) {
+    // LayerNorm BACKWARD as the epilogue: the GEMM result (+ add_src) is dz, the gradient reaching a LayerNorm output;
+    // with the saved pre-LN rows s = ln_in, (mean, rstd) = ln_stats and gamma this writes
+    //   ds = rstd (g - mean_c(g) - xhat mean_c(g xhat)),  g = dz gamma,  xhat = (s - mean) rstd
+    // to `out` and accumulates d_gamma += sum dz xhat, d_beta += sum dz, d_colsum += sum ds (the bias gradient of the
+    // linear layer in front of the LayerNorm).  dz itself never reaches memory.
+    static_assert(EPI != 3 || NT == 128, "LayerNorm-backward epilogue needs the whole row in one CTA");
+    constexpr int C4 = 32;
+    constexpr int RPW = TM / (LTHREADS / 32);                  // rows per warp (16 or 8)
+    constexpr int RB = 4, NB = RPW / RB;                       // rows per batch
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma) + lane);
+    float4 res[RB], sx[RB];
+    float2 st[RB];
+    auto fetch = [&](int batch) {
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int row = row0 + warp + (LTHREADS / 32) * (batch * RB + j);
+        const bool ok = row < a.n_rows;
+        res[j] = (ok && a.add_src) ? __ldg(reinterpret_cast<const float4*>(a.add_src + (int64_t)row * a.ld_add) + lane)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        sx[j] = ok ? __ldg(reinterpret_cast<const float4*>(a.ln_in + (int64_t)row * NT) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        st[j] = ok ? __ldg(reinterpret_cast<const float2*>(a.ln_stats + 2 * (int64_t)row)) : make_float2(0.f, 0.f);
+      }
+    };
+    fetch(0);
+    tc::mbar_wait(&mbar, (n_chunks - 1) & 1);
+    tc::fence_after_sync();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+      const int c0 = hsel * 64 + half * 32;
+      tc::tmem_ld32(t_lane + c0, v);
+      tc::tmem_ld_wait();
+      if (drains) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *ctile<C4>(sC, trow, (c0 + c) >> 2) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
+    }
+    __syncthreads();
+    float4 accg = make_float4(0.f, 0.f, 0.f, 0.f), accb = accg, accs = accg;
+#pragma unroll 1
+    for (int batch = 0; batch < NB; ++batch) {
+      float4 dz[RB], xh[RB];
+      float p1[RB], p2[RB], rs[RB];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int r = warp + (LTHREADS / 32) * (batch * RB + j);
+        dz[j] = *ctile<C4>(sC, r, lane);
+        dz[j].x += res[j].x; dz[j].y += res[j].y; dz[j].z += res[j].z; dz[j].w += res[j].w;
+        rs[j] = st[j].y;
+        xh[j] = make_float4((sx[j].x - st[j].x) * rs[j], (sx[j].y - st[j].x) * rs[j], (sx[j].z - st[j].x) * rs[j],
+                            (sx[j].w - st[j].x) * rs[j]);
+      }
+      if (batch + 1 < NB) fetch(batch + 1);
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const float gx = dz[j].x * g4.x, gy = dz[j].y * g4.y, gz = dz[j].z * g4.z, gw = dz[j].w * g4.w;
+        p1[j] = (gx + gy) + (gz + gw);
+        p2[j] = (gx * xh[j].x + gy * xh[j].y) + (gz * xh[j].z + gw * xh[j].w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+          p1[j] += __shfl_xor_sync(0xffffffffu, p1[j], o);
+          p2[j] += __shfl_xor_sync(0xffffffffu, p2[j], o);
+        }
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        const int row = row0 + warp + (LTHREADS / 32) * (batch * RB + j);
+        if (row < a.n_rows) {
+          const float m1 = p1[j] * (1.0f / NT), m2 = p2[j] * (1.0f / NT);
+          const float4 o = make_float4(rs[j] * (dz[j].x * g4.x - m1 - xh[j].x * m2), rs[j] * (dz[j].y * g4.y - m1 - xh[j].y * m2),
+                                       rs[j] * (dz[j].z * g4.z - m1 - xh[j].z * m2), rs[j] * (dz[j].w * g4.w - m1 - xh[j].w * m2));
+          reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[lane] = o;
+          accg.x += dz[j].x * xh[j].x; accg.y += dz[j].y * xh[j].y; accg.z += dz[j].z * xh[j].z; accg.w += dz[j].w * xh[j].w;
+          accb.x += dz[j].x; accb.y += dz[j].y; accb.z += dz[j].z; accb.w += dz[j].w;
+          accs.x += o.x; accs.y += o.y; accs.z += o.z; accs.w += o.w;
+        }
+      }
+    }
+    __syncthreads();                                           // the accumulator tile is dead: reuse it for the column sums
+    float* part = sC;                                          // [8 warps][3][128]
+    reinterpret_cast<float4*>(part + (warp * 3 + 0) * NT)[lane] = accg;
+    reinterpret_cast<float4*>(part + (warp * 3 + 1) * NT)[lane] = accb;
+    reinterpret_cast<float4*>(part + (warp * 3 + 2) * NT)[lane] = accs;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * NT; i += LTHREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < LTHREADS / 32; ++w) t += part[w * 3 * NT + i];
+      float* dst = i < NT ? a.ln_dgamma : (i < 2 * NT ? a.ln_dbeta : a.ln_dcolsum);
+      if (dst) atomicAdd(dst + (i % NT), t);
+    }
   } else {
     constexpr int C4 = 16;                                     // 64-column panels
     constexpr int NP = NT / 64;                                // panels
@@ -397,7 +492,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
 template <int NT, int EPI, bool POS, int TMR>
 int launch_linear_impl(const LinArgs& a, cudaStream_t stream) {
   constexpr int per_prec = TMR * KC * 2 + NT * KC * 2;
-  constexpr int epi_bytes = TMR * (EPI == 1 ? 128 : 64) * 4;          // fp32 staging tile of the epilogue
+  constexpr int epi_bytes = TMR * ((EPI == 1 || EPI == 3) ? 128 : 64) * 4;          // fp32 staging tile of the epilogue
   const int operands = (a.precision == 3 ? 2 : 1) * per_prec;
   const int smem = (operands > epi_bytes ? operands : epi_bytes) + 1024;
   static bool configured = false;
@@ -660,7 +755,7 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
   GM_REQUIRE(p->K > 0 && p->K % KC == 0, "tc_linear: K=%d must be a positive multiple of %d", p->K, KC);
   GM_REQUIRE(p->N_total > 0 && p->N_total % 128 == 0, "tc_linear: N=%d must be a multiple of 128", p->N_total);
   GM_REQUIRE(p->precision == 1 || p->precision == 3, "tc_linear: precision must be 1 (bf16) or 3 (bf16x3)");
-  GM_REQUIRE(p->epilogue >= 0 && p->epilogue <= 2, "tc_linear: unknown epilogue %d", p->epilogue);
+  GM_REQUIRE(p->epilogue >= 0 && p->epilogue <= 3, "tc_linear: unknown epilogue %d", p->epilogue);
   GM_REQUIRE(p->lda % 4 == 0 && p->ldw % 4 == 0 && p->ldo % 4 == 0, "tc_linear: leading dimensions must be multiples of 4");
   if (p->n_rows == 0) return GEOMAE_OK;
   LinArgs a;
@@ -676,6 +771,7 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
   a.gelu_u = p->gelu_u; a.ldu = p->ldu; a.precision = p->precision;
   a.w_early = gm_weights_stable() ? 1 : 0;
   a.dot_src = p->dot_src; a.ld_dot = p->ld_dot; a.dot_out = p->dot_out;
+  a.ln_dgamma = a.ln_dbeta = a.ln_dcolsum = nullptr;
   GM_REQUIRE(!p->dot_src || (p->dot_out && p->epilogue == 0 && p->N_total == 128 && p->pos_slabs == 0 && p->ld_dot % 4 == 0),
              "tc_linear: the per-head dot side output needs epilogue 0, N = 128, no position prologue");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -683,6 +779,12 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
     GM_REQUIRE(p->N_total == 128 && p->bias && p->add_src && p->ln_gamma && p->ln_beta,
                "tc_linear: LayerNorm epilogue needs N=128, bias, residual, gamma, beta");
     return launch_linear<128, 1>(a, stream);
+  }
+  if (p->epilogue == 3) {
+    GM_REQUIRE(p->N_total == 128 && p->ln_gamma && p->ln_in && p->ln_stats && p->ln_dgamma && p->ln_dbeta && !p->bias,
+               "tc_linear: LayerNorm-backward epilogue needs N=128, gamma, saved rows + stats, gradient accumulators, no bias");
+    a.ln_dgamma = p->ln_dgamma; a.ln_dbeta = p->ln_dbeta; a.ln_dcolsum = p->ln_dcolsum;
+    return launch_linear<128, 3>(a, stream);
   }
   if (p->epilogue == 2) {
     GM_REQUIRE(p->gelu_u, "tc_linear: gelu-grad epilogue needs u");

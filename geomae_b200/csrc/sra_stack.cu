@@ -160,7 +160,6 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
                       const float* d_out, float* d_in, float* scratch) {
   const int n = (int)c->n_tokens, d = c->d_model, f = c->ffn, p = c->precision;
   const int64_t set = scratch_floats(c);
-  const float* dz = d_out;
   cudaEvent_t side_done[2] = {nullptr, nullptr};
   struct StableGuard { ~StableGuard() { gm_set_weights_stable(false); } } guard;
   gm_set_weights_stable(true);      // backward re-uses the images packed by the forward pass of this step
@@ -180,23 +179,23 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     const geomae_sra_windows& w = c->shift[L.shift];
     const float* x = l == 0 ? x_in : saved[l - 1].z;
     float* dx = l == 0 ? d_in : dxb;
-    if (side_done[l & 1]) GM_CUDA(cudaStreamWaitEvent(main, side_done[l & 1], 0));   // set (l&1) free again
     // ---- dX chain of the layer, back to back on `main` (no stream operations in between, so consecutive kernels
-    // overlap through programmatic dependent launch)
-    {
+    // overlap through programmatic dependent launch).  Both LayerNorm backwards are GEMM epilogues (epilogue 3): the
+    // gradient reaching a LayerNorm output never touches memory.  ds2 of this layer was written by the layer above
+    // (its dx GEMM, below) — only the top layer runs the stand-alone LayerNorm backward on d_out.
+    if (l == n_layers - 1) {
+      if (side_done[l & 1]) GM_CUDA(cudaStreamWaitEvent(main, side_done[l & 1], 0));
       Span span(4, 0.0, main);
-      GM_TRY(geomae_layernorm_bwd(dz, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, L.g_lin2_b, main));
+      GM_TRY(geomae_layernorm_bwd(d_out, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, L.g_lin2_b, main));
     }
     geomae_linear_args e{};
     e.gelu_u = S.u; e.ldu = f; e.epilogue = 2;
     GM_TRY(lin(ds2, d, n, d, L.lin2_w, f, d, 1, nullptr, f, du, f, p, main, &e, L.p_lin2));
-    geomae_linear_args e1{};
-    e1.add_src = ds2; e1.ld_add = d;
-    GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, dy, d, p, main, &e1, L.p_lin1));
-    {
-      Span span(4, 0.0, main);
-      GM_TRY(geomae_layernorm_bwd(dy, S.s1, S.st1, L.norm1_w, n, d, ds1, L.g_norm1_w, L.g_norm1_b, L.g_out_proj_b, main));
-    }
+    geomae_linear_args e1{};           // dy = du W1 + ds2, then LayerNorm-1 backward in the epilogue -> ds1
+    e1.add_src = ds2; e1.ld_add = d; e1.epilogue = 3;
+    e1.ln_gamma = L.norm1_w; e1.ln_in = S.s1; e1.ln_stats = S.st1;
+    e1.ln_dgamma = L.g_norm1_w; e1.ln_dbeta = L.g_norm1_b; e1.ln_dcolsum = L.g_out_proj_b;
+    GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, ds1, d, p, main, &e1, L.p_lin1));
     geomae_linear_args ed{};          // bf16 mode: D = dO . O per (token, head) leaves this GEMM's epilogue
     if (p == 1) { ed.dot_src = S.attn; ed.ld_dot = d; ed.dot_out = dd; }
     GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main, &ed, L.p_out_proj));
@@ -211,7 +210,18 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     }
     geomae_linear_args e2{};
     e2.add_src = ds1; e2.ld_add = d;
-    GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, dx, d, p, main, &e2, L.p_in_proj));
+    if (l > 0) {                       // dx = dqkv W_in + ds1 is the dz of the layer below: its LayerNorm-2 backward here
+      const geomae_sra_layer& Lb = layers[l - 1];
+      const geomae_sra_saved& Sb = saved[l - 1];
+      float* ds2_below = scratch + (int64_t)((l - 1) & 1) * set;      // slot 0 of the other scratch set
+      if (side_done[(l - 1) & 1]) GM_CUDA(cudaStreamWaitEvent(main, side_done[(l - 1) & 1], 0));   // that set is free again
+      e2.epilogue = 3;
+      e2.ln_gamma = Lb.norm2_w; e2.ln_in = Sb.s2; e2.ln_stats = Sb.st2;
+      e2.ln_dgamma = Lb.g_norm2_w; e2.ln_dbeta = Lb.g_norm2_b; e2.ln_dcolsum = Lb.g_lin2_b;
+      GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, ds2_below, d, p, main, &e2, L.p_in_proj));
+    } else {
+      GM_TRY(lin(dqkv, 3 * d, n, 3 * d, L.in_proj_w, d, 3 * d, 1, nullptr, d, dx, d, p, main, &e2, L.p_in_proj));
+    }
     // ---- the four weight gradients of the layer on `side`, one hand-off per layer; they overlap the next
     // layer's dX chain (bias gradients of linear2 / out_proj come from the LayerNorm backward above)
     GM_TRY(hand_off(main, side));
@@ -221,7 +231,6 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, side, c->pos_table, w.tok_cell, 2, 0));
     side_done[l & 1] = g_lanes.event();
     GM_CUDA(cudaEventRecord(side_done[l & 1], side));
-    dz = dx;
   }
   GM_TRY(hand_off(side, main));   // join
   return GEOMAE_OK;

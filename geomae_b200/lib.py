@@ -56,7 +56,8 @@ class LinearArgs(C.Structure):
                 ("ln_stats", C.c_void_p),
                 ("gelu_u", C.c_void_p), ("ldu", C.c_int32),
                 ("epilogue", C.c_int32), ("precision", C.c_int32), ("Wp_hi", C.c_void_p), ("Wp_lo", C.c_void_p),
-                ("dot_src", C.c_void_p), ("ld_dot", C.c_int32), ("dot_out", C.c_void_p)]
+                ("dot_src", C.c_void_p), ("ld_dot", C.c_int32), ("dot_out", C.c_void_p),
+                ("ln_dgamma", C.c_void_p), ("ln_dbeta", C.c_void_p), ("ln_dcolsum", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):

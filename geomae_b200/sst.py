@@ -292,7 +292,7 @@ class _SRAStackFn(torch.autograd.Function):
                               device=x.device)
         L.run("sra_stack_backward", C.byref(ctx.c), len(ctx.stack.layers), ctx.layers, ctx.saved, L.ptr(x), L.ptr(dz),
               L.ptr(dx), L.ptr(scratch), L.stream_ptr(x.device))
-        L.add_launches((11 if ctx.c.precision == 1 else 12) * len(ctx.stack.layers) - 1)
+        L.add_launches((9 if ctx.c.precision == 1 else 10) * len(ctx.stack.layers))    # + the top LayerNorm backward
         return dx, None, None, None, None
 
 
@@ -329,7 +329,7 @@ class _SRADualStackFn(torch.autograd.Function):
                               device=x.device)
         L.run("sra_stack2_backward", C.byref(c), nl, la, saved_a, lb, saved_b, L.ptr(x), L.ptr(dza), L.ptr(dzb), L.ptr(dxa),
               L.ptr(dxb), L.ptr(scratch), L.stream_ptr(x.device))
-        L.add_launches((22 if c.precision == 1 else 24) * nl - 1)
+        L.add_launches((18 if c.precision == 1 else 20) * nl + 1)
         return dxa + dxb, None, None, None, None, None
 
 

@@ -311,6 +311,11 @@ typedef struct geomae_linear_args {
    * out[row, .] * dot_src[row, .]  (h = 0..7).  The attention backward needs D = dO . O per (token, head); the
    * GEMM that produces dO computes it on the way out instead of both attention passes re-reading dO and O. */
   const float* dot_src; int32_t ld_dot; float* dot_out;
+  /* epilogue 3 (N_total == 128, no bias): LayerNorm BACKWARD.  acc (+ add_src) is the gradient dz reaching a LayerNorm
+   * output; with ln_in (saved pre-LN rows, INPUT here), ln_stats (mean, rstd) and ln_gamma the kernel writes
+   * out = d(pre-LN rows) and accumulates (+=) ln_dgamma, ln_dbeta and (optional) ln_dcolsum = column sums of out.
+   * replaces: ATen layer_norm backward after the matching dX GEMM — dz is never stored. */
+  float* ln_dgamma; float* ln_dbeta; float* ln_dcolsum;
 } geomae_linear_args;
 
 int geomae_tc_linear(const geomae_linear_args* args, void* stream);
