@@ -158,10 +158,12 @@ def run_reference(args):
     samples = 1                      # bounded sample: one frame per step keeps K+W steps within minutes
     for _ in range(min(args.warmup, 1)):
         cpu_reference_step(samples, args.sweeps, threads)
-    times = []
-    for i in range(max(1, min(args.steps, 5))):
+    times, t0 = [], time.perf_counter()
+    for i in range(max(1, args.steps)):
         t, n = cpu_reference_step(samples, args.sweeps, threads, seed=10 + i)
         times.append(t / n)
+        if time.perf_counter() - t0 > 150.0:        # keep the whole arm within a few minutes
+            break
     sec_per_frame = float(np.mean(times))
     v = 1.0 / sec_per_frame
     sample = f"{len(times)} steps x {samples} frame (fwd+bwd, full 6+2+2-block model, no optimiser), {threads} threads"
@@ -276,10 +278,10 @@ def main():
     L.run("profile_enable", 1)
     ms_prof = timed_loop(step_resident, K)
     per_call = L.stop_timing()
-    prof_ms, prof_n, prof_fl = (C.c_double * 5)(), (C.c_int64 * 5)(), (C.c_double * 5)()
-    L.run("profile_read", prof_ms, prof_n, prof_fl)
+    prof_ms, prof_n, prof_fl, prof_by = (C.c_double * 5)(), (C.c_int64 * 5)(), (C.c_double * 5)(), (C.c_double * 5)()
+    L.run("profile_read", prof_ms, prof_n, prof_fl, prof_by)
     L.run("profile_enable", 0)
-    prof_ms, prof_n, prof_fl = list(prof_ms), list(prof_n), list(prof_fl)
+    prof_ms, prof_n, prof_fl, prof_by = list(prof_ms), list(prof_n), list(prof_fl), list(prof_by)
     barrier()
     for i in range(min(W, 2)):
         step_host(i)
@@ -308,7 +310,8 @@ def main():
     tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured" if peaks else "fallback"
-    fam_names = ["k_tc_linear", "k_tc_wgrad", "k_sra_fwd", "k_sra_bwd_q+k_sra_bwd_kv", "k_ln_bwd"]
+    attn = ("k_sra_tc_fwd", "k_sra_tc_bwd") if args.sra_impl == "tc1" else ("k_sra_fwd", "k_sra_bwd_q+k_sra_bwd_kv")
+    fam_names = ["k_tc_linear", "k_tc_wgrad", attn[0], attn[1], "k_ln_bwd"]
     roof, fam_table = None, {}
     if prof_ms is not None and sum(prof_ms) > 0:
         sq = attention_pair_counts()
@@ -319,15 +322,27 @@ def main():
         prof_fl[3] = pairs * bb.nhead[0] * 160.0    # bwd: 5 products
         for f, nm in enumerate(fam_names):
             if prof_n[f]:
+                sec = prof_ms[f] * 1e-3
                 fam_table[nm] = dict(ms_per_step=prof_ms[f] / K, launches_per_step=prof_n[f] / K,
-                                     tflops=prof_fl[f] / (prof_ms[f] * 1e-3) / 1e12 if prof_fl[f] else None)
+                                     avg_launch_us=1e3 * prof_ms[f] / prof_n[f],
+                                     algorithmic_gb_per_step=prof_by[f] / K / 1e9, gbs=prof_by[f] / sec / 1e9,
+                                     hbm_frac=prof_by[f] / sec / 1e9 / hbm_peak,
+                                     tflops=prof_fl[f] / sec / 1e12 if prof_fl[f] else None,
+                                     tensor_frac=prof_fl[f] / sec / 1e12 / tens_peak if prof_fl[f] else None)
+        # The dominant kernel family by device time.  Every SRA kernel is HBM-bound by arithmetic intensity: the dense
+        # layers do 2*K*N flop per token against 4*(K+N) B (K, N <= 384: 24-77 flop/B, ridge = peak flops / peak B/s
+        # ~ 210 flop/B), attention with head_dim 16 even less.  So the roofline is bytes: achieved = algorithmic bytes
+        # of the family's launches (counted per launch in csrc/sra_stack.cu) / their CUDA-event time.
         top = max(range(5), key=lambda f: prof_ms[f])
-        ach = prof_fl[top] / (prof_ms[top] * 1e-3) / 1e12
-        roof = dict(kernel=fam_names[top], bound="tensor", achieved=ach, peak=tens_peak, unit="TFLOP/s",
-                    frac=ach / tens_peak, traffic=None, peak_source=peak_src,
-                    avg_launch_ms=prof_ms[top] / prof_n[top], launches=int(prof_n[top]),
-                    note="sum of per-launch device time of the family / timed wall time = share; kernels of different "
-                         "streams overlap, so shares can add up to more than 1",
+        ach = prof_by[top] / (prof_ms[top] * 1e-3) / 1e9
+        roof = dict(kernel=fam_names[top], bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
+                    traffic=None, peak_source=peak_src, avg_launch_ms=prof_ms[top] / prof_n[top], launches=int(prof_n[top]),
+                    algorithmic_bytes_per_launch=prof_by[top] / prof_n[top],
+                    tensor_tflops=prof_fl[top] / (prof_ms[top] * 1e-3) / 1e12 if prof_fl[top] else None,
+                    tensor_peak_tflops=tens_peak,
+                    note="timed with CUDA events on the launching stream around every launch of the family in a separate "
+                         "instrumented pass over the same K steps; launches of concurrent streams overlap, so family "
+                         "shares can add up to more than 1; the ncu launch list of the same command is under profiles/",
                     share_of_step=prof_ms[top] / ms_prof, instrumented_ms_per_step=ms_prof / K)
     aux = hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src)
     line = dict(
@@ -348,10 +363,15 @@ def main():
         loss=last.get("loss_host"))
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sec, n = cpu_reference_step(1, args.sweeps, threads)
-        sec, n = cpu_reference_step(1, args.sweeps, threads, seed=2)
-        line["cpu_baseline"] = dict(value=n / sec, unit="frames/s", cores=threads, kind="port",
-                                    sample="1 frame fwd+bwd of the oracle port (full model), second of two runs")
+        cpu_reference_step(1, args.sweeps, threads)                       # warm-up (thread pools, allocator)
+        t_cpu, n_cpu, t0 = 0.0, 0, time.perf_counter()
+        while time.perf_counter() - t0 < 12.0 and n_cpu < 64:             # bounded sample: ~12 s of host work
+            sec, n = cpu_reference_step(1, args.sweeps, threads, seed=2 + n_cpu)
+            t_cpu += sec
+            n_cpu += n
+        line["cpu_baseline"] = dict(value=n_cpu / t_cpu, unit="frames/s", cores=threads, kind="port",
+                                    sample=f"{n_cpu} single-frame steps (fwd+bwd of the full 6+2+2-block model, no optimiser) "
+                                           f"of the oracle port in {t_cpu:.1f} s, torch CPU fp32 on {threads} threads")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

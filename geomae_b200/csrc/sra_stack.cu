@@ -16,8 +16,9 @@ struct Prof {
   cudaEvent_t start[MAX_SPANS], stop[MAX_SPANS];
   int family[MAX_SPANS];
   double flops[MAX_SPANS];
+  double bytes[MAX_SPANS];
   int created = 0;
-  cudaEvent_t* begin(int fam, double fl, cudaStream_t st) {
+  cudaEvent_t* begin(int fam, double fl, double by, cudaStream_t st) {
     if (!on || n >= MAX_SPANS) return nullptr;
     if (n >= created) {
       if (cudaEventCreate(&start[n]) != cudaSuccess || cudaEventCreate(&stop[n]) != cudaSuccess) return nullptr;
@@ -25,6 +26,7 @@ struct Prof {
     }
     family[n] = fam;
     flops[n] = fl;
+    bytes[n] = by;
     cudaEventRecord(start[n], st);
     return &stop[n++];
   }
@@ -34,7 +36,9 @@ Prof g_prof;
 struct Span {
   cudaEvent_t* stop;
   cudaStream_t st;
-  Span(int fam, double flops, void* stream) : st((cudaStream_t)stream) { stop = g_prof.begin(fam, flops, st); }
+  Span(int fam, double flops, void* stream, double bytes = 0.0) : st((cudaStream_t)stream) {
+    stop = g_prof.begin(fam, flops, bytes, st);
+  }
   ~Span() { if (stop) cudaEventRecord(*stop, st); }
 };
 
@@ -44,7 +48,14 @@ int lin(const float* A, int lda, int n, int K, const float* W, int ldw, int w_ro
   a.A = A; a.lda = lda; a.n_rows = n; a.K = K; a.W = W; a.ldw = ldw; a.w_rows = w_rows; a.w_mn_major = mn;
   if (packed) { a.Wp_hi = packed[0]; a.Wp_lo = packed[1]; }
   a.bias = bias; a.N_total = N; a.out = out; a.ldo = ldo; a.precision = prec;
-  Span span(0, 2.0 * n * (double)K * N, stream);
+  // algorithmic bytes of the launch: A rows, bf16 weight image, output rows, plus every per-row side operand / output
+  double bytes = 4.0 * n * ((double)K + N) + 2.0 * (double)K * N;
+  if (a.add_src) bytes += 4.0 * n * N;
+  if (a.epilogue == 1) bytes += 4.0 * n * (N + 2.0);          // saved pre-LN rows + (mean, rstd)
+  if (a.epilogue == 2) bytes += 4.0 * n * N;                  // GELU input
+  if (a.epilogue == 3) bytes += 4.0 * n * (N + 2.0);          // saved pre-LN rows + (mean, rstd) read back
+  if (a.dot_src) bytes += 4.0 * n * (N + 8.0);
+  Span span(0, 2.0 * n * (double)K * N, stream, bytes);
   return geomae_tc_linear(&a, stream);
 }
 
@@ -55,7 +66,7 @@ int wgrad(const float* dY, int ldy, const float* X, int ldx, int n, float* dW, i
   a.dY = dY; a.ldy = ldy; a.X = X; a.ldx = ldx; a.n_rows = n; a.pos_table = pos; a.tok_cell = cell;
   a.pos_slabs = pos_slabs; a.x_gelu = gelu; a.dW = dW; a.ldw = ldw; a.db = db; a.M_total = M; a.N_total = N;
   a.precision = prec;
-  Span span(1, 2.0 * n * (double)M * N, stream);
+  Span span(1, 2.0 * n * (double)M * N, stream, 4.0 * n * ((double)M + N) + 4.0 * (double)M * N);
   return geomae_tc_wgrad(&a, stream);
 }
 
@@ -103,7 +114,7 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
     GM_TRY(lin(x, d, n, d, L.in_proj_w, d, 3 * d, 0, L.in_proj_b, 3 * d, S.qkv, 3 * d, p, stream, &e, L.p_in_proj));
     gm_set_weights_stable(true);    // from here on the images were complete before the predecessor kernel started
     {
-      Span span(2, 0.0, stream);
+      Span span(2, 0.0, stream, 4.0 * n * (3.0 * d + d + c->n_heads));
       if (p == 1)    // bf16 mode: QK^T / PV tiles on the tensor cores (sra_attention_tc.cu)
         GM_TRY(geomae_sra_attention_tc_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
       else
@@ -185,7 +196,7 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     // (its dx GEMM, below) — only the top layer runs the stand-alone LayerNorm backward on d_out.
     if (l == n_layers - 1) {
       if (side_done[l & 1]) GM_CUDA(cudaStreamWaitEvent(main, side_done[l & 1], 0));
-      Span span(4, 0.0, main);
+      Span span(4, 0.0, main, 4.0 * n * (3.0 * d + 2.0));
       GM_TRY(geomae_layernorm_bwd(d_out, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, L.g_lin2_b, main));
     }
     geomae_linear_args e{};
@@ -200,7 +211,7 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     if (p == 1) { ed.dot_src = S.attn; ed.ld_dot = d; ed.dot_out = dd; }
     GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main, &ed, L.p_out_proj));
     {
-      Span span(3, 0.0, main);
+      Span span(3, 0.0, main, 4.0 * n * (3.0 * d + d + 2.0 * c->n_heads + 3.0 * d));
       if (p == 1)
         GM_TRY(geomae_sra_attention_tc_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
                                            dd, main));
@@ -291,16 +302,17 @@ extern "C" int geomae_profile_enable(int32_t on) {
 }
 
 // Synchronises the device; ms[f], launches[f], flops[f] for the 5 families (see Prof).
-extern "C" int geomae_profile_read(double* ms, int64_t* launches, double* flops) {
+extern "C" int geomae_profile_read(double* ms, int64_t* launches, double* flops, double* bytes) {
   GM_REQUIRE(ms && launches && flops, "profile_read: null argument");
   GM_CUDA(cudaDeviceSynchronize());
-  for (int f = 0; f < Prof::FAMILIES; ++f) { ms[f] = 0.0; launches[f] = 0; flops[f] = 0.0; }
+  for (int f = 0; f < Prof::FAMILIES; ++f) { ms[f] = 0.0; launches[f] = 0; flops[f] = 0.0; if (bytes) bytes[f] = 0.0; }
   for (int i = 0; i < g_prof.n; ++i) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, g_prof.start[i], g_prof.stop[i]) != cudaSuccess) continue;
     ms[g_prof.family[i]] += t;
     launches[g_prof.family[i]] += 1;
     flops[g_prof.family[i]] += g_prof.flops[i];
+    if (bytes) bytes[g_prof.family[i]] += g_prof.bytes[i];
   }
   g_prof.n = 0;
   return GEOMAE_OK;

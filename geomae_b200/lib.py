@@ -173,7 +173,7 @@ class _Sigs:
                             C.c_float, _p, _p]
     geomae_pack_weights = [_i32, _p, _p, _p, _p, _p, _p]
     geomae_profile_enable = [_i32]
-    geomae_profile_read = [_p, _p, _p]
+    geomae_profile_read = [_p, _p, _p, _p]
     geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                          C.c_float, C.c_float, _i64, _p, _p]
 

@@ -443,7 +443,8 @@ int geomae_geom_loss_bwd(const geomae_voxel_cfg* cfg, const geomae_scatter_io* i
  * bench.py for the roofline entry.  Families: 0 tc_linear, 1 tc_wgrad, 2 attention fwd, 3 attention bwd
  * (2 kernels per span), 4 layernorm bwd.  geomae_profile_read synchronises the device and resets the log. */
 int geomae_profile_enable(int32_t on);
-int geomae_profile_read(double* ms /*[5]*/, int64_t* launches /*[5]*/, double* flops /*[5]*/);
+int geomae_profile_read(double* ms /*[5]*/, int64_t* launches /*[5]*/, double* flops /*[5]*/,
+                        double* bytes /*[5] algorithmic bytes of the launches, may be NULL*/);
 
 /* ---------------------------------------------------------------- optimiser */
 
