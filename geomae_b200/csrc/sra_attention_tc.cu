@@ -117,6 +117,34 @@ __device__ __forceinline__ void stage_rows_bf16(uint8_t* dst0, const float* __re
   }
 }
 
+// The same staging from bf16 rows in global memory (rows of 128 bf16 = 256 B at src[tok*ld + col ..]): pure 16-byte
+// cp.async copies, no registers, no conversion; rows in [rows, rows_pad) are zero-filled.  16 consecutive threads move
+// one 256-byte row.  Completion: cp_async_wait_all() + __syncthreads() by the caller.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+template <int NSRC>
+__device__ __forceinline__ void stage_rows_cp(uint8_t* dst0, const __nv_bfloat16* __restrict__ src0, int ld0, int col0,
+                                              uint8_t* dst1, const __nv_bfloat16* __restrict__ src1, int ld1, int col1,
+                                              const int32_t* __restrict__ win_tok, int p_start, int rows, int rows_pad) {
+  constexpr int PER_ROW = 16 * NSRC;
+  for (int idx = threadIdx.x; idx < rows_pad * PER_ROW; idx += 256) {
+    const int r = idx / PER_ROW, c = idx % PER_ROW;
+    const int which = c >> 4, ch = c & 15;
+    uint8_t* dst = (which ? dst1 : dst0) + r * RSB + ch * 16;
+    if (r < rows) {
+      const int64_t tok = __ldg(win_tok + p_start + r);
+      const __nv_bfloat16* src = which ? src1 + tok * ld1 + col1 : src0 + tok * ld0 + col0;
+      cp_async16(dst, src + ch * 8);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
 // per-(row, head) D = dO . O (fp32, from global) and log2-domain LSE for `rows` CSR positions starting at p_start
 __device__ __forceinline__ void stage_lse_d(float* sL, float* sD, const float* __restrict__ lse,
                                             const float* __restrict__ d_out, const float* __restrict__ out,
@@ -165,10 +193,18 @@ __device__ __forceinline__ void locate_rows(RowMeta& m, int p0, int n, const int
 }
 
 // write a [rows][128] fp32 tile staged in shared memory (row stride OS) to dst[tok * ld + col ..], 512 B per row
-__device__ __forceinline__ void flush_tile(const float* sO, const RowMeta& m, int rows, float* dst, int ld, int col) {
+__device__ __forceinline__ void flush_tile(const float* sO, const RowMeta& m, int rows, float* dst, int ld, int col,
+                                           bool as_bf16 = false) {
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  for (int r = wrp; r < rows; r += 8)
-    reinterpret_cast<float4*>(dst + (int64_t)m.tok[r] * ld + col)[lane] = *reinterpret_cast<const float4*>(sO + r * OS + lane * 4);
+  for (int r = wrp; r < rows; r += 8) {
+    const float4 v = *reinterpret_cast<const float4*>(sO + r * OS + lane * 4);
+    if (as_bf16) {
+      __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(dst) + (int64_t)m.tok[r] * ld + col;
+      reinterpret_cast<uint2*>(d16)[lane] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    } else {
+      reinterpret_cast<float4*>(dst + (int64_t)m.tok[r] * ld + col)[lane] = v;
+    }
+  }
 }
 
 // accumulator fragments of one head (two n-tiles of 8 dims) -> staging tile rows r0+g, r0+g+8
@@ -187,10 +223,13 @@ template <int TQ, int KC>
 __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__ qkv, int n,
                                                        const int32_t* __restrict__ win_ptr,
                                                        const int32_t* __restrict__ win_tok,
-                                                       const int32_t* __restrict__ tok_win, float* out, float* lse) {
+                                                       const int32_t* __restrict__ tok_win, float* out, float* lse,
+                                                       int io_flags) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ RowMeta meta;
   __shared__ float s_lse[TQ * NH];
+  const bool qkv16 = io_flags & 1;
+  const __nv_bfloat16* qkv_h = reinterpret_cast<const __nv_bfloat16*>(qkv);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TQ * RSB;
   uint8_t* sV = sK + KC * RSB;
@@ -201,7 +240,9 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__
   gm_pdl_wait();
   gm_pdl_trigger();
   locate_rows<TQ>(meta, p0, n, win_ptr, win_tok, tok_win);
-  stage_rows_bf16<1>(sQ, qkv, 3 * DM, 0, QSCALE, nullptr, nullptr, 0, 0, win_tok, p0, nq, TQ);
+  if (qkv16) stage_rows_cp<1>(sQ, qkv_h, 3 * DM, 0, nullptr, nullptr, 0, 0, win_tok, p0, nq, TQ);
+  else stage_rows_bf16<1>(sQ, qkv, 3 * DM, 0, 1.0f, nullptr, nullptr, 0, 0, win_tok, p0, nq, TQ);
+  cp_async_wait_all();
   __syncthreads();
   const int lo = meta.beg[0], hi = meta.end[nq - 1];
   float mx[MT][2], ls[MT][2], o0[MT][4], o1[MT][4];
@@ -216,7 +257,9 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__
     const int rows = min(KC, hi - c0);
     const int rows_pad = (rows + 15) & ~15;
     if (c0 > lo) __syncthreads();          // previous chunk fully consumed
-    stage_rows_bf16<2>(sK, qkv, 3 * DM, DM, 1.0f, sV, qkv, 3 * DM, 2 * DM, win_tok, c0, rows, rows_pad);
+    if (qkv16) stage_rows_cp<2>(sK, qkv_h, 3 * DM, DM, sV, qkv_h, 3 * DM, 2 * DM, win_tok, c0, rows, rows_pad);
+    else stage_rows_bf16<2>(sK, qkv, 3 * DM, DM, 1.0f, sV, qkv, 3 * DM, 2 * DM, win_tok, c0, rows, rows_pad);
+    cp_async_wait_all();
     __syncthreads();
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -236,15 +279,15 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__
             mma16816(s0, qa, kb0, kb1);
             ldb(kb0, kb1, sK, kb * 16 + 8, h * 16);
             mma16816(s1, qa, kb0, kb1);
-            const int k0 = kb * 16 + 2 * t, k1 = k0 + 8;
-            s0[0] = (k0 >= b0 && k0 < e0) ? s0[0] : -INFINITY;
-            s0[1] = (k0 + 1 >= b0 && k0 + 1 < e0) ? s0[1] : -INFINITY;
-            s1[0] = (k1 >= b0 && k1 < e0) ? s1[0] : -INFINITY;
-            s1[1] = (k1 + 1 >= b0 && k1 + 1 < e0) ? s1[1] : -INFINITY;
-            s0[2] = (k0 >= b1 && k0 < e1) ? s0[2] : -INFINITY;
-            s0[3] = (k0 + 1 >= b1 && k0 + 1 < e1) ? s0[3] : -INFINITY;
-            s1[2] = (k1 >= b1 && k1 < e1) ? s1[2] : -INFINITY;
-            s1[3] = (k1 + 1 >= b1 && k1 + 1 < e1) ? s1[3] : -INFINITY;
+            const int k0 = kb * 16 + 2 * t, k1 = k0 + 8;       // scores -> exp2 domain (scale 1/sqrt(hd) * log2 e), window mask
+            s0[0] = (k0 >= b0 && k0 < e0) ? s0[0] * QSCALE : -INFINITY;
+            s0[1] = (k0 + 1 >= b0 && k0 + 1 < e0) ? s0[1] * QSCALE : -INFINITY;
+            s1[0] = (k1 >= b0 && k1 < e0) ? s1[0] * QSCALE : -INFINITY;
+            s1[1] = (k1 + 1 >= b0 && k1 + 1 < e0) ? s1[1] * QSCALE : -INFINITY;
+            s0[2] = (k0 >= b1 && k0 < e1) ? s0[2] * QSCALE : -INFINITY;
+            s0[3] = (k0 + 1 >= b1 && k0 + 1 < e1) ? s0[3] * QSCALE : -INFINITY;
+            s1[2] = (k1 >= b1 && k1 < e1) ? s1[2] * QSCALE : -INFINITY;
+            s1[3] = (k1 + 1 >= b1 && k1 + 1 < e1) ? s1[3] * QSCALE : -INFINITY;
             float m0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
             float m1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
             m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
@@ -296,9 +339,12 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
                                              const float* __restrict__ out, const float* __restrict__ lse,
                                              const float* __restrict__ d_out, int n, const int32_t* __restrict__ win_ptr,
                                              const int32_t* __restrict__ win_tok, const int32_t* __restrict__ tok_win,
-                                             float* d_qkv, const float* __restrict__ dd) {
+                                             float* d_qkv, const float* __restrict__ dd, int io_flags) {
   constexpr int MT = TQ / 16;
-  uint8_t* sA = smem;                       // own rows, operand 1: Q*scale (queries) | K*scale (keys)
+  const bool qkv16 = io_flags & 1, dout16 = io_flags & 2, dqkv16 = io_flags & 4;
+  const __nv_bfloat16* qkv_h = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  const __nv_bfloat16* dout_h = reinterpret_cast<const __nv_bfloat16*>(d_out);
+  uint8_t* sA = smem;                       // own rows, operand 1: Q (queries) | K (keys)
   uint8_t* sB = sA + TQ * RSB;              // own rows, operand 2: dO       (queries) | V       (keys)
   uint8_t* sC = sB + TQ * RSB;              // chunk rows, operand 1: K      (queries) | Q       (keys)
   uint8_t* sD = sC + KC * RSB;              // chunk rows, operand 2: V      (queries) | dO      (keys)
@@ -311,12 +357,24 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
   gm_pdl_wait();
   gm_pdl_trigger();
   locate_rows<TQ>(meta, p0, n, win_ptr, win_tok, tok_win);
+  // rows of 128 channels from qkv (column block cb) or d_out, fp32 (converted while staged) or bf16 (cp.async)
+  auto stage_q = [&](uint8_t* dst, int cb, int p_start, int rows, int rows_pad) {
+    if (qkv16) stage_rows_cp<1>(dst, qkv_h, 3 * DM, cb * DM, nullptr, nullptr, 0, 0, win_tok, p_start, rows, rows_pad);
+    else stage_rows_bf16<1>(dst, qkv, 3 * DM, cb * DM, 1.0f, nullptr, nullptr, 0, 0, win_tok, p_start, rows, rows_pad);
+  };
+  auto stage_g = [&](uint8_t* dst, int p_start, int rows, int rows_pad) {
+    if (dout16) stage_rows_cp<1>(dst, dout_h, DM, 0, nullptr, nullptr, 0, 0, win_tok, p_start, rows, rows_pad);
+    else stage_rows_bf16<1>(dst, d_out, DM, 0, 1.0f, nullptr, nullptr, 0, 0, win_tok, p_start, rows, rows_pad);
+  };
   if (!AS_KEYS) {
-    stage_rows_bf16<2>(sA, qkv, 3 * DM, 0, QSCALE, sB, d_out, DM, 0, win_tok, p0, nq, TQ);
+    stage_q(sA, 0, p0, nq, TQ);
+    stage_g(sB, p0, nq, TQ);
     stage_lse_d(sL, sDd, lse, d_out, out, dd, win_tok, p0, nq);
   } else {
-    stage_rows_bf16<2>(sA, qkv, 3 * DM, DM, QSCALE, sB, qkv, 3 * DM, 2 * DM, win_tok, p0, nq, TQ);
+    stage_q(sA, 1, p0, nq, TQ);
+    stage_q(sB, 2, p0, nq, TQ);
   }
+  cp_async_wait_all();
   __syncthreads();
   const int lo = meta.beg[0], hi = meta.end[nq - 1];
   float a0[MT][4], a1[MT][4];                              // dQ | dK
@@ -333,11 +391,14 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
     const int rows_pad = (rows + 15) & ~15;
     if (c0 > lo || !AS_KEYS) __syncthreads();     // previous chunk consumed (queries pass: own-row sL/sDd published)
     if (!AS_KEYS) {
-      stage_rows_bf16<2>(sC, qkv, 3 * DM, DM, 1.0f, sD, qkv, 3 * DM, 2 * DM, win_tok, c0, rows, rows_pad);
+      stage_q(sC, 1, c0, rows, rows_pad);
+      stage_q(sD, 2, c0, rows, rows_pad);
     } else {
-      stage_rows_bf16<2>(sC, qkv, 3 * DM, 0, 1.0f, sD, d_out, DM, 0, win_tok, c0, rows, rows_pad);
+      stage_q(sC, 0, c0, rows, rows_pad);
+      stage_g(sD, c0, rows, rows_pad);
       stage_lse_d(sL, sDd, lse, d_out, out, dd, win_tok, c0, rows);
     }
+    cp_async_wait_all();
     __syncthreads();
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -386,7 +447,7 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
                 const bool valid = kk[c] >= bb && kk[c] < ee;
                 const float lz = AS_KEYS ? lc[c] : (r ? lr1 : lr0);
                 const float dz = AS_KEYS ? dc[c] : (r ? dr1 : dr0);
-                const float p = valid ? exp2f(sc[r][c] - lz) : 0.f;
+                const float p = valid ? exp2f(fmaf(sc[r][c], QSCALE, -lz)) : 0.f;
                 pr[r][c] = p;
                 dsv[r][c] = valid ? p * (dp[r][c] - dz) : 0.f;   // dS = P * (dP - D)
               }
@@ -414,13 +475,13 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) put_frag(sO, mt * 16, h, a0[mt], a1[mt], 0.25f, 0.25f);
   __syncthreads();
-  flush_tile(sO, meta, nq, d_qkv, 3 * DM, AS_KEYS ? DM : 0);
+  flush_tile(sO, meta, nq, d_qkv, 3 * DM, AS_KEYS ? DM : 0, dqkv16);
   if (AS_KEYS) {
     __syncthreads();
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) put_frag(sO, mt * 16, h, v0[mt], v1[mt], 1.0f, 1.0f);
     __syncthreads();
-    flush_tile(sO, meta, nq, d_qkv, 3 * DM, 2 * DM);
+    flush_tile(sO, meta, nq, d_qkv, 3 * DM, 2 * DM, dqkv16);
   }
 }
 
@@ -430,13 +491,13 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_bwd(const float* __restrict__
                                                        int n, const int32_t* __restrict__ win_ptr,
                                                        const int32_t* __restrict__ win_tok,
                                                        const int32_t* __restrict__ tok_win, float* d_qkv,
-                                                       const float* __restrict__ dd) {
+                                                       const float* __restrict__ dd, int io_flags) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ RowMeta meta;
   if (blockIdx.y == 0)
-    sra_bwd_body<TQ, KC, false>(smem, meta, qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd);
+    sra_bwd_body<TQ, KC, false>(smem, meta, qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags);
   else
-    sra_bwd_body<TQ, KC, true>(smem, meta, qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd);
+    sra_bwd_body<TQ, KC, true>(smem, meta, qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags);
 }
 
 constexpr int KC_FWD = 128, KC_BWD = 112;
@@ -446,27 +507,28 @@ static_assert(64 * OS * 4 <= 2 * KC_FWD * RSB && 64 * OS * 4 <= 2 * KC_BWD * RSB
 
 template <int TQ>
 int launch_fwd(const float* qkv, int n, const int32_t* win_ptr, const int32_t* win_tok, const int32_t* tok_win, float* out,
-               float* lse, cudaStream_t st) {
+               float* lse, int io_flags, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     GM_CUDA(cudaFuncSetAttribute(k_sra_tc_fwd<TQ, KC_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd<TQ>()));
     configured = true;
   }
   GM_CUDA(gm_launch_pdl(k_sra_tc_fwd<TQ, KC_FWD>, dim3(gm_div_up(n, TQ)), dim3(256), (size_t)smem_fwd<TQ>(), st, qkv, n,
-                        win_ptr, win_tok, tok_win, out, lse));
+                        win_ptr, win_tok, tok_win, out, lse, io_flags));
   return GEOMAE_OK;
 }
 
 template <int TQ>
 int launch_bwd(const float* qkv, const float* out, const float* lse, const float* d_out, int n, const int32_t* win_ptr,
-               const int32_t* win_tok, const int32_t* tok_win, float* d_qkv, const float* dd, cudaStream_t st) {
+               const int32_t* win_tok, const int32_t* tok_win, float* d_qkv, const float* dd, int io_flags,
+               cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     GM_CUDA(cudaFuncSetAttribute(k_sra_tc_bwd<TQ, KC_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bwd<TQ>()));
     configured = true;
   }
   GM_CUDA(gm_launch_pdl(k_sra_tc_bwd<TQ, KC_BWD>, dim3(gm_div_up(n, TQ), 2), dim3(256), (size_t)smem_bwd<TQ>(), st, qkv, out,
-                        lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd));
+                        lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags));
   return GEOMAE_OK;
 }
 
@@ -474,7 +536,7 @@ int launch_bwd(const float* qkv, const float* out, const float* lse, const float
 
 extern "C" int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
                                            const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse,
-                                           void* stream) {
+                                           int32_t io_flags, void* stream) {
   GM_REQUIRE(n_heads == NH, "sra_attention_tc: built for %d heads of 16 channels (got %d)", NH, n_heads);
   if (n_tokens == 0) return GEOMAE_OK;
   GM_REQUIRE(qkv && win_ptr && win_tok && tok_win && out && lse, "sra_attention_tc_fwd: null argument");
@@ -482,20 +544,21 @@ extern "C" int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, i
   const int n = (int)n_tokens;
   // small token sets (the encoder sees 30 % of the pillars): 32-query CTAs so the grid still covers the SMs
   if (gm_div_up(n, 64) < 2 * GM_NUM_SMS)
-    return launch_fwd<32>(qkv, n, win_ptr, win_tok, tok_win, out, lse, (cudaStream_t)stream);
-  return launch_fwd<64>(qkv, n, win_ptr, win_tok, tok_win, out, lse, (cudaStream_t)stream);
+    return launch_fwd<32>(qkv, n, win_ptr, win_tok, tok_win, out, lse, io_flags, (cudaStream_t)stream);
+  return launch_fwd<64>(qkv, n, win_ptr, win_tok, tok_win, out, lse, io_flags, (cudaStream_t)stream);
 }
 
 extern "C" int geomae_sra_attention_tc_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
                                            int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
                                            const int32_t* win_tok, const int32_t* tok_win, float* d_qkv, const float* dd,
-                                           void* stream) {
+                                           int32_t io_flags, void* stream) {
   GM_REQUIRE(n_heads == NH, "sra_attention_tc: built for %d heads of 16 channels (got %d)", NH, n_heads);
   if (n_tokens == 0) return GEOMAE_OK;
   GM_REQUIRE(qkv && out && lse && d_out && win_ptr && win_tok && tok_win && d_qkv, "sra_attention_tc_bwd: null argument");
+  GM_REQUIRE(!(io_flags & 2) || dd, "sra_attention_tc_bwd: a bf16 d_out needs the precomputed D = dO.O (dd)");
   GM_REQUIRE(n_tokens < (int64_t)1 << 31, "sra_attention_tc: too many tokens");
   const int n = (int)n_tokens;
   if (gm_div_up(n, 64) < GM_NUM_SMS)
-    return launch_bwd<32>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, (cudaStream_t)stream);
-  return launch_bwd<64>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, (cudaStream_t)stream);
+    return launch_bwd<32>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags, (cudaStream_t)stream);
+  return launch_bwd<64>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags, (cudaStream_t)stream);
 }

@@ -34,6 +34,8 @@ struct LinArgs {
   int w_early;      // packed weights may be fetched before gm_pdl_wait() (see common.cuh)
   const float* dot_src; int ld_dot; float* dot_out;   // EPI 0, N = 128: dot_out[row, h] = sum_head out * dot_src
   float* ln_dgamma; float* ln_dbeta; float* ln_dcolsum;   // EPI 3 accumulators (+=)
+  int a_bf16;       // A rows are bf16 (lda in elements): staged with plain 16-byte copies, precision 1 only
+  int out_bf16;     // EPI 0 / 2: `out` rows are written as bf16 (ldo in elements)
 };
 
 // Exact-erf GELU (F.gelu default, sst_basic_block.py:153-154) and its derivative, evaluated with the
@@ -121,6 +123,32 @@ __device__ __forceinline__ void stage_tile(uint8_t* dst_hi, uint8_t* dst_lo, con
   }
 }
 
+// The same tile from bf16 rows (a tensor that only ever serves as an MMA operand is stored in bf16 by its producer:
+// numerically identical to rounding at staging time, half the bytes, no conversion): 16-byte chunks straight into
+// the swizzled layout.
+template <int ROWS, int COLS, int NTHR>
+__device__ __forceinline__ void stage_tile_bf16(uint8_t* dst, const __nv_bfloat16* __restrict__ src, int ld, int row0,
+                                                int row_end, int col0) {
+  constexpr int CPR = COLS / 8;
+  constexpr int BLOCK_BYTES = ROWS * tc::LINE_BYTES;
+  constexpr int ITEMS = ROWS * CPR / NTHR;
+  uint4 v[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = k * NTHR + threadIdx.x;
+    const int r = i / CPR, c8 = i % CPR;
+    const int grow = row0 + r;
+    v[k] = grow < row_end ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)grow * ld + col0 + c8 * 8))
+                          : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int i = k * NTHR + threadIdx.x;
+    const int r = i / CPR, c8 = i % CPR;
+    *reinterpret_cast<uint4*>(dst + (uint32_t)(c8 >> 3) * BLOCK_BYTES + tc::swz(r, c8 & 7)) = v[k];
+  }
+}
+
 constexpr int LTHREADS = 256;  // k_tc_linear: 8 warps stage; warps w and w+4 share TMEM lane quarter w%4 and split the columns
 
 // fp32 accumulator tile in shared memory, [128 rows][C4 float4], XOR-swizzled so that both the row-per-thread
@@ -190,8 +218,11 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
       tc::fence_after_sync();
     }
     if (packed && threadIdx.x == 0 && !(w_early && kc == 0)) fetch_weights(kc);
-    stage_tile<TM, KC, LTHREADS, POS>(sA, x3 ? sAlo : nullptr, a.A, a.lda, row0, a.n_rows, k0,
-                                      use_pos ? a.pos_table : nullptr, a.tok_cell, a.K, a.a_gelu != 0);
+    if (!POS && a.a_bf16)
+      stage_tile_bf16<TM, KC, LTHREADS>(sA, reinterpret_cast<const __nv_bfloat16*>(a.A), a.lda, row0, a.n_rows, k0);
+    else
+      stage_tile<TM, KC, LTHREADS, POS>(sA, x3 ? sAlo : nullptr, a.A, a.lda, row0, a.n_rows, k0,
+                                        use_pos ? a.pos_table : nullptr, a.tok_cell, a.K, a.a_gelu != 0);
     if (!packed) {
       if (a.w_mn_major)   // rows = k, columns = n
         stage_tile<KC, NT, LTHREADS, false>(sB, x3 ? sBlo : nullptr, a.W, a.ldw, k0, a.w_rows, n0, nullptr, nullptr, 0, false);
@@ -461,7 +492,13 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
             o.x += bias4.x + pre[k].x; o.y += bias4.y + pre[k].y;
             o.z += bias4.z + pre[k].z; o.w += bias4.w + pre[k].w;
           }
-          *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + n0 + pc * 64 + c4 * 4) = o;
+          if (a.out_bf16) {
+            __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)row * a.ldo + n0 + pc * 64 + c4 * 4;
+            const __nv_bfloat162 lo2 = __floats2bfloat162_rn(o.x, o.y), hi2 = __floats2bfloat162_rn(o.z, o.w);
+            *reinterpret_cast<uint2*>(o16) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo2), *reinterpret_cast<const uint32_t*>(&hi2));
+          } else {
+            *reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo + n0 + pc * 64 + c4 * 4) = o;
+          }
           if constexpr (EPI == 0 && NT == 128 && !POS) dotv[k] = o;
         }
       }
@@ -542,6 +579,7 @@ struct WgradArgs {
   const float* pos_table; const int32_t* tok_cell; int pos_slabs; int x_gelu;
   float* dW; int ldw; float* db; int M_total; int N_total;
   int tiles_per_cta; int precision;
+  int dy_bf16;      // dY rows are bf16 (ldy in elements), precision 1 only
 };
 
 template <int NT>
@@ -590,7 +628,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_tc_wgrad(const WgradArgs a) {
       tc::mbar_wait(&mbar, (it - 1) & 1);
       tc::fence_after_sync();
     }
-    stage_tile<TM, 128, NTHREADS, false>(sA, x3 ? sAlo : nullptr, a.dY, a.ldy, row0, a.n_rows, m0, nullptr, nullptr, 0, false);
+    if (a.dy_bf16)
+      stage_tile_bf16<TM, 128, NTHREADS>(sA, reinterpret_cast<const __nv_bfloat16*>(a.dY), a.ldy, row0, a.n_rows, m0);
+    else
+      stage_tile<TM, 128, NTHREADS, false>(sA, x3 ? sAlo : nullptr, a.dY, a.ldy, row0, a.n_rows, m0, nullptr, nullptr, 0, false);
     if (use_pos)
       stage_tile<TM, NT, NTHREADS, true>(sB, x3 ? sBlo : nullptr, a.X, a.ldx, row0, a.n_rows, n0, a.pos_table, a.tok_cell,
                                          a.N_total, false);
@@ -772,6 +813,10 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
   a.w_early = gm_weights_stable() ? 1 : 0;
   a.dot_src = p->dot_src; a.ld_dot = p->ld_dot; a.dot_out = p->dot_out;
   a.ln_dgamma = a.ln_dbeta = a.ln_dcolsum = nullptr;
+  a.a_bf16 = p->a_bf16; a.out_bf16 = p->out_bf16;
+  GM_REQUIRE(!p->a_bf16 || (p->precision == 1 && !p->pos_table && !p->a_gelu && p->lda % 8 == 0),
+             "tc_linear: bf16 A rows need precision 1, no position / GELU prologue, lda %% 8 == 0");
+  GM_REQUIRE(!p->out_bf16 || (p->epilogue == 0 || p->epilogue == 2), "tc_linear: bf16 output only for epilogues 0 and 2");
   GM_REQUIRE(!p->dot_src || (p->dot_out && p->epilogue == 0 && p->N_total == 128 && p->pos_slabs == 0 && p->ld_dot % 4 == 0),
              "tc_linear: the per-head dot side output needs epilogue 0, N = 128, no position prologue");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -805,6 +850,8 @@ extern "C" int geomae_tc_wgrad(const geomae_wgrad_args* p, void* stream_) {
   a.pos_table = p->pos_table; a.tok_cell = p->tok_cell; a.pos_slabs = p->pos_slabs; a.x_gelu = p->x_gelu;
   a.dW = p->dW; a.ldw = p->ldw; a.db = p->db; a.M_total = p->M_total; a.N_total = p->N_total;
   a.precision = p->precision;
+  a.dy_bf16 = p->dy_bf16;
+  GM_REQUIRE(!p->dy_bf16 || (p->precision == 1 && p->ldy % 8 == 0), "tc_wgrad: bf16 dY rows need precision 1, ldy %% 8 == 0");
   const int n_tiles = gm_div_up(p->n_rows, TM);
   const int slabs = (p->M_total / 128) * ((p->N_total % 256 == 0 && !p->db) ? p->N_total / 256 : p->N_total / 128);
   int splits = (2 * GM_NUM_SMS + slabs - 1) / slabs;           // aim at ~2 CTAs per SM

@@ -49,7 +49,7 @@ int lin(const float* A, int lda, int n, int K, const float* W, int ldw, int w_ro
   if (packed) { a.Wp_hi = packed[0]; a.Wp_lo = packed[1]; }
   a.bias = bias; a.N_total = N; a.out = out; a.ldo = ldo; a.precision = prec;
   // algorithmic bytes of the launch: A rows, bf16 weight image, output rows, plus every per-row side operand / output
-  double bytes = 4.0 * n * ((double)K + N) + 2.0 * (double)K * N;
+  double bytes = (a.a_bf16 ? 2.0 : 4.0) * n * (double)K + (a.out_bf16 ? 2.0 : 4.0) * n * (double)N + 2.0 * (double)K * N;
   if (a.add_src) bytes += 4.0 * n * N;
   if (a.epilogue == 1) bytes += 4.0 * n * (N + 2.0);          // saved pre-LN rows + (mean, rstd)
   if (a.epilogue == 2) bytes += 4.0 * n * N;                  // GELU input
@@ -61,12 +61,13 @@ int lin(const float* A, int lda, int n, int K, const float* W, int ldw, int w_ro
 
 int wgrad(const float* dY, int ldy, const float* X, int ldx, int n, float* dW, int ldw, float* db, int M, int N,
           int prec, void* stream, const float* pos = nullptr, const int32_t* cell = nullptr, int pos_slabs = 0,
-          int gelu = 0) {
+          int gelu = 0, int dy_bf16 = 0) {
   geomae_wgrad_args a{};
+  a.dy_bf16 = dy_bf16;
   a.dY = dY; a.ldy = ldy; a.X = X; a.ldx = ldx; a.n_rows = n; a.pos_table = pos; a.tok_cell = cell;
   a.pos_slabs = pos_slabs; a.x_gelu = gelu; a.dW = dW; a.ldw = ldw; a.db = db; a.M_total = M; a.N_total = N;
   a.precision = prec;
-  Span span(1, 2.0 * n * (double)M * N, stream, 4.0 * n * ((double)M + N) + 4.0 * (double)M * N);
+  Span span(1, 2.0 * n * (double)M * N, stream, (dy_bf16 ? 2.0 : 4.0) * n * (double)M + 4.0 * n * (double)N + 4.0 * (double)M * N);
   return geomae_tc_wgrad(&a, stream);
 }
 
@@ -85,6 +86,7 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
              c->d_model, c->n_heads);
   GM_REQUIRE(c->ffn % 128 == 0, "sra_stack: ffn width must be a multiple of 128");
   const int n = (int)c->n_tokens, d = c->d_model, f = c->ffn, p = c->precision;
+  const int b16 = p == 1 ? 1 : 0;     // bf16 mode: tensors that are only MMA operands (qkv, du, da, dqkv) live in bf16
   if (n == 0) return GEOMAE_OK;
   const float* x = x_in;
   {  // refresh the packed bf16 weight images of every layer (weights change every optimiser step): one launch
@@ -111,12 +113,13 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
     const geomae_sra_windows& w = c->shift[L.shift];
     geomae_linear_args e{};
     e.pos_table = c->pos_table; e.tok_cell = w.tok_cell; e.pos_slabs = 2;
+    e.out_bf16 = b16;                 // q|k|v only ever feed the attention MMAs: stored as bf16 in the bf16 mode
     GM_TRY(lin(x, d, n, d, L.in_proj_w, d, 3 * d, 0, L.in_proj_b, 3 * d, S.qkv, 3 * d, p, stream, &e, L.p_in_proj));
     gm_set_weights_stable(true);    // from here on the images were complete before the predecessor kernel started
     {
       Span span(2, 0.0, stream, 4.0 * n * (3.0 * d + d + c->n_heads));
       if (p == 1)    // bf16 mode: QK^T / PV tiles on the tensor cores (sra_attention_tc.cu)
-        GM_TRY(geomae_sra_attention_tc_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
+        GM_TRY(geomae_sra_attention_tc_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, b16, stream));
       else
         GM_TRY(geomae_sra_attention_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, stream));
     }
@@ -170,6 +173,7 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
                       const geomae_sra_layer* layers, const geomae_sra_saved* saved, const float* x_in,
                       const float* d_out, float* d_in, float* scratch) {
   const int n = (int)c->n_tokens, d = c->d_model, f = c->ffn, p = c->precision;
+  const int b16 = p == 1 ? 1 : 0;     // see geomae_sra_stack_forward
   const int64_t set = scratch_floats(c);
   cudaEvent_t side_done[2] = {nullptr, nullptr};
   struct StableGuard { ~StableGuard() { gm_set_weights_stable(false); } } guard;
@@ -200,27 +204,28 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
       GM_TRY(geomae_layernorm_bwd(d_out, S.s2, S.st2, L.norm2_w, n, d, ds2, L.g_norm2_w, L.g_norm2_b, L.g_lin2_b, main));
     }
     geomae_linear_args e{};
-    e.gelu_u = S.u; e.ldu = f; e.epilogue = 2;
+    e.gelu_u = S.u; e.ldu = f; e.epilogue = 2; e.out_bf16 = b16;
     GM_TRY(lin(ds2, d, n, d, L.lin2_w, f, d, 1, nullptr, f, du, f, p, main, &e, L.p_lin2));
     geomae_linear_args e1{};           // dy = du W1 + ds2, then LayerNorm-1 backward in the epilogue -> ds1
     e1.add_src = ds2; e1.ld_add = d; e1.epilogue = 3;
     e1.ln_gamma = L.norm1_w; e1.ln_in = S.s1; e1.ln_stats = S.st1;
     e1.ln_dgamma = L.g_norm1_w; e1.ln_dbeta = L.g_norm1_b; e1.ln_dcolsum = L.g_out_proj_b;
+    e1.a_bf16 = b16;
     GM_TRY(lin(du, f, n, f, L.lin1_w, d, f, 1, nullptr, d, ds1, d, p, main, &e1, L.p_lin1));
     geomae_linear_args ed{};          // bf16 mode: D = dO . O per (token, head) leaves this GEMM's epilogue
-    if (p == 1) { ed.dot_src = S.attn; ed.ld_dot = d; ed.dot_out = dd; }
+    if (p == 1) { ed.dot_src = S.attn; ed.ld_dot = d; ed.dot_out = dd; ed.out_bf16 = 1; }
     GM_TRY(lin(ds1, d, n, d, L.out_proj_w, d, d, 1, nullptr, d, da, d, p, main, &ed, L.p_out_proj));
     {
       Span span(3, 0.0, main, 4.0 * n * (3.0 * d + d + 2.0 * c->n_heads + 3.0 * d));
       if (p == 1)
         GM_TRY(geomae_sra_attention_tc_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
-                                           dd, main));
+                                           dd, 1 | 2 | 4, main));
       else
         GM_TRY(geomae_sra_attention_bwd(S.qkv, S.attn, S.lse, da, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, dqkv,
                                         dd, main));
     }
     geomae_linear_args e2{};
-    e2.add_src = ds1; e2.ld_add = d;
+    e2.add_src = ds1; e2.ld_add = d; e2.a_bf16 = b16;
     if (l > 0) {                       // dx = dqkv W_in + ds1 is the dz of the layer below: its LayerNorm-2 backward here
       const geomae_sra_layer& Lb = layers[l - 1];
       const geomae_sra_saved& Sb = saved[l - 1];
@@ -237,9 +242,9 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     // layer's dX chain (bias gradients of linear2 / out_proj come from the LayerNorm backward above)
     GM_TRY(hand_off(main, side));
     GM_TRY(wgrad(ds2, d, S.u, f, n, L.g_lin2_w, f, nullptr, d, f, p, side, nullptr, nullptr, 0, 1));
-    GM_TRY(wgrad(du, f, S.y, d, n, L.g_lin1_w, d, L.g_lin1_b, f, d, p, side));
+    GM_TRY(wgrad(du, f, S.y, d, n, L.g_lin1_w, d, L.g_lin1_b, f, d, p, side, nullptr, nullptr, 0, 0, b16));
     GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, nullptr, d, d, p, side));
-    GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, side, c->pos_table, w.tok_cell, 2, 0));
+    GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, side, c->pos_table, w.tok_cell, 2, 0, b16));
     side_done[l & 1] = g_lanes.event();
     GM_CUDA(cudaEventRecord(side_done[l & 1], side));
   }

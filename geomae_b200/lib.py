@@ -57,14 +57,15 @@ class LinearArgs(C.Structure):
                 ("gelu_u", C.c_void_p), ("ldu", C.c_int32),
                 ("epilogue", C.c_int32), ("precision", C.c_int32), ("Wp_hi", C.c_void_p), ("Wp_lo", C.c_void_p),
                 ("dot_src", C.c_void_p), ("ld_dot", C.c_int32), ("dot_out", C.c_void_p),
-                ("ln_dgamma", C.c_void_p), ("ln_dbeta", C.c_void_p), ("ln_dcolsum", C.c_void_p)]
+                ("ln_dgamma", C.c_void_p), ("ln_dbeta", C.c_void_p), ("ln_dcolsum", C.c_void_p),
+                ("a_bf16", C.c_int32), ("out_bf16", C.c_int32)]
 
 
 class WgradArgs(C.Structure):
     _fields_ = [("dY", C.c_void_p), ("ldy", C.c_int32), ("X", C.c_void_p), ("ldx", C.c_int32), ("n_rows", C.c_int32),
                 ("pos_table", C.c_void_p), ("tok_cell", C.c_void_p), ("pos_slabs", C.c_int32), ("x_gelu", C.c_int32),
                 ("dW", C.c_void_p), ("ldw", C.c_int32), ("db", C.c_void_p), ("M_total", C.c_int32),
-                ("N_total", C.c_int32), ("precision", C.c_int32)]
+                ("N_total", C.c_int32), ("precision", C.c_int32), ("dy_bf16", C.c_int32)]
 
 
 class SRAWindows(C.Structure):
@@ -146,8 +147,8 @@ class _Sigs:
     geomae_scatter_reduce_bwd = [_p, _i64, _i32, _p, _p, _p, _i32, _p, _p]
     geomae_sra_attention_fwd = [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]
     geomae_sra_attention_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
-    geomae_sra_attention_tc_fwd = [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]
-    geomae_sra_attention_tc_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
+    geomae_sra_attention_tc_fwd = [_p, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p]
+    geomae_sra_attention_tc_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _i32, _p]
     geomae_tc_linear = [C.POINTER(LinearArgs), _p]
     geomae_tc_wgrad = [C.POINTER(WgradArgs), _p]
     geomae_sra_stack_forward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p]

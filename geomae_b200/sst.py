@@ -13,20 +13,26 @@ from .windows import WindowLayout, pos_table
 
 
 def _attn_fwd(qkv, win, n_heads, tc=False):
-    """tc=False: fp32 SIMT kernel (parity mode); tc=True: bf16 tensor-core kernel (csrc/sra_attention_tc.cu)."""
+    """tc=False: fp32 SIMT kernel (parity mode); tc=True: bf16 tensor-core kernel (csrc/sra_attention_tc.cu; qkv may be
+    fp32 or bf16 rows)."""
     n, three_d = qkv.shape
-    out = torch.empty((n, three_d // 3), dtype=qkv.dtype, device=qkv.device)
+    out = torch.empty((n, three_d // 3), dtype=torch.float32, device=qkv.device)
     lse = torch.empty((n, n_heads), dtype=torch.float32, device=qkv.device)
-    L.run("sra_attention_tc_fwd" if tc else "sra_attention_fwd", L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]),
-          L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(out), L.ptr(lse), L.stream_ptr(qkv.device))
+    args = (L.ptr(qkv), n, n_heads, L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(out), L.ptr(lse))
+    if tc:
+        L.run("sra_attention_tc_fwd", *args, int(qkv.dtype == torch.bfloat16), L.stream_ptr(qkv.device))
+    else:
+        L.run("sra_attention_fwd", *args, L.stream_ptr(qkv.device))
     return out, lse
 
 
 def _attn_bwd(qkv, out, lse, d_out, win, n_heads, tc=False, dd=None):
     d_qkv = torch.empty_like(qkv)
     if tc:
+        flags = int(qkv.dtype == torch.bfloat16) | (2 if d_out.dtype == torch.bfloat16 else 0) | \
+            (4 if d_qkv.dtype == torch.bfloat16 else 0)
         L.run("sra_attention_tc_bwd", L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(d_out), qkv.shape[0], n_heads,
-              L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(d_qkv), L.ptr(dd),
+              L.ptr(win["win_ptr"]), L.ptr(win["win_tok"]), L.ptr(win["tok_win"]), L.ptr(d_qkv), L.ptr(dd), flags,
               L.stream_ptr(qkv.device))
         return d_qkv
     scratch = torch.empty((qkv.shape[0], n_heads), dtype=torch.float32, device=qkv.device)
@@ -114,8 +120,8 @@ class _SRALayerFn(torch.autograd.Function):
 
 def sra_attention(qkv, win, n_heads, tc=False):
     L.require_cuda(qkv, "qkv")
-    if qkv.dtype != torch.float32:
-        raise RuntimeError("sra_attention expects float32 q|k|v rows")
+    if qkv.dtype != torch.float32 and not (tc and qkv.dtype == torch.bfloat16):
+        raise RuntimeError("sra_attention expects float32 q|k|v rows (bfloat16 only with tc=True)")
     return _SRAAttention.apply(qkv, win, n_heads, tc)
 
 

@@ -276,12 +276,15 @@ int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* ls
  * when precision == 1 (the bf16 benchmark mode); precision == 3 keeps the fp32 kernels.
  * replaces: nn.MultiheadAttention core inside WindowAttention.forward
  *           (models/sst/sst_basic_block.py:26-61) and its autograd backward. */
+/* io_flags: bit 0: qkv rows are bf16 [n, 3*d_model]; bit 1: d_out rows are bf16 (needs dd); bit 2: d_qkv is written
+ * as bf16.  bf16 rows are moved with 16-byte cp.async copies (no registers, no conversion). */
 int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
-                                const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse, void* stream);
+                                const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse, int32_t io_flags,
+                                void* stream);
 int geomae_sra_attention_tc_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
                                 int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr, const int32_t* win_tok,
                                 const int32_t* tok_win, float* d_qkv, const float* dd /* [n_tokens, n_heads] D = dO.O, or NULL */,
-                                void* stream);
+                                int32_t io_flags, void* stream);
 
 /* ------------------------------------------------ tensor-core dense layers */
 
@@ -316,6 +319,10 @@ typedef struct geomae_linear_args {
    * out = d(pre-LN rows) and accumulates (+=) ln_dgamma, ln_dbeta and (optional) ln_dcolsum = column sums of out.
    * replaces: ATen layer_norm backward after the matching dX GEMM — dz is never stored. */
   float* ln_dgamma; float* ln_dbeta; float* ln_dcolsum;
+  /* bf16 storage of tensors that only ever serve as tensor-core operands (precision 1): a_bf16: A rows are bf16
+   * (lda in elements; no position / GELU prologue); out_bf16: epilogue 0 / 2 writes bf16 rows (ldo in elements).
+   * Numerically identical to the fp32-storage path, which rounds the same values to bf16 when staging them. */
+  int32_t a_bf16; int32_t out_bf16;
 } geomae_linear_args;
 
 int geomae_tc_linear(const geomae_linear_args* args, void* stream);
@@ -337,6 +344,7 @@ typedef struct geomae_wgrad_args {
   const float* pos_table; const int32_t* tok_cell; int32_t pos_slabs; int32_t x_gelu;
   float* dW; int32_t ldw; float* db; int32_t M_total; int32_t N_total;
   int32_t precision;
+  int32_t dy_bf16;     /* dY rows are bf16 (ldy in elements), precision 1 */
 } geomae_wgrad_args;
 
 int geomae_tc_wgrad(const geomae_wgrad_args* args, void* stream);

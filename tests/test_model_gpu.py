@@ -164,6 +164,32 @@ def test_sra_attention_tensor_core_kernel(small):
                 assert float((got - want).abs().max()) < 0.15, (name, n_rows, s)
 
 
+def test_sra_attention_tensor_core_kernel_bf16_rows(small):
+    """Same kernel fed with bf16 q|k|v rows (cp.async staging) and writing a bf16 d_qkv: must equal the fp32-row call on
+    the same bf16-rounded values up to the rounding of the bf16 output."""
+    from geomae_b200.sst import sra_attention
+    from geomae_b200.windows import WindowLayout, WindowSpec
+    _, cfg, _, g, pb = small
+    spec = WindowSpec(cfg.window_shape, cfg.shifts)
+    rows = np.concatenate([g["ids_keep"], g["ids_mask"]])[:3000]
+    lay = WindowLayout.from_pillars(spec, pb, torch.from_numpy(rows).to(DEV))
+    n = rows.shape[0]
+    gen = torch.Generator().manual_seed(2)
+    qkv16 = torch.randn(n, 384, generator=gen).to(DEV).bfloat16()
+    d_out = torch.randn(n, 128, generator=gen).to(DEV)
+    for s in (0, 1):
+        a = qkv16.float().requires_grad_(True)
+        b = qkv16.clone().requires_grad_(True)
+        out_a = sra_attention(a, lay.shift(s), 8, tc=True)
+        out_b = sra_attention(b, lay.shift(s), 8, tc=True)
+        out_a.backward(d_out)
+        out_b.backward(d_out)
+        torch.cuda.synchronize()
+        assert b.grad.dtype == torch.bfloat16
+        torch.testing.assert_close(out_b, out_a, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(b.grad.float(), a.grad, rtol=1e-2, atol=1e-3)
+
+
 def test_scatter_reduce_modes(small):
     from geomae_b200.voxel_encoder import scatter_reduce
     _, _, frames, _, pb = small

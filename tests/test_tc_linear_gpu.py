@@ -116,3 +116,41 @@ def test_layernorm_backward():
     torch.testing.assert_close(colsum, s.grad.sum(0), rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(dg, gamma.grad, rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(db, beta.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_bf16_operand_storage_is_equivalent():
+    """precision 1 with bf16 A rows / bf16 output rows == the fp32-storage call on the same values (the kernel rounds its
+    operands to bf16 anyway); the bf16 output is the rounded fp32 output."""
+    from geomae_b200.dense import tc_linear, tc_wgrad
+    from geomae_b200 import lib as L
+    import ctypes as C
+    n = 3001
+    x = rnd(n, 256, seed=40)
+    w = rnd(128, 256, seed=41) * 0.1
+    ref = tc_linear(x.bfloat16().float(), w, n_out=128, precision=1)
+    # bf16 A rows
+    a = L.LinearArgs()
+    x16 = x.bfloat16().contiguous()
+    out = torch.empty(n, 128, device="cuda")
+    a.A, a.lda, a.n_rows, a.K = x16.data_ptr(), 256, n, 256
+    a.W, a.ldw, a.w_rows, a.w_mn_major = w.data_ptr(), 256, 128, 0
+    a.N_total, a.out, a.ldo, a.precision, a.a_bf16 = 128, out.data_ptr(), 128, 1, 1
+    L.run("tc_linear", C.byref(a), L.stream_ptr(x.device))
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    # bf16 output rows
+    out16 = torch.empty(n, 128, device="cuda", dtype=torch.bfloat16)
+    a.out, a.out_bf16 = out16.data_ptr(), 1
+    L.run("tc_linear", C.byref(a), L.stream_ptr(x.device))
+    torch.testing.assert_close(out16, ref.bfloat16(), rtol=0, atol=0)
+    # bf16 dY rows in the weight gradient
+    dy = rnd(n, 128, seed=42)
+    xx = rnd(n, 128, seed=43)
+    dw_ref = torch.zeros(128, 128, device="cuda")
+    tc_wgrad(dy.bfloat16().float(), xx, dw_ref, None, precision=1)
+    dw = torch.zeros(128, 128, device="cuda")
+    g = L.WgradArgs()
+    dy16 = dy.bfloat16().contiguous()
+    g.dY, g.ldy, g.X, g.ldx, g.n_rows = dy16.data_ptr(), 128, xx.data_ptr(), 128, n
+    g.dW, g.ldw, g.M_total, g.N_total, g.precision, g.dy_bf16 = dw.data_ptr(), 128, 128, 128, 1, 1
+    L.run("tc_wgrad", C.byref(g), L.stream_ptr(x.device))
+    torch.testing.assert_close(dw, dw_ref, rtol=1e-4, atol=1e-3)
