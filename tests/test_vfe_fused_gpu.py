@@ -1,0 +1,109 @@
+"""Fused DynamicScatterVFE (csrc/vfe_fused.cu) against the op-by-op path of the same module
+(decorate -> nn.Linear -> naiveSyncBN1d -> ReLU -> scatter-max -> gather/cat -> ...), forward, parameter gradients
+and running statistics — on one rank, and on two ranks (gloo process group over CUDA tensors, both on cuda:0) where
+the op-by-op path is the reference's all_gather / all_reduce form of naiveSyncBN1d (mmdet3d/ops/norm.py:55-86)."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(seed):
+    import geomae_b200  # noqa: F401
+    from geomae_b200.registry import Config, build_voxel_encoder
+    cfg = Config.fromfile(os.path.join(ROOT, "configs/mae_sst/geomae_nus_pretrain.py"))
+    torch.manual_seed(seed)
+    vfe = build_voxel_encoder(cfg.model["voxel_encoder"]).cuda().train()
+    with torch.no_grad():
+        for layer in vfe.vfe_layers:                      # non-trivial affine parameters
+            layer.norm.weight.uniform_(0.5, 1.5)
+            layer.norm.bias.uniform_(-0.3, 0.3)
+    return cfg, vfe
+
+
+def _run(vfe, cfg, frames, fused, d_seed):
+    from geomae_b200.voxel import VoxelGeometry, scatter_frames
+    m = cfg.model
+    geom = VoxelGeometry(tuple(m["voxel_layer"]["point_cloud_range"]), tuple(m["voxel_layer"]["voxel_size"]),
+                         tuple(m["sub_voxel_layer_med"]["voxel_size"]), tuple(m["sub_voxel_layer_low"]["voxel_size"]),
+                         tuple(m["sub_voxel_ratio_med"]), tuple(m["sub_voxel_ratio_low"]))
+    pb = scatter_frames(geom, frames)
+    vfe.fused = fused
+    vfe.tc_precision = 3
+    for p in vfe.parameters():
+        p.grad = None
+    out, coors = vfe(pb)
+    g = torch.Generator(device="cuda").manual_seed(d_seed)
+    d = torch.randn(out.shape, generator=g, device="cuda")
+    (out * d).sum().backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.clone() for k, p in vfe.named_parameters()}
+    stats = {k: b.clone() for k, b in vfe.named_buffers()}
+    return out.detach().clone(), grads, stats
+
+
+def _compare(a, b, what):
+    out_a, g_a, s_a = a
+    out_b, g_b, s_b = b
+    # pre-BN rows reach |x| ~ 50 (raw metres): fp32 rounding of the two evaluation orders shows up at ~1e-5 of that
+    torch.testing.assert_close(out_a, out_b, rtol=1e-3, atol=2e-4, msg=lambda m: f"{what} output: {m}")
+    for k in g_a:
+        err = float((g_a[k] - g_b[k]).norm() / (g_b[k].norm() + 1e-12))
+        assert err < 1e-3, (what, k, err)
+    for k in s_a:
+        torch.testing.assert_close(s_a[k].float(), s_b[k].float(), rtol=1e-4, atol=1e-5, msg=lambda m: f"{what} {k}: {m}")
+
+
+def _frames(seeds, scale=0.3):
+    from geomae_b200.synthetic import make_frame
+    return [torch.from_numpy(make_frame(s, point_scale=scale)).cuda() for s in seeds]
+
+
+def test_fused_equals_op_by_op_single_rank():
+    cfg, vfe = _build(0)
+    state = {k: v.clone() for k, v in vfe.state_dict().items()}
+    frames = _frames([11, 12, 13])
+    ref = _run(vfe, cfg, frames, fused=False, d_seed=5)
+    vfe.load_state_dict(state)
+    got = _run(vfe, cfg, frames, fused=True, d_seed=5)
+    _compare(got, ref, "single rank")
+
+
+def _worker(rank, world, port, q):
+    try:
+        import torch.distributed as dist
+        sys.path.insert(0, ROOT)
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        cfg, vfe = _build(0)
+        state = {k: v.clone() for k, v in vfe.state_dict().items()}
+        frames = _frames([21 + 2 * rank, 22 + 2 * rank], scale=0.2 + 0.15 * rank)   # different point counts per rank
+        ref = _run(vfe, cfg, frames, fused=False, d_seed=7 + rank)
+        vfe.load_state_dict(state)
+        got = _run(vfe, cfg, frames, fused=True, d_seed=7 + rank)
+        _compare(got, ref, f"rank {rank}")
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL: " + repr(e) + "\n" + traceback.format_exc()))
+
+
+def test_fused_equals_reference_form_sync_bn_two_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29640 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in sorted(res):
+        assert msg == "ok", f"rank {rank}: {msg}"
