@@ -450,8 +450,9 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
     constexpr int NP = NT / 64;                                // panels
     constexpr int RI = TM * C4 / LTHREADS;                     // rows per thread and panel (8)
     const int c4 = threadIdx.x % C4, rbase = threadIdx.x / C4; // this thread: column quad c4 of rows rbase + 16 k
-    const float* esrc = EPI == 2 ? a.gelu_u : a.add_src;       // the per-element global operand (may be null for EPI 0)
-    const int eld = EPI == 2 ? a.ldu : a.ld_add;
+    const bool dot_mode = EPI == 0 && NT == 128 && !POS && a.dot_src != nullptr;   // `pre` then carries dot_src, not add_src
+    const float* esrc = EPI == 2 ? a.gelu_u : (dot_mode ? a.dot_src : a.add_src);  // per-element global operand (may be null)
+    const int eld = EPI == 2 ? a.ldu : (dot_mode ? a.ld_dot : a.ld_add);
     float4 pre[RI], bias4;
     auto fetch = [&](int pc) {
       bias4 = (EPI == 0 && a.bias) ? __ldg(reinterpret_cast<const float4*>(a.bias + n0 + pc * 64 + c4 * 4))
@@ -489,8 +490,11 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
             const float4 u = pre[k];
             o.x *= gelu_grad_f(u.x); o.y *= gelu_grad_f(u.y); o.z *= gelu_grad_f(u.z); o.w *= gelu_grad_f(u.w);
           } else {
-            o.x += bias4.x + pre[k].x; o.y += bias4.y + pre[k].y;
-            o.z += bias4.z + pre[k].z; o.w += bias4.w + pre[k].w;
+            if (dot_mode) { o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w; }
+            else {
+              o.x += bias4.x + pre[k].x; o.y += bias4.y + pre[k].y;
+              o.z += bias4.z + pre[k].z; o.w += bias4.w + pre[k].w;
+            }
           }
           if (a.out_bf16) {
             __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(a.out) + (int64_t)row * a.ldo + n0 + pc * 64 + c4 * 4;
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(LTHREADS, 2) k_tc_linear(const LinArgs a) {
             const int row = row0 + rbase + (LTHREADS / C4) * k;
             float part = 0.f;
             if (row < a.n_rows) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.dot_src + (int64_t)row * a.ld_dot + n0 + pc * 64 + c4 * 4));
+              const float4 s4 = pre[k];       // dot_src, prefetched with the panel
               part = (dotv[k].x * s4.x + dotv[k].y * s4.y) + (dotv[k].z * s4.z + dotv[k].w * s4.w);
             }
             part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -819,6 +823,7 @@ extern "C" int geomae_tc_linear(const geomae_linear_args* p, void* stream_) {
   GM_REQUIRE(!p->out_bf16 || (p->epilogue == 0 || p->epilogue == 2), "tc_linear: bf16 output only for epilogues 0 and 2");
   GM_REQUIRE(!p->dot_src || (p->dot_out && p->epilogue == 0 && p->N_total == 128 && p->pos_slabs == 0 && p->ld_dot % 4 == 0),
              "tc_linear: the per-head dot side output needs epilogue 0, N = 128, no position prologue");
+  GM_REQUIRE(!p->dot_src || !p->add_src, "tc_linear: the per-head dot side output cannot be combined with add_src");
   cudaStream_t stream = (cudaStream_t)stream_;
   if (p->epilogue == 1) {
     GM_REQUIRE(p->N_total == 128 && p->bias && p->add_src && p->ln_gamma && p->ln_beta,
@@ -854,7 +859,11 @@ extern "C" int geomae_tc_wgrad(const geomae_wgrad_args* p, void* stream_) {
   GM_REQUIRE(!p->dy_bf16 || (p->precision == 1 && p->ldy % 8 == 0), "tc_wgrad: bf16 dY rows need precision 1, ldy %% 8 == 0");
   const int n_tiles = gm_div_up(p->n_rows, TM);
   const int slabs = (p->M_total / 128) * ((p->N_total % 256 == 0 && !p->db) ? p->N_total / 256 : p->N_total / 128);
-  int splits = (2 * GM_NUM_SMS + slabs - 1) / slabs;           // aim at ~2 CTAs per SM
+  // target CTAs per SM x 2 (GEOMAE_WGRAD_CTAS_X2 overrides).  Measured on the 4-frame step: 1 per SM 5.09 ms, 2 per SM
+  // 5.14 ms, 1 per 2 SMs 5.23 ms — more CTAs mean more red.add flushes of the same dW addresses, fewer mean longer chains.
+  static int ctas_x2 = -1;
+  if (ctas_x2 < 0) { const char* e = getenv("GEOMAE_WGRAD_CTAS_X2"); ctas_x2 = e ? atoi(e) : 2; if (ctas_x2 < 1) ctas_x2 = 2; }
+  int splits = (ctas_x2 * GM_NUM_SMS / 2 + slabs - 1) / slabs;
   if (splits > n_tiles) splits = n_tiles;
   a.tiles_per_cta = gm_div_up(n_tiles, splits);
   // the 256-wide variant fills its TMEM allocation with the accumulator: no bias column there
