@@ -60,24 +60,40 @@ __global__ void __launch_bounds__(TPB) k_geom(VoxGeom g, const uint32_t* __restr
   const int4 pc = __ldg(reinterpret_cast<const int4*>(pillar_coors) + v);
   const float4 ctr = __ldg(reinterpret_cast<const float4*>(pillar_mean) + v);
   float zz = 0.f, zy = 0.f, zx = 0.f, yy = 0.f, yx = 0.f, xx = 0.f;
-  int k = 0;
-  for (int dy = -1; dy <= 1; ++dy)
-    for (int dx = -1; dx <= 1; ++dx, ++k) {
-      const int ny = pc.z + dy, nx = pc.w + dx;
-      int nid = -1;
-      if (ny >= 0 && ny < g.grid[0][1] && nx >= 0 && nx < g.grid[0][0])
-        nid = cell_rank(bitmap, word_rank, top_cell(g, pc.x, ny, nx));
-      if (pair) pair[(int64_t)k * n + v] = nid;
-      if (nid < 0) continue;
-      uint32_t m = __ldg(med_mask + nid);
-      const float4* row = reinterpret_cast<const float4*>(med_mean) + __ldg(med_ptr + nid);
-      for (; m; m &= m - 1, ++row) {
-        const float4 c = __ldg(row);
-        const float dz = __fsub_rn(c.z, ctr.z), dyy = __fsub_rn(c.y, ctr.y), dxx = __fsub_rn(c.x, ctr.x);
-        zz = fmaf(dz, dz, zz); zy = fmaf(dz, dyy, zy); zx = fmaf(dz, dxx, zx);
-        yy = fmaf(dyy, dyy, yy); yx = fmaf(dyy, dxx, yx); xx = fmaf(dxx, dxx, xx);
-      }
+  // Three phases so that the loads of all nine neighbours are in flight together (the walk used to be nine serial
+  // chains of four dependent loads): (1) occupancy words + ranks, (2) slot masks + CSR offsets, (3) centroid rows.
+  // Accumulation order (neighbour k, then slot) is unchanged, so the moments are bit-identical.
+  int nid[9];
+  uint32_t bw[9];
+  int wr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int ny = pc.z + k / 3 - 1, nx = pc.w + k % 3 - 1;
+    const bool in = ny >= 0 && ny < g.grid[0][1] && nx >= 0 && nx < g.grid[0][0];
+    const int64_t cell = in ? top_cell(g, pc.x, ny, nx) : 0;
+    bw[k] = in ? __ldg(bitmap + (cell >> 5)) : 0u;
+    wr[k] = in ? __ldg(word_rank + (cell >> 5)) : 0;
+    const uint32_t bit = 1u << (cell & 31);
+    nid[k] = (in && (bw[k] & bit)) ? wr[k] + __popc(bw[k] & (bit - 1)) : -1;
+  }
+  uint32_t msk[9];
+  int ptr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (pair) pair[(int64_t)k * n + v] = nid[k];
+    msk[k] = nid[k] >= 0 ? __ldg(med_mask + nid[k]) : 0u;
+    ptr[k] = nid[k] >= 0 ? __ldg(med_ptr + nid[k]) : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4* row = reinterpret_cast<const float4*>(med_mean) + ptr[k];
+    for (uint32_t m = msk[k]; m; m &= m - 1, ++row) {
+      const float4 c = __ldg(row);
+      const float dz = __fsub_rn(c.z, ctr.z), dyy = __fsub_rn(c.y, ctr.y), dxx = __fsub_rn(c.x, ctr.x);
+      zz = fmaf(dz, dz, zz); zy = fmaf(dz, dyy, zy); zx = fmaf(dz, dxx, zx);
+      yy = fmaf(dyy, dyy, yy); yx = fmaf(dyy, dxx, yx); xx = fmaf(dxx, dxx, xx);
     }
+  }
   if (cov6) {
     float* o = cov6 + v * 6;
     o[0] = zz; o[1] = zy; o[2] = zx; o[3] = yy; o[4] = yx; o[5] = xx;

@@ -10,6 +10,11 @@ struct VoxGeom {
   int grid[3][3];     // [scale][x,y,z]
   int ratio[3][3];    // [scale][z,y,x]
   int n_frames;
+  // shift[s][a] >= 0: on axis a the voxel of scale s is exactly 2^shift low-scale voxels (sizes and grids), so its
+  // coordinate is the low-scale coordinate >> shift — bit-exact with the independent IEEE divide, because dividing by
+  // v * 2^k only changes the exponent of the quotient (every GeoMAE config qualifies).  -1: divide.
+  int shift[3][3];
+  int parent_is_top;  // the parent BEV cell of every sub-voxel is the point's own pillar cell (x, y shifts consistent)
 };
 
 __device__ __forceinline__ int vox_coord(float p, float lo, float vs, int g) {
@@ -26,9 +31,13 @@ struct PointKeys {
 
 __device__ __forceinline__ void point_keys(const VoxGeom& g, const float* p, PointKeys& k) {
 #pragma unroll
-  for (int s = 0; s < 3; ++s)
+  for (int a = 0; a < 3; ++a) {
+    const int lowc = vox_coord(p[a], g.lo[a], g.vs[2][a], g.grid[2][a]);
+    k.c[2][a] = lowc;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) k.c[s][a] = vox_coord(p[a], g.lo[a], g.vs[s][a], g.grid[s][a]);
+    for (int s = 0; s < 2; ++s)
+      k.c[s][a] = g.shift[s][a] >= 0 ? (lowc >> g.shift[s][a]) : vox_coord(p[a], g.lo[a], g.vs[s][a], g.grid[s][a]);
+  }
 }
 
 __device__ __forceinline__ int frame_of(const int32_t* __restrict__ off, int n_frames, int64_t idx) {
@@ -89,6 +98,22 @@ inline int gm_make_geom(const geomae_voxel_cfg* cfg, int n_frames, VoxGeom* g) {
     g->ratio[2][a] = cfg->ratio_low[a];
   }
   g->n_frames = n_frames;
+  for (int s = 0; s < 3; ++s)
+    for (int a = 0; a < 3; ++a) {
+      g->shift[s][a] = -1;
+      for (int k = 0; k <= 8; ++k)      // exact fp32 comparisons: v_s == v_low * 2^k and grid_low == grid_s * 2^k
+        if (g->vs[s][a] == g->vs[2][a] * (float)(1 << k) && g->grid[2][a] == g->grid[s][a] * (1 << k)) {
+          g->shift[s][a] = k;
+          break;
+        }
+    }
+  // parent cell (cy / ry, cx / rx) of a sub-voxel == the pillar cell when both are shifts of the same low coordinate
+  g->parent_is_top = 1;
+  for (int s = 1; s < 3; ++s)
+    for (int a = 0; a < 2; ++a) {       // x, y
+      const int r = g->ratio[s][2 - a]; // ratio is stored (z, y, x)
+      if (g->shift[0][a] < 0 || g->shift[s][a] < 0 || (1 << (g->shift[0][a] - g->shift[s][a])) != r) g->parent_is_top = 0;
+    }
   const int slots_med = cfg->ratio_med[0] * cfg->ratio_med[1] * cfg->ratio_med[2];
   const int slots_low = cfg->ratio_low[0] * cfg->ratio_low[1] * cfg->ratio_low[2];
   GM_REQUIRE(slots_med >= 1 && slots_med <= 32, "sub_voxel_ratio_med has %d slots, supported 1..32", slots_med);

@@ -181,13 +181,15 @@ __global__ void __launch_bounds__(TPB) k_assign(VoxGeom g, const float* __restri
   int64_t cell;
   int slot;
   sub_parent(g, 1, k, cell, slot);
-  int par = max(cell_rank(bitmap, word_rank, cell), 0);  // missing parent aliases row 0 like the reference's zero table
+  // missing parent aliases row 0 like the reference's zero table; with consistent power-of-two scales the parent is the
+  // point's own pillar and the two extra bitmap look-ups disappear
+  int par = g.parent_is_top ? pid : max(cell_rank(bitmap, word_rank, cell), 0);
   if (par < cap) {
     const uint32_t bit = 1u << slot;
     if (!(*(volatile uint32_t*)(med_mask + par) & bit)) atomicOr(med_mask + par, bit);
   }
   sub_parent(g, 2, k, cell, slot);
-  par = max(cell_rank(bitmap, word_rank, cell), 0);
+  par = g.parent_is_top ? pid : max(cell_rank(bitmap, word_rank, cell), 0);
   if (par < cap) {
     uint32_t* w = low_mask + 4 * (int64_t)par + (slot >> 5);
     const uint32_t bit = 1u << (slot & 31);
@@ -299,12 +301,13 @@ __global__ void __launch_bounds__(TPB) k_sub_accum(VoxGeom g, const float* __res
   int slot;
   sub_parent(g, 1, k, cell, slot);
   int par = max(cell_rank(bitmap, word_rank, cell), 0);
+  const int par_med = par;
   if (par < cap) {
     const int row = __ldg(med_ptr + par) + __popc(__ldg(med_mask + par) & ((1u << slot) - 1u));
     if (row < sub_cap) red_add4(med_mean + 4 * (int64_t)row, p[0], p[1], p[2], 1.0f);
   }
   sub_parent(g, 2, k, cell, slot);
-  par = max(cell_rank(bitmap, word_rank, cell), 0);
+  par = g.parent_is_top ? par_med : max(cell_rank(bitmap, word_rank, cell), 0);
   if (par < cap) {
     const uint4 m = __ldg(reinterpret_cast<const uint4*>(low_mask) + par);
     const int row = __ldg(low_ptr + par) + rank128(m, slot);
