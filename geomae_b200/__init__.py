@@ -6,3 +6,4 @@ Importing the package registers the reference's registry names (DETECTORS
 from . import backbone, detector, losses, norm, voxel_encoder  # noqa: F401  (registration side effects)
 from .registry import Config, build_detector, build_model  # noqa: F401
 from .voxel import Voxelization, VoxelGeometry, scatter_frames  # noqa: F401
+from . import ops  # noqa: F401  (the reference's `mmdet3d.ops` names for this path)
