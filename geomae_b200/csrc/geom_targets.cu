@@ -13,33 +13,36 @@ namespace {
 
 constexpr int TPB = 128;
 
-__device__ __forceinline__ void jacobi3(double a[3][3], double v[3][3]) {
+// Cyclic Jacobi on a symmetric 3x3 matrix in fp32 — the arithmetic the reference's own solver uses (torch.svd of an
+// fp32 batch runs cuSOLVER's batched Jacobi).  a = {a00, a01, a02, a11, a12, a22}; v's COLUMNS converge to the
+// eigenvectors.  Rotations use the stable small-angle root t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)).
+__device__ __forceinline__ void jacobi3f(float a[3][3], float v[3][3]) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 16; ++sweep) {
-    const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-    const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
-    if (off <= 1e-30 * diag || off == 0.0) break;
+    for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.f : 0.f;
+  for (int sweep = 0; sweep < 8; ++sweep) {
+    const float off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+    const float diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+    if (off <= 1e-15f * diag || off == 0.f) break;  // off-diagonal norm below 3e-8 of the diagonal's: fp32 converged
 #pragma unroll
     for (int pq = 0; pq < 3; ++pq) {
       const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
-      const double apq = a[p][q];
-      if (apq == 0.0) continue;
-      const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-      const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      const float apq = a[p][q];
+      if (apq == 0.f) continue;
+      const float theta = (a[q][q] - a[p][p]) / (2.f * apq);
+      const float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));
+      const float c = rsqrtf(fmaf(t, t, 1.f)), s = t * c;
       const int r = 3 - p - q;
-      const double app = a[p][p], aqq = a[q][q], arp = a[r][p], arq = a[r][q];
-      a[p][p] = app - t * apq;
-      a[q][q] = aqq + t * apq;
-      a[p][q] = a[q][p] = 0.0;
+      const float arp = a[r][p], arq = a[r][q];
+      a[p][p] = fmaf(-t, apq, a[p][p]);
+      a[q][q] = fmaf(t, apq, a[q][q]);
+      a[p][q] = a[q][p] = 0.f;
       a[r][p] = a[p][r] = c * arp - s * arq;
       a[r][q] = a[q][r] = s * arp + c * arq;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const double vip = v[i][p], viq = v[i][q];
+        const float vip = v[i][p], viq = v[i][q];
         v[i][p] = c * vip - s * viq;
         v[i][q] = s * vip + c * viq;
       }
@@ -47,7 +50,12 @@ __device__ __forceinline__ void jacobi3(double a[3][3], double v[3][3]) {
   }
 }
 
-__global__ void __launch_bounds__(TPB) k_geom(VoxGeom g, const uint32_t* __restrict__ bitmap,
+// One thread per pillar.  (1) the 3x3 BEV neighbourhood through the occupancy bitmap: per neighbour row ONE 64-bit
+// window of the bitmap + one word rank cover all three cells; (2) slot masks + CSR offsets of the occupied
+// neighbours; (3) their middle-scale centroid rows -> six moments in registers, accumulated in (neighbour, slot)
+// order; (4) fp32 Jacobi eigenvectors, eigenvalues re-evaluated as fp64 Rayleigh quotients of the fp32 matrix (second
+// order in the eigenvector error), curvature in fp64 like the reference's .double() tail (…_ssl.py:604-607).
+__global__ void __launch_bounds__(TPB) k_geom(VoxGeom g, const uint32_t* __restrict__ bitmap, int n_words,
                                               const int32_t* __restrict__ word_rank,
                                               const int32_t* __restrict__ pillar_coors,
                                               const float* __restrict__ pillar_mean,
@@ -59,22 +67,32 @@ __global__ void __launch_bounds__(TPB) k_geom(VoxGeom g, const uint32_t* __restr
   if (v >= n) return;
   const int4 pc = __ldg(reinterpret_cast<const int4*>(pillar_coors) + v);
   const float4 ctr = __ldg(reinterpret_cast<const float4*>(pillar_mean) + v);
-  float zz = 0.f, zy = 0.f, zx = 0.f, yy = 0.f, yx = 0.f, xx = 0.f;
-  // Three phases so that the loads of all nine neighbours are in flight together (the walk used to be nine serial
-  // chains of four dependent loads): (1) occupancy words + ranks, (2) slot masks + CSR offsets, (3) centroid rows.
-  // Accumulation order (neighbour k, then slot) is unchanged, so the moments are bit-identical.
+  const int gx = g.grid[0][0], gy = g.grid[0][1];
   int nid[9];
-  uint32_t bw[9];
-  int wr[9];
+  {
+    uint64_t win[3];
+    int wr[3], o0[3];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int ny = pc.z + k / 3 - 1, nx = pc.w + k % 3 - 1;
-    const bool in = ny >= 0 && ny < g.grid[0][1] && nx >= 0 && nx < g.grid[0][0];
-    const int64_t cell = in ? top_cell(g, pc.x, ny, nx) : 0;
-    bw[k] = in ? __ldg(bitmap + (cell >> 5)) : 0u;
-    wr[k] = in ? __ldg(word_rank + (cell >> 5)) : 0;
-    const uint32_t bit = 1u << (cell & 31);
-    nid[k] = (in && (bw[k] & bit)) ? wr[k] + __popc(bw[k] & (bit - 1)) : -1;
+    for (int r = 0; r < 3; ++r) {
+      const int ny = pc.z + r - 1;
+      const bool in = ny >= 0 && ny < gy;
+      const int64_t cm = in ? top_cell(g, pc.x, ny, pc.w) : 0;  // centre cell of the row
+      const int64_t c0 = cm > 0 ? cm - 1 : 0;
+      const int wi = (int)(c0 >> 5);
+      o0[r] = (int)(cm - 1 - ((int64_t)wi << 5));               // bit offset of cell (ny, x-1) in the window (may be -1)
+      const uint32_t lo = in ? __ldg(bitmap + wi) : 0u;
+      const uint32_t hi = (in && wi + 1 < n_words) ? __ldg(bitmap + wi + 1) : 0u;
+      wr[r] = in ? __ldg(word_rank + wi) : 0;
+      win[r] = ((uint64_t)hi << 32) | lo;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int r = k / 3, nx = pc.w + k % 3 - 1;
+      const int o = o0[r] + k % 3;
+      const bool in = nx >= 0 && nx < gx && o >= 0;               // row validity is folded into win == 0
+      const uint64_t bit = 1ull << (o & 63);
+      nid[k] = (in && (win[r] & bit)) ? wr[r] + __popcll(win[r] & (bit - 1)) : -1;
+    }
   }
   uint32_t msk[9];
   int ptr[9];
@@ -84,6 +102,7 @@ __global__ void __launch_bounds__(TPB) k_geom(VoxGeom g, const uint32_t* __restr
     msk[k] = nid[k] >= 0 ? __ldg(med_mask + nid[k]) : 0u;
     ptr[k] = nid[k] >= 0 ? __ldg(med_ptr + nid[k]) : 0;
   }
+  float zz = 0.f, zy = 0.f, zx = 0.f, yy = 0.f, yx = 0.f, xx = 0.f;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     const float4* row = reinterpret_cast<const float4*>(med_mean) + ptr[k];
@@ -98,30 +117,55 @@ __global__ void __launch_bounds__(TPB) k_geom(VoxGeom g, const uint32_t* __restr
     float* o = cov6 + v * 6;
     o[0] = zz; o[1] = zy; o[2] = zx; o[3] = yy; o[4] = yx; o[5] = xx;
   }
-  double a[3][3] = {{zz, zy, zx}, {zy, yy, yx}, {zx, yx, xx}}, ev[3][3];
-  jacobi3(a, ev);
-  double lam[3] = {fabs(a[0][0]), fabs(a[1][1]), fabs(a[2][2])};
-  int idx[3] = {0, 1, 2};
-  // stable descending sort of three values (ties keep index order -> zero matrix gives (0,0,1))
-  if (lam[idx[1]] > lam[idx[0]]) { int t = idx[0]; idx[0] = idx[1]; idx[1] = t; }
-  if (lam[idx[2]] > lam[idx[1]]) { int t = idx[1]; idx[1] = idx[2]; idx[2] = t; }
-  if (lam[idx[1]] > lam[idx[0]]) { int t = idx[0]; idx[0] = idx[1]; idx[1] = t; }
-  double nz = ev[0][idx[2]], ny_ = ev[1][idx[2]], nx_ = ev[2][idx[2]];
-  const double inv = 1.0 / sqrt(nz * nz + ny_ * ny_ + nx_ * nx_);
+  float a[3][3] = {{zz, zy, zx}, {zy, yy, yx}, {zx, yx, xx}}, ev[3][3];
+  jacobi3f(a, ev);
+  // eigenvalues: Rayleigh quotients of the ORIGINAL matrix in fp64 (removes the rounding the fp32 rotations
+  // accumulate on the diagonal); the matrix is a Gram matrix, so they are the singular values
+  double lam[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double e0 = ev[0][j], e1 = ev[1][j], e2 = ev[2][j];
+    const double q = e0 * ((double)zz * e0 + (double)zy * e1 + (double)zx * e2) +
+                     e1 * ((double)zy * e0 + (double)yy * e1 + (double)yx * e2) +
+                     e2 * ((double)zx * e0 + (double)yx * e1 + (double)xx * e2);
+    const double nn = e0 * e0 + e1 * e1 + e2 * e2;
+    lam[j] = fabs(q / nn);
+  }
+  // stable descending sort of the three (value, vector) pairs (ties keep index order -> zero matrix gives (0,0,1))
+  float e[3][3];  // e[j] = eigenvector j as (z, y, x)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { e[j][0] = ev[0][j]; e[j][1] = ev[1][j]; e[j][2] = ev[2][j]; }
+  auto cswap = [&](int i, int j) {
+    if (lam[j] > lam[i]) {
+      const double tl = lam[i]; lam[i] = lam[j]; lam[j] = tl;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const float tv = e[i][c]; e[i][c] = e[j][c]; e[j][c] = tv; }
+    }
+  };
+  cswap(0, 1);
+  cswap(1, 2);
+  cswap(0, 1);
+  float nz = e[2][0], ny_ = e[2][1], nx_ = e[2][2];
+  const float inv = rsqrtf(nz * nz + ny_ * ny_ + nx_ * nx_);
   nz *= inv; ny_ *= inv; nx_ *= inv;
+  {  // one Newton step on the normalisation: rsqrtf is a 2-ulp approximation
+    const float n2 = nz * nz + ny_ * ny_ + nx_ * nx_;
+    const float fix = fmaf(-0.5f, n2 - 1.f, 1.f);
+    nz *= fix; ny_ *= fix; nx_ *= fix;
+  }
   // documented sign convention: first non-zero component of (z,y,x) is positive
-  const double lead = (fabs(nz) > 1e-12) ? nz : ((fabs(ny_) > 1e-12) ? ny_ : nx_);
-  if (lead < 0) { nz = -nz; ny_ = -ny_; nx_ = -nx_; }
-  normal[v * 3 + 0] = (float)nz;
-  normal[v * 3 + 1] = (float)ny_;
-  normal[v * 3 + 2] = (float)nx_;
-  const float s0 = (float)lam[idx[0]], s1 = (float)lam[idx[1]], s2 = (float)lam[idx[2]];
+  const float lead = (fabsf(nz) > 1e-12f) ? nz : ((fabsf(ny_) > 1e-12f) ? ny_ : nx_);
+  if (lead < 0.f) { nz = -nz; ny_ = -ny_; nx_ = -nx_; }
+  normal[v * 3 + 0] = nz;
+  normal[v * 3 + 1] = ny_;
+  normal[v * 3 + 2] = nx_;
+  const float s0 = (float)lam[0], s1 = (float)lam[1], s2 = (float)lam[2];
   if (singular) { singular[v * 3 + 0] = s0; singular[v * 3 + 1] = s1; singular[v * 3 + 2] = s2; }
   const double e0 = (double)s0 + 1e-9, e1 = (double)s1 + 1e-9, e2 = (double)s2 + 1e-9;
-  const double sum = e0 + e1 + e2;
-  curvature[v * 3 + 0] = e0 / sum;
-  curvature[v * 3 + 1] = e1 / sum;
-  curvature[v * 3 + 2] = e2 / sum;
+  const double rsum = 1.0 / (e0 + e1 + e2);
+  curvature[v * 3 + 0] = e0 * rsum;
+  curvature[v * 3 + 1] = e1 * rsum;
+  curvature[v * 3 + 2] = e2 * rsum;
 }
 
 // (c - (coor*size + min)) / size, each step rounded like the reference's separate torch ops
@@ -209,7 +253,7 @@ extern "C" int geomae_geom_targets(const geomae_voxel_cfg* cfg, const geomae_sca
   int rc = gm_make_geom(cfg, io->n_frames, &g);
   if (rc) return rc;
   k_geom<<<gm_div_up(n_pillars, TPB), TPB, 0, (cudaStream_t)stream>>>(
-      g, io->bitmap, io->word_rank, io->pillar_coors, io->pillar_mean, io->med_mask, io->med_ptr, io->med_mean,
+      g, io->bitmap, gm_div_up((int64_t)io->n_frames * g.grid[0][0] * g.grid[0][1], 32), io->word_rank, io->pillar_coors, io->pillar_mean, io->med_mask, io->med_ptr, io->med_mean,
       n_pillars, normal, curvature, cov6, singular, pair);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;

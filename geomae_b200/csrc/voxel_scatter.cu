@@ -17,30 +17,56 @@ namespace {
 
 constexpr int TPB = 256;
 constexpr int MAX_STRIDE = 8;
+// Point passes: one CTA stages a tile of TPB*PPT consecutive records (20 KB at the 5-float nuScenes record) with all
+// of a thread's 128-bit loads in flight together, then every thread owns PPT points (tile-strided, so the shared
+// reads of a 5-word record are bank-conflict free and the per-point global writes are coalesced).
+constexpr int PPT = 4;
+constexpr int TILE = TPB * PPT;
+constexpr int TILE_VEC = TILE * MAX_STRIDE / 4 / TPB;  // 128-bit loads per thread at the widest record
 
-// Stage TPB consecutive point records through shared memory with 128-bit loads.
-__device__ __forceinline__ bool load_tile(const float* __restrict__ pts, int64_t n, int stride, float* tile,
-                                          int64_t& idx, float* p) {
-  const int64_t p0 = (int64_t)blockIdx.x * TPB;
-  const int nvalid = (int)min((int64_t)TPB, n - p0);
-  const int nfloat = nvalid * stride;
-  const float* src = pts + p0 * stride;
+struct TileInfo {
+  int64_t p0;   // first point of the tile
+  int nvalid;   // points in the tile
+  int b0;       // frame of the first point
+};
+
+__device__ __forceinline__ TileInfo load_tile(const float* __restrict__ pts, int64_t n, int stride,
+                                              const int32_t* __restrict__ frame_off, int n_frames, float* tile) {
+  TileInfo t;
+  t.p0 = (int64_t)blockIdx.x * TILE;
+  t.nvalid = (int)min((int64_t)TILE, n - t.p0);
+  const int nfloat = t.nvalid * stride;
+  const float* src = pts + t.p0 * stride;
   if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
     const int nvec = nfloat >> 2;
     const float4* src4 = reinterpret_cast<const float4*>(src);
-    float4* dst4 = reinterpret_cast<float4*>(tile);
-    for (int i = threadIdx.x; i < nvec; i += TPB) dst4[i] = __ldg(src4 + i);
+    float4 v[TILE_VEC];
+#pragma unroll
+    for (int k = 0; k < TILE_VEC; ++k) {
+      const int i = threadIdx.x + k * TPB;
+      if (i < nvec) v[k] = __ldg(src4 + i);
+    }
+    // the frame of the tile's first point (one binary search per thread on broadcast addresses) resolves while the
+    // tile loads are in flight; points then advance linearly from it
+    t.b0 = frame_off ? frame_of(frame_off, n_frames, t.p0) : 0;
+#pragma unroll
+    for (int k = 0; k < TILE_VEC; ++k) {
+      const int i = threadIdx.x + k * TPB;
+      if (i < nvec) reinterpret_cast<float4*>(tile)[i] = v[k];
+    }
     for (int i = (nvec << 2) + threadIdx.x; i < nfloat; i += TPB) tile[i] = __ldg(src + i);
   } else {
     for (int i = threadIdx.x; i < nfloat; i += TPB) tile[i] = __ldg(src + i);
+    t.b0 = frame_off ? frame_of(frame_off, n_frames, t.p0) : 0;
   }
   __syncthreads();
-  idx = p0 + threadIdx.x;
-  if ((int)threadIdx.x >= nvalid) return false;
-  p[0] = tile[threadIdx.x * stride + 0];
-  p[1] = tile[threadIdx.x * stride + 1];
-  p[2] = tile[threadIdx.x * stride + 2];
-  return true;
+  return t;
+}
+
+// frame of point idx, walking forward from the tile's first frame (empty frames are skipped like frame_of does)
+__device__ __forceinline__ int frame_from(const int32_t* __restrict__ off, int n_frames, int b, int64_t idx) {
+  while (b + 1 < n_frames && (int64_t)__ldg(off + b + 1) <= idx) ++b;
+  return b;
 }
 
 __device__ __forceinline__ void red_add4(float* addr, float x, float y, float z, float w) {
@@ -52,27 +78,40 @@ __device__ __forceinline__ void red_add4(float* addr, float x, float y, float z,
 __global__ void __launch_bounds__(TPB) k_mark(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
                                               const int32_t* __restrict__ frame_off, uint32_t* bitmap,
                                               int32_t* coors_top, int32_t* coors_med, int32_t* coors_low) {
-  __shared__ __align__(16) float tile[TPB * MAX_STRIDE];
-  int64_t idx;
-  float p[3];
-  if (!load_tile(pts, n, stride, tile, idx, p)) return;
-  PointKeys k;
-  k.b = frame_of(frame_off, g.n_frames, idx);
-  point_keys(g, p, k);
-  const int64_t cell = top_cell(g, k.b, k.c[0][1], k.c[0][0]);
-  const uint32_t bit = 1u << (cell & 31);
-  uint32_t* w = bitmap + (cell >> 5);
-  if (!(*(volatile uint32_t*)w & bit)) atomicOr(w, bit);
+  extern __shared__ __align__(16) float tile[];
+  const TileInfo t = load_tile(pts, n, stride, frame_off, g.n_frames, tile);
   int32_t* outs[3] = {coors_top, coors_med, coors_low};
+  int64_t cell[PPT];
 #pragma unroll
-  for (int s = 0; s < 3; ++s)
-    if (outs[s]) reinterpret_cast<int4*>(outs[s])[idx] = make_int4(k.b, k.c[s][2], k.c[s][1], k.c[s][0]);
+  for (int j = 0; j < PPT; ++j) {
+    const int l = threadIdx.x + j * TPB;
+    cell[j] = -1;
+    if (l < t.nvalid) {
+      const float p[3] = {tile[l * stride], tile[l * stride + 1], tile[l * stride + 2]};
+      PointKeys k;
+      k.b = frame_from(frame_off, g.n_frames, t.b0, t.p0 + l);
+      point_keys(g, p, k);
+      cell[j] = top_cell(g, k.b, k.c[0][1], k.c[0][0]);
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+        if (outs[s]) reinterpret_cast<int4*>(outs[s])[t.p0 + l] = make_int4(k.b, k.c[s][2], k.c[s][1], k.c[s][0]);
+    }
+  }
+  uint32_t seen[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) seen[j] = cell[j] >= 0 ? *(volatile uint32_t*)(bitmap + (cell[j] >> 5)) : ~0u;
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const uint32_t bit = 1u << (cell[j] & 31);
+    if (!(seen[j] & bit)) atomicOr(bitmap + (cell[j] >> 5), bit);
+  }
 }
 
 // ---------------------------------------------------------------- pass 2: rank the bitmap
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_CHUNK = TPB * SCAN_ITEMS;
 constexpr int SCAN_MAX_BLOCKS = 16384;
+constexpr int RANK_LIST = 2048;  // set cells expanded per round of k_bitmap_rank
 
 __device__ __forceinline__ int block_base(const int32_t* __restrict__ sums, int* smem) {
   int v = 0;
@@ -103,11 +142,16 @@ __global__ void __launch_bounds__(TPB) k_bitmap_sums(const uint32_t* __restrict_
   }
 }
 
+// word ranks, the pillar rows (coordinates + zeroed accumulators, written row-coalesced from a shared list of the
+// CTA's set cells) and counts[4 + b] = first pillar row of frame b (b = 0..n_frames) — the host learns the per-sample
+// pillar counts (needed by the random mask split) from the same single read that returns the totals
 __global__ void __launch_bounds__(TPB) k_bitmap_rank(VoxGeom g, const uint32_t* __restrict__ bitmap, int n_words,
                                                      const int32_t* __restrict__ sums, int32_t* word_rank,
                                                      int32_t* counts, int32_t* pillar_coors, float* pillar_mean,
-                                                     uint32_t* med_mask, uint32_t* low_mask, int64_t cap) {
+                                                     uint32_t* med_mask, uint32_t* low_mask, int64_t cap,
+                                                     int write_frame_starts) {
   __shared__ int smem[40];
+  __shared__ uint32_t list[RANK_LIST];
   const int blk_base = block_base(sums, smem);
   const int w0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
   uint32_t words[SCAN_ITEMS];
@@ -118,46 +162,65 @@ __global__ void __launch_bounds__(TPB) k_bitmap_rank(VoxGeom g, const uint32_t* 
     mine += __popc(words[i]);
   }
   int total;
-  int rank = blk_base + gm_block_excl_scan(mine, &total, smem);
+  const int local = gm_block_excl_scan(mine, &total, smem);  // rank inside the CTA of this thread's first set cell
+  const uint32_t cells_per_frame = (uint32_t)(g.grid[0][0] * g.grid[0][1]);
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
     const int v = blk_base + total;
     counts[0] = (int)min((int64_t)v, cap);
     counts[3] = v > cap ? 1 : 0;
+    if (write_frame_starts) counts[4 + g.n_frames] = counts[0];
   }
-  const int cells_per_frame = g.grid[0][0] * g.grid[0][1];
+  {
+    int r = blk_base + local;
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    if (w0 + i >= n_words) break;
-    word_rank[w0 + i] = rank;
-    uint32_t w = words[i];
-    while (w) {
-      const int bit = __ffs(w) - 1;
-      w &= w - 1;
-      if (rank < cap) {
-        const int64_t cell = ((int64_t)(w0 + i) << 5) + bit;
-        const int b = (int)(cell / cells_per_frame);
-        const int r = (int)(cell - (int64_t)b * cells_per_frame);
-        if (pillar_coors)
-          reinterpret_cast<int4*>(pillar_coors)[rank] = make_int4(b, 0, r / g.grid[0][0], r % g.grid[0][0]);
-        if (pillar_mean) reinterpret_cast<float4*>(pillar_mean)[rank] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (med_mask) med_mask[rank] = 0u;
-        if (low_mask) reinterpret_cast<uint4*>(low_mask)[rank] = make_uint4(0u, 0u, 0u, 0u);
-      }
-      ++rank;
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      if (w0 + i < n_words) word_rank[w0 + i] = r;
+      r += __popc(words[i]);
     }
   }
-}
-
-// first pillar row of every frame: counts[4 + b] (b = 0..n_frames), so the host learns the per-sample pillar
-// counts (needed by the random mask split) from the same single read that returns the totals
-__global__ void k_frame_starts(VoxGeom g, const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
-                               int32_t* counts) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > g.n_frames) return;
-  if (b == g.n_frames) { counts[4 + b] = counts[0]; return; }
-  const int64_t cell = (int64_t)b * g.grid[0][0] * g.grid[0][1];
-  const uint32_t w = bitmap[cell >> 5];
-  counts[4 + b] = word_rank[cell >> 5] + __popc(w & ((1u << (cell & 31)) - 1u));
+  if (write_frame_starts && w0 < n_words) {
+    // frames whose first cell lies in this thread's SCAN_ITEMS*32 cells
+    const uint32_t c0 = (uint32_t)w0 << 5, c1 = c0 + SCAN_ITEMS * 32;
+    for (uint32_t b = (c0 + cells_per_frame - 1) / cells_per_frame; b < (uint32_t)g.n_frames; ++b) {
+      const uint32_t cell = b * cells_per_frame;
+      if (cell >= c1) break;
+      int r = blk_base + local;
+      const int wi = (int)((cell - c0) >> 5);
+#pragma unroll
+      for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (i < wi) r += __popc(words[i]);
+        else if (i == wi) r += __popc(words[i] & ((1u << (cell & 31)) - 1u));
+      counts[4 + b] = (int)min((int64_t)r, cap);
+    }
+  }
+  if (!pillar_coors) return;
+  for (int r0 = 0; r0 < total; r0 += RANK_LIST) {
+    int r = local;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      uint32_t w = words[i];
+      while (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        if (r >= r0 && r < r0 + RANK_LIST) list[r - r0] = ((uint32_t)(w0 + i) << 5) + bit;
+        ++r;
+      }
+    }
+    __syncthreads();
+    const int cnt = min(RANK_LIST, total - r0);
+    for (int i = threadIdx.x; i < cnt; i += TPB) {
+      const int64_t row = (int64_t)blk_base + r0 + i;
+      if (row >= cap) break;
+      const uint32_t cell = list[i];
+      const uint32_t b = cell / cells_per_frame, rem = cell - b * cells_per_frame;
+      const uint32_t y = rem / (uint32_t)g.grid[0][0], x = rem - y * (uint32_t)g.grid[0][0];
+      reinterpret_cast<int4*>(pillar_coors)[row] = make_int4((int)b, 0, (int)y, (int)x);
+      reinterpret_cast<float4*>(pillar_mean)[row] = make_float4(0.f, 0.f, 0.f, 0.f);
+      med_mask[row] = 0u;
+      reinterpret_cast<uint4*>(low_mask)[row] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------- pass 3: point -> pillar, pillar sums, slot masks
@@ -167,33 +230,49 @@ __global__ void __launch_bounds__(TPB) k_assign(VoxGeom g, const float* __restri
                                                 const int32_t* __restrict__ word_rank, int64_t cap,
                                                 int32_t* point_pillar, float* pillar_mean, uint32_t* med_mask,
                                                 uint32_t* low_mask) {
-  __shared__ __align__(16) float tile[TPB * MAX_STRIDE];
-  int64_t idx;
-  float p[3];
-  if (!load_tile(pts, n, stride, tile, idx, p)) return;
-  PointKeys k;
-  k.b = frame_of(frame_off, g.n_frames, idx);
-  point_keys(g, p, k);
-  const int pid = cell_rank(bitmap, word_rank, top_cell(g, k.b, k.c[0][1], k.c[0][0]));
-  point_pillar[idx] = pid;
-  if (pid < 0 || pid >= cap) return;
-  red_add4(pillar_mean + 4 * (int64_t)pid, p[0], p[1], p[2], 1.0f);
-  int64_t cell;
-  int slot;
-  sub_parent(g, 1, k, cell, slot);
-  // missing parent aliases row 0 like the reference's zero table; with consistent power-of-two scales the parent is the
-  // point's own pillar and the two extra bitmap look-ups disappear
-  int par = g.parent_is_top ? pid : max(cell_rank(bitmap, word_rank, cell), 0);
-  if (par < cap) {
-    const uint32_t bit = 1u << slot;
-    if (!(*(volatile uint32_t*)(med_mask + par) & bit)) atomicOr(med_mask + par, bit);
+  extern __shared__ __align__(16) float tile[];
+  const TileInfo t = load_tile(pts, n, stride, frame_off, g.n_frames, tile);
+  // phase 1: all look-ups of the thread's points in flight together (the reductions below are ordering barriers)
+  int pid[PPT], par_m[PPT], par_l[PPT], slot_m[PPT], slot_l[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int l = threadIdx.x + j * TPB;
+    pid[j] = par_m[j] = par_l[j] = -1;
+    slot_m[j] = slot_l[j] = 0;
+    if (l < t.nvalid) {
+      const float p[3] = {tile[l * stride], tile[l * stride + 1], tile[l * stride + 2]};
+      PointKeys k;
+      k.b = frame_from(frame_off, g.n_frames, t.b0, t.p0 + l);
+      point_keys(g, p, k);
+      pid[j] = cell_rank(bitmap, word_rank, top_cell(g, k.b, k.c[0][1], k.c[0][0]));
+      int64_t cell;
+      sub_parent(g, 1, k, cell, slot_m[j]);
+      // missing parent aliases row 0 like the reference's zero table; with consistent power-of-two scales the parent
+      // is the point's own pillar and the two extra bitmap look-ups disappear
+      par_m[j] = g.parent_is_top ? pid[j] : max(cell_rank(bitmap, word_rank, cell), 0);
+      sub_parent(g, 2, k, cell, slot_l[j]);
+      par_l[j] = g.parent_is_top ? pid[j] : max(cell_rank(bitmap, word_rank, cell), 0);
+    }
   }
-  sub_parent(g, 2, k, cell, slot);
-  par = g.parent_is_top ? pid : max(cell_rank(bitmap, word_rank, cell), 0);
-  if (par < cap) {
-    uint32_t* w = low_mask + 4 * (int64_t)par + (slot >> 5);
-    const uint32_t bit = 1u << (slot & 31);
-    if (!(*(volatile uint32_t*)w & bit)) atomicOr(w, bit);
+  uint32_t seen_m[PPT], seen_l[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const bool ok = pid[j] >= 0 && pid[j] < cap;
+    seen_m[j] = (ok && par_m[j] < cap) ? *(volatile uint32_t*)(med_mask + par_m[j]) : ~0u;
+    seen_l[j] = (ok && par_l[j] < cap) ? *(volatile uint32_t*)(low_mask + 4 * (int64_t)par_l[j] + (slot_l[j] >> 5)) : ~0u;
+  }
+  // phase 2: writes
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int l = threadIdx.x + j * TPB;
+    if (l >= t.nvalid) continue;
+    point_pillar[t.p0 + l] = pid[j];
+    if (pid[j] < 0 || pid[j] >= cap) continue;
+    red_add4(pillar_mean + 4 * (int64_t)pid[j], tile[l * stride], tile[l * stride + 1], tile[l * stride + 2], 1.0f);
+    const uint32_t bm = 1u << slot_m[j];
+    if (!(seen_m[j] & bm)) atomicOr(med_mask + par_m[j], bm);
+    const uint32_t bl = 1u << (slot_l[j] & 31);
+    if (!(seen_l[j] & bl)) atomicOr(low_mask + 4 * (int64_t)par_l[j] + (slot_l[j] >> 5), bl);
   }
 }
 
@@ -255,15 +334,11 @@ __global__ void __launch_bounds__(TPB) k_sub_ptr(int32_t* counts, const uint32_t
     if (v < n) {
       med_ptr[v] = pm;
       low_ptr[v] = pl;
-      // finish the pillar mean (sum -> mean), zero this pillar's sub-voxel accumulators
+      // finish the pillar mean (sum -> mean)
       float4* pmn = reinterpret_cast<float4*>(pillar_mean) + v;
       float4 a = *pmn;
       a.x = __fdiv_rn(a.x, a.w); a.y = __fdiv_rn(a.y, a.w); a.z = __fdiv_rn(a.z, a.w);
       *pmn = a;
-      for (int j = 0; j < cm[i]; ++j)
-        if (pm + j < sub_cap) reinterpret_cast<float4*>(med_mean)[pm + j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int j = 0; j < cl[i]; ++j)
-        if (pl + j < sub_cap) reinterpret_cast<float4*>(low_mean)[pl + j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     pm += cm[i];
     pl += cl[i];
@@ -274,6 +349,11 @@ __global__ void __launch_bounds__(TPB) k_sub_ptr(int32_t* counts, const uint32_t
       counts[2] = pl;
     }
   }
+  // zero the CTA's contiguous range of sub-voxel accumulators, row-coalesced
+  for (int i = threadIdx.x; i < tot_m; i += TPB)
+    if (base_m + i < sub_cap) reinterpret_cast<float4*>(med_mean)[base_m + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < tot_l; i += TPB)
+    if (base_l + i < sub_cap) reinterpret_cast<float4*>(low_mean)[base_l + i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
     med_ptr[0] = low_ptr[0] = 0;
     counts[1] = counts[2] = 0;
@@ -284,34 +364,60 @@ __global__ void __launch_bounds__(TPB) k_sub_ptr(int32_t* counts, const uint32_t
 __global__ void __launch_bounds__(TPB) k_sub_accum(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
                                                    const int32_t* __restrict__ frame_off,
                                                    const uint32_t* __restrict__ bitmap,
-                                                   const int32_t* __restrict__ word_rank, int64_t cap, int64_t sub_cap,
-                                                   const uint32_t* __restrict__ med_mask,
+                                                   const int32_t* __restrict__ word_rank,
+                                                   const int32_t* __restrict__ point_pillar, int64_t cap,
+                                                   int64_t sub_cap, const uint32_t* __restrict__ med_mask,
                                                    const uint32_t* __restrict__ low_mask,
                                                    const int32_t* __restrict__ med_ptr,
                                                    const int32_t* __restrict__ low_ptr, float* med_mean,
                                                    float* low_mean) {
-  __shared__ __align__(16) float tile[TPB * MAX_STRIDE];
-  int64_t idx;
-  float p[3];
-  if (!load_tile(pts, n, stride, tile, idx, p)) return;
-  PointKeys k;
-  k.b = frame_of(frame_off, g.n_frames, idx);
-  point_keys(g, p, k);
-  int64_t cell;
-  int slot;
-  sub_parent(g, 1, k, cell, slot);
-  int par = max(cell_rank(bitmap, word_rank, cell), 0);
-  const int par_med = par;
-  if (par < cap) {
-    const int row = __ldg(med_ptr + par) + __popc(__ldg(med_mask + par) & ((1u << slot) - 1u));
-    if (row < sub_cap) red_add4(med_mean + 4 * (int64_t)row, p[0], p[1], p[2], 1.0f);
+  extern __shared__ __align__(16) float tile[];
+  const TileInfo t = load_tile(pts, n, stride, frame_off, g.n_frames, tile);
+  int row_m[PPT], row_l[PPT];
+  int par_m[PPT], par_l[PPT], slot_m[PPT], slot_l[PPT];
+  // phase 1a: parents (the stored point -> pillar row when the parent is the point's own pillar)
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int l = threadIdx.x + j * TPB;
+    par_m[j] = par_l[j] = -1;
+    slot_m[j] = slot_l[j] = 0;
+    if (l < t.nvalid) {
+      const float p[3] = {tile[l * stride], tile[l * stride + 1], tile[l * stride + 2]};
+      PointKeys k;
+      k.b = g.parent_is_top ? 0 : frame_from(frame_off, g.n_frames, t.b0, t.p0 + l);
+      point_keys(g, p, k);
+      int64_t cell_m, cell_l;
+      sub_parent(g, 1, k, cell_m, slot_m[j]);
+      sub_parent(g, 2, k, cell_l, slot_l[j]);
+      if (g.parent_is_top) {
+        par_m[j] = par_l[j] = __ldg(point_pillar + t.p0 + l);
+      } else {
+        par_m[j] = max(cell_rank(bitmap, word_rank, cell_m), 0);
+        par_l[j] = max(cell_rank(bitmap, word_rank, cell_l), 0);
+      }
+      if (par_m[j] >= cap) par_m[j] = -1;
+      if (par_l[j] >= cap) par_l[j] = -1;
+    }
   }
-  sub_parent(g, 2, k, cell, slot);
-  par = g.parent_is_top ? par_med : max(cell_rank(bitmap, word_rank, cell), 0);
-  if (par < cap) {
-    const uint4 m = __ldg(reinterpret_cast<const uint4*>(low_mask) + par);
-    const int row = __ldg(low_ptr + par) + rank128(m, slot);
-    if (row < sub_cap) red_add4(low_mean + 4 * (int64_t)row, p[0], p[1], p[2], 1.0f);
+  // phase 1b: CSR rows
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    row_m[j] = row_l[j] = -1;
+    if (par_m[j] >= 0)
+      row_m[j] = __ldg(med_ptr + par_m[j]) + __popc(__ldg(med_mask + par_m[j]) & ((1u << slot_m[j]) - 1u));
+    if (par_l[j] >= 0) {
+      const uint4 m = __ldg(reinterpret_cast<const uint4*>(low_mask) + par_l[j]);
+      row_l[j] = __ldg(low_ptr + par_l[j]) + rank128(m, slot_l[j]);
+    }
+  }
+  // phase 2: reductions
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int l = threadIdx.x + j * TPB;
+    if (l >= t.nvalid) continue;
+    const float x = tile[l * stride], y = tile[l * stride + 1], z = tile[l * stride + 2];
+    if (row_m[j] >= 0 && row_m[j] < sub_cap) red_add4(med_mean + 4 * (int64_t)row_m[j], x, y, z, 1.0f);
+    if (row_l[j] >= 0 && row_l[j] < sub_cap) red_add4(low_mean + 4 * (int64_t)row_l[j], x, y, z, 1.0f);
   }
 }
 
@@ -349,13 +455,18 @@ __global__ void __launch_bounds__(TPB) k_token_of_cell(VoxGeom g, const int32_t*
 __global__ void __launch_bounds__(TPB) k_dynamic_voxelize(const float* __restrict__ pts, int64_t n, int stride, float lx,
                                                           float ly, float lz, float vx, float vy, float vz, int gx,
                                                           int gy, int gz, int32_t* coors) {
-  __shared__ __align__(16) float tile[TPB * MAX_STRIDE];
-  int64_t idx;
-  float p[3];
-  if (!load_tile(pts, n, stride, tile, idx, p)) return;
-  coors[idx * 3 + 0] = vox_coord(p[2], lz, vz, gz);
-  coors[idx * 3 + 1] = vox_coord(p[1], ly, vy, gy);
-  coors[idx * 3 + 2] = vox_coord(p[0], lx, vx, gx);
+  extern __shared__ __align__(16) float tile[];
+  const TileInfo t = load_tile(pts, n, stride, nullptr, 0, tile);
+  int32_t* out = coors + t.p0 * 3;
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int l = threadIdx.x + j * TPB;
+    if (l < t.nvalid) {
+      out[l * 3 + 0] = vox_coord(tile[l * stride + 2], lz, vz, gz);
+      out[l * 3 + 1] = vox_coord(tile[l * stride + 1], ly, vy, gy);
+      out[l * 3 + 2] = vox_coord(tile[l * stride + 0], lx, vx, gx);
+    }
+  }
 }
 
 }  // namespace
@@ -381,7 +492,7 @@ extern "C" int geomae_dynamic_voxelize(const float* points, int64_t n, int32_t s
   int32_t grid[3];
   int rc = geomae_grid_size(range_min, range_max, voxel_xyz, grid);
   if (rc) return rc;
-  k_dynamic_voxelize<<<gm_div_up(n, TPB), TPB, 0, (cudaStream_t)stream>>>(
+  k_dynamic_voxelize<<<gm_div_up(n, TILE), TPB, (size_t)TILE * stride * sizeof(float), (cudaStream_t)stream>>>(
       points, n, stride, range_min[0], range_min[1], range_min[2], voxel_xyz[0], voxel_xyz[1], voxel_xyz[2], grid[0],
       grid[1], grid[2], coors);
   GM_LAUNCH_CHECK();
@@ -408,28 +519,32 @@ extern "C" int geomae_voxel_scatter(const geomae_voxel_cfg* cfg, const geomae_sc
   const int sub_blocks = gm_div_up(io->cap, SCAN_CHUNK);
   GM_REQUIRE(scan_blocks <= SCAN_MAX_BLOCKS && sub_blocks <= SCAN_MAX_BLOCKS,
              "voxel_scatter: grid too large for one launch (%d / %d scan blocks)", scan_blocks, sub_blocks);
+  GM_REQUIRE(n_cells < ((int64_t)1 << 31), "voxel_scatter: %lld BEV cells in the batch, supported < 2^31",
+             (long long)n_cells);
   const int64_t n = io->n_points;
-  const int pblocks = gm_div_up(n > 0 ? n : 1, TPB);
+  const int pblocks = gm_div_up(n > 0 ? n : 1, TILE);
+  const size_t tile_bytes = (size_t)TILE * io->stride * sizeof(float);
   GM_CUDA(cudaMemsetAsync(io->bitmap, 0, (size_t)n_words * 4, stream));
   if (n > 0)
-    k_mark<<<pblocks, TPB, 0, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap, io->coors_top,
-                                        io->coors_med, io->coors_low);
+    k_mark<<<pblocks, TPB, tile_bytes, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap,
+                                                 io->coors_top, io->coors_med, io->coors_low);
   k_bitmap_sums<<<scan_blocks, TPB, 0, stream>>>(io->bitmap, n_words, io->scan_tmp);
   k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, io->bitmap, n_words, io->scan_tmp, io->word_rank, io->counts,
                                                  io->pillar_coors, io->pillar_mean, io->med_mask, io->low_mask,
-                                                 io->cap);
-  k_frame_starts<<<gm_div_up(io->n_frames + 1, 64), 64, 0, stream>>>(g, io->bitmap, io->word_rank, io->counts);
+                                                 io->cap, 1);
   if (n > 0)
-    k_assign<<<pblocks, TPB, 0, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap, io->word_rank,
-                                          io->cap, io->point_pillar, io->pillar_mean, io->med_mask, io->low_mask);
+    k_assign<<<pblocks, TPB, tile_bytes, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap,
+                                                   io->word_rank, io->cap, io->point_pillar, io->pillar_mean,
+                                                   io->med_mask, io->low_mask);
   int32_t* sub_sums = io->scan_tmp + SCAN_MAX_BLOCKS;  // scan_tmp holds 3*SCAN_MAX_BLOCKS ints
   k_sub_sums<<<sub_blocks, TPB, 0, stream>>>(io->counts, io->med_mask, io->low_mask, sub_sums);
   k_sub_ptr<<<sub_blocks, TPB, 0, stream>>>(io->counts, io->med_mask, io->low_mask, sub_sums, io->pillar_mean,
                                             io->med_ptr, io->low_ptr, io->med_mean, io->low_mean, io->n_points);
   if (n > 0) {
-    k_sub_accum<<<pblocks, TPB, 0, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap,
-                                             io->word_rank, io->cap, io->n_points, io->med_mask, io->low_mask,
-                                             io->med_ptr, io->low_ptr, io->med_mean, io->low_mean);
+    k_sub_accum<<<pblocks, TPB, tile_bytes, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap,
+                                                      io->word_rank, io->point_pillar, io->cap, io->n_points,
+                                                      io->med_mask, io->low_mask, io->med_ptr, io->low_ptr,
+                                                      io->med_mean, io->low_mean);
     k_sub_finalize<<<GM_NUM_SMS * 4, TPB, 0, stream>>>(io->counts, io->med_mean, io->low_mean, io->n_points);
   }
   GM_LAUNCH_CHECK();
@@ -454,7 +569,7 @@ extern "C" int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* c
   if (n > 0) k_mark_coors<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap);
   k_bitmap_sums<<<scan_blocks, TPB, 0, stream>>>(bitmap, n_words, scan_tmp);
   k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, bitmap, n_words, scan_tmp, word_rank, counts, nullptr, nullptr,
-                                                 nullptr, nullptr, n > 0 ? n : 1);
+                                                 nullptr, nullptr, n > 0 ? n : 1, 0);
   if (n > 0) k_token_of_cell<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap, word_rank, tok_of_pillar);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
