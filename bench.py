@@ -125,7 +125,7 @@ def hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src, n_frames=256):
     b_sc = 24.0 * p + 32.0 * v + 20.0 * (vm + vl)
     b_gt = 20.0 * vm + 28.0 * v + 24.0 * v
     out = []
-    for name, t, b in (("geomae_voxel_scatter (9 launches)", t_sc, b_sc), ("k_geom (geom_targets)", t_gt, b_gt)):
+    for name, t, b in (("geomae_voxel_scatter (9 kernels)", t_sc, b_sc), ("k_geom (geom_targets)", t_gt, b_gt)):
         ach = b / (t * 1e-3) / 1e9
         out.append(dict(kernel=name, bound="hbm", frames=n_frames, points=p, pillars=v, ms=t, algorithmic_bytes=b,
                         achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src))

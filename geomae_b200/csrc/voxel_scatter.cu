@@ -28,7 +28,17 @@ struct TileInfo {
   int64_t p0;   // first point of the tile
   int nvalid;   // points in the tile
   int b0;       // frame of the first point
+  bool one_frame;  // every point of the tile belongs to frame b0
 };
+
+__device__ __forceinline__ void tile_frame(TileInfo& t, const int32_t* __restrict__ frame_off, int n_frames) {
+  t.b0 = 0;
+  t.one_frame = true;
+  if (frame_off) {
+    t.b0 = frame_of(frame_off, n_frames, t.p0);
+    t.one_frame = t.p0 + t.nvalid <= (int64_t)__ldg(frame_off + t.b0 + 1);
+  }
+}
 
 __device__ __forceinline__ TileInfo load_tile(const float* __restrict__ pts, int64_t n, int stride,
                                               const int32_t* __restrict__ frame_off, int n_frames, float* tile) {
@@ -48,7 +58,7 @@ __device__ __forceinline__ TileInfo load_tile(const float* __restrict__ pts, int
     }
     // the frame of the tile's first point (one binary search per thread on broadcast addresses) resolves while the
     // tile loads are in flight; points then advance linearly from it
-    t.b0 = frame_off ? frame_of(frame_off, n_frames, t.p0) : 0;
+    tile_frame(t, frame_off, n_frames);
 #pragma unroll
     for (int k = 0; k < TILE_VEC; ++k) {
       const int i = threadIdx.x + k * TPB;
@@ -57,16 +67,118 @@ __device__ __forceinline__ TileInfo load_tile(const float* __restrict__ pts, int
     for (int i = (nvec << 2) + threadIdx.x; i < nfloat; i += TPB) tile[i] = __ldg(src + i);
   } else {
     for (int i = threadIdx.x; i < nfloat; i += TPB) tile[i] = __ldg(src + i);
-    t.b0 = frame_off ? frame_of(frame_off, n_frames, t.p0) : 0;
+    tile_frame(t, frame_off, n_frames);
   }
   __syncthreads();
   return t;
 }
 
 // frame of point idx, walking forward from the tile's first frame (empty frames are skipped like frame_of does)
-__device__ __forceinline__ int frame_from(const int32_t* __restrict__ off, int n_frames, int b, int64_t idx) {
-  while (b + 1 < n_frames && (int64_t)__ldg(off + b + 1) <= idx) ++b;
+__device__ __forceinline__ int frame_from(const int32_t* __restrict__ off, int n_frames, const TileInfo& t, int l) {
+  int b = t.b0;
+  if (!t.one_frame)
+    while (b + 1 < n_frames && (int64_t)__ldg(off + b + 1) <= t.p0 + l) ++b;
   return b;
+}
+
+// Everything the passes need to know about one point.
+struct PointInfo {
+  int cell;            // BEV cell of the pillar
+  int slot_m, slot_l;  // slot ids inside the parent pillar
+  int cell_m, cell_l;  // parent BEV cells (== cell on the fast path)
+};
+
+// General path: independent IEEE divides per scale, parents by integer division of the sub-voxel coordinates.
+__device__ __forceinline__ PointInfo point_info(const VoxGeom& g, const float* rec, int b, int4* c_top, int4* c_med,
+                                                int4* c_low) {
+  PointInfo r;
+  PointKeys k;
+  k.b = b;
+  point_keys(g, rec, k);
+  r.cell = (int)top_cell(g, b, k.c[0][1], k.c[0][0]);
+  int64_t cell;
+  sub_parent(g, 1, k, cell, r.slot_m);
+  r.cell_m = (int)cell;
+  sub_parent(g, 2, k, cell, r.slot_l);
+  r.cell_l = (int)cell;
+  if (c_top) *c_top = make_int4(b, k.c[0][2], k.c[0][1], k.c[0][0]);
+  if (c_med) *c_med = make_int4(b, k.c[1][2], k.c[1][1], k.c[1][0]);
+  if (c_low) *c_low = make_int4(b, k.c[2][2], k.c[2][1], k.c[2][0]);
+  return r;
+}
+
+// Fast path (VoxGeom::fast): shifts and masks of one low-scale coordinate per axis; the sub-voxel parents are the
+// point's own pillar.  Straight-line integer code.
+__device__ __forceinline__ PointInfo point_info_fast(const VoxGeom& g, int cx, int cy, int cz, int b, int4* c_top,
+                                                     int4* c_med, int4* c_low) {
+  PointInfo r;
+  const int tx = cx >> g.shift[0][0], ty = cy >> g.shift[0][1];
+  const int mx = cx >> g.shift[1][0], my = cy >> g.shift[1][1], mz = cz >> g.shift[1][2];
+  r.cell = r.cell_m = r.cell_l = (b * g.grid[0][1] + ty) * g.grid[0][0] + tx;
+  r.slot_m = ((mz & g.smask[1][2]) << g.sshift[1][2]) | ((my & g.smask[1][1]) << g.sshift[1][1]) | (mx & g.smask[1][0]);
+  r.slot_l = ((cz & g.smask[2][2]) << g.sshift[2][2]) | ((cy & g.smask[2][1]) << g.sshift[2][1]) | (cx & g.smask[2][0]);
+  if (c_top) *c_top = make_int4(b, cz >> g.shift[0][2], ty, tx);
+  if (c_med) *c_med = make_int4(b, mz, my, mx);
+  if (c_low) *c_low = make_int4(b, cz, cy, cx);
+  return r;
+}
+
+// PointInfo of the thread's PPT points.  The fast path first runs branch-free over all of them (reciprocal multiply,
+// twelve independent chains the scheduler can interleave), then repairs the rare coordinates that sit within qeps of
+// a voxel boundary with the IEEE divide.
+template <bool FAST>
+__device__ __forceinline__ void tile_point_info(const VoxGeom& g, const float* tile, int stride, const TileInfo& t,
+                                                const int32_t* __restrict__ frame_off, bool need_frame,
+                                                PointInfo* info, int32_t* coors_top, int32_t* coors_med,
+                                                int32_t* coors_low) {
+  int b[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) b[j] = t.b0;
+  if (need_frame && !t.one_frame) {
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      const int l = threadIdx.x + j * TPB;
+      if (l < t.nvalid) b[j] = frame_from(frame_off, g.n_frames, t, l);
+    }
+  }
+  int cx[PPT], cy[PPT], cz[PPT];
+  if (FAST) {
+    unsigned redo = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      const int l = min(threadIdx.x + j * TPB, t.nvalid - 1);  // clamped: out-of-tile lanes compute a dummy
+      bool rx, ry, rz;
+      cx[j] = vox_coord_try(tile[l * stride], g.lo[0], g.rvs[0], g.qeps[0], g.grid[2][0], rx);
+      cy[j] = vox_coord_try(tile[l * stride + 1], g.lo[1], g.rvs[1], g.qeps[1], g.grid[2][1], ry);
+      cz[j] = vox_coord_try(tile[l * stride + 2], g.lo[2], g.rvs[2], g.qeps[2], g.grid[2][2], rz);
+      redo |= (rx ? 1u : 0u) << (3 * j) | (ry ? 2u : 0u) << (3 * j) | (rz ? 4u : 0u) << (3 * j);
+    }
+    if (redo) {
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        const int l = min(threadIdx.x + j * TPB, t.nvalid - 1);
+        if (redo >> (3 * j) & 1u) cx[j] = vox_coord(tile[l * stride], g.lo[0], g.vs[2][0], g.grid[2][0]);
+        if (redo >> (3 * j) & 2u) cy[j] = vox_coord(tile[l * stride + 1], g.lo[1], g.vs[2][1], g.grid[2][1]);
+        if (redo >> (3 * j) & 4u) cz[j] = vox_coord(tile[l * stride + 2], g.lo[2], g.vs[2][2], g.grid[2][2]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int l = threadIdx.x + j * TPB;
+    const bool ok = l < t.nvalid;
+    const int64_t i = t.p0 + l;
+    int4* ct = (ok && coors_top) ? reinterpret_cast<int4*>(coors_top) + i : nullptr;
+    int4* cm = (ok && coors_med) ? reinterpret_cast<int4*>(coors_med) + i : nullptr;
+    int4* cl = (ok && coors_low) ? reinterpret_cast<int4*>(coors_low) + i : nullptr;
+    if (FAST) {
+      info[j] = point_info_fast(g, cx[j], cy[j], cz[j], b[j], ct, cm, cl);
+    } else if (ok) {
+      const float rec[3] = {tile[l * stride], tile[l * stride + 1], tile[l * stride + 2]};
+      info[j] = point_info(g, rec, b[j], ct, cm, cl);
+    }
+    if (!ok) info[j].cell = -1;
+  }
 }
 
 __device__ __forceinline__ void red_add4(float* addr, float x, float y, float z, float w) {
@@ -75,28 +187,17 @@ __device__ __forceinline__ void red_add4(float* addr, float x, float y, float z,
 }
 
 // ---------------------------------------------------------------- pass 1: mark occupancy
-__global__ void __launch_bounds__(TPB) k_mark(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
+template <bool FAST>
+__global__ void __launch_bounds__(TPB, 6) k_mark(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
                                               const int32_t* __restrict__ frame_off, uint32_t* bitmap,
                                               int32_t* coors_top, int32_t* coors_med, int32_t* coors_low) {
   extern __shared__ __align__(16) float tile[];
   const TileInfo t = load_tile(pts, n, stride, frame_off, g.n_frames, tile);
-  int32_t* outs[3] = {coors_top, coors_med, coors_low};
-  int64_t cell[PPT];
+  PointInfo info[PPT];
+  tile_point_info<FAST>(g, tile, stride, t, frame_off, true, info, coors_top, coors_med, coors_low);
+  int cell[PPT];
 #pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int l = threadIdx.x + j * TPB;
-    cell[j] = -1;
-    if (l < t.nvalid) {
-      const float p[3] = {tile[l * stride], tile[l * stride + 1], tile[l * stride + 2]};
-      PointKeys k;
-      k.b = frame_from(frame_off, g.n_frames, t.b0, t.p0 + l);
-      point_keys(g, p, k);
-      cell[j] = top_cell(g, k.b, k.c[0][1], k.c[0][0]);
-#pragma unroll
-      for (int s = 0; s < 3; ++s)
-        if (outs[s]) reinterpret_cast<int4*>(outs[s])[t.p0 + l] = make_int4(k.b, k.c[s][2], k.c[s][1], k.c[s][0]);
-    }
-  }
+  for (int j = 0; j < PPT; ++j) cell[j] = info[j].cell;
   uint32_t seen[PPT];
 #pragma unroll
   for (int j = 0; j < PPT; ++j) seen[j] = cell[j] >= 0 ? *(volatile uint32_t*)(bitmap + (cell[j] >> 5)) : ~0u;
@@ -149,7 +250,7 @@ __global__ void __launch_bounds__(TPB) k_bitmap_rank(VoxGeom g, const uint32_t* 
                                                      const int32_t* __restrict__ sums, int32_t* word_rank,
                                                      int32_t* counts, int32_t* pillar_coors, float* pillar_mean,
                                                      uint32_t* med_mask, uint32_t* low_mask, int64_t cap,
-                                                     int write_frame_starts) {
+                                                     int write_frame_starts, int zero_acc) {
   __shared__ int smem[40];
   __shared__ uint32_t list[RANK_LIST];
   const int blk_base = block_base(sums, smem);
@@ -215,8 +316,10 @@ __global__ void __launch_bounds__(TPB) k_bitmap_rank(VoxGeom g, const uint32_t* 
       const uint32_t b = cell / cells_per_frame, rem = cell - b * cells_per_frame;
       const uint32_t y = rem / (uint32_t)g.grid[0][0], x = rem - y * (uint32_t)g.grid[0][0];
       reinterpret_cast<int4*>(pillar_coors)[row] = make_int4((int)b, 0, (int)y, (int)x);
-      reinterpret_cast<float4*>(pillar_mean)[row] = make_float4(0.f, 0.f, 0.f, 0.f);
-      med_mask[row] = 0u;
+      if (zero_acc) {  // the hierarchical (fast) path never accumulates into these
+        reinterpret_cast<float4*>(pillar_mean)[row] = make_float4(0.f, 0.f, 0.f, 0.f);
+        med_mask[row] = 0u;
+      }
       reinterpret_cast<uint4*>(low_mask)[row] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
@@ -224,7 +327,15 @@ __global__ void __launch_bounds__(TPB) k_bitmap_rank(VoxGeom g, const uint32_t* 
 }
 
 // ---------------------------------------------------------------- pass 3: point -> pillar, pillar sums, slot masks
-__global__ void __launch_bounds__(TPB) k_assign(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
+__device__ __forceinline__ int cell_rank32(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ word_rank,
+                                           int cell) {
+  const uint32_t w = __ldg(bitmap + (cell >> 5));
+  const uint32_t bit = 1u << (cell & 31);
+  return (w & bit) ? __ldg(word_rank + (cell >> 5)) + __popc(w & (bit - 1)) : -1;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(TPB, 6) k_assign(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
                                                 const int32_t* __restrict__ frame_off,
                                                 const uint32_t* __restrict__ bitmap,
                                                 const int32_t* __restrict__ word_rank, int64_t cap,
@@ -233,51 +344,50 @@ __global__ void __launch_bounds__(TPB) k_assign(VoxGeom g, const float* __restri
   extern __shared__ __align__(16) float tile[];
   const TileInfo t = load_tile(pts, n, stride, frame_off, g.n_frames, tile);
   // phase 1: all look-ups of the thread's points in flight together (the reductions below are ordering barriers)
+  PointInfo info[PPT];
+  tile_point_info<FAST>(g, tile, stride, t, frame_off, true, info, nullptr, nullptr, nullptr);
   int pid[PPT], par_m[PPT], par_l[PPT], slot_m[PPT], slot_l[PPT];
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
-    const int l = threadIdx.x + j * TPB;
     pid[j] = par_m[j] = par_l[j] = -1;
-    slot_m[j] = slot_l[j] = 0;
-    if (l < t.nvalid) {
-      const float p[3] = {tile[l * stride], tile[l * stride + 1], tile[l * stride + 2]};
-      PointKeys k;
-      k.b = frame_from(frame_off, g.n_frames, t.b0, t.p0 + l);
-      point_keys(g, p, k);
-      pid[j] = cell_rank(bitmap, word_rank, top_cell(g, k.b, k.c[0][1], k.c[0][0]));
-      int64_t cell;
-      sub_parent(g, 1, k, cell, slot_m[j]);
-      // missing parent aliases row 0 like the reference's zero table; with consistent power-of-two scales the parent
-      // is the point's own pillar and the two extra bitmap look-ups disappear
-      par_m[j] = g.parent_is_top ? pid[j] : max(cell_rank(bitmap, word_rank, cell), 0);
-      sub_parent(g, 2, k, cell, slot_l[j]);
-      par_l[j] = g.parent_is_top ? pid[j] : max(cell_rank(bitmap, word_rank, cell), 0);
+    slot_m[j] = info[j].slot_m;
+    slot_l[j] = info[j].slot_l;
+    if (info[j].cell >= 0) {
+      pid[j] = cell_rank32(bitmap, word_rank, info[j].cell);
+      // missing parent aliases row 0 like the reference's zero table; on the fast path the parent is the point's own
+      // pillar and the two extra bitmap look-ups disappear
+      par_m[j] = FAST ? pid[j] : max(cell_rank32(bitmap, word_rank, info[j].cell_m), 0);
+      par_l[j] = FAST ? pid[j] : max(cell_rank32(bitmap, word_rank, info[j].cell_l), 0);
     }
   }
   uint32_t seen_m[PPT], seen_l[PPT];
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     const bool ok = pid[j] >= 0 && pid[j] < cap;
-    seen_m[j] = (ok && par_m[j] < cap) ? *(volatile uint32_t*)(med_mask + par_m[j]) : ~0u;
+    seen_m[j] = (!FAST && ok && par_m[j] < cap) ? *(volatile uint32_t*)(med_mask + par_m[j]) : ~0u;
     seen_l[j] = (ok && par_l[j] < cap) ? *(volatile uint32_t*)(low_mask + 4 * (int64_t)par_l[j] + (slot_l[j] >> 5)) : ~0u;
   }
-  // phase 2: writes
+  // phase 2: writes.  Fast path: only the low-scale slot bit — the middle-scale masks and all three levels of sums
+  // follow hierarchically from the low-scale sub-voxels (k_sub_sums / k_sub_reduce), which halves the L2 reductions
+  // these passes are bound by.
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     const int l = threadIdx.x + j * TPB;
     if (l >= t.nvalid) continue;
     point_pillar[t.p0 + l] = pid[j];
     if (pid[j] < 0 || pid[j] >= cap) continue;
-    red_add4(pillar_mean + 4 * (int64_t)pid[j], tile[l * stride], tile[l * stride + 1], tile[l * stride + 2], 1.0f);
-    const uint32_t bm = 1u << slot_m[j];
-    if (!(seen_m[j] & bm)) atomicOr(med_mask + par_m[j], bm);
+    if (!FAST) {
+      red_add4(pillar_mean + 4 * (int64_t)pid[j], tile[l * stride], tile[l * stride + 1], tile[l * stride + 2], 1.0f);
+      const uint32_t bm = 1u << slot_m[j];
+      if (!(seen_m[j] & bm)) atomicOr(med_mask + par_m[j], bm);
+    }
     const uint32_t bl = 1u << (slot_l[j] & 31);
     if (!(seen_l[j] & bl)) atomicOr(low_mask + 4 * (int64_t)par_l[j] + (slot_l[j] >> 5), bl);
   }
 }
 
 // ---------------------------------------------------------------- pass 4: CSR offsets of the sub-voxels
-__global__ void __launch_bounds__(TPB) k_sub_sums(const int32_t* __restrict__ counts, const uint32_t* __restrict__ med_mask,
+__global__ void __launch_bounds__(TPB) k_sub_sums(VoxGeom g, const int32_t* __restrict__ counts, uint32_t* med_mask,
                                                   const uint32_t* __restrict__ low_mask, int32_t* sums) {
   __shared__ int smem[2][TPB / 32];
   const int n = counts[0];
@@ -287,9 +397,16 @@ __global__ void __launch_bounds__(TPB) k_sub_sums(const int32_t* __restrict__ co
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i)
       if (base + i < n) {
-        vm += __popc(med_mask[base + i]);
         const uint4 m = reinterpret_cast<const uint4*>(low_mask)[base + i];
         vl += __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+        uint32_t mm;
+        if (g.fast) {  // the middle-scale occupancy follows from the low-scale one
+          mm = med_mask_of_low(g, m);
+          med_mask[base + i] = mm;
+        } else {
+          mm = med_mask[base + i];
+        }
+        vm += __popc(mm);
       }
   }
   vm = gm_warp_sum_i(vm);
@@ -306,7 +423,7 @@ __global__ void __launch_bounds__(TPB) k_sub_sums(const int32_t* __restrict__ co
 __global__ void __launch_bounds__(TPB) k_sub_ptr(int32_t* counts, const uint32_t* __restrict__ med_mask,
                                                  const uint32_t* __restrict__ low_mask, const int32_t* __restrict__ sums,
                                                  float* pillar_mean, int32_t* med_ptr, int32_t* low_ptr, float* med_mean,
-                                                 float* low_mean, int64_t sub_cap) {
+                                                 float* low_mean, int64_t sub_cap, int hierarchical) {
   __shared__ int smem[40];
   const int n = counts[0];
   if (blockIdx.x * SCAN_CHUNK >= n && blockIdx.x != 0) return;
@@ -328,17 +445,19 @@ __global__ void __launch_bounds__(TPB) k_sub_ptr(int32_t* counts, const uint32_t
   int tot_m, tot_l;
   int pm = base_m + gm_block_excl_scan(sm_, &tot_m, smem);
   int pl = base_l + gm_block_excl_scan(sl_, &tot_l, smem);
+  const int pm0 = pm;
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; ++i) {
     const int v = v0 + i;
     if (v < n) {
       med_ptr[v] = pm;
       low_ptr[v] = pl;
-      // finish the pillar mean (sum -> mean)
-      float4* pmn = reinterpret_cast<float4*>(pillar_mean) + v;
-      float4 a = *pmn;
-      a.x = __fdiv_rn(a.x, a.w); a.y = __fdiv_rn(a.y, a.w); a.z = __fdiv_rn(a.z, a.w);
-      *pmn = a;
+      if (!hierarchical) {  // finish the pillar mean (sum -> mean); the hierarchical path does it in k_sub_reduce
+        float4* pmn = reinterpret_cast<float4*>(pillar_mean) + v;
+        float4 a = *pmn;
+        a.x = __fdiv_rn(a.x, a.w); a.y = __fdiv_rn(a.y, a.w); a.z = __fdiv_rn(a.z, a.w);
+        *pmn = a;
+      }
     }
     pm += cm[i];
     pl += cl[i];
@@ -349,8 +468,17 @@ __global__ void __launch_bounds__(TPB) k_sub_ptr(int32_t* counts, const uint32_t
       counts[2] = pl;
     }
   }
+  if (hierarchical) {
+    // the hierarchical path only accumulates into the low-scale rows; each middle-scale row is tagged with its pillar
+    // (in the count lane, overwritten by k_med_reduce) so that pass can run one thread per row
+    int row = pm0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+      for (int j = 0; j < cm[i]; ++j, ++row)
+        if (row < sub_cap) med_mean[4 * (int64_t)row + 3] = __int_as_float(v0 + i);
+  }
   // zero the CTA's contiguous range of sub-voxel accumulators, row-coalesced
-  for (int i = threadIdx.x; i < tot_m; i += TPB)
+  for (int i = threadIdx.x; i < (hierarchical ? 0 : tot_m); i += TPB)
     if (base_m + i < sub_cap) reinterpret_cast<float4*>(med_mean)[base_m + i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = threadIdx.x; i < tot_l; i += TPB)
     if (base_l + i < sub_cap) reinterpret_cast<float4*>(low_mean)[base_l + i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -361,7 +489,8 @@ __global__ void __launch_bounds__(TPB) k_sub_ptr(int32_t* counts, const uint32_t
 }
 
 // ---------------------------------------------------------------- pass 5: sub-voxel sums
-__global__ void __launch_bounds__(TPB) k_sub_accum(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
+template <bool FAST>
+__global__ void __launch_bounds__(TPB, 6) k_sub_accum(VoxGeom g, const float* __restrict__ pts, int64_t n, int stride,
                                                    const int32_t* __restrict__ frame_off,
                                                    const uint32_t* __restrict__ bitmap,
                                                    const int32_t* __restrict__ word_rank,
@@ -372,28 +501,25 @@ __global__ void __launch_bounds__(TPB) k_sub_accum(VoxGeom g, const float* __res
                                                    const int32_t* __restrict__ low_ptr, float* med_mean,
                                                    float* low_mean) {
   extern __shared__ __align__(16) float tile[];
-  const TileInfo t = load_tile(pts, n, stride, frame_off, g.n_frames, tile);
+  // on the fast path the parent is the stored point -> pillar row: no frame index, no bitmap look-up
+  const TileInfo t = load_tile(pts, n, stride, FAST ? nullptr : frame_off, g.n_frames, tile);
   int row_m[PPT], row_l[PPT];
   int par_m[PPT], par_l[PPT], slot_m[PPT], slot_l[PPT];
-  // phase 1a: parents (the stored point -> pillar row when the parent is the point's own pillar)
+  // phase 1a: parents
+  PointInfo info[PPT];
+  tile_point_info<FAST>(g, tile, stride, t, frame_off, !FAST, info, nullptr, nullptr, nullptr);
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     const int l = threadIdx.x + j * TPB;
     par_m[j] = par_l[j] = -1;
-    slot_m[j] = slot_l[j] = 0;
-    if (l < t.nvalid) {
-      const float p[3] = {tile[l * stride], tile[l * stride + 1], tile[l * stride + 2]};
-      PointKeys k;
-      k.b = g.parent_is_top ? 0 : frame_from(frame_off, g.n_frames, t.b0, t.p0 + l);
-      point_keys(g, p, k);
-      int64_t cell_m, cell_l;
-      sub_parent(g, 1, k, cell_m, slot_m[j]);
-      sub_parent(g, 2, k, cell_l, slot_l[j]);
-      if (g.parent_is_top) {
+    slot_m[j] = info[j].slot_m;
+    slot_l[j] = info[j].slot_l;
+    if (info[j].cell >= 0) {
+      if (FAST) {
         par_m[j] = par_l[j] = __ldg(point_pillar + t.p0 + l);
       } else {
-        par_m[j] = max(cell_rank(bitmap, word_rank, cell_m), 0);
-        par_l[j] = max(cell_rank(bitmap, word_rank, cell_l), 0);
+        par_m[j] = max(cell_rank32(bitmap, word_rank, info[j].cell_m), 0);
+        par_l[j] = max(cell_rank32(bitmap, word_rank, info[j].cell_l), 0);
       }
       if (par_m[j] >= cap) par_m[j] = -1;
       if (par_l[j] >= cap) par_l[j] = -1;
@@ -403,7 +529,7 @@ __global__ void __launch_bounds__(TPB) k_sub_accum(VoxGeom g, const float* __res
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     row_m[j] = row_l[j] = -1;
-    if (par_m[j] >= 0)
+    if (!FAST && par_m[j] >= 0)
       row_m[j] = __ldg(med_ptr + par_m[j]) + __popc(__ldg(med_mask + par_m[j]) & ((1u << slot_m[j]) - 1u));
     if (par_l[j] >= 0) {
       const uint4 m = __ldg(reinterpret_cast<const uint4*>(low_mask) + par_l[j]);
@@ -416,9 +542,71 @@ __global__ void __launch_bounds__(TPB) k_sub_accum(VoxGeom g, const float* __res
     const int l = threadIdx.x + j * TPB;
     if (l >= t.nvalid) continue;
     const float x = tile[l * stride], y = tile[l * stride + 1], z = tile[l * stride + 2];
-    if (row_m[j] >= 0 && row_m[j] < sub_cap) red_add4(med_mean + 4 * (int64_t)row_m[j], x, y, z, 1.0f);
+    if (!FAST && row_m[j] >= 0 && row_m[j] < sub_cap) red_add4(med_mean + 4 * (int64_t)row_m[j], x, y, z, 1.0f);
     if (row_l[j] >= 0 && row_l[j] < sub_cap) red_add4(low_mean + 4 * (int64_t)row_l[j], x, y, z, 1.0f);
   }
+}
+
+// Fast path, after the low-scale sums are complete.  k_med_reduce, one thread per middle-scale row: its sum = the sum
+// of its (nested) low-scale children, visited in slot order; the children turn from (sum, count) into (mean, count)
+// on the way.  k_top_reduce, one thread per pillar: pillar sum = sum of its middle-scale rows in slot order; both
+// levels become means.  The result depends only on the low-scale sums.
+__device__ __forceinline__ float4 mean_of(const float4 a) {
+  return make_float4(__fdiv_rn(a.x, a.w), __fdiv_rn(a.y, a.w), __fdiv_rn(a.z, a.w), a.w);
+}
+
+__global__ void __launch_bounds__(TPB) k_med_reduce(VoxGeom g, const int32_t* __restrict__ counts,
+                                                    const uint32_t* __restrict__ med_mask,
+                                                    const uint32_t* __restrict__ low_mask,
+                                                    const int32_t* __restrict__ med_ptr,
+                                                    const int32_t* __restrict__ low_ptr, float* med_mean,
+                                                    float* low_mean, int64_t sub_cap) {
+  const int64_t row = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (row >= min((int64_t)counts[1], sub_cap)) return;
+  const int v = __float_as_int(med_mean[4 * row + 3]);  // pillar tag written by k_sub_ptr
+  const uint4 ml = __ldg(reinterpret_cast<const uint4*>(low_mask) + v);
+  const int lp = __ldg(low_ptr + v);
+  const int ms = (int)__fns(__ldg(med_mask + v), 0, (int)(row - __ldg(med_ptr + v)) + 1);  // slot of this row
+  const int mx = ms & g.smask[1][0], my = (ms >> g.sshift[1][1]) & g.smask[1][1], mz = (ms >> g.sshift[1][2]) & g.smask[1][2];
+  const int nz = 1 << g.shift[1][2], ny = 1 << g.shift[1][1], nx = 1 << g.shift[1][0];  // low sub-voxels per middle one
+  const uint32_t wl[4] = {ml.x, ml.y, ml.z, ml.w};
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int dz = 0; dz < nz; ++dz)
+    for (int dy = 0; dy < ny; ++dy)
+      for (int dx = 0; dx < nx; ++dx) {
+        const int s = (((mz << g.shift[1][2]) + dz) << g.sshift[2][2]) | (((my << g.shift[1][1]) + dy) << g.sshift[2][1]) |
+                      ((mx << g.shift[1][0]) + dx);
+        if (!((wl[(s >> 5) & 3] >> (s & 31)) & 1u)) continue;
+        const int64_t lrow = (int64_t)lp + rank128(ml, s);
+        if (lrow >= sub_cap) continue;
+        float4* q = reinterpret_cast<float4*>(low_mean) + lrow;
+        const float4 a = *q;
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        *q = mean_of(a);
+      }
+  reinterpret_cast<float4*>(med_mean)[row] = acc;
+}
+
+__global__ void __launch_bounds__(TPB) k_top_reduce(const int32_t* __restrict__ counts,
+                                                    const int32_t* __restrict__ med_ptr, float* pillar_mean,
+                                                    float* med_mean, int64_t sub_cap) {
+  const int v = blockIdx.x * TPB + threadIdx.x;
+  if (v >= counts[0]) return;
+  const int r0 = __ldg(med_ptr + v), r1 = (int)min((int64_t)__ldg(med_ptr + v + 1), sub_cap);
+  float4 top = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < r1; r += 8) {
+    float4 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      a[i] = r + i < r1 ? reinterpret_cast<const float4*>(med_mean)[r + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (r + i < r1) {
+        top.x += a[i].x; top.y += a[i].y; top.z += a[i].z; top.w += a[i].w;
+        reinterpret_cast<float4*>(med_mean)[r + i] = mean_of(a[i]);
+      }
+  }
+  reinterpret_cast<float4*>(pillar_mean)[v] = mean_of(top);
 }
 
 __global__ void __launch_bounds__(TPB) k_sub_finalize(const int32_t* __restrict__ counts, float* med_mean,
@@ -526,26 +714,35 @@ extern "C" int geomae_voxel_scatter(const geomae_voxel_cfg* cfg, const geomae_sc
   const size_t tile_bytes = (size_t)TILE * io->stride * sizeof(float);
   GM_CUDA(cudaMemsetAsync(io->bitmap, 0, (size_t)n_words * 4, stream));
   if (n > 0)
-    k_mark<<<pblocks, TPB, tile_bytes, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap,
-                                                 io->coors_top, io->coors_med, io->coors_low);
+    (g.fast ? k_mark<true> : k_mark<false>)<<<pblocks, TPB, tile_bytes, stream>>>(
+        g, io->points, n, io->stride, io->frame_offsets, io->bitmap, io->coors_top, io->coors_med, io->coors_low);
   k_bitmap_sums<<<scan_blocks, TPB, 0, stream>>>(io->bitmap, n_words, io->scan_tmp);
   k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, io->bitmap, n_words, io->scan_tmp, io->word_rank, io->counts,
                                                  io->pillar_coors, io->pillar_mean, io->med_mask, io->low_mask,
-                                                 io->cap, 1);
+                                                 io->cap, 1, g.fast ? 0 : 1);
   if (n > 0)
-    k_assign<<<pblocks, TPB, tile_bytes, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap,
-                                                   io->word_rank, io->cap, io->point_pillar, io->pillar_mean,
-                                                   io->med_mask, io->low_mask);
+    (g.fast ? k_assign<true> : k_assign<false>)<<<pblocks, TPB, tile_bytes, stream>>>(
+        g, io->points, n, io->stride, io->frame_offsets, io->bitmap, io->word_rank, io->cap, io->point_pillar,
+        io->pillar_mean, io->med_mask, io->low_mask);
   int32_t* sub_sums = io->scan_tmp + SCAN_MAX_BLOCKS;  // scan_tmp holds 3*SCAN_MAX_BLOCKS ints
-  k_sub_sums<<<sub_blocks, TPB, 0, stream>>>(io->counts, io->med_mask, io->low_mask, sub_sums);
+  k_sub_sums<<<sub_blocks, TPB, 0, stream>>>(g, io->counts, io->med_mask, io->low_mask, sub_sums);
   k_sub_ptr<<<sub_blocks, TPB, 0, stream>>>(io->counts, io->med_mask, io->low_mask, sub_sums, io->pillar_mean,
-                                            io->med_ptr, io->low_ptr, io->med_mean, io->low_mean, io->n_points);
+                                            io->med_ptr, io->low_ptr, io->med_mean, io->low_mean, io->n_points,
+                                            g.fast);
   if (n > 0) {
-    k_sub_accum<<<pblocks, TPB, tile_bytes, stream>>>(g, io->points, n, io->stride, io->frame_offsets, io->bitmap,
-                                                      io->word_rank, io->point_pillar, io->cap, io->n_points,
-                                                      io->med_mask, io->low_mask, io->med_ptr, io->low_ptr,
-                                                      io->med_mean, io->low_mean);
-    k_sub_finalize<<<GM_NUM_SMS * 4, TPB, 0, stream>>>(io->counts, io->med_mean, io->low_mean, io->n_points);
+    (g.fast ? k_sub_accum<true> : k_sub_accum<false>)<<<pblocks, TPB, tile_bytes, stream>>>(
+        g, io->points, n, io->stride, io->frame_offsets, io->bitmap, io->word_rank, io->point_pillar, io->cap,
+        io->n_points, io->med_mask, io->low_mask, io->med_ptr, io->low_ptr, io->med_mean, io->low_mean);
+    if (g.fast) {
+      // sub-voxel and pillar counts are bounded by the point count; surplus CTAs exit on the device-side counts
+      k_med_reduce<<<gm_div_up(io->n_points, TPB), TPB, 0, stream>>>(g, io->counts, io->med_mask, io->low_mask,
+                                                                     io->med_ptr, io->low_ptr, io->med_mean,
+                                                                     io->low_mean, io->n_points);
+      k_top_reduce<<<gm_div_up(io->cap, TPB), TPB, 0, stream>>>(io->counts, io->med_ptr, io->pillar_mean,
+                                                                io->med_mean, io->n_points);
+    }
+    else
+      k_sub_finalize<<<GM_NUM_SMS * 4, TPB, 0, stream>>>(io->counts, io->med_mean, io->low_mean, io->n_points);
   }
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
@@ -569,7 +766,7 @@ extern "C" int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* c
   if (n > 0) k_mark_coors<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap);
   k_bitmap_sums<<<scan_blocks, TPB, 0, stream>>>(bitmap, n_words, scan_tmp);
   k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, bitmap, n_words, scan_tmp, word_rank, counts, nullptr, nullptr,
-                                                 nullptr, nullptr, n > 0 ? n : 1, 0);
+                                                 nullptr, nullptr, n > 0 ? n : 1, 0, 0);
   if (n > 0) k_token_of_cell<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap, word_rank, tok_of_pillar);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;

@@ -75,7 +75,12 @@ def check_against_oracle(cfg, frames, ids_mask=None, atol=3e-6, min_well_frac=0.
     assert (np.abs(cov - tgt["cov"]) <= 3e-4 * scale + 1e-9).all()
     s_ref = tgt["singular"]
     np.testing.assert_allclose(sing.cpu().numpy(), s_ref, rtol=5e-4, atol=2e-5 * s_ref.max())
-    np.testing.assert_allclose(curv.cpu().numpy(), tgt["curvature"], rtol=1e-3, atol=5e-4)
+    # curvature = (S + 1e-9) / sum: where the moments are at the level of the centroids' rounding noise
+    # ((4e-6 m)^2 per point, summation order differs between the float atomics and the CPU loop) the ratio against
+    # the 1e-9 floor is noise-dominated; hold those pillars to a loose bound and the rest to the tight one
+    solid = s_ref[:, 0] > 1e-6
+    np.testing.assert_allclose(curv.cpu().numpy()[solid], tgt["curvature"][solid], rtol=1e-3, atol=5e-4)
+    np.testing.assert_allclose(curv.cpu().numpy()[~solid], tgt["curvature"][~solid], rtol=0, atol=0.1)
     well = (s_ref[:, 1] - s_ref[:, 2]) > 1e-3 * np.maximum(s_ref[:, 0], 1e-12)
     mine = align_sign(tgt["normal"], normal.cpu().numpy())
     assert well.sum() >= min_well_frac * v
@@ -155,3 +160,35 @@ def test_waymo_shaped_geometry():
                        sub_voxel_size_med=(0.16, 0.16, 1.5), sub_voxel_size_low=(0.08, 0.08, 0.75),
                        grid_size=(1, 468, 468))
     check_against_oracle(cfg, [make_frame(7, preset="waymo", point_scale=0.3)])
+
+
+def test_non_power_of_two_geometry_takes_the_general_path():
+    """Ratios of 3 between the scales: no shift relation, parents by integer division of the sub-voxel coordinates
+    (the kernels' general path; every GeoMAE config takes the shift/mask path)."""
+    from geomae_b200.synthetic import make_frame
+    cfg = O.PathConfig(pc_range=(-48.0, -48.0, -5.0, 48.0, 48.0, 3.0), voxel_size=(0.3, 0.3, 8),
+                       sub_voxel_size_med=(0.1, 0.1, 4), sub_voxel_size_low=(0.1, 0.1, 1),
+                       sub_voxel_ratio_med=(2, 3, 3), sub_voxel_ratio_low=(8, 3, 3), grid_size=(1, 320, 320))
+    check_against_oracle(cfg, [make_frame(11, point_scale=0.3), make_frame(12, point_scale=0.2)])
+
+
+def test_voxel_boundary_points_fast_path():
+    """Points placed on and one ulp either side of voxel boundaries of all three scales: the reciprocal-multiply
+    coordinate of the shift/mask path must agree with the IEEE divide bit for bit."""
+    cfg = O.PathConfig()
+    rng = np.random.default_rng(5)
+    n = 20000
+    lo = np.array(cfg.pc_range[:3], np.float32)
+    vs = np.array(cfg.sub_voxel_size_low, np.float32)
+    k = np.stack([rng.integers(-3, 1604, n), rng.integers(-3, 1604, n), rng.integers(-2, 11, n)], axis=1)
+    p = (k.astype(np.float32) * vs + lo).astype(np.float32)
+    nudge = rng.integers(-2, 3, (n, 3))
+    for _ in range(2):
+        p = np.where(nudge > 0, np.nextafter(p, np.float32(1e9)), np.where(nudge < 0, np.nextafter(p, np.float32(-1e9)), p))
+        nudge = nudge - np.sign(nudge)
+    pts = np.concatenate([p.astype(np.float32), rng.uniform(0, 1, (n, 2)).astype(np.float32)], axis=1)
+    pb = run_gpu(cfg, [pts[: n // 2], pts[n // 2:]])
+    for name, size in (("coors_top", cfg.voxel_size), ("coors_med", cfg.sub_voxel_size_med),
+                       ("coors_low", cfg.sub_voxel_size_low)):
+        ref = np.concatenate([O.dynamic_voxelize(f, size, cfg.pc_range) for f in (pts[: n // 2], pts[n // 2:])])
+        assert np.array_equal(getattr(pb, name)[:n, 1:].cpu().numpy(), ref), name
