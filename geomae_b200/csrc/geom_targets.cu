@@ -29,9 +29,14 @@ __device__ __forceinline__ void jacobi3f(float a[3][3], float v[3][3]) {
     for (int pq = 0; pq < 3; ++pq) {
       const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
       const float apq = a[p][q];
-      if (apq == 0.f) continue;
-      const float theta = (a[q][q] - a[p][p]) / (2.f * apq);
-      const float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f)));
+      if (fabsf(apq) < 1e-30f) {  // also keeps the reciprocal below out of the flushed-denormal range
+        a[p][q] = a[q][p] = 0.f;
+        continue;
+      }
+      // the rotation only has to be a rotation (c, s below) by roughly the annihilating angle: reciprocal-unit
+      // divides instead of IEEE ones; theta^2 overflowing to inf gives t = 0, the correct limit
+      const float theta = __fdividef(a[q][q] - a[p][p], 2.f * apq);
+      const float t = copysignf(__fdividef(1.f, fabsf(theta) + sqrtf(fmaf(theta, theta, 1.f))), theta);
       const float c = rsqrtf(fmaf(t, t, 1.f)), s = t * c;
       const int r = 3 - p - q;
       const float arp = a[r][p], arq = a[r][q];

@@ -166,6 +166,7 @@ inline int gm_make_geom(const geomae_voxel_cfg* cfg, int n_frames, VoxGeom* g) {
       while ((1 << sh) < r * (1 << g->sshift[s][a])) ++sh;
     }
   }
+  if (g->fast && g->shift[1][0] + g->shift[1][1] + g->shift[1][2] > 5) g->fast = 0;  // <= 32 low per middle sub-voxel
   for (int a = 0; a < 3; ++a) {
     g->smask[0][a] = g->sshift[0][a] = 0;
     g->rvs[a] = 1.0f / g->vs[2][a];

@@ -551,8 +551,13 @@ __global__ void __launch_bounds__(TPB, 6) k_sub_accum(VoxGeom g, const float* __
 // of its (nested) low-scale children, visited in slot order; the children turn from (sum, count) into (mean, count)
 // on the way.  k_top_reduce, one thread per pillar: pillar sum = sum of its middle-scale rows in slot order; both
 // levels become means.  The result depends only on the low-scale sums.
+// (sum, count) -> (mean, count).  One correctly rounded reciprocal of the (small integer) count serves the three
+// quotients: q = x * r, then q + fma(-w, q, x) * r — Markstein's correction, which rounds like the IEEE divide.
 __device__ __forceinline__ float4 mean_of(const float4 a) {
-  return make_float4(__fdiv_rn(a.x, a.w), __fdiv_rn(a.y, a.w), __fdiv_rn(a.z, a.w), a.w);
+  const float r = __frcp_rn(a.w);
+  const float qx = a.x * r, qy = a.y * r, qz = a.z * r;
+  return make_float4(fmaf(fmaf(-a.w, qx, a.x), r, qx), fmaf(fmaf(-a.w, qy, a.y), r, qy),
+                     fmaf(fmaf(-a.w, qz, a.z), r, qz), a.w);
 }
 
 __global__ void __launch_bounds__(TPB) k_med_reduce(VoxGeom g, const int32_t* __restrict__ counts,
@@ -568,22 +573,34 @@ __global__ void __launch_bounds__(TPB) k_med_reduce(VoxGeom g, const int32_t* __
   const int lp = __ldg(low_ptr + v);
   const int ms = (int)__fns(__ldg(med_mask + v), 0, (int)(row - __ldg(med_ptr + v)) + 1);  // slot of this row
   const int mx = ms & g.smask[1][0], my = (ms >> g.sshift[1][1]) & g.smask[1][1], mz = (ms >> g.sshift[1][2]) & g.smask[1][2];
-  const int nz = 1 << g.shift[1][2], ny = 1 << g.shift[1][1], nx = 1 << g.shift[1][0];  // low sub-voxels per middle one
-  const uint32_t wl[4] = {ml.x, ml.y, ml.z, ml.w};
+  const int sx = g.shift[1][0], sy = g.shift[1][1], sz = g.shift[1][2];
+  const int nchild = 1 << (sx + sy + sz);               // low sub-voxels per middle one (<= 32 on the fast path)
+  const int p1 = __popc(ml.x), p2 = p1 + __popc(ml.y), p3 = p2 + __popc(ml.z);
+  // slot of child c = s0 + (dz, dy, dx) placed in the low-scale bit fields; the fields of s0 have their low bits clear
+  const int s0 = ((mz << sz) << g.sshift[2][2]) | ((my << sy) << g.sshift[2][1]) | (mx << sx);
+  auto child_slot = [&](int c) {
+    return s0 + ((c >> (sx + sy)) << g.sshift[2][2]) + (((c >> sx) & ((1 << sy) - 1)) << g.sshift[2][1]) + (c & ((1 << sx) - 1));
+  };
+  auto word_of = [&](int wi) { return wi == 0 ? ml.x : wi == 1 ? ml.y : wi == 2 ? ml.z : ml.w; };
+  // present children first (cheap bit tests), then a loop that only visits those: a warp iterates max-over-lanes of
+  // the PRESENT children (typically 2-4), not over all candidates
+  uint32_t present = 0u;
+  for (int c = 0; c < nchild; ++c) {
+    const int s = child_slot(c);
+    present |= ((word_of(s >> 5) >> (s & 31)) & 1u) << c;
+  }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int dz = 0; dz < nz; ++dz)
-    for (int dy = 0; dy < ny; ++dy)
-      for (int dx = 0; dx < nx; ++dx) {
-        const int s = (((mz << g.shift[1][2]) + dz) << g.sshift[2][2]) | (((my << g.shift[1][1]) + dy) << g.sshift[2][1]) |
-                      ((mx << g.shift[1][0]) + dx);
-        if (!((wl[(s >> 5) & 3] >> (s & 31)) & 1u)) continue;
-        const int64_t lrow = (int64_t)lp + rank128(ml, s);
-        if (lrow >= sub_cap) continue;
-        float4* q = reinterpret_cast<float4*>(low_mean) + lrow;
-        const float4 a = *q;
-        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-        *q = mean_of(a);
-      }
+  for (; present; present &= present - 1) {               // ascending child index = slot order
+    const int s = child_slot(__ffs(present) - 1);
+    const int wi = s >> 5;
+    const int64_t lrow = (int64_t)lp + (wi == 0 ? 0 : wi == 1 ? p1 : wi == 2 ? p2 : p3) +
+                         __popc(word_of(wi) & ((1u << (s & 31)) - 1u));
+    if (lrow >= sub_cap) continue;
+    float4* q = reinterpret_cast<float4*>(low_mean) + lrow;
+    const float4 a = *q;
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    *q = mean_of(a);
+  }
   reinterpret_cast<float4*>(med_mean)[row] = acc;
 }
 

@@ -86,7 +86,12 @@ typedef struct geomae_scatter_io {
 
 /* One pass structure over the raw points: voxelise at three scales, build the sorted
  * pillar list without a sort (occupancy bitmap + popcount ranks), point->pillar map,
- * and per-pillar / per-sub-voxel centroids.
+ * and per-pillar / per-sub-voxel centroids.  n_frames * grid_y * grid_x must stay below 2^31.
+ * When the three scales are nested power-of-two multiples (every GeoMAE config) the voxel
+ * coordinates of all scales derive from one low-scale coordinate per axis (bit-exact with the
+ * reference's independent IEEE divides) and the middle-scale / pillar sums are formed
+ * hierarchically from the low-scale sums; other geometries take the general path (independent
+ * divides, one reduction per point and scale).
  * replaces: MultiSubVoxelDynamicVoxelNetSSL.voxelize / sub_voxelize_low / sub_voxelize_med
  *           (detectors/multi_sub_voxel_dynamic_voxelnet_ssl.py:307-377), scatter_v2(mode='avg')
  *           (ops/sst/sst_ops.py:8-39), get_centroid_per_voxel x3 (…_ssl.py:726-768) and the
