@@ -29,6 +29,16 @@ from oracle import ref_harness as H  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
+# geometries other than the reference config's (BASELINE.json configs[3] / configs[4]): the reference code is generic
+# in range / voxel sizes / grid (it reads them from the config), so the UNMODIFIED detector is built from its own
+# config with only those values replaced (apply_geometry)
+WAYMO_GEOMETRY = dict(pc_range=(-74.88, -74.88, -2.0, 74.88, 74.88, 4.0), voxel_size=(0.32, 0.32, 6),
+                      sub_voxel_size_med=(0.16, 0.16, 1.5), sub_voxel_size_low=(0.08, 0.08, 0.75),
+                      grid_size=(1, 468, 468))
+DENSE_GEOMETRY = dict(pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), voxel_size=(0.1, 0.1, 8),
+                      sub_voxel_size_med=(0.05, 0.05, 2), sub_voxel_size_low=(0.025, 0.025, 1),
+                      grid_size=(1, 1024, 1024))
+
 CASES = {
     # name: (frame kwargs per sample, enc blocks, dec blocks, store full tensors?)
     "small_b2": dict(frames=[dict(seed=11, point_scale=0.08), dict(seed=12, point_scale=0.04, sweeps=6)],
@@ -37,6 +47,12 @@ CASES = {
                                   param_seed=4, mask_seed=6),
     "full_b2": dict(frames=[dict(seed=31), dict(seed=32)], enc=6, dec=2, full=False,
                     param_seed=7, mask_seed=8),
+    # BASELINE.json configs[3]: Waymo-shaped frames (64 beams), 0.32 m pillars, 468 x 468 grid
+    "waymo_b2": dict(frames=[dict(seed=41, preset="waymo", point_scale=0.12), dict(seed=42, preset="waymo", point_scale=0.06)],
+                     enc=1, dec=1, full=False, param_seed=9, mask_seed=10, geometry=WAYMO_GEOMETRY),
+    # BASELINE.json configs[4]: dense-grid stress, 0.1 m pillars on the nuScenes range (1024 x 1024 grid), multi-sweep
+    "dense_b1": dict(frames=[dict(seed=51, point_scale=0.25, sweeps=3)], enc=1, dec=1, full=False,
+                     param_seed=11, mask_seed=12, geometry=DENSE_GEOMETRY),
 }
 
 
@@ -45,13 +61,49 @@ def case_frames(case):
 
 
 def case_cfg(case):
-    return O.PathConfig(enc_blocks=case["enc"], dec_blocks=case["dec"])
+    return O.PathConfig(enc_blocks=case["enc"], dec_blocks=case["dec"], **case.get("geometry", {}))
+
+
+def apply_geometry(model_cfg, geometry, base=None):
+    """Copy of a model config dict (the reference's or ours: same keys) with range, the three voxel sizes, grid_size,
+    spatial_shape and output_shape replaced.  Voxel sizes are recognised by VALUE (the config repeats them in seven sub-dicts)."""
+    base = base or O.PathConfig()
+    sizes = {tuple(base.voxel_size): tuple(geometry["voxel_size"]),
+             tuple(base.sub_voxel_size_med): tuple(geometry["sub_voxel_size_med"]),
+             tuple(base.sub_voxel_size_low): tuple(geometry["sub_voxel_size_low"])}
+    gz, gy, gx = geometry["grid_size"]
+
+    def walk(node):
+        if isinstance(node, dict):
+            out = type(node)()
+            for k, v in node.items():
+                if k == "point_cloud_range":
+                    out[k] = list(geometry["pc_range"])
+                elif k in ("voxel_size", "sub_voxel_size_low", "sub_voxel_size_med", "sub_voxel_size_top") and \
+                        tuple(v) in sizes:
+                    out[k] = sizes[tuple(v)]
+                elif k == "grid_size":
+                    out[k] = (gz, gy, gx)
+                elif k == "spatial_shape":
+                    out[k] = [gz, gy, gx]
+                elif k == "output_shape":
+                    out[k] = [gy, gx]
+                else:
+                    out[k] = walk(v)
+            return out
+        if isinstance(node, (list, tuple)):
+            return type(node)(walk(v) for v in node)
+        return node
+    return walk(model_cfg)
 
 
 def run_reference(case):
     frames = case_frames(case)
     cfg = case_cfg(case)
-    det = H.build_detector(seed=0, encoder_blocks=case["enc"], decoder_blocks=case["dec"])
+    model_cfg = None
+    if "geometry" in case:
+        model_cfg = apply_geometry(H.load_config_model(), case["geometry"])
+    det = H.build_detector(model_cfg, seed=0, encoder_blocks=case["enc"], decoder_blocks=case["dec"])
     params = O.init_params(cfg, case["param_seed"])
     sd = det.state_dict()
     missing = [k for k in params if k not in sd]

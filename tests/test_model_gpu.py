@@ -217,10 +217,13 @@ def test_scatter_reduce_modes(small):
         np.testing.assert_allclose(y.grad.cpu().numpy(), x.grad.numpy(), **tol)
 
 
-def build_model(cfg, params, impl="tc3"):
+def build_model(cfg, params, impl="tc3", geometry=None):
     import geomae_b200  # noqa: F401
     from geomae_b200.registry import Config, build_model as build
+    from oracle.make_golden import apply_geometry
     mcfg = Config.fromfile(OWN_CFG).model
+    if geometry is not None:   # same replacement the golden generator applied to the reference's own config
+        mcfg = apply_geometry(mcfg, geometry)
     mcfg["backbone"] = dict(mcfg["backbone"], encoder_num_blocks=cfg.enc_blocks, decoder_num_blocks=cfg.dec_blocks)
     model = build(mcfg)
     sd = model.state_dict()
@@ -233,7 +236,7 @@ def build_model(cfg, params, impl="tc3"):
 def run_parity(name, loss_tol=1e-4, grad_tol=2e-3, impl="tc3"):
     case, cfg, frames, g = load_case(name)
     params = O.init_params(cfg, case["param_seed"])
-    model = build_model(cfg, params, impl)
+    model = build_model(cfg, params, impl, case.get("geometry"))
     ids = (torch.from_numpy(g["ids_keep"]).to(DEV), torch.from_numpy(g["ids_mask"]).to(DEV))
     pts = [torch.from_numpy(f).to(DEV) for f in frames]
     model.keep_targets = True
@@ -282,6 +285,13 @@ def test_train_step_parity_config0():
 @pytest.mark.parametrize("impl", ["tc3", "glue"])
 def test_train_step_parity_full_config(impl):
     run_parity("full_b2", loss_tol=1e-4, grad_tol=5e-3, impl=impl)
+
+
+@pytest.mark.parametrize("name", ["waymo_b2", "dense_b1"])
+def test_train_step_parity_other_geometries(name):
+    """BASELINE.json configs[3] / configs[4] shapes (Waymo-shaped 468 x 468 grid; dense 1024 x 1024 grid) against the
+    oracle and the losses of the unmodified reference run on the same geometry."""
+    run_parity(name, loss_tol=1e-4, grad_tol=5e-3)
 
 
 def test_bf16_mode_stays_close():

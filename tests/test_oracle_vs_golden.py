@@ -124,3 +124,22 @@ def test_full_config_two_frames():
         if abs(got - ref) > 5e-3 * max(ref, 1e-6) + 1e-7:
             bad.append((k, got, ref))
     assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("name", ["waymo_b2", "dense_b1"])
+def test_other_geometries(name):
+    """BASELINE.json configs[3] / configs[4] shapes: Waymo-shaped 0.32 m pillars on a 468 x 468 grid and the dense-grid
+    stress (0.1 m pillars, 1024 x 1024).  The unmodified reference ran with only range / voxel sizes / grid replaced
+    in its own config (oracle/make_golden.py::apply_geometry)."""
+    case, cfg, g, params, losses, pred, tgt, trace = _run(name)
+    assert trace["voxel_features"].shape[0] == int(g["n_pillars"])
+    got = float(trace["voxel_features"].detach().double().abs().sum())
+    assert abs(got - float(g["voxel_features_absum"])) <= 1e-4 * float(g["voxel_features_absum"])
+    _check_losses(g, losses, 1e-4)
+    bad = []
+    for k, p in params.items():
+        ref = float(g["gradnorm/" + k])
+        got = float(p.grad.double().norm())
+        if abs(got - ref) > 5e-3 * max(ref, 1e-6) + 1e-7:
+            bad.append((k, got, ref))
+    assert not bad, bad[:5]

@@ -192,3 +192,11 @@ def test_voxel_boundary_points_fast_path():
                        ("coors_low", cfg.sub_voxel_size_low)):
         ref = np.concatenate([O.dynamic_voxelize(f, size, cfg.pc_range) for f in (pts[: n // 2], pts[n // 2:])])
         assert np.array_equal(getattr(pb, name)[:n, 1:].cpu().numpy(), ref), name
+
+
+def test_dense_grid_geometry():
+    """0.1 m pillars on the nuScenes range (1024 x 1024 grid, 4096-wide low-scale grid): BASELINE.json configs[4]."""
+    from tests.golden_util import load_case
+    case, cfg, frames, g = load_case("dense_b1")
+    pb, _ = check_against_oracle(cfg, frames, g["ids_mask"])
+    assert pb.n_pillars == int(g["n_pillars"])
