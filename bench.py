@@ -124,11 +124,23 @@ def hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src, n_frames=256):
     t_gt = timed(lambda: pb.geom_targets())
     b_sc = 24.0 * p + 32.0 * v + 20.0 * (vm + vl)
     b_gt = 20.0 * vm + 28.0 * v + 24.0 * v
+    # DRAM traffic of the same stages from the committed ncu --set full capture (same batch size, 256 frames)
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_v4_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("frames") == n_frames:
+            traffic = {"scatter": tj["voxel_scatter"]["traffic_bytes"], "geom": tj["k_geom"]["traffic_bytes"],
+                       "source": "profiles/r01_v4_traffic.json"}
+    except (OSError, ValueError, KeyError):
+        pass
     out = []
-    for name, t, b in (("geomae_voxel_scatter (9 kernels)", t_sc, b_sc), ("k_geom (geom_targets)", t_gt, b_gt)):
+    for name, key, t, b in (("geomae_voxel_scatter (9 kernels)", "scatter", t_sc, b_sc),
+                            ("k_geom (geom_targets)", "geom", t_gt, b_gt)):
         ach = b / (t * 1e-3) / 1e9
         out.append(dict(kernel=name, bound="hbm", frames=n_frames, points=p, pillars=v, ms=t, algorithmic_bytes=b,
-                        achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src))
+                        achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src,
+                        traffic=traffic.get(key), traffic_source=traffic.get("source")))
     return out
 
 
@@ -336,7 +348,12 @@ def main():
         top = max(range(5), key=lambda f: prof_ms[f])
         ach = prof_by[top] / (prof_ms[top] * 1e-3) / 1e9
         roof = dict(kernel=fam_names[top], bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
-                    traffic=None, peak_source=peak_src, avg_launch_ms=prof_ms[top] / prof_n[top], launches=int(prof_n[top]),
+                    traffic=None,
+                    traffic_note="no single per-launch figure: the family mixes 7.3 k-token (encoder) and 24.5 k-token "
+                                 "(decoder) launches; ncu --set full of the decoder launches "
+                                 "(profiles/r01_launches_v3_bf16_operands.md) shows 25-44 MB read per launch, equal to "
+                                 "their algorithmic input bytes, and outputs that stay in the 126 MB L2",
+                    peak_source=peak_src, avg_launch_ms=prof_ms[top] / prof_n[top], launches=int(prof_n[top]),
                     algorithmic_bytes_per_launch=prof_by[top] / prof_n[top],
                     tensor_tflops=prof_fl[top] / (prof_ms[top] * 1e-3) / 1e12 if prof_fl[top] else None,
                     tensor_peak_tflops=tens_peak,
