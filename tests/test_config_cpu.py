@@ -49,3 +49,21 @@ def test_own_config_equals_reference_model_dict():
             return [norm(v) for v in x]
         return x
     assert norm(a) == norm(b)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference tree not present")
+def test_checkpoint_compatibility_with_the_unmodified_reference_detector():
+    """A checkpoint written by the reference (`epoch_*.pth` = its state_dict) loads strictly into this model and the
+    other way round: same keys (parameters AND buffers), same shapes, same dtypes."""
+    from oracle import ref_harness as H
+    det = H.build_detector(seed=0)
+    ref_sd = det.state_dict()
+    model = build_model(Config.fromfile(OWN_CFG).model)
+    own_sd = model.state_dict()
+    assert list(ref_sd.keys()) == list(own_sd.keys())
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(own_sd[k].shape) and v.dtype == own_sd[k].dtype, k
+    model.load_state_dict(ref_sd, strict=True)
+    det.load_state_dict(model.state_dict(), strict=True)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, ref_sd[k]), k
