@@ -225,3 +225,76 @@ def test_empty_frame_full_slots_and_single_voxel():
     v = pb.n_pillars
     low_bits = np.unpackbits(pb.low_mask[:v].cpu().numpy().astype(np.uint32).view(np.uint8), axis=1).sum(1)
     assert low_bits.max() == 128 and int(pb.med_mask[:v].cpu().numpy().astype(np.uint32).max()) == 0xFFFF
+
+
+def test_roofline_batch_properties():
+    """The 256-frame batch the HBM roofline of bench.py is quoted on (6.9 M points, beyond L2): size-independent
+    properties of the scatter outputs, and equality of its first frames with a small batch of the same frames (the
+    small-batch path is what the oracle comparisons above validate)."""
+    from geomae_b200.synthetic import make_frame
+    from geomae_b200.voxel import scatter_frames
+    cfg = O.PathConfig()
+    dev = torch.device("cuda:0")
+    base = [torch.from_numpy(make_frame(s + 1)).to(dev) for s in range(8)]
+    n_frames = 256
+    big = scatter_frames(geometry(cfg), [base[i % 8] for i in range(n_frames)])
+    small = scatter_frames(geometry(cfg), base)
+    v, n_med, n_low = big.sizes()
+    vs, ms, ls = small.sizes()
+    p = big.points.shape[0]
+    ps = small.points.shape[0]
+    assert p == 32 * ps and v == 32 * vs and n_med == 32 * ms and n_low == 32 * ls
+    assert big.pillars_per_frame() == small.pillars_per_frame() * 32
+    coors = big.pillar_coors[:v].cpu().numpy().astype(np.int64)
+    # sorted, unique (b, y, x) rows
+    key = (coors[:, 0] * 400 + coors[:, 2]) * 400 + coors[:, 3]
+    assert (np.diff(key) > 0).all() and (coors[:, 1] == 0).all()
+    # every point is counted exactly once at every scale
+    pm = big.pillar_mean[:v].cpu().numpy()
+    mm = big.med_mean[:n_med].cpu().numpy()
+    lm = big.low_mean[:n_low].cpu().numpy()
+    assert pm[:, 3].sum(dtype=np.float64) == p and mm[:, 3].sum(dtype=np.float64) == p and lm[:, 3].sum(dtype=np.float64) == p
+    # CSR offsets are the exclusive prefix sums of the slot-mask popcounts
+    med_mask = big.med_mask[:v].cpu().numpy().astype(np.uint32)
+    low_mask = big.low_mask[:v].cpu().numpy().astype(np.uint32)
+    pop_m = np.unpackbits(med_mask.view(np.uint8).reshape(v, 4), axis=1).sum(1).astype(np.int64)
+    pop_l = np.unpackbits(low_mask.view(np.uint8).reshape(v, 16), axis=1).sum(1).astype(np.int64)
+    med_ptr = big.med_ptr[:v + 1].cpu().numpy().astype(np.int64)
+    low_ptr = big.low_ptr[:v + 1].cpu().numpy().astype(np.int64)
+    assert np.array_equal(med_ptr, np.concatenate([[0], np.cumsum(pop_m)])) and med_ptr[-1] == n_med
+    assert np.array_equal(low_ptr, np.concatenate([[0], np.cumsum(pop_l)])) and low_ptr[-1] == n_low
+    # a pillar's count is the sum of its sub-voxels' counts, its centroid their count-weighted mean
+    cnt_m = np.add.reduceat(mm[:, 3].astype(np.float64), med_ptr[:-1])
+    cnt_l = np.add.reduceat(lm[:, 3].astype(np.float64), low_ptr[:-1])
+    assert np.array_equal(cnt_m, pm[:, 3]) and np.array_equal(cnt_l, pm[:, 3])
+    wsum = np.add.reduceat(mm[:, :3].astype(np.float64) * mm[:, 3:4], med_ptr[:-1], axis=0)
+    np.testing.assert_allclose(wsum / pm[:, 3:4], pm[:, :3], rtol=2e-6, atol=3e-6)
+    # point -> pillar map: in range, and consistent with the pillar of the same point in the small batch
+    pp = big.point_pillar[:p].cpu().numpy().astype(np.int64)
+    assert pp.min() >= 0 and pp.max() < v
+    pp_small = small.point_pillar[:ps].cpu().numpy().astype(np.int64)
+    for rep in (0, 1, 17, 31):       # frames 8*rep .. 8*rep+7 are the small batch again
+        assert np.array_equal(pp[rep * ps:(rep + 1) * ps], pp_small + rep * vs), rep
+        sl = slice(rep * vs, (rep + 1) * vs)
+        ref = small.pillar_coors[:vs].cpu().numpy().astype(np.int64)
+        assert np.array_equal(coors[sl, 1:], ref[:, 1:]) and np.array_equal(coors[sl, 0], ref[:, 0] + 8 * rep)
+        assert np.array_equal(med_mask[sl], small.med_mask[:vs].cpu().numpy().astype(np.uint32))
+        assert np.array_equal(low_mask[sl], small.low_mask[:vs].cpu().numpy().astype(np.uint32))
+        np.testing.assert_allclose(pm[sl], small.pillar_mean[:vs].cpu().numpy(), rtol=2e-6, atol=3e-6)
+        np.testing.assert_allclose(mm[rep * ms:(rep + 1) * ms], small.med_mean[:ms].cpu().numpy(), rtol=2e-6, atol=3e-6)
+        np.testing.assert_allclose(lm[rep * ls:(rep + 1) * ls], small.low_mean[:ls].cpu().numpy(), rtol=2e-6, atol=3e-6)
+    # geometric targets of the big batch: neighbour table equal to the small batch's (shifted), unit normals,
+    # curvature rows that sum to one
+    normal, curv, cov6, sing, pair = big.geom_targets(want_debug=True)
+    _, curv_s, _, sing_s, pair_s = small.geom_targets(want_debug=True)
+    pair = pair.cpu().numpy().astype(np.int64)
+    pair_s = pair_s.cpu().numpy().astype(np.int64)
+    for rep in (0, 31):
+        want = np.where(pair_s >= 0, pair_s + rep * vs, -1)
+        assert np.array_equal(pair[:, rep * vs:(rep + 1) * vs], want), rep
+        s_ref = sing_s.cpu().numpy()
+        solid = s_ref[:, 0] > 1e-6
+        got = curv[rep * vs:(rep + 1) * vs].cpu().numpy()
+        np.testing.assert_allclose(got[solid], curv_s.cpu().numpy()[solid], rtol=1e-3, atol=5e-4)
+    np.testing.assert_allclose(np.linalg.norm(normal.cpu().numpy(), axis=1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(curv.cpu().numpy().sum(1), 1.0, atol=1e-9)
