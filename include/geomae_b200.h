@@ -470,6 +470,24 @@ int geomae_adamw_step(float* params, const float* grads, float* exp_avg, float* 
                       int64_t n_decay, double* partials, float grad_scale, float max_norm, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int64_t step, float* stats, void* stream);
 
+/* ------------------------------------------------- data step in front of the path */
+
+/* Per-sample augmentation + range filter of a concatenated batch, fused with a stable compaction:
+ *   (x, y, z) -> ((x c - y s) * scale, (x s + y c) * scale, z * scale), y = -y if flip bit 0, x = -x if flip bit 1,
+ *   keep iff range_min < (x, y, z) < range_max (strict); further channels are copied unchanged.
+ * frame_params: [n_frames, 4] = cos, sin, scale, flip bits (as a float).  Survivors keep their input order;
+ * out_frame_offsets [n_frames+1] are the new frame starts (last = number of survivors).  out_points must hold
+ * n_points rows, scan_tmp ceil(n_points/1024)+1 ints.  Caller-allocated, no device sync.
+ * replaces: GlobalRotScaleTrans, RandomFlip3D and PointsRangeFilter of the pretraining pipeline
+ *           (configs/mae_sst/…6x_1e-5.py:181-193; datasets/pipelines/transforms_3d.py:95-123,670-718,849-883;
+ *           core/points/base_points.py:139-179,207-229,263-269; core/points/lidar_points.py:28-33), which the reference
+ *           applies per sample on the data-loader workers.  PointShuffle (transforms_3d.py:771-790) is not reproduced:
+ *           everything downstream is order-free. */
+int geomae_augment_filter(const float* points, int64_t n_points, int32_t stride, const int32_t* frame_offsets,
+                          int32_t n_frames, const float* frame_params, const float range_min[3],
+                          const float range_max[3], float* out_points, int32_t* out_frame_offsets,
+                          int32_t* scan_tmp, int64_t scan_tmp_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

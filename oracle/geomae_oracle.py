@@ -591,3 +591,33 @@ def init_params(cfg: PathConfig, seed=0):
         p[f"voxel_encoder.vfe_layers.{i}.norm.weight"] = 1 + small(c)
         p[f"voxel_encoder.vfe_layers.{i}.norm.bias"] = small(c)
     return p
+
+
+# ---------------------------------------------------------------------------
+# N2  data step in front of the path: augmentation + range filter
+# ---------------------------------------------------------------------------
+def augment_filter(frames, params, pc_range):
+    """GlobalRotScaleTrans (translation std 0) -> RandomFlip3D -> PointsRangeFilter on each frame
+    (datasets/pipelines/transforms_3d.py:670-718,95-123,849-883 via core/points/base_points.py:139-179,263-269,207-229
+    and lidar_points.py:28-33).  params: [B,4] float32 rows (cos, sin, scale, flip bits: 1 horizontal, 2 vertical).
+    fp32 arithmetic with every product and sum rounded separately:
+        x' = (x c - y s) * scale,  y' = (x s + y c) * scale,  z' = z * scale;  strict  min < p' < max.
+    Returns the list of filtered frames (input order kept, further channels untouched)."""
+    lo = np.asarray(pc_range[:3], np.float32)
+    hi = np.asarray(pc_range[3:], np.float32)
+    out = []
+    for f, (c, s, sc, fl) in zip(frames, np.asarray(params, np.float32)):
+        f = np.asarray(f, np.float32)
+        x, y, z = f[:, 0], f[:, 1], f[:, 2]
+        xr = (x * c - y * s) * sc
+        yr = (x * s + y * c) * sc
+        zr = z * sc
+        if int(fl) & 1:
+            yr = -yr
+        if int(fl) & 2:
+            xr = -xr
+        keep = (xr > lo[0]) & (yr > lo[1]) & (zr > lo[2]) & (xr < hi[0]) & (yr < hi[1]) & (zr < hi[2])
+        g = f.copy()
+        g[:, 0], g[:, 1], g[:, 2] = xr, yr, zr
+        out.append(np.ascontiguousarray(g[keep]))
+    return out
