@@ -73,3 +73,89 @@ def augment_filter(points: torch.Tensor, frame_offsets: torch.Tensor, augs, poin
     L.run("augment_filter", L.ptr(points), n, stride, L.ptr(frame_offsets), n_frames, L.ptr(params),
           L.f3(rng[:3]), L.f3(rng[3:]), L.ptr(out), L.ptr(out_off), L.ptr(tmp), C.c_int64(n_tmp), L.stream_ptr(dev))
     return out, out_off
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# On-disk formats: nuScenes `.pcd.bin` sweeps and the `nuscenes_ssl_infos_*.pkl` index.
+# Host-side numpy, statement for statement what the reference's loaders do (they are numpy too); the result is the raw
+# [N, 5] float32 frame that goes to the device once and through `augment_filter`.
+# ---------------------------------------------------------------------------------------------------------------------
+def read_points_bin(path: str, load_dim: int = 5, use_dim=5) -> np.ndarray:
+    """`LoadPointsFromFile` (datasets/pipelines/loading.py:382-427): a flat float32 file of `load_dim`-float records
+    (nuScenes: x, y, z, intensity, ring index), columns `use_dim` kept."""
+    if isinstance(use_dim, int):
+        use_dim = list(range(use_dim))
+    pts = np.fromfile(path, dtype=np.float32) if not path.endswith(".npy") else np.load(path)
+    return pts.reshape(-1, load_dim)[:, use_dim]
+
+
+def remove_close(points: np.ndarray, radius: float = 1.0) -> np.ndarray:
+    """`LoadPointsFromMultiSweeps._remove_close` (loading.py:160-181): drop points with |x| < r AND |y| < r."""
+    x_filt = np.abs(points[:, 0]) < radius
+    y_filt = np.abs(points[:, 1]) < radius
+    return points[np.logical_not(np.logical_and(x_filt, y_filt))]
+
+
+def load_multi_sweeps(points: np.ndarray, info: dict, sweeps_num: int = 9, load_dim: int = 5,
+                      use_dim=(0, 1, 2, 3, 4), pad_empty_sweeps: bool = True, remove_close_points: bool = True,
+                      test_mode: bool = False, rng=np.random, read=None) -> np.ndarray:
+    """`LoadPointsFromMultiSweeps.__call__` (loading.py:183-230) with the arguments of the GeoMAE pretraining config
+    (…6x_1e-5.py:174-180): key frame with its time channel zeroed, then up to `sweeps_num` earlier sweeps, each moved
+    into the key frame's lidar coordinates and stamped with its time lag in channel 4.
+    `info` = an entry of `NuScenesSSLIndex.get_data_info`; `rng` must offer `choice` (training draws the sweeps
+    without replacement when more than `sweeps_num` exist)."""
+    read = read or (lambda p: np.fromfile(p, dtype=np.float32))
+    points = np.array(points, dtype=np.float32, copy=True)
+    points[:, 4] = 0
+    sweep_points_list = [points]
+    ts = info["timestamp"]
+    if pad_empty_sweeps and len(info["sweeps"]) == 0:
+        for _ in range(sweeps_num):
+            sweep_points_list.append(remove_close(points) if remove_close_points else points)
+    else:
+        if len(info["sweeps"]) <= sweeps_num:
+            choices = np.arange(len(info["sweeps"]))
+        elif test_mode:
+            choices = np.arange(sweeps_num)
+        else:
+            choices = rng.choice(len(info["sweeps"]), sweeps_num, replace=False)
+        for idx in choices:
+            sweep = info["sweeps"][idx]
+            points_sweep = np.copy(read(sweep["data_path"])).reshape(-1, load_dim)
+            if remove_close_points:
+                points_sweep = remove_close(points_sweep)
+            sweep_ts = sweep["timestamp"] / 1e6
+            points_sweep[:, :3] = points_sweep[:, :3] @ sweep["sensor2lidar_rotation"].T
+            points_sweep[:, :3] += sweep["sensor2lidar_translation"]
+            points_sweep[:, 4] = ts - sweep_ts
+            sweep_points_list.append(points_sweep)
+    return np.concatenate(sweep_points_list, axis=0)[:, list(use_dim)]
+
+
+class NuScenesSSLIndex:
+    """The `nuscenes_ssl_infos_*.pkl` index as `NuScenesDatasetSSL` reads it (datasets/nuscenes_ssl_dataset.py:176-206,
+    228-235): `{'infos': [...], 'metadata': {'version': ...}}`, entries sorted by timestamp, every `load_interval`-th
+    kept; an entry yields the loader inputs (`pts_filename`, `sweeps`, `timestamp` in seconds)."""
+
+    def __init__(self, ann_file: str, load_interval: int = 1):
+        import pickle
+        with open(ann_file, "rb") as f:
+            data = pickle.load(f)
+        infos = list(sorted(data["infos"], key=lambda e: e["timestamp"]))
+        self.data_infos = infos[::load_interval]
+        self.metadata = data["metadata"]
+        self.version = self.metadata["version"]
+
+    def __len__(self):
+        return len(self.data_infos)
+
+    def get_data_info(self, index: int) -> dict:
+        info = self.data_infos[index]
+        return dict(sample_idx=info["token"], pts_filename=info["lidar_path"], sweeps=info["sweeps"],
+                    timestamp=info["timestamp"] / 1e6)
+
+    def load_frame(self, index: int, sweeps_num: int = 9, test_mode: bool = False, rng=np.random) -> np.ndarray:
+        """Raw multi-sweep frame [N, 5] float32 of entry `index` (the first two stages of the train pipeline)."""
+        info = self.get_data_info(index)
+        key = read_points_bin(info["pts_filename"], 5, 5)
+        return load_multi_sweeps(key, info, sweeps_num=sweeps_num, test_mode=test_mode, rng=rng)

@@ -323,6 +323,50 @@ def install(voxel_layer=None):
     return _INSTALLED
 
 
+def load_pipeline_loading():
+    """The reference's datasets/pipelines/loading.py (LoadPointsFromFile, LoadPointsFromMultiSweeps) loaded by path on
+    top of install(): real point classes (core/points/{base,lidar}_points.py), stubbed mmcv file client (disk reads)
+    and mmdet pipeline registry."""
+    env = install()
+    if "loading" in env:
+        return env["loading"]
+
+    def load(dotted, rel):
+        spec = importlib.util.spec_from_file_location(dotted, os.path.join(REF_ROOT, "mmdet3d", rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[dotted] = m
+        spec.loader.exec_module(m)
+        return m
+
+    pts_pkg = _pkg("mmdet3d.core.points")
+    base = load("mmdet3d.core.points.base_points", "core/points/base_points.py")
+    lidar = load("mmdet3d.core.points.lidar_points", "core/points/lidar_points.py")
+
+    def get_points_type(points_type):
+        assert points_type == "LIDAR"
+        return lidar.LiDARPoints
+    pts_pkg.BasePoints, pts_pkg.LiDARPoints, pts_pkg.get_points_type = base.BasePoints, lidar.LiDARPoints, get_points_type
+    sys.modules["mmdet3d.core"].points = pts_pkg
+
+    class FileClient:
+        def __init__(self, backend="disk", **_):
+            assert backend == "disk"
+
+        def get(self, path):
+            with open(path, "rb") as f:
+                return f.read()
+    mmcv = sys.modules["mmcv"]
+    mmcv.FileClient = FileClient
+    mmcv.check_file_exist = lambda p: os.path.exists(p) or (_ for _ in ()).throw(FileNotFoundError(p))
+    _pkg("mmdet.datasets")
+    _mod("mmdet.datasets.builder", PIPELINES=Registry("pipeline"))
+    _mod("mmdet.datasets.pipelines", LoadAnnotations=object, LoadImageFromFile=object)
+    _pkg("mmdet3d.datasets")
+    _pkg("mmdet3d.datasets.pipelines")
+    env["loading"] = load("mmdet3d.datasets.pipelines.loading", "datasets/pipelines/loading.py")
+    return env["loading"]
+
+
 def load_config_model(config_rel: str = MAE_CONFIG) -> dict:
     """exec the reference config file and return its ``model`` dict."""
     ns: dict = {}
