@@ -90,46 +90,56 @@ def read_points_bin(path: str, load_dim: int = 5, use_dim=5) -> np.ndarray:
 
 
 def remove_close(points: np.ndarray, radius: float = 1.0) -> np.ndarray:
-    """`LoadPointsFromMultiSweeps._remove_close` (loading.py:160-181): drop points with |x| < r AND |y| < r."""
-    x_filt = np.abs(points[:, 0]) < radius
-    y_filt = np.abs(points[:, 1]) < radius
-    return points[np.logical_not(np.logical_and(x_filt, y_filt))]
+    """Points inside the square |x| < radius and |y| < radius around the sensor (ego-vehicle returns) are dropped
+    (`LoadPointsFromMultiSweeps._remove_close`, loading.py:160-181)."""
+    inside = (np.abs(points[:, 0]) < radius) & (np.abs(points[:, 1]) < radius)
+    return points[~inside]
+
+
+def _pick_sweeps(n_available: int, sweeps_num: int, test_mode: bool, rng) -> np.ndarray:
+    """Which of the `n_available` earlier sweeps join the key frame: all of them when there are at most `sweeps_num`,
+    the nearest `sweeps_num` at test time, a draw without replacement in training (loading.py:208-215)."""
+    if n_available <= sweeps_num:
+        return np.arange(n_available)
+    if test_mode:
+        return np.arange(sweeps_num)
+    return rng.choice(n_available, sweeps_num, replace=False)
+
+
+def _sweep_in_key_frame(raw: np.ndarray, sweep: dict, key_time: float, load_dim: int, drop_close: bool) -> np.ndarray:
+    """One earlier sweep in the key frame's lidar coordinates, channel 4 = its time lag in seconds.  The arithmetic
+    keeps the reference's types on purpose (loading.py:218-226): float32 points times the float64 sensor->lidar
+    rotation, rounded back to float32, then the float64 translation added in place."""
+    pts = np.array(raw, dtype=np.float32).reshape(-1, load_dim)
+    if drop_close:
+        pts = remove_close(pts)
+    pts[:, :3] = pts[:, :3] @ sweep["sensor2lidar_rotation"].T
+    pts[:, :3] += sweep["sensor2lidar_translation"]
+    pts[:, 4] = key_time - sweep["timestamp"] / 1e6
+    return pts
 
 
 def load_multi_sweeps(points: np.ndarray, info: dict, sweeps_num: int = 9, load_dim: int = 5,
                       use_dim=(0, 1, 2, 3, 4), pad_empty_sweeps: bool = True, remove_close_points: bool = True,
                       test_mode: bool = False, rng=np.random, read=None) -> np.ndarray:
-    """`LoadPointsFromMultiSweeps.__call__` (loading.py:183-230) with the arguments of the GeoMAE pretraining config
-    (…6x_1e-5.py:174-180): key frame with its time channel zeroed, then up to `sweeps_num` earlier sweeps, each moved
-    into the key frame's lidar coordinates and stamped with its time lag in channel 4.
-    `info` = an entry of `NuScenesSSLIndex.get_data_info`; `rng` must offer `choice` (training draws the sweeps
-    without replacement when more than `sweeps_num` exist)."""
-    read = read or (lambda p: np.fromfile(p, dtype=np.float32))
-    points = np.array(points, dtype=np.float32, copy=True)
-    points[:, 4] = 0
-    sweep_points_list = [points]
-    ts = info["timestamp"]
-    if pad_empty_sweeps and len(info["sweeps"]) == 0:
-        for _ in range(sweeps_num):
-            sweep_points_list.append(remove_close(points) if remove_close_points else points)
+    """What `LoadPointsFromMultiSweeps` (loading.py:100-235) produces with the arguments of the GeoMAE pretraining
+    config (…6x_1e-5.py:174-180): the key frame with its time channel zeroed, followed by up to `sweeps_num` earlier
+    sweeps moved into the key frame's coordinates; a key frame without sweeps is padded with copies of itself.
+    `info` = an entry of `NuScenesSSLIndex.get_data_info`; `rng` must offer `choice`; `read(path)` returns the flat
+    float32 contents of a sweep file."""
+    read = read or (lambda path: np.fromfile(path, dtype=np.float32))
+    key = np.array(points, dtype=np.float32, copy=True)
+    key[:, 4] = 0
+    parts = [key]
+    sweeps = info["sweeps"]
+    if pad_empty_sweeps and not sweeps:
+        filler = remove_close(key) if remove_close_points else key
+        parts += [filler] * sweeps_num
     else:
-        if len(info["sweeps"]) <= sweeps_num:
-            choices = np.arange(len(info["sweeps"]))
-        elif test_mode:
-            choices = np.arange(sweeps_num)
-        else:
-            choices = rng.choice(len(info["sweeps"]), sweeps_num, replace=False)
-        for idx in choices:
-            sweep = info["sweeps"][idx]
-            points_sweep = np.copy(read(sweep["data_path"])).reshape(-1, load_dim)
-            if remove_close_points:
-                points_sweep = remove_close(points_sweep)
-            sweep_ts = sweep["timestamp"] / 1e6
-            points_sweep[:, :3] = points_sweep[:, :3] @ sweep["sensor2lidar_rotation"].T
-            points_sweep[:, :3] += sweep["sensor2lidar_translation"]
-            points_sweep[:, 4] = ts - sweep_ts
-            sweep_points_list.append(points_sweep)
-    return np.concatenate(sweep_points_list, axis=0)[:, list(use_dim)]
+        for i in _pick_sweeps(len(sweeps), sweeps_num, test_mode, rng):
+            parts.append(_sweep_in_key_frame(read(sweeps[i]["data_path"]), sweeps[i], info["timestamp"], load_dim,
+                                             remove_close_points))
+    return np.concatenate(parts, axis=0)[:, list(use_dim)]
 
 
 class NuScenesSSLIndex:
