@@ -1,0 +1,222 @@
+// Weight gradients of one SRA EncoderLayer in ONE launch, fed by TMA (bf16 mode):
+//   dW2  += ds2^T gelu(u)      dW1 += du^T y  (+ db1)      dWo += ds1^T O      dWin += dqkv^T (x+pos | x)  (+ dbin)
+// i.e. the weight / bias gradient GEMMs autograd runs for nn.Linear / nn.MultiheadAttention in
+// models/sst/sst_basic_block.py:55,94-100.  Every operand is a token-major bf16 tensor [n, C] that the forward /
+// backward chain kernels saved; dW = dY^T X contracts over TOKENS, so both MMA operands are MN-major views of
+// [128 tokens x 64 channels] boxes, which is exactly what a 2-D tiled TMA load with the 128-byte swizzle writes into
+// shared memory — no thread ever touches an operand.  A CTA owns one [128 x 128] slab of one dW and a range of
+// 128-token tiles: warp 0 issues cp.async.bulk.tensor loads (UTMALDG) into a 3-stage ring, one thread of warp 1
+// issues tcgen05.mma (+ an N = 16 MMA against a constant "ones" block whose result column is the bias gradient),
+// the accumulator stays in TMEM over the whole token range and four warps flush it once with vector reductions.
+// The round-1 kernel re-staged fp32 rows through registers per slab (2-6 % tensor-pipe activity, 25 % of the step).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int WT = 128;                       // tokens per stage = K of one stage
+constexpr int STAGES = 3;
+constexpr int BLK = 16384;                    // one [128 x 64] bf16 box
+constexpr int STAGE_BYTES = 4 * BLK;          // dY box pair + X box pair
+constexpr int OFF_ONES = STAGES * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_ONES + BLK;
+constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+constexpr int MAX_SLABS = 8;
+constexpr int NTHR = 192;
+
+struct Slab { int a_map, a_col, b_map, b_col; float* dW; int ldw; float* db; };
+struct WgArgs { int n_tiles; int tiles_per_cta; Slab slab[MAX_SLABS]; };
+struct WgMaps { CUtensorMap m[9]; };
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          tc::smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(NTHR, 1) k_wgrad_tma(const __grid_constant__ WgMaps maps, const WgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sOnes = sm + OFF_ONES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_bar = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Slab s = a.slab[blockIdx.y];
+  const int tile_begin = blockIdx.x * a.tiles_per_cta;
+  const int tile_end = min(tile_begin + a.tiles_per_cta, a.n_tiles);
+  if (tile_begin >= tile_end) return;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(acc_bar, 1);
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+  // constant "ones" block: element (token row, column 0) = 1.0 -> D[m][0] = sum over tokens of dY[tok][m]
+  for (int i = threadIdx.x; i < WT * 8; i += NTHR) {
+    const int r = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c == 0) v.x = 0x00003F80u;
+    *reinterpret_cast<uint4*>(sOnes + tc::swz(r, c)) = v;
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  gm_pdl_wait();
+  gm_pdl_trigger();
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* ma = &maps.m[s.a_map];
+      const CUtensorMap* mb = &maps.m[s.b_map];
+      uint32_t cnt = 0;
+      for (int t = tile_begin; t < tile_end; ++t, ++cnt) {
+        const uint32_t slot = cnt % STAGES, ph = (cnt / STAGES) & 1;
+        uint8_t* st = sm + slot * STAGE_BYTES;
+        tc::mbar_wait(&empty[slot], ph ^ 1);
+        tc::mbar_expect_tx(&full[slot], STAGE_BYTES);
+        tma_load_2d(st, ma, s.a_col, t * WT, &full[slot]);
+        tma_load_2d(st + BLK, ma, s.a_col + 64, t * WT, &full[slot]);
+        tma_load_2d(st + 2 * BLK, mb, s.b_col, t * WT, &full[slot]);
+        tma_load_2d(st + 3 * BLK, mb, s.b_col + 64, t * WT, &full[slot]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, 128, 1, 1);
+      const uint32_t idesc_b = tc::make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t ones = tc::smem_u32(sOnes);
+      const bool bias = s.db != nullptr;
+      uint32_t cnt = 0;
+      for (int t = tile_begin; t < tile_end; ++t, ++cnt) {
+        const uint32_t slot = cnt % STAGES, ph = (cnt / STAGES) & 1;
+        tc::mbar_wait(&full[slot], ph);
+        tc::fence_after_sync();
+        const uint32_t A = tc::smem_u32(sm + slot * STAGE_BYTES), B = A + 2 * BLK;
+#pragma unroll
+        for (int j = 0; j < WT / 16; ++j) {            // 16 tokens per MMA: two 8-row swizzle atoms
+          const uint32_t off = (uint32_t)j * 2 * tc::ATOM_BYTES;
+          const uint64_t da = tc::make_desc(A + off, BLK, tc::ATOM_BYTES);
+          const bool acc = cnt > 0 || j > 0;
+          tc::mma_bf16(tmem, da, tc::make_desc(B + off, BLK, tc::ATOM_BYTES), idesc, acc);
+          if (bias) tc::mma_bf16(tmem + 128, da, tc::make_desc(ones + off, BLK, tc::ATOM_BYTES), idesc_b, acc);
+        }
+        tc::mma_commit(&empty[slot]);
+      }
+      tc::mma_commit(acc_bar);
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quarter warp % 4 -> dW rows, one vector reduction per 4 columns
+    tc::mbar_wait(acc_bar, 0);
+    tc::fence_after_sync();
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    float* o = s.dW + (int64_t)m * s.ldw;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(t_lane + c0, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; c += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c0 + c), "f"(v[c]), "f"(v[c + 1]),
+                     "f"(v[c + 2]), "f"(v[c + 3])
+                     : "memory");
+    }
+    if (s.db) {
+      float v[32];
+      tc::tmem_ld32(t_lane + 128, v);
+      tc::tmem_ld_wait();
+      atomicAdd(s.db + m, v[0]);
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_free(tmem, 256);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// [128 tokens x 64 columns] bf16 boxes of a row-major [n, cols] tensor, 128-byte swizzle, rows past n read as zeros
+int make_map(CUtensorMap* map, const void* base, int64_t n, int cols) {
+  EncodeTiledFn fn = encode_fn();
+  GM_REQUIRE(fn, "sra_wgrad: cuTensorMapEncodeTiled is not available from this driver");
+  GM_REQUIRE(((uintptr_t)base & 15) == 0, "sra_wgrad: operand tensors must be 16-byte aligned");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)WT};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GM_REQUIRE(rc == CUDA_SUCCESS, "sra_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)rc);
+  return GEOMAE_OK;
+}
+
+}  // namespace
+
+extern "C" int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* p, void* stream) {
+  GM_REQUIRE(p, "sra_wgrad_layer: null argument");
+  GM_REQUIRE(p->n_tokens >= 0 && p->n_tokens < ((int64_t)1 << 31) - 256, "sra_wgrad_layer: bad token count");
+  if (p->n_tokens == 0) return GEOMAE_OK;
+  GM_REQUIRE(p->ds2_16 && p->g16 && p->du16 && p->y16 && p->ds1_16 && p->attn16 && p->dqkv16 && p->xp16 && p->xb16,
+             "sra_wgrad_layer: null operand tensor");
+  GM_REQUIRE(p->g_lin2_w && p->g_lin1_w && p->g_out_proj_w && p->g_in_proj_w, "sra_wgrad_layer: null gradient buffer");
+  const int64_t n = p->n_tokens;
+  WgMaps maps;
+  const void* base[9] = {p->ds2_16, p->g16, p->du16, p->y16, p->ds1_16, p->attn16, p->dqkv16, p->xp16, p->xb16};
+  const int cols[9] = {128, 256, 256, 128, 128, 128, 384, 128, 128};
+  for (int i = 0; i < 9; ++i) {
+    const int rc = make_map(&maps.m[i], base[i], n, cols[i]);
+    if (rc) return rc;
+  }
+  WgArgs a;
+  a.n_tiles = gm_div_up(n, WT);
+  int splits = GM_NUM_SMS / MAX_SLABS;                  // 18 token ranges x 8 slabs = 144 CTAs
+  if (splits > a.n_tiles) splits = a.n_tiles;
+  a.tiles_per_cta = gm_div_up(a.n_tiles, splits);
+  splits = gm_div_up(a.n_tiles, a.tiles_per_cta);
+  // slab = [128 dY columns] x [128 X columns]:            dY map, col, X map, col, dW,                 ld, db
+  a.slab[0] = Slab{0, 0, 1, 0, p->g_lin2_w, 256, nullptr};                        // dW2[:, 0:128]   = ds2^T g[:, 0:128]
+  a.slab[1] = Slab{0, 0, 1, 128, p->g_lin2_w + 128, 256, nullptr};                // dW2[:, 128:256]
+  a.slab[2] = Slab{2, 0, 3, 0, p->g_lin1_w, 128, p->g_lin1_b};                    // dW1[0:128]      = du[:, 0:128]^T y
+  a.slab[3] = Slab{2, 128, 3, 0, p->g_lin1_w + 128 * 128, 128, p->g_lin1_b ? p->g_lin1_b + 128 : nullptr};
+  a.slab[4] = Slab{4, 0, 5, 0, p->g_out_proj_w, 128, nullptr};                    // dWo             = ds1^T O
+  a.slab[5] = Slab{6, 0, 7, 0, p->g_in_proj_w, 128, p->g_in_proj_b};              // dWin[q rows]    = dq^T (x + pos)
+  a.slab[6] = Slab{6, 128, 7, 0, p->g_in_proj_w + 128 * 128, 128, p->g_in_proj_b ? p->g_in_proj_b + 128 : nullptr};
+  a.slab[7] = Slab{6, 256, 8, 0, p->g_in_proj_w + 256 * 128, 128, p->g_in_proj_b ? p->g_in_proj_b + 256 : nullptr};
+  static bool configured = false;
+  if (!configured) {
+    GM_CUDA(cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  GM_CUDA(gm_launch_pdl(k_wgrad_tma, dim3(splits, MAX_SLABS), dim3(NTHR), (size_t)SMEM_BYTES, (cudaStream_t)stream, maps, a));
+  return GEOMAE_OK;
+}

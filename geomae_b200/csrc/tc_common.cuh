@@ -138,3 +138,31 @@ __device__ __forceinline__ uint4 pack8(const float* f, uint4* lo) {
 }
 
 }  // namespace tc
+
+// Exact-erf GELU (F.gelu default, sst_basic_block.py:153-154) and its derivative, evaluated with the
+// Abramowitz-Stegun 7.1.26 rational form erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z)
+// (|error| <= 1.5e-7, i.e. fp32 rounding level): one MUFU.RCP + one MUFU.EX2 + 8 FMAs.  libdevice erff + expf
+// cost ~70 dependent instructions per element, which made the GELU prologue / GELU-gradient epilogue the
+// longest phase of three kernels (128 evaluations per thread at 8 warps per SM).  exp(-z^2) = exp(-x^2/2) is
+// shared between erf and the Gaussian density of the derivative.
+struct GeluParts { float cdf; float pdf_x; };    // Phi(x), x * phi(x)
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // argument in [1, inf): 1 ulp
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));  // 2 ulp; flushes to 0 below 2^-126
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  GeluParts r;
+  r.cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  r.pdf_x = x * e * 0.3989422804014327f;
+  return r;
+}
+__device__ __forceinline__ float gelu_f(float x) { return x * gelu_parts(x).cdf; }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const GeluParts g = gelu_parts(x);
+  return g.cdf + g.pdf_x;
+}

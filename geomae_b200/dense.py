@@ -117,3 +117,42 @@ class _TCLinearFn(torch.autograd.Function):
 def tc_linear_module(x, linear: torch.nn.Linear, precision):
     """nn.Linear forward/backward on the tensor cores (in/out features must be multiples of 128)."""
     return _TCLinearFn.apply(x, linear.weight, linear.bias, precision)
+
+
+def sra_chain_fwd(x, *, attn=None, layer=None, next_in_proj=None, pos_table=None, tok_cell_next=None):
+    """Fused forward chain of one EncoderLayer on 128-token tiles (geomae_sra_chain_fwd, csrc/sra_chain.cu).
+
+    layer = dict(Wo, bo, W1, b1, W2, b2, g1, be1, g2, be2, eps) runs out-proj+LN1 -> FFN -> LN2 on `attn` (bf16 [n,128]);
+    next_in_proj = (Win [384,128], bin [384]) appends the next layer's in-projection of (z + pos | z) (or of x itself
+    when layer is None: the stack prologue).  Returns a dict of the produced tensors."""
+    n = x.shape[0]
+    dev = x.device
+    a = L.ChainFwdArgs()
+    a.n_tokens, a.mode, a.x = n, (1 if layer is not None else 0) | (2 if next_in_proj is not None else 0), x.data_ptr()
+    out, keep = {}, []
+    f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)       # noqa: E731
+    b16 = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)      # noqa: E731
+    if layer is not None:
+        a.attn = attn.data_ptr()
+        for key, field in (("Wo", "p_out_proj"), ("W1", "p_lin1"), ("W2", "p_lin2")):
+            img = pack_weight(layer[key], want_lo=False)[0]
+            keep.append(img)
+            setattr(a, field, img.data_ptr())
+        for key, field in (("bo", "out_proj_b"), ("b1", "lin1_b"), ("b2", "lin2_b"), ("g1", "norm1_w"), ("be1", "norm1_b"),
+                           ("g2", "norm2_w"), ("be2", "norm2_b")):
+            setattr(a, field, layer[key].data_ptr())
+        a.ln_eps = layer["eps"]
+        out.update(s1=f32(n, 128), st1=f32(n, 2), s2=f32(n, 128), st2=f32(n, 2), z=f32(n, 128), y16=b16(n, 128),
+                   u16=b16(n, 256), g16=b16(n, 256))
+        for k in ("s1", "st1", "s2", "st2", "z", "y16", "u16", "g16"):
+            setattr(a, k, out[k].data_ptr())
+    if next_in_proj is not None:
+        Win, bin_ = next_in_proj
+        img = pack_weight(Win, want_lo=False)[0]
+        keep.append(img)
+        a.p_in_proj_next, a.in_proj_b_next = img.data_ptr(), bin_.data_ptr()
+        a.pos_table, a.tok_cell_next = pos_table.data_ptr(), tok_cell_next.data_ptr()
+        out.update(xp16=b16(n, 128), xb16=b16(n, 128), qkv16=b16(n, 384))
+        a.xp16_next, a.xb16_next, a.qkv16_next = out["xp16"].data_ptr(), out["xb16"].data_ptr(), out["qkv16"].data_ptr()
+    L.run("sra_chain_fwd", C.byref(a), L.stream_ptr(dev))
+    return out

@@ -93,6 +93,15 @@ class SRASaved(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("qkv", "attn", "lse", "s1", "st1", "y", "u", "s2", "st2", "z")]
 
 
+class ChainFwdArgs(C.Structure):
+    _fields_ = ([("n_tokens", C.c_int64), ("mode", C.c_int32), ("x", C.c_void_p), ("attn", C.c_void_p)] +
+                [(k, C.c_void_p) for k in ("p_out_proj", "p_lin1", "p_lin2", "p_in_proj_next", "out_proj_b", "lin1_b",
+                                           "lin2_b", "in_proj_b_next", "norm1_w", "norm1_b", "norm2_w", "norm2_b")] +
+                [("ln_eps", C.c_float), ("pos_table", C.c_void_p), ("tok_cell_next", C.c_void_p)] +
+                [(k, C.c_void_p) for k in ("s1", "st1", "s2", "st2", "z", "y16", "u16", "g16", "xp16_next",
+                                           "xb16_next", "qkv16_next")])
+
+
 class LossArgs(C.Structure):
     _fields_ = [("rows", C.c_void_p), ("m", C.c_int64), ("reg_low", C.c_void_p), ("reg_med", C.c_void_p),
                 ("reg_top", C.c_void_p), ("nor_top", C.c_void_p), ("cls_low", C.c_void_p), ("cls_med", C.c_void_p),
@@ -157,6 +166,7 @@ class _Sigs:
                                  C.POINTER(SRASaved), _p, _p]
     geomae_sra_stack2_backward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved),
                                   C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p, _p, _p]
+    geomae_sra_chain_fwd = [C.POINTER(ChainFwdArgs), _p]
     geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]
     geomae_geom_loss_fwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p]
     geomae_geom_loss_bwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p, _p, _p, _p,

@@ -423,6 +423,30 @@ int geomae_sra_stack2_backward(const geomae_sra_ctx* ctx, int32_t n_layers, cons
                                const geomae_sra_saved* saved_b, const float* x_in, const float* d_out_a,
                                const float* d_out_b, float* d_in_a, float* d_in_b, float* scratch, void* stream);
 
+/* ---------------------------------------- fused token-local layer chains (bf16 mode) */
+
+/* Forward chain of one EncoderLayer for every 128-token tile in ONE persistent, warp-specialised tcgen05 kernel
+ * (csrc/sra_chain.cu):  s1 = x + attn Wo^T + bo ; y = LN1(s1) ; u = y W1^T + b1 ; g = gelu(u) ; s2 = y + g W2^T + b2 ;
+ * z = LN2(s2) ; and (mode bit 1) the in-projection of the NEXT layer, q|k = (z + pos) Wqk^T + b, v = z Wv^T + b.
+ * mode: bit 0 = this layer's chain, bit 1 = next in-projection (mode 2 alone = in-projection of x: the stack prologue).
+ * p_*: packed bf16 "hi" images from geomae_pack_weights.  bf16 tensors are row-major [n, cols]:
+ *   attn [n,128] (attention output), y16 [n,128], u16 [n,256] (pre-GELU), g16 [n,256] (gelu(u)),
+ *   xp16_next / xb16_next [n,128] (z + pos / z, the operands of the next layer's in-projection weight gradient),
+ *   qkv16_next [n,384].  fp32: s1, s2 [n,128] pre-LayerNorm rows, st1, st2 [n,2] (mean, rstd), z [n,128].
+ * replaces: out_proj of nn.MultiheadAttention + EncoderLayer.forward (models/sst/sst_basic_block.py:55,85-102) and
+ *           the in_proj of the next layer's WindowAttention (:41-55) — library GEMMs + ~8 elementwise kernels. */
+typedef struct geomae_chain_fwd_args {
+  int64_t n_tokens; int32_t mode;
+  const float* x; const void* attn;
+  const void *p_out_proj, *p_lin1, *p_lin2, *p_in_proj_next;
+  const float *out_proj_b, *lin1_b, *lin2_b, *in_proj_b_next, *norm1_w, *norm1_b, *norm2_w, *norm2_b; float ln_eps;
+  const float* pos_table; const int32_t* tok_cell_next;
+  float *s1, *st1, *s2, *st2, *z;
+  void *y16, *u16, *g16, *xp16_next, *xb16_next, *qkv16_next;
+} geomae_chain_fwd_args;
+
+int geomae_sra_chain_fwd(const geomae_chain_fwd_args* args, void* stream);
+
 /* -------------------------------------------------------------------- losses */
 
 typedef struct geomae_loss_args {

@@ -1,0 +1,81 @@
+"""Fused token-local SRA chain kernels (csrc/sra_chain.cu) against torch fp32 with the kernel's rounding points
+(bf16 operands of every tensor-core product, fp32 accumulation / LayerNorm / GELU / residuals)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def make_layer(seed):
+    return dict(Wo=rnd(128, 128, scale=0.1, seed=seed), bo=rnd(128, scale=0.1, seed=seed + 1),
+                W1=rnd(256, 128, scale=0.1, seed=seed + 2), b1=rnd(256, scale=0.1, seed=seed + 3),
+                W2=rnd(128, 256, scale=0.1, seed=seed + 4), b2=rnd(128, scale=0.1, seed=seed + 5),
+                g1=1 + 0.1 * rnd(128, seed=seed + 6), be1=0.1 * rnd(128, seed=seed + 7),
+                g2=1 + 0.1 * rnd(128, seed=seed + 8), be2=0.1 * rnd(128, seed=seed + 9), eps=1e-5)
+
+
+def reference(x, attn, lay, nxt, table, cell):
+    out = {}
+    z = x
+    if lay is not None:
+        s1 = x + attn.float() @ bf(lay["Wo"]).T + lay["bo"]
+        y = F.layer_norm(s1, (128,), lay["g1"], lay["be1"], lay["eps"])
+        u = bf(y) @ bf(lay["W1"]).T + lay["b1"]
+        g = F.gelu(u)
+        s2 = y + bf(g) @ bf(lay["W2"]).T + lay["b2"]
+        z = F.layer_norm(s2, (128,), lay["g2"], lay["be2"], lay["eps"])
+        out.update(s1=s1, y=y, u=u, g=g, s2=s2, z=z,
+                   st1=torch.stack([s1.mean(1), torch.rsqrt(s1.var(1, unbiased=False) + lay["eps"])], 1),
+                   st2=torch.stack([s2.mean(1), torch.rsqrt(s2.var(1, unbiased=False) + lay["eps"])], 1))
+    if nxt is not None:
+        Win, bin_ = nxt
+        xp, xb = bf(z + table[cell.long()]), bf(z)
+        out.update(xp=xp, xb=xb, qkv=torch.cat([xp @ bf(Win[:256]).T + bin_[:256], xb @ bf(Win[256:]).T + bin_[256:]], 1))
+    return out
+
+
+def close(got, ref, what, atol, mean_tol):
+    d = (got.float() - ref).abs()
+    assert torch.isfinite(got.float()).all(), what
+    assert d.max().item() <= atol, (what, "max", d.max().item())
+    assert d.mean().item() <= mean_tol, (what, "mean", d.mean().item())
+
+
+# 100: one partial tile; 1000: several tiles; 148*128+37: more tiles than CTAs (persistent loop, phase flips)
+@pytest.mark.parametrize("n", [100, 1000, 148 * 128 * 2 + 37])
+@pytest.mark.parametrize("mode", [3, 1, 2])
+def test_chain_forward(n, mode):
+    from geomae_b200.dense import sra_chain_fwd
+    x = rnd(n, 128, seed=1)
+    attn = rnd(n, 128, seed=2).to(torch.bfloat16)
+    lay = make_layer(10) if mode & 1 else None
+    nxt = (rnd(384, 128, scale=0.1, seed=30), rnd(384, scale=0.1, seed=31)) if mode & 2 else None
+    table = rnd(144, 128, seed=4)
+    cell = torch.randint(0, 144, (n,), dtype=torch.int32, device="cuda")
+    got = sra_chain_fwd(x, attn=attn, layer=lay, next_in_proj=nxt, pos_table=table, tok_cell_next=cell)
+    torch.cuda.synchronize()
+    ref = reference(x, attn, lay, nxt, table, cell)
+    if lay is not None:
+        close(got["s1"], ref["s1"], "s1", 2e-4, 2e-5)
+        close(got["st1"], ref["st1"], "st1", 2e-4, 2e-5)
+        close(got["y16"], ref["y"], "y16", 4e-2, 4e-3)          # bf16 storage: half an ulp of |y| <= 4
+        # downstream of a bf16 rounding of y / g a last-bit difference in fp32 flips single operand roundings
+        close(got["u16"], ref["u"], "u16", 4e-2, 3e-3)
+        close(got["g16"], ref["g"], "g16", 4e-2, 3e-3)
+        close(got["s2"], ref["s2"], "s2", 2e-2, 2e-4)
+        close(got["z"], ref["z"], "z", 2e-2, 2e-4)
+        close(got["st2"][:, 0], ref["st2"][:, 0], "st2 mean", 2e-3, 2e-5)
+    if nxt is not None:
+        close(got["xp16"], ref["xp"], "xp16", 6e-2, 3e-4)
+        close(got["xb16"], ref["xb"], "xb16", 6e-2, 3e-4)
+        close(got["qkv16"], ref["qkv"], "qkv16", 8e-2, 6e-3)
