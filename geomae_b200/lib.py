@@ -102,6 +102,12 @@ class ChainFwdArgs(C.Structure):
                                            "xb16_next", "qkv16_next")])
 
 
+class WgradLayerArgs(C.Structure):
+    _fields_ = [("n_tokens", C.c_int64)] + [(k, C.c_void_p) for k in (
+        "ds2_16", "g16", "du16", "y16", "ds1_16", "attn16", "dqkv16", "xp16", "xb16", "g_lin2_w", "g_lin1_w", "g_lin1_b",
+        "g_out_proj_w", "g_in_proj_w", "g_in_proj_b")]
+
+
 class LossArgs(C.Structure):
     _fields_ = [("rows", C.c_void_p), ("m", C.c_int64), ("reg_low", C.c_void_p), ("reg_med", C.c_void_p),
                 ("reg_top", C.c_void_p), ("nor_top", C.c_void_p), ("cls_low", C.c_void_p), ("cls_med", C.c_void_p),
@@ -167,6 +173,7 @@ class _Sigs:
     geomae_sra_stack2_backward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved),
                                   C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p, _p, _p]
     geomae_sra_chain_fwd = [C.POINTER(ChainFwdArgs), _p]
+    geomae_sra_wgrad_layer = [C.POINTER(WgradLayerArgs), _p]
     geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]
     geomae_geom_loss_fwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p]
     geomae_geom_loss_bwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p, _p, _p, _p,

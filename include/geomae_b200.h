@@ -447,6 +447,21 @@ typedef struct geomae_chain_fwd_args {
 
 int geomae_sra_chain_fwd(const geomae_chain_fwd_args* args, void* stream);
 
+/* Weight / bias gradients of one EncoderLayer in ONE TMA-fed tcgen05 launch (csrc/sra_wgrad.cu), accumulated (+=)
+ * with vector reductions:  g_lin2_w [128,256] += ds2^T g ; g_lin1_w [256,128] += du^T y, g_lin1_b += colsum du ;
+ * g_out_proj_w [128,128] += ds1^T attn ; g_in_proj_w [384,128] += dq|dk ^T xp, dv^T xb ; g_in_proj_b += colsum dqkv.
+ * Operands are bf16 row-major: ds2_16, y16, ds1_16, attn16, xp16, xb16 [n,128]; g16, du16 [n,256]; dqkv16 [n,384]
+ * (16-byte aligned).  Bias buffers may be NULL.
+ * replaces: the weight-gradient GEMMs + bias column sums autograd runs for linear1 / linear2 / out_proj / in_proj
+ *           of models/sst/sst_basic_block.py:55,94-100. */
+typedef struct geomae_wgrad_layer_args {
+  int64_t n_tokens;
+  const void *ds2_16, *g16, *du16, *y16, *ds1_16, *attn16, *dqkv16, *xp16, *xb16;
+  float *g_lin2_w, *g_lin1_w, *g_lin1_b, *g_out_proj_w, *g_in_proj_w, *g_in_proj_b;
+} geomae_wgrad_layer_args;
+
+int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* args, void* stream);
+
 /* -------------------------------------------------------------------- losses */
 
 typedef struct geomae_loss_args {

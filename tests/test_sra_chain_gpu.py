@@ -79,3 +79,32 @@ def test_chain_forward(n, mode):
         close(got["xp16"], ref["xp"], "xp16", 6e-2, 3e-4)
         close(got["xb16"], ref["xb"], "xb16", 6e-2, 3e-4)
         close(got["qkv16"], ref["qkv"], "qkv16", 8e-2, 6e-3)
+
+
+@pytest.mark.parametrize("n", [100, 1000, 148 * 128 + 37])
+def test_wgrad_layer_tma(n):
+    """All weight / bias gradients of a layer from bf16 operands in one TMA-fed launch; accumulates into the buffers."""
+    import ctypes as C
+    from geomae_b200 import lib as L
+    b16 = lambda cols, seed: rnd(n, cols, seed=seed).to(torch.bfloat16)      # noqa: E731
+    t = dict(ds2_16=b16(128, 1), g16=b16(256, 2), du16=b16(256, 3), y16=b16(128, 4), ds1_16=b16(128, 5),
+             attn16=b16(128, 6), dqkv16=b16(384, 7), xp16=b16(128, 8), xb16=b16(128, 9))
+    init = 0.5
+    g = dict(g_lin2_w=torch.full((128, 256), init, device="cuda"), g_lin1_w=torch.full((256, 128), init, device="cuda"),
+             g_lin1_b=torch.full((256,), init, device="cuda"), g_out_proj_w=torch.full((128, 128), init, device="cuda"),
+             g_in_proj_w=torch.full((384, 128), init, device="cuda"), g_in_proj_b=torch.full((384,), init, device="cuda"))
+    a = L.WgradLayerArgs()
+    a.n_tokens = n
+    for k, v in {**t, **g}.items():
+        setattr(a, k, v.data_ptr())
+    L.run("sra_wgrad_layer", C.byref(a), L.stream_ptr(torch.device("cuda")))
+    torch.cuda.synchronize()
+    f = {k: v.double() for k, v in t.items()}
+    ref = dict(g_lin2_w=f["ds2_16"].T @ f["g16"], g_lin1_w=f["du16"].T @ f["y16"], g_lin1_b=f["du16"].sum(0),
+               g_out_proj_w=f["ds1_16"].T @ f["attn16"],
+               g_in_proj_w=torch.cat([f["dqkv16"][:, :256].T @ f["xp16"], f["dqkv16"][:, 256:].T @ f["xb16"]], 0),
+               g_in_proj_b=f["dqkv16"].sum(0))
+    scale = (n ** 0.5)
+    for k in g:
+        d = (g[k].double() - init - ref[k]).abs().max().item()
+        assert d <= 2e-5 * scale + 1e-4, (k, d)
