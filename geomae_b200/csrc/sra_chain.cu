@@ -418,6 +418,430 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const FwdArgs a) {
   }
 }
 
+
+// ================================================================================================================
+//   backward (k_sra_chain_bwd), per 128-token tile, gradients flowing down through the same token-local chain:
+//     dz  = dqkv' Win' + ds1'            in-projection backward of the layer ABOVE (' = that layer), or dz given
+//     ds2 = LN2-backward(dz; s2)         d_gamma2 += sum dz xhat2, d_beta2 += sum dz
+//     du  = (ds2 W2) * gelu'(u)
+//     dy  = du W1 + ds2                  ds2 is PRE-LOADED into the TMEM accumulator (tcgen05.st), the MMA adds onto it
+//     ds1 = LN1-backward(dy; s1)         d_gamma1, d_beta1
+//     dO  = ds1 Wo ; D = dO . O per head (the attention backward's row term)
+//   dX = dY W uses the weights as MN-major B operands straight from the same packed images ([128 out-rows x 64 in-cols]
+//   blocks, N = 64 per MMA).  bf16 copies of ds2, du, ds1 feed the TMA weight-gradient kernel (sra_wgrad.cu); the bias
+//   gradients of linear2 / out_proj are column sums of ds2 / ds1 and ride along there.
+constexpr int B_OFF_OP = 0;
+constexpr int B_ST_BYTES = 36864;                       // band-2 operand tile | 2 x [128][144 B] u sub-bands | [128][272 B] O rows
+constexpr int B_OFF_ST = B_OFF_OP + 4 * BLK;
+constexpr int B_OFF_RING = B_OFF_ST + B_ST_BYTES;
+constexpr int B_OFF_R = B_OFF_RING + RING * BLK;
+constexpr int B_OFF_PAR = B_OFF_R + CT * R_LD * 4;      // gamma2 | gamma1
+constexpr int B_OFF_RED = B_OFF_PAR + 256 * 4;          // [128][2] float2
+constexpr int B_OFF_BAR = B_OFF_RED + CT * 2 * 8;
+constexpr int B_SMEM_BYTES = B_OFF_BAR + 256 + 1024;
+constexpr int UH_LD = 144;                              // bytes per row of a u sub-band tile (128 B + 16 B pad)
+constexpr int UH_BYTES = CT * UH_LD;
+static_assert(B_OFF_ST % 1024 == 0 && B_OFF_RING % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+static_assert(2 * UH_BYTES <= B_ST_BYTES && CT * ST_LD <= B_ST_BYTES && 2 * BLK <= B_ST_BYTES, "staging tile too small");
+
+struct BwdArgs {
+  int n; int mode;
+  const __nv_bfloat16* dqkv_up; const float* ds1_up; const uint8_t* Win_up; const float* dz_in;
+  const float *s2, *st2, *s1, *st1; const __nv_bfloat16 *u16, *attn16;
+  const uint8_t *W2, *W1, *Wo; const float *g2, *g1;
+  __nv_bfloat16 *ds2_16, *du16, *ds1_16, *dO16; float *ds1, *dd, *dx;
+  float *d_g2, *d_be2, *d_g1, *d_be1;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// LayerNorm backward of one row half held in v (= dz), xhat recomputed from the saved pre-LN row in R (overwritten in
+// place with dz * xhat for the d_gamma column sums).  On return v holds d(pre-LN row), dzc the untouched dz.
+__device__ __forceinline__ void ln_backward_row(float* v, float* xh, float* myR, const float* gamma, float mean, float rstd,
+                                                float2* red, int r, int hsel) {
+  float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; c += 4) {
+    const float4 s4 = *reinterpret_cast<const float4*>(myR + c);
+    const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+    float t[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      xh[c + e] = (s[e] - mean) * rstd;
+      const float g = v[c + e] * gamma[c + e];
+      p1 += g;
+      p2 = fmaf(g, xh[c + e], p2);
+      t[e] = v[c + e] * xh[c + e];
+    }
+    *reinterpret_cast<float4*>(myR + c) = make_float4(t[0], t[1], t[2], t[3]);
+  }
+  red[r * 2 + hsel] = make_float2(p1, p2);
+  compute_sync();
+  const float2 ra = red[r * 2], rb = red[r * 2 + 1];
+  const float m1 = (ra.x + rb.x) * (1.0f / 128.f), m2 = (ra.y + rb.y) * (1.0f / 128.f);
+#pragma unroll
+  for (int c = 0; c < 64; ++c) {
+    const float dzv = v[c];
+    v[c] = rstd * (dzv * gamma[c] - m1 - xh[c] * m2);
+    xh[c] = dzv;                                      // keep dz for the d_beta column sums
+  }
+}
+
+__global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = sm + B_OFF_OP;
+  uint8_t* sA2 = sA + 2 * BLK;
+  uint8_t* sG = sA;
+  uint8_t* sT = sm + B_OFF_ST;
+  uint8_t* sRing = sm + B_OFF_RING;
+  float* sR = reinterpret_cast<float*>(sm + B_OFF_R);
+  float* sPar = reinterpret_cast<float*>(sm + B_OFF_PAR);
+  float2* sRed = reinterpret_cast<float2*>(sm + B_OFF_RED);
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(sm + B_OFF_BAR);
+  uint64_t* w_empty = w_full + RING;
+  uint64_t* a_ready = w_empty + RING;      // [4]: 0 dqkv' bands (+ ds1' pre-load), 1 ds2, 2 du (+ ds2 pre-load), 3 ds1
+  uint64_t* acc_full = a_ready + 4;        // [4]: 0 dz, 1 du_pre, 2 dy, 3 dO
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (a.n + CT - 1) / CT;
+  const bool up = a.mode & 1, chain = (a.mode & 2) != 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&a_ready[i], NCOMP); tc::mbar_init(&acc_full[i], 1); }
+  }
+  if (warp == 9) tc::tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x < NCOMP && chain) sPar[threadIdx.x] = threadIdx.x < 128 ? a.g2[threadIdx.x] : a.g1[threadIdx.x - 128];
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  gm_pdl_wait();
+  gm_pdl_trigger();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      auto push = [&](const uint8_t* img, int nblk) {
+        for (int b = 0; b < nblk; ++b, ++cnt) {
+          const uint32_t slot = cnt % RING, ph = (cnt / RING) & 1;
+          tc::mbar_wait(&w_empty[slot], ph ^ 1);
+          tc::mbar_expect_tx(&w_full[slot], BLK);
+          tc::bulk_g2s(sRing + slot * BLK, img + (size_t)b * BLK, BLK, &w_full[slot]);
+        }
+      };
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (up) push(a.Win_up, 6);
+        if (chain) { push(a.W2, 4); push(a.W1, 4); push(a.Wo, 2); }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, 64, 0, 1);     // A K-major, B MN-major, N = 64
+      uint32_t cnt = 0;
+      // one ring block = W[128 K-rows (out features) x 64 N-cols (in features)]: 8 MMAs of K = 16 against the
+      // K = 128 operand band at `a_addr` (two 64-column blocks)
+      auto mma_block = [&](uint32_t a_addr, uint32_t tcol, bool acc) {
+        const uint32_t slot = cnt % RING, ph = (cnt / RING) & 1;
+        tc::mbar_wait(&w_full[slot], ph);
+        tc::fence_after_sync();
+        const uint32_t b_addr = tc::smem_u32(sRing + slot * BLK);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          tc::mma_bf16(tmem + tcol, tc::make_desc(a_addr + (uint32_t)(j >> 2) * BLK + (j & 3) * 32, 16, tc::ATOM_BYTES),
+                       tc::make_desc(b_addr + (uint32_t)j * 2 * tc::ATOM_BYTES, BLK, tc::ATOM_BYTES), idesc, acc || j > 0);
+        tc::mma_commit(&w_empty[slot]);
+        ++cnt;
+      };
+      const uint32_t A = tc::smem_u32(sA), A2 = tc::smem_u32(sA2), A3 = tc::smem_u32(sT);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        if (up) {
+          tc::mbar_wait(&a_ready[0], par);            // dz acc [0,128) (pre-loaded with ds1') += dqkv' Win'
+          tc::fence_after_sync();
+          for (int b = 0; b < 3; ++b)
+            for (int c = 0; c < 2; ++c) mma_block(b == 0 ? A : (b == 1 ? A2 : A3), c * 64, true);
+          tc::mma_commit(&acc_full[0]);
+        }
+        if (chain) {
+          tc::mbar_wait(&a_ready[1], par);            // du_pre acc [128,384) = ds2 W2
+          tc::fence_after_sync();
+          for (int c = 0; c < 4; ++c) mma_block(A, 128 + c * 64, false);
+          tc::mma_commit(&acc_full[1]);
+          tc::mbar_wait(&a_ready[2], par);            // dy acc [0,128) (pre-loaded with ds2) += du W1
+          tc::fence_after_sync();
+          for (int b = 0; b < 2; ++b)
+            for (int c = 0; c < 2; ++c) mma_block(A + b * 2 * BLK, c * 64, true);
+          tc::mma_commit(&acc_full[2]);
+          tc::mbar_wait(&a_ready[3], par);            // dO acc [384,512) = ds1 Wo
+          tc::fence_after_sync();
+          for (int c = 0; c < 2; ++c) mma_block(A, 384 + c * 64, false);
+          tc::mma_commit(&acc_full[3]);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, hsel = warp >> 2;
+    const int r = q * 32 + lane;
+    const int c0 = hsel * 64;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
+    float* myR = sR + r * R_LD + c0;
+    const int cs_col = threadIdx.x & 127, cs_row0 = (threadIdx.x >> 7) * 64;     // column-sum ownership
+    float acc_dg2 = 0.f, acc_db2 = 0.f, acc_dg1 = 0.f, acc_db1 = 0.f;
+    auto load_rows_f32 = [&](const float* src, int row0, int m) {
+      for (int i = threadIdx.x; i < CT * 32; i += NCOMP) {
+        const int rr = i >> 5, c4 = i & 31;
+        float* dst = sR + rr * R_LD + c4 * 4;
+        if (rr < m) cp_async16(dst, src + (int64_t)(row0 + rr) * 128 + c4 * 4);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    // 128 columns [col0, col0+128) of a bf16 row-major [n, ld] tensor -> swizzled two-block operand tile
+    auto load_band = [&](uint8_t* tile, const __nv_bfloat16* src, int ld, int col0, int row0, int m) {
+      for (int i = threadIdx.x; i < CT * 16; i += NCOMP) {
+        const int rr = i >> 4, c = i & 15;
+        uint8_t* dst = tile + op_off(rr, c);
+        if (rr < m) cp_async16(dst, src + (int64_t)(row0 + rr) * ld + col0 + c * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    auto load_u = [&](int sb, int row0, int m) {       // u columns [64 sb, 64 sb + 64) -> half (sb & 1) of the staging tile
+      uint8_t* half = sT + (sb & 1) * UH_BYTES;
+      for (int i = threadIdx.x; i < CT * 8; i += NCOMP) {
+        const int rr = i >> 3, c = i & 7;
+        uint8_t* dst = half + rr * UH_LD + c * 16;
+        if (rr < m) cp_async16(dst, a.u16 + (int64_t)(row0 + rr) * 256 + sb * 64 + c * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    auto load_o = [&](int row0, int m) {
+      for (int i = threadIdx.x; i < CT * 16; i += NCOMP) {
+        const int rr = i >> 4, c = i & 15;
+        uint8_t* dst = sT + rr * ST_LD + c * 16;
+        if (rr < m) cp_async16(dst, a.attn16 + (int64_t)(row0 + rr) * 128 + c * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    auto prefetch_early = [&](int tile) {              // R and the first two dqkv' bands
+      const int row0 = tile * CT, m = min(CT, a.n - row0);
+      load_rows_f32(up ? a.ds1_up : a.dz_in, row0, m);
+      if (up) {
+        load_band(sA, a.dqkv_up, 384, 0, row0, m);
+        load_band(sA2, a.dqkv_up, 384, 128, row0, m);
+      }
+      cp_commit();
+    };
+    auto prefetch_late = [&](int tile) {               // third band into the staging tile
+      const int row0 = tile * CT, m = min(CT, a.n - row0);
+      if (up) load_band(sT, a.dqkv_up, 384, 256, row0, m);
+      cp_commit();
+    };
+    // column sums over the tile rows of R (fp32) and of the bf16 tile in A2
+    auto column_sums = [&](float& acc_r, float& acc_t) {
+      float s0 = 0.f, s1 = 0.f;
+      const uint32_t coff = (uint32_t)(cs_col & 7) * 2;
+#pragma unroll 8
+      for (int rr = cs_row0; rr < cs_row0 + 64; ++rr) {
+        s0 += sR[rr * R_LD + cs_col];
+        s1 += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sA2 + op_off(rr, cs_col >> 3) + coff));
+      }
+      acc_r += s0;
+      acc_t += s1;
+    };
+    int it = 0;
+    if ((int)blockIdx.x < n_tiles) { prefetch_early(blockIdx.x); prefetch_late(blockIdx.x); }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t par = it & 1;
+      const int row0 = tile * CT, m = min(CT, a.n - row0);
+      const int grow = row0 + r;
+      const int ntile = tile + gridDim.x;
+      float v[64], xh[64];
+      cp_wait<0>();
+      compute_sync();                                  // R = ds1' (or dz), dqkv' bands complete
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(myR + c);
+        v[c] = t4.x; v[c + 1] = t4.y; v[c + 2] = t4.z; v[c + 3] = t4.w;
+      }
+      if (up) {
+        tmem_st32(t_lane + c0, v);                     // accumulator starts at ds1' (fp32 residual-gradient path)
+        tmem_st32(t_lane + c0 + 32, v + 32);
+        tmem_st_wait();
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        mbar_arrive(&a_ready[0]);
+      }
+      compute_sync();                                  // every thread has read its R row
+      if (chain) { load_rows_f32(a.s2, row0, m); cp_commit(); }
+      if (up) {
+        tc::mbar_wait(&acc_full[0], par);
+        tc::fence_after_sync();
+        tc::tmem_ld32(t_lane + c0, v);
+        tc::tmem_ld32(t_lane + c0 + 32, v + 32);
+        tc::tmem_ld_wait();
+      }
+      if (!chain) {
+        // ---------------- input gradient of the stack: dx = dz
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(myR + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        compute_sync();
+        store_rows_f32(sR, a.dx, row0, m);
+        compute_sync();
+        if (ntile < n_tiles) { prefetch_early(ntile); prefetch_late(ntile); }
+        continue;
+      }
+      // ---------------- LayerNorm-2 backward
+      load_u(0, row0, m);
+      cp_commit();
+      float2 st = r < m ? __ldg(reinterpret_cast<const float2*>(a.st2 + 2 * (int64_t)grow)) : make_float2(0.f, 0.f);
+      cp_wait<0>();
+      compute_sync();                                  // s2 in R, u sub-band 0 in the staging tile
+      ln_backward_row(v, xh, myR, sPar + c0, st.x, st.y, sRed, r, hsel);       // v = ds2, xh = dz, R = dz * xhat2
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+        *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
+        *reinterpret_cast<uint4*>(sA2 + op_off(r, (c0 + c) >> 3)) = pack8f(xh + c);
+      }
+      tmem_st32(t_lane + c0, v);                       // dy accumulator starts at ds2
+      tmem_st32(t_lane + c0 + 32, v + 32);
+      tmem_st_wait();
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      mbar_arrive(&a_ready[1]);
+      compute_sync();
+      column_sums(acc_dg2, acc_db2);
+      store_rows_op<2>(sA, a.ds2_16, 128, row0, m);
+      compute_sync();
+      load_rows_f32(a.s1, row0, m);
+      cp_commit();
+      // ---------------- du = (ds2 W2) * gelu'(u): four 64-column sub-bands, 32 columns per thread
+      tc::mbar_wait(&acc_full[1], par);
+      tc::fence_after_sync();
+      // (the dy accumulator pre-load above is ordered before a_ready[2] below)
+#pragma unroll 1
+      for (int sb = 0; sb < 4; ++sb) {
+        if (sb + 1 < 4) { load_u(sb + 1, row0, m); cp_commit(); cp_wait<1>(); }
+        else cp_wait<0>();
+        compute_sync();                                // u sub-band sb visible
+        float w[32];
+        tc::tmem_ld32(t_lane + 128 + sb * 64 + hsel * 32, w);
+        tc::tmem_ld_wait();
+        const uint8_t* urow = sT + (sb & 1) * UH_BYTES + r * UH_LD + hsel * 64;
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          const uint4 u4 = *reinterpret_cast<const uint4*>(urow + c * 2);
+          const __nv_bfloat162* u2 = reinterpret_cast<const __nv_bfloat162*>(&u4);
+          float d8[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 uf = __bfloat1622float2(u2[e]);
+            d8[2 * e] = w[c + 2 * e] * gelu_grad_f(uf.x);
+            d8[2 * e + 1] = w[c + 2 * e + 1] * gelu_grad_f(uf.y);
+          }
+          *reinterpret_cast<uint4*>(sG + (uint32_t)sb * BLK + tc::swz(r, hsel * 4 + (c >> 3))) = pack8f(d8);
+        }
+        if (sb == 3) {
+          tc::fence_async_smem();
+          tc::fence_before_sync();
+          mbar_arrive(&a_ready[2]);
+        }
+        compute_sync();                                // sub-band tile free again, du columns complete
+      }
+      store_rows_op<4>(sG, a.du16, 256, row0, m);
+      load_o(row0, m);
+      cp_commit();
+      // ---------------- LayerNorm-1 backward on dy
+      tc::mbar_wait(&acc_full[2], par);
+      tc::fence_after_sync();
+      tc::tmem_ld32(t_lane + c0, v);
+      tc::tmem_ld32(t_lane + c0 + 32, v + 32);
+      tc::tmem_ld_wait();
+      st = r < m ? __ldg(reinterpret_cast<const float2*>(a.st1 + 2 * (int64_t)grow)) : make_float2(0.f, 0.f);
+      cp_wait<0>();
+      compute_sync();                                  // s1 in R, O rows in the staging tile; du16 copy-out finished
+      ln_backward_row(v, xh, myR, sPar + 128 + c0, st.x, st.y, sRed, r, hsel);  // v = ds1, xh = dy, R = dy * xhat1
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+        *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
+        *reinterpret_cast<uint4*>(sA2 + op_off(r, (c0 + c) >> 3)) = pack8f(xh + c);
+      }
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      mbar_arrive(&a_ready[3]);
+      compute_sync();
+      column_sums(acc_dg1, acc_db1);
+      store_rows_op<2>(sA, a.ds1_16, 128, row0, m);
+      compute_sync();
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(myR + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      compute_sync();
+      store_rows_f32(sR, a.ds1, row0, m);              // fp32 ds1: the residual-gradient term of the layer below
+      compute_sync();
+      // ---------------- dO = ds1 Wo ; D = dO . O per head
+      tc::mbar_wait(&acc_full[3], par);
+      tc::fence_after_sync();
+      if (ntile < n_tiles) prefetch_early(ntile);      // R, A, A2 are free
+      tc::tmem_ld32(t_lane + 384 + c0, v);
+      tc::tmem_ld32(t_lane + 384 + c0 + 32, v + 32);
+      tc::tmem_ld_wait();
+      {
+        uint8_t* orow = sT + r * ST_LD + c0 * 2;
+        float dh[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float d = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; c += 8) {
+            const uint4 o4 = *reinterpret_cast<const uint4*>(orow + (h * 16 + c) * 2);
+            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&o4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 of = __bfloat1622float2(o2[e]);
+              d = fmaf(v[h * 16 + c + 2 * e], of.x, d);
+              d = fmaf(v[h * 16 + c + 2 * e + 1], of.y, d);
+            }
+            *reinterpret_cast<uint4*>(orow + (h * 16 + c) * 2) = pack8f(v + h * 16 + c);      // dO over O, in place
+          }
+          dh[h] = d;
+        }
+        if (r < m) *reinterpret_cast<float4*>(a.dd + (int64_t)grow * 8 + hsel * 4) = make_float4(dh[0], dh[1], dh[2], dh[3]);
+      }
+      compute_sync();
+      store_rows_st(sT, a.dO16, 128, 0, row0, m);
+      compute_sync();
+      if (ntile < n_tiles) prefetch_late(ntile);
+    }
+    if (chain) {
+      atomicAdd(a.d_g2 + cs_col, acc_dg2);
+      atomicAdd(a.d_be2 + cs_col, acc_db2);
+      atomicAdd(a.d_g1 + cs_col, acc_dg1);
+      atomicAdd(a.d_be1 + cs_col, acc_db1);
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc::fence_after_sync();
+    tc::tmem_free(tmem, 512);
+  }
+}
+
 }  // namespace
 
 extern "C" int geomae_sra_chain_fwd(const geomae_chain_fwd_args* p, void* stream) {
@@ -454,5 +878,40 @@ extern "C" int geomae_sra_chain_fwd(const geomae_chain_fwd_args* p, void* stream
   const int n_tiles = gm_div_up(a.n, CT);
   const int grid = n_tiles < GM_NUM_SMS ? n_tiles : GM_NUM_SMS;
   GM_CUDA(gm_launch_pdl(k_sra_chain_fwd, dim3(grid), dim3(NTHR), (size_t)SMEM_BYTES, (cudaStream_t)stream, a));
+  return GEOMAE_OK;
+}
+
+extern "C" int geomae_sra_chain_bwd(const geomae_chain_bwd_args* p, void* stream) {
+  GM_REQUIRE(p, "sra_chain_bwd: null argument");
+  GM_REQUIRE(p->n_tokens >= 0 && p->n_tokens < ((int64_t)1 << 31) - 256, "sra_chain_bwd: bad token count");
+  GM_REQUIRE((p->mode & 3) != 0 && (p->mode & ~3) == 0, "sra_chain_bwd: mode must be 1, 2 or 3");
+  if (p->n_tokens == 0) return GEOMAE_OK;
+  const bool up = p->mode & 1, chain = (p->mode & 2) != 0;
+  if (up) GM_REQUIRE(p->dqkv16_up && p->ds1_up && p->p_in_proj_up, "sra_chain_bwd: the in-projection backward needs dqkv, ds1 and packed weights of the layer above");
+  else GM_REQUIRE(p->dz_in, "sra_chain_bwd: dz_in is null");
+  if (chain)
+    GM_REQUIRE(p->s2 && p->st2 && p->s1 && p->st1 && p->u16 && p->attn16 && p->p_lin2 && p->p_lin1 && p->p_out_proj &&
+                   p->norm2_w && p->norm1_w && p->ds2_16 && p->du16 && p->ds1_16 && p->dattn16 && p->ds1 && p->dd &&
+                   p->g_norm2_w && p->g_norm2_b && p->g_norm1_w && p->g_norm1_b,
+               "sra_chain_bwd: the layer chain needs every saved tensor, packed weight, output and gradient buffer");
+  else GM_REQUIRE(p->dx, "sra_chain_bwd: dx is null");
+  BwdArgs a;
+  a.n = (int)p->n_tokens; a.mode = p->mode;
+  a.dqkv_up = (const __nv_bfloat16*)p->dqkv16_up; a.ds1_up = p->ds1_up; a.Win_up = (const uint8_t*)p->p_in_proj_up; a.dz_in = p->dz_in;
+  a.s2 = p->s2; a.st2 = p->st2; a.s1 = p->s1; a.st1 = p->st1;
+  a.u16 = (const __nv_bfloat16*)p->u16; a.attn16 = (const __nv_bfloat16*)p->attn16;
+  a.W2 = (const uint8_t*)p->p_lin2; a.W1 = (const uint8_t*)p->p_lin1; a.Wo = (const uint8_t*)p->p_out_proj;
+  a.g2 = p->norm2_w; a.g1 = p->norm1_w;
+  a.ds2_16 = (__nv_bfloat16*)p->ds2_16; a.du16 = (__nv_bfloat16*)p->du16; a.ds1_16 = (__nv_bfloat16*)p->ds1_16;
+  a.dO16 = (__nv_bfloat16*)p->dattn16; a.ds1 = p->ds1; a.dd = p->dd; a.dx = p->dx;
+  a.d_g2 = p->g_norm2_w; a.d_be2 = p->g_norm2_b; a.d_g1 = p->g_norm1_w; a.d_be1 = p->g_norm1_b;
+  static bool configured = false;
+  if (!configured) {
+    GM_CUDA(cudaFuncSetAttribute(k_sra_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_BYTES));
+    configured = true;
+  }
+  const int n_tiles = gm_div_up(a.n, CT);
+  const int grid = n_tiles < GM_NUM_SMS ? n_tiles : GM_NUM_SMS;
+  GM_CUDA(gm_launch_pdl(k_sra_chain_bwd, dim3(grid), dim3(NTHR), (size_t)B_SMEM_BYTES, (cudaStream_t)stream, a));
   return GEOMAE_OK;
 }

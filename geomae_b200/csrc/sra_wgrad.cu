@@ -204,11 +204,11 @@ extern "C" int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* p, void* st
   a.tiles_per_cta = gm_div_up(a.n_tiles, splits);
   splits = gm_div_up(a.n_tiles, a.tiles_per_cta);
   // slab = [128 dY columns] x [128 X columns]:            dY map, col, X map, col, dW,                 ld, db
-  a.slab[0] = Slab{0, 0, 1, 0, p->g_lin2_w, 256, nullptr};                        // dW2[:, 0:128]   = ds2^T g[:, 0:128]
+  a.slab[0] = Slab{0, 0, 1, 0, p->g_lin2_w, 256, p->g_lin2_b};                        // dW2[:, 0:128]   = ds2^T g[:, 0:128]
   a.slab[1] = Slab{0, 0, 1, 128, p->g_lin2_w + 128, 256, nullptr};                // dW2[:, 128:256]
   a.slab[2] = Slab{2, 0, 3, 0, p->g_lin1_w, 128, p->g_lin1_b};                    // dW1[0:128]      = du[:, 0:128]^T y
   a.slab[3] = Slab{2, 128, 3, 0, p->g_lin1_w + 128 * 128, 128, p->g_lin1_b ? p->g_lin1_b + 128 : nullptr};
-  a.slab[4] = Slab{4, 0, 5, 0, p->g_out_proj_w, 128, nullptr};                    // dWo             = ds1^T O
+  a.slab[4] = Slab{4, 0, 5, 0, p->g_out_proj_w, 128, p->g_out_proj_b};                    // dWo             = ds1^T O
   a.slab[5] = Slab{6, 0, 7, 0, p->g_in_proj_w, 128, p->g_in_proj_b};              // dWin[q rows]    = dq^T (x + pos)
   a.slab[6] = Slab{6, 128, 7, 0, p->g_in_proj_w + 128 * 128, 128, p->g_in_proj_b ? p->g_in_proj_b + 128 : nullptr};
   a.slab[7] = Slab{6, 256, 8, 0, p->g_in_proj_w + 256 * 128, 128, p->g_in_proj_b ? p->g_in_proj_b + 256 : nullptr};

@@ -105,7 +105,15 @@ class ChainFwdArgs(C.Structure):
 class WgradLayerArgs(C.Structure):
     _fields_ = [("n_tokens", C.c_int64)] + [(k, C.c_void_p) for k in (
         "ds2_16", "g16", "du16", "y16", "ds1_16", "attn16", "dqkv16", "xp16", "xb16", "g_lin2_w", "g_lin1_w", "g_lin1_b",
-        "g_out_proj_w", "g_in_proj_w", "g_in_proj_b")]
+        "g_out_proj_w", "g_in_proj_w", "g_in_proj_b", "g_lin2_b", "g_out_proj_b")]
+
+
+class ChainBwdArgs(C.Structure):
+    _fields_ = ([("n_tokens", C.c_int64), ("mode", C.c_int32)] +
+                [(k, C.c_void_p) for k in (
+                    "dqkv16_up", "ds1_up", "p_in_proj_up", "dz_in", "s2", "st2", "s1", "st1", "u16", "attn16", "p_lin2",
+                    "p_lin1", "p_out_proj", "norm2_w", "norm1_w", "ds2_16", "du16", "ds1_16", "dattn16", "ds1", "dd", "dx",
+                    "g_norm2_w", "g_norm2_b", "g_norm1_w", "g_norm1_b")])
 
 
 class LossArgs(C.Structure):
@@ -173,6 +181,7 @@ class _Sigs:
     geomae_sra_stack2_backward = [C.POINTER(SRACtx), _i32, C.POINTER(SRALayer), C.POINTER(SRASaved),
                                   C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p, _p, _p]
     geomae_sra_chain_fwd = [C.POINTER(ChainFwdArgs), _p]
+    geomae_sra_chain_bwd = [C.POINTER(ChainBwdArgs), _p]
     geomae_sra_wgrad_layer = [C.POINTER(WgradLayerArgs), _p]
     geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]
     geomae_geom_loss_fwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p]

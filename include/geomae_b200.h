@@ -447,9 +447,31 @@ typedef struct geomae_chain_fwd_args {
 
 int geomae_sra_chain_fwd(const geomae_chain_fwd_args* args, void* stream);
 
+/* Backward of the same chain (k_sra_chain_bwd), gradients flowing DOWN through one EncoderLayer per 128-token tile:
+ *   mode bit 0: dz = dqkv16_up Win_up + ds1_up  (in-projection backward of the layer ABOVE; else dz = dz_in, fp32)
+ *   mode bit 1: ds2 = LN2-bwd(dz) ; du = (ds2 W2) gelu'(u) ; dy = du W1 + ds2 ; ds1 = LN1-bwd(dy) ; dattn = ds1 Wo ;
+ *               dd[n,8] = per-head dot(dattn, attn)  (the attention backward's row term D)
+ *   mode 1 alone writes dx = dz (the input gradient of the stack's first layer).
+ * Outputs: ds2_16, ds1_16, dattn16 [n,128], du16 [n,256] bf16 (operands of geomae_sra_wgrad_layer and of the attention
+ * backward), ds1 [n,128] fp32 (residual-gradient term of the layer below); g_norm* accumulate (+=).  The bias
+ * gradients of linear2 / out_proj are column sums of ds2 / ds1 and are produced by geomae_sra_wgrad_layer.
+ * replaces: autograd of EncoderLayer.forward + the MultiheadAttention projections
+ *           (models/sst/sst_basic_block.py:55,85-102): 5 dX GEMMs, 2 LayerNorm backwards, GELU backward. */
+typedef struct geomae_chain_bwd_args {
+  int64_t n_tokens; int32_t mode;
+  const void* dqkv16_up; const float* ds1_up; const void* p_in_proj_up; const float* dz_in;
+  const float *s2, *st2, *s1, *st1; const void *u16, *attn16;
+  const void *p_lin2, *p_lin1, *p_out_proj; const float *norm2_w, *norm1_w;
+  void *ds2_16, *du16, *ds1_16, *dattn16; float *ds1, *dd, *dx;
+  float *g_norm2_w, *g_norm2_b, *g_norm1_w, *g_norm1_b;
+} geomae_chain_bwd_args;
+
+int geomae_sra_chain_bwd(const geomae_chain_bwd_args* args, void* stream);
+
 /* Weight / bias gradients of one EncoderLayer in ONE TMA-fed tcgen05 launch (csrc/sra_wgrad.cu), accumulated (+=)
  * with vector reductions:  g_lin2_w [128,256] += ds2^T g ; g_lin1_w [256,128] += du^T y, g_lin1_b += colsum du ;
- * g_out_proj_w [128,128] += ds1^T attn ; g_in_proj_w [384,128] += dq|dk ^T xp, dv^T xb ; g_in_proj_b += colsum dqkv.
+ * g_out_proj_w [128,128] += ds1^T attn ; g_in_proj_w [384,128] += dq|dk ^T xp, dv^T xb ; g_in_proj_b += colsum dqkv ;
+ * g_lin2_b += colsum ds2 ; g_out_proj_b += colsum ds1.
  * Operands are bf16 row-major: ds2_16, y16, ds1_16, attn16, xp16, xb16 [n,128]; g16, du16 [n,256]; dqkv16 [n,384]
  * (16-byte aligned).  Bias buffers may be NULL.
  * replaces: the weight-gradient GEMMs + bias column sums autograd runs for linear1 / linear2 / out_proj / in_proj
@@ -457,7 +479,7 @@ int geomae_sra_chain_fwd(const geomae_chain_fwd_args* args, void* stream);
 typedef struct geomae_wgrad_layer_args {
   int64_t n_tokens;
   const void *ds2_16, *g16, *du16, *y16, *ds1_16, *attn16, *dqkv16, *xp16, *xb16;
-  float *g_lin2_w, *g_lin1_w, *g_lin1_b, *g_out_proj_w, *g_in_proj_w, *g_in_proj_b;
+  float *g_lin2_w, *g_lin1_w, *g_lin1_b, *g_out_proj_w, *g_in_proj_w, *g_in_proj_b, *g_lin2_b, *g_out_proj_b;
 } geomae_wgrad_layer_args;
 
 int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* args, void* stream);

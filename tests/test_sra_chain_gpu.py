@@ -45,10 +45,12 @@ def reference(x, attn, lay, nxt, table, cell):
 
 
 def close(got, ref, what, atol, mean_tol):
+    """max error within atol + 2 bf16 ulps of the value, mean error within mean_tol + half a bf16 ulp of the mean magnitude."""
     d = (got.float() - ref).abs()
     assert torch.isfinite(got.float()).all(), what
-    assert d.max().item() <= atol, (what, "max", d.max().item())
-    assert d.mean().item() <= mean_tol, (what, "mean", d.mean().item())
+    excess = (d - 2.0 ** -7 * ref.abs()).max().item()
+    assert excess <= atol, (what, "max", excess, d.max().item())
+    assert d.mean().item() <= mean_tol + 2.0 ** -9 * ref.abs().mean().item(), (what, "mean", d.mean().item())
 
 
 # 100: one partial tile; 1000: several tiles; 148*128+37: more tiles than CTAs (persistent loop, phase flips)
@@ -108,3 +110,86 @@ def test_wgrad_layer_tma(n):
     for k in g:
         d = (g[k].double() - init - ref[k]).abs().max().item()
         assert d <= 2e-5 * scale + 1e-4, (k, d)
+
+
+def ln_bwd_ref(dz, s, gamma, eps):
+    mean = s.mean(1, keepdim=True)
+    rstd = torch.rsqrt(s.var(1, unbiased=False, keepdim=True) + eps)
+    xh = (s - mean) * rstd
+    g = dz * gamma
+    ds = rstd * (g - g.mean(1, keepdim=True) - xh * (g * xh).mean(1, keepdim=True))
+    return ds, xh, torch.cat([mean, rstd], 1)
+
+
+@pytest.mark.parametrize("n", [100, 1000, 148 * 128 * 2 + 37])
+@pytest.mark.parametrize("mode", [3, 2, 1])
+def test_chain_backward(n, mode):
+    import ctypes as C
+    from geomae_b200 import lib as L
+    from geomae_b200.dense import pack_weight
+    up, chain = bool(mode & 1), bool(mode & 2)
+    lay = make_layer(10)
+    Win = rnd(384, 128, scale=0.1, seed=30)
+    dqkv = rnd(n, 384, seed=40).to(torch.bfloat16)
+    ds1_up, dz_in = rnd(n, 128, seed=41), rnd(n, 128, seed=42)
+    s2, s1 = rnd(n, 128, seed=43) + 0.3, rnd(n, 128, seed=44) - 0.2
+    u16 = rnd(n, 256, seed=45).to(torch.bfloat16)
+    attn16 = rnd(n, 128, seed=46).to(torch.bfloat16)
+    dev = torch.device("cuda")
+    f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)     # noqa: E731
+    b16 = lambda *s: torch.zeros(s, dtype=torch.bfloat16, device=dev)    # noqa: E731
+    # ---- reference
+    dz = dqkv.float() @ bf(Win) + ds1_up if up else dz_in
+    if chain:
+        ds2, xh2, st2 = ln_bwd_ref(dz, s2, lay["g2"], lay["eps"])
+        uu = u16.float().double()
+        gelu_grad = (0.5 * (1 + torch.erf(uu / 2 ** 0.5)) + uu * torch.exp(-uu * uu / 2) / (2 * torch.pi) ** 0.5).float()
+        du = (bf(ds2) @ bf(lay["W2"])) * gelu_grad
+        dy = bf(du) @ bf(lay["W1"]) + ds2
+        ds1, xh1, st1 = ln_bwd_ref(dy, s1, lay["g1"], lay["eps"])
+        dO = bf(ds1) @ bf(lay["Wo"])
+        dd = (dO * attn16.float()).view(n, 8, 16).sum(-1)
+    # ---- kernel
+    a = L.ChainBwdArgs()
+    a.n_tokens, a.mode = n, mode
+    keep = []
+    if up:
+        img = pack_weight(Win, want_lo=False)[0]
+        keep.append(img)
+        a.dqkv16_up, a.ds1_up, a.p_in_proj_up = dqkv.data_ptr(), ds1_up.data_ptr(), img.data_ptr()
+    else:
+        a.dz_in = dz_in.data_ptr()
+    out = {}
+    if chain:
+        for key, field in (("W2", "p_lin2"), ("W1", "p_lin1"), ("Wo", "p_out_proj")):
+            img = pack_weight(lay[key], want_lo=False)[0]
+            keep.append(img)
+            setattr(a, field, img.data_ptr())
+        a.s2, a.st2, a.s1, a.st1 = s2.data_ptr(), st2.contiguous().data_ptr(), s1.data_ptr(), st1.contiguous().data_ptr()
+        keep += [st2, st1]
+        st2c, st1c = st2.contiguous(), st1.contiguous()
+        a.st2, a.st1 = st2c.data_ptr(), st1c.data_ptr()
+        a.u16, a.attn16, a.norm2_w, a.norm1_w = u16.data_ptr(), attn16.data_ptr(), lay["g2"].data_ptr(), lay["g1"].data_ptr()
+        out = dict(ds2_16=b16(n, 128), du16=b16(n, 256), ds1_16=b16(n, 128), dattn16=b16(n, 128), ds1=f32(n, 128),
+                   dd=f32(n, 8), g_norm2_w=f32(128), g_norm2_b=f32(128), g_norm1_w=f32(128), g_norm1_b=f32(128))
+        for k, v in out.items():
+            setattr(a, k, v.data_ptr())
+    else:
+        out = dict(dx=f32(n, 128))
+        a.dx = out["dx"].data_ptr()
+    L.run("sra_chain_bwd", C.byref(a), L.stream_ptr(dev))
+    torch.cuda.synchronize()
+    if not chain:
+        close(out["dx"], dz, "dx", 2e-3, 2e-5)
+        return
+    close(out["ds2_16"], ds2, "ds2_16", 6e-2, 3e-3)
+    close(out["du16"], du, "du16", 6e-2, 3e-3)
+    close(out["ds1"], ds1, "ds1", 3e-2, 4e-4)
+    close(out["ds1_16"], ds1, "ds1_16", 8e-2, 4e-3)
+    close(out["dattn16"], dO, "dattn16", 6e-2, 3e-3)
+    close(out["dd"], dd, "dd", 0.3, 3e-3)          # 16-term dots of O(5) gradients: rare operand-rounding flips upstream
+    s = n ** 0.5
+    for key, ref in (("g_norm2_w", (dz * xh2).sum(0)), ("g_norm2_b", dz.sum(0)), ("g_norm1_w", (dy * xh1).sum(0)),
+                     ("g_norm1_b", dy.sum(0))):
+        d = (out[key] - ref).abs().max().item()
+        assert d <= 2e-2 * s + 1e-3, (key, d)
