@@ -30,7 +30,6 @@ sys.path.insert(0, ROOT)
 
 OWN_CFG = os.path.join(ROOT, "configs/mae_sst/geomae_nus_pretrain.py")
 METRIC = "pretrain frames/sec on nuScenes-shaped synthetic sweeps"
-WORKLOAD = "mae_sst nuScenes config, synthetic 30k-pt sweeps, 1xB200 (BASELINE.json configs[1])"
 
 
 def parse():
@@ -39,8 +38,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--samples-per-gpu", type=int, default=4)     # data.samples_per_gpu of the config
-    ap.add_argument("--sweeps", type=int, default=1)
+    ap.add_argument("--workload", default="nus", choices=["nus", "nus10sweep", "waymo", "dense"],
+                    help="nus = BASELINE.json configs[1] (the metric's configuration); the others are configs[3]/[4] and the "
+                         "10-sweep nuScenes input (geomae_b200/workloads.py)")
+    ap.add_argument("--samples-per-gpu", type=int, default=0)     # 0: the workload's default (4 = data.samples_per_gpu)
+    ap.add_argument("--sweeps", type=int, default=0)              # 0: the workload's default
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--list-only", action="store_true",
                     help="profiler runs: W warm-up + K resident steps, then exit without the e2e / roofline / CPU legs")
@@ -50,9 +52,20 @@ def parse():
     return ap.parse_args()
 
 
-def make_batches(rank, n_batches, samples, sweeps):
+def workload_of(args):
+    from geomae_b200.workloads import WORKLOADS
+    w = dict(WORKLOADS[args.workload])
+    w["frame"] = dict(w["frame"])
+    if args.sweeps:
+        w["frame"]["sweeps"] = args.sweeps
+    if args.samples_per_gpu:
+        w["samples_per_gpu"] = args.samples_per_gpu
+    return w
+
+
+def make_batches(rank, n_batches, samples, frame_kw):
     from geomae_b200.synthetic import make_frame
-    return [[make_frame(1000 * rank + it * 16 + s + 1, sweeps=sweeps) for s in range(samples)] for it in range(n_batches)]
+    return [[make_frame(1000 * rank + it * 16 + s + 1, **frame_kw) for s in range(samples)] for it in range(n_batches)]
 
 
 class ClockSampler:
@@ -101,10 +114,12 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm))
 
 
-def hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src, n_frames=256):
-    """HBM-bound stages on a batch large enough to leave L2 (256 frames ~ 7 M points, 140 MB of records):
+def hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src, n_frames=None):
+    """HBM-bound stages on a batch large enough to leave L2 (~7 M points, 140 MB of records: 256 one-sweep frames):
     achieved = algorithmic bytes (SURVEY.md §8d formulas, counted from the device-side totals) / CUDA-event time."""
     from geomae_b200.voxel import scatter_frames
+    if n_frames is None:
+        n_frames = max(8, min(256, int(round(7.0e6 / max(1, pool[0][0].shape[0])))))
     frames = [torch.from_numpy(pool[i % len(pool)][i % len(pool[0])]).to(dev) for i in range(n_frames)]
     pb = scatter_frames(model.geom, frames)
     v, vm, vl = pb.sizes()
@@ -144,13 +159,63 @@ def hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src, n_frames=256):
     return out
 
 
-def cpu_reference_step(samples, sweeps, threads, seed=1):
-    """One forward+backward of the oracle port on the host cores; returns (seconds, frames)."""
+def sra_length_bin_sweep(dev, tens_peak, tokens=196608):
+    """BASELINE.json configs[4] "SRA length-bin sweep": the window-attention kernels on synthetic CSR layouts whose
+    windows ALL have length L (the reference's bucket sizes), ~200 k tokens each; flops = 64 / 160 per (query, key, head)."""
+    from geomae_b200 import lib as L
+    out = []
+    for Lw in (16, 32, 64, 144):
+        nw = tokens // Lw
+        n = nw * Lw
+        win_ptr = torch.arange(0, n + 1, Lw, dtype=torch.int32, device=dev)
+        g = torch.Generator(device="cpu").manual_seed(Lw)
+        perm = torch.randperm(n, generator=g).to(dev)
+        win_tok = perm.int()                                   # window w holds tokens perm[w*L : (w+1)*L]
+        tok_win = torch.empty(n, dtype=torch.int32, device=dev)
+        tok_win[perm] = (torch.arange(n, device=dev) // Lw).int()
+        qkv = (torch.randn(n, 384, device=dev) * 0.5).to(torch.bfloat16)
+        attn = torch.empty(n, 128, dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(n, 8, dtype=torch.float32, device=dev)
+        d_out = (torch.randn(n, 128, device=dev) * 0.5).to(torch.bfloat16)
+        dd = torch.randn(n, 8, device=dev)
+        dqkv = torch.empty_like(qkv)
+        st = L.stream_ptr(dev)
+
+        def fwd():
+            L.run("sra_attention_tc_fwd", L.ptr(qkv), n, 8, L.ptr(win_ptr), L.ptr(win_tok), L.ptr(tok_win), L.ptr(attn),
+                  L.ptr(lse), 1 | 8, st)
+
+        def bwd():
+            L.run("sra_attention_tc_bwd", L.ptr(qkv), L.ptr(attn), L.ptr(lse), L.ptr(d_out), n, 8, L.ptr(win_ptr),
+                  L.ptr(win_tok), L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4, st)
+        res = dict(window_length=Lw, windows=nw, tokens=n)
+        for name, fn, fl in (("fwd", fwd, 64.0), ("bwd", bwd, 160.0)):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_ = e0.elapsed_time(e1) / 5
+            tf = fl * 8 * nw * Lw * Lw / (ms_ * 1e-3) / 1e12
+            res[name] = dict(ms=ms_, tflops=tf, tensor_frac=tf / tens_peak, tokens_per_us=n / (ms_ * 1e3))
+        out.append(res)
+    return out
+
+
+def cpu_reference_step(samples, frame_kw, threads, seed=1, geometry=None, blocks=None):
+    """One forward+backward of the oracle port on the host cores; returns (seconds, frames).  blocks=(enc, dec)
+    shrinks the model (BASELINE.json configs[0]: "1 SST block")."""
     from geomae_b200.synthetic import make_frame
     from oracle import geomae_oracle as O
     torch.set_num_threads(threads)
-    cfg = O.PathConfig()
-    frames = [make_frame(seed + s, sweeps=sweeps) for s in range(samples)]
+    kw = dict(geometry or {})
+    if blocks:
+        kw.update(enc_blocks=blocks[0], dec_blocks=blocks[1])
+    cfg = O.PathConfig(**kw)
+    frames = [make_frame(seed + s, **frame_kw) for s in range(samples)]
     params = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, 0).items()}
     rows, _, _ = O.unique_rows(O.batch_voxelize(frames, cfg.voxel_size, cfg.pc_range))
     keep, mask = O.vanilla_mask_ids(rows, len(frames), cfg.mask_ratio, seed)
@@ -168,11 +233,13 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     samples = 1                      # bounded sample: one frame per step keeps K+W steps within minutes
+    wl = workload_of(args)
+    WORKLOAD = wl["label"]
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(samples, args.sweeps, threads)
+        cpu_reference_step(samples, wl["frame"], threads, geometry=wl["geometry"])
     times, t0 = [], time.perf_counter()
     for i in range(max(1, args.steps)):
-        t, n = cpu_reference_step(samples, args.sweeps, threads, seed=10 + i)
+        t, n = cpu_reference_step(samples, wl["frame"], threads, seed=10 + i, geometry=wl["geometry"])
         times.append(t / n)
         if time.perf_counter() - t0 > 150.0:        # keep the whole arm within a few minutes
             break
@@ -183,7 +250,7 @@ def run_reference(args):
         metric=METRIC, value=v, unit="frames/s", n_gpus=args.gpus, steps=len(times), warmup=min(args.warmup, 1),
         ms_per_step=1e3 * sec_per_frame * samples, higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype="f32", data="synthetic", impl="reference",
-        config=dict(workload=WORKLOAD, samples_per_step=samples, sweeps=args.sweeps),
+        config=dict(workload=WORKLOAD, samples_per_step=samples, sweeps=wl["frame"].get("sweeps", 1)),
         cpu_baseline=dict(value=v, unit="frames/s", cores=threads, kind="port", sample=sample),
         e2e=dict(value=v, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
@@ -208,15 +275,18 @@ def main():
     from geomae_b200.registry import Config, build_model
     from geomae_b200.train import FlatTrainer
 
+    from geomae_b200.workloads import with_geometry
+    wl = workload_of(args)
+    WORKLOAD = wl["label"]
     cfg = Config.fromfile(OWN_CFG)
     torch.manual_seed(0)
-    model = build_model(cfg.model).to(dev).train()
+    model = build_model(with_geometry(cfg.model, wl["geometry"])).to(dev).train()
     model.set_impl(args.sra_impl)
     opt = cfg.optimizer
     trainer = FlatTrainer(model, lr=opt["lr"], betas=opt["betas"], weight_decay=opt["weight_decay"],
                           max_grad_norm=cfg.optimizer_config["grad_clip"]["max_norm"])
-    K, W, S = args.steps, args.warmup, args.samples_per_gpu
-    pool = make_batches(rank, min(K + W, 8), S, args.sweeps)
+    K, W, S = args.steps, args.warmup, wl["samples_per_gpu"]
+    pool = make_batches(rank, min(K + W, 8), S, wl["frame"])
     host = [[torch.from_numpy(f).pin_memory() for f in b] for b in pool]
     resident = [[f.to(dev) for f in b] for b in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -322,9 +392,20 @@ def main():
     tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured" if peaks else "fallback"
-    attn = ("k_sra_tc_fwd", "k_sra_tc_bwd") if args.sra_impl == "tc1" else ("k_sra_fwd", "k_sra_bwd_q+k_sra_bwd_kv")
-    fam_names = ["k_tc_linear", "k_tc_wgrad", attn[0], attn[1], "k_ln_bwd"]
+    fused = args.sra_impl == "tc1"
+    attn = ("k_sra_tc_fwd", "k_sra_tc_bwd") if fused else ("k_sra_fwd", "k_sra_bwd_q+k_sra_bwd_kv")
+    fam_names = ["k_sra_chain_fwd+k_sra_chain_bwd" if fused else "k_tc_linear", "k_wgrad_tma" if fused else "k_tc_wgrad",
+                 attn[0], attn[1], "k_ln_bwd"]
     roof, fam_table = None, {}
+    # DRAM traffic per launch of the SRA kernels from the committed ncu --set full capture of this command
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == args.workload and tj.get("sra_impl") == args.sra_impl:
+            traffic = tj.get("kernels", {})
+    except (OSError, ValueError):
+        pass
     if prof_ms is not None and sum(prof_ms) > 0:
         sq = attention_pair_counts()
         bb = model.backbone
@@ -337,37 +418,56 @@ def main():
                 sec = prof_ms[f] * 1e-3
                 fam_table[nm] = dict(ms_per_step=prof_ms[f] / K, launches_per_step=prof_n[f] / K,
                                      avg_launch_us=1e3 * prof_ms[f] / prof_n[f],
-                                     algorithmic_gb_per_step=prof_by[f] / K / 1e9, gbs=prof_by[f] / sec / 1e9,
-                                     hbm_frac=prof_by[f] / sec / 1e9 / hbm_peak,
+                                     algorithmic_gflop_per_step=prof_fl[f] / K / 1e9,
                                      tflops=prof_fl[f] / sec / 1e12 if prof_fl[f] else None,
-                                     tensor_frac=prof_fl[f] / sec / 1e12 / tens_peak if prof_fl[f] else None)
-        # The dominant kernel family by device time.  Every SRA kernel is HBM-bound by arithmetic intensity: the dense
-        # layers do 2*K*N flop per token against 4*(K+N) B (K, N <= 384: 24-77 flop/B, ridge = peak flops / peak B/s
-        # ~ 210 flop/B), attention with head_dim 16 even less.  So the roofline is bytes: achieved = algorithmic bytes
-        # of the family's launches (counted per launch in csrc/sra_stack.cu) / their CUDA-event time.
-        top = max(range(5), key=lambda f: prof_ms[f])
-        ach = prof_by[top] / (prof_ms[top] * 1e-3) / 1e9
-        roof = dict(kernel=fam_names[top], bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
-                    traffic=None,
-                    traffic_note="no single per-launch figure: the family mixes 7.3 k-token (encoder) and 24.5 k-token "
-                                 "(decoder) launches; ncu --set full of the decoder launches "
-                                 "(profiles/r01_launches_v3_bf16_operands.md) shows 25-44 MB read per launch, equal to "
-                                 "their algorithmic input bytes, and outputs that stay in the 126 MB L2",
-                    peak_source=peak_src, avg_launch_ms=prof_ms[top] / prof_n[top], launches=int(prof_n[top]),
-                    algorithmic_bytes_per_launch=prof_by[top] / prof_n[top],
-                    tensor_tflops=prof_fl[top] / (prof_ms[top] * 1e-3) / 1e12 if prof_fl[top] else None,
-                    tensor_peak_tflops=tens_peak,
+                                     tensor_frac=prof_fl[f] / sec / 1e12 / tens_peak if prof_fl[f] else None,
+                                     algorithmic_gb_per_step=prof_by[f] / K / 1e9, gbs=prof_by[f] / sec / 1e9,
+                                     hbm_frac=prof_by[f] / sec / 1e9 / hbm_peak)
+        # the SRA layer (projections + attention + FFN) is bounded by the TENSOR pipe:
+        # achieved = algorithmic flops of the family's launches / their CUDA-event time, peak = the measured sustained
+        # bf16 cuBLAS rate.  The byte view of the same launches is kept as a secondary key (hbm_view).
+        top = max(range(4), key=lambda f: prof_ms[f])
+        ach = prof_fl[top] / (prof_ms[top] * 1e-3) / 1e12
+        tr = traffic.get(fam_names[top], {})
+        roof = dict(kernel=fam_names[top], bound="tensor", achieved=ach, peak=tens_peak, unit="TFLOP/s", frac=ach / tens_peak,
+                    traffic=tr.get("dram_bytes_per_launch"), traffic_source=tr.get("source"),
+                    peak_source=peak_src + " (bf16_tflops_sustained: the kernel is timed inside a long step)",
+                    avg_launch_ms=prof_ms[top] / prof_n[top], launches=int(prof_n[top]),
+                    algorithmic_flops_per_launch=prof_fl[top] / prof_n[top],
+                    hbm_view=dict(algorithmic_bytes_per_launch=prof_by[top] / prof_n[top],
+                                  achieved_gbs=prof_by[top] / (prof_ms[top] * 1e-3) / 1e9, peak_gbs=hbm_peak,
+                                  frac=prof_by[top] / (prof_ms[top] * 1e-3) / 1e9 / hbm_peak),
+                    whole_step=dict(algorithmic_gflop=sum(prof_fl[:4]) / K / 1e9,
+                                    tflops=sum(prof_fl[:4]) / K / (ms / K * 1e-3) / 1e12,
+                                    tensor_frac=sum(prof_fl[:4]) / K / (ms / K * 1e-3) / 1e12 / tens_peak),
                     note="timed with CUDA events on the launching stream around every launch of the family in a separate "
                          "instrumented pass over the same K steps; launches of concurrent streams overlap, so family "
                          "shares can add up to more than 1; the ncu launch list of the same command is under profiles/",
                     share_of_step=prof_ms[top] / ms_prof, instrumented_ms_per_step=ms_prof / K)
+    # bf16-mode vs parity-mode (bf16x3 + fp32 attention) loss on one identical batch, same weights, same mask split
+    loss_delta = None
+    if args.sra_impl != "tc3":
+        with torch.no_grad():
+            tg = model.last_targets
+            ids = (tg["ids_keep"], tg["ids_mask"])
+            batch = resident[(K - 1) % len(resident)]
+            out = {}
+            for impl in (args.sra_impl, "tc3"):
+                model.set_impl(impl)
+                model.forward_train(points=batch, img_metas=None, ids=ids)
+                out[impl] = model.last_loss_vector.double().sum().item() if getattr(model, "last_loss_vector", None) is not None else None
+            model.set_impl(args.sra_impl)
+        if out[args.sra_impl] is not None and out["tc3"]:
+            loss_delta = dict(loss=out[args.sra_impl], loss_tc3=out["tc3"],
+                              rel=abs(out[args.sra_impl] - out["tc3"]) / abs(out["tc3"]))
     aux = hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src)
     line = dict(
         metric=METRIC, value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=K, warmup=W,
         ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype={"tc1": "bf16", "tc3": "bf16x3 (fp32-equivalent)", "glue": "f32"}[args.sra_impl],
         data="synthetic",
-        config=dict(workload=WORKLOAD, samples_per_gpu=S, sweeps=args.sweeps, points_per_frame=int(pool[0][0].shape[0]),
+        config=dict(workload=WORKLOAD, workload_key=args.workload, samples_per_gpu=S, sweeps=wl["frame"].get("sweeps", 1),
+                    points_per_frame=int(pool[0][0].shape[0]),
                     parallelism=f"dp{world}", l2="flushed between steps (256 MiB write, outside the timed events)",
                     sra_impl=args.sra_impl,
                     precision={"tc1": "SRA GEMMs bf16 operands / fp32 TMEM accumulate; activations, LayerNorm, softmax, VFE, targets, losses fp32",
@@ -377,18 +477,29 @@ def main():
                  ms_per_step=ms_e2e / K),
         gpu_launches=launches, clocks=clocks, roofline=roof, kernel_families=fam_table, hbm_kernels=aux,
         kernel_ms_per_step={k: round(v[0] / K, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
-        loss=last.get("loss_host"))
+        loss=last.get("loss_host"), loss_delta_vs_tc3=loss_delta)
+    if args.workload == "dense" and world == 1:
+        line["sra_length_bins"] = sra_length_bin_sweep(dev, tens_peak)
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cpu_reference_step(1, args.sweeps, threads)                       # warm-up (thread pools, allocator)
-        t_cpu, n_cpu, t0 = 0.0, 0, time.perf_counter()
-        while time.perf_counter() - t0 < 12.0 and n_cpu < 64:             # bounded sample: ~12 s of host work
-            sec, n = cpu_reference_step(1, args.sweeps, threads, seed=2 + n_cpu)
-            t_cpu += sec
-            n_cpu += n
+
+        def sample_cpu(budget, **kw):
+            cpu_reference_step(1, wl["frame"], threads, geometry=wl["geometry"], **kw)      # warm-up (thread pools, allocator)
+            t_cpu, n_cpu, t0 = 0.0, 0, time.perf_counter()
+            while time.perf_counter() - t0 < budget and n_cpu < 64:       # bounded sample of host work
+                sec, n = cpu_reference_step(1, wl["frame"], threads, seed=2 + n_cpu, geometry=wl["geometry"], **kw)
+                t_cpu += sec
+                n_cpu += n
+            return n_cpu, t_cpu
+        n_cpu, t_cpu = sample_cpu(12.0)
         line["cpu_baseline"] = dict(value=n_cpu / t_cpu, unit="frames/s", cores=threads, kind="port",
                                     sample=f"{n_cpu} single-frame steps (fwd+bwd of the full 6+2+2-block model, no optimiser) "
                                            f"of the oracle port in {t_cpu:.1f} s, torch CPU fp32 on {threads} threads")
+        if args.workload == "nus":      # BASELINE.json configs[0]: single frame, 1 SST block, CPU reference path
+            n0, t0_ = sample_cpu(6.0, blocks=(1, 1))
+            line["cpu_baseline"]["config0"] = dict(value=n0 / t0_, unit="frames/s", cores=threads, kind="port",
+                                                   sample=f"{n0} single-frame steps of the 1-encoder-block / 1-decoder-block "
+                                                          f"model (BASELINE.json configs[0]) in {t0_:.1f} s")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -13,7 +13,7 @@ void gm_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* geomae_last_error(void) { return g_err; }
-extern "C" int geomae_abi_version(void) { return 1; }
+extern "C" int geomae_abi_version(void) { return 2; }
 
 static thread_local bool g_weights_stable = false;
 void gm_set_weights_stable(bool stable) { g_weights_stable = stable; }

@@ -177,6 +177,11 @@ extern "C" int geomae_geom_loss_fwd(const geomae_voxel_cfg* cfg, const geomae_sc
   VoxGeom g;
   int rc = gm_make_geom(cfg, sc->n_frames, &g);
   if (rc) return rc;
+  // k_loss rebuilds every sub-voxel coordinate from its parent pillar (cz = slot / (ry rx): one z cell per pillar) and
+  // relies on every sub-voxel's parent cell being the point's own pillar (nested power-of-two scales); geometries
+  // outside that (several pillar cells in z, non-nested ratios) would silently normalise against the wrong origin.
+  GM_REQUIRE(g.parent_is_top && g.grid[0][2] == 1,
+             "geom_loss: needs nested sub-voxel scales and a single pillar cell in z (got grid z = %d)", g.grid[0][2]);
   LossIO io;
   rc = fill(&io, a, cfg);
   if (rc) return rc;
@@ -205,6 +210,11 @@ extern "C" int geomae_geom_loss_bwd(const geomae_voxel_cfg* cfg, const geomae_sc
   VoxGeom g;
   int rc = gm_make_geom(cfg, sc->n_frames, &g);
   if (rc) return rc;
+  // k_loss rebuilds every sub-voxel coordinate from its parent pillar (cz = slot / (ry rx): one z cell per pillar) and
+  // relies on every sub-voxel's parent cell being the point's own pillar (nested power-of-two scales); geometries
+  // outside that (several pillar cells in z, non-nested ratios) would silently normalise against the wrong origin.
+  GM_REQUIRE(g.parent_is_top && g.grid[0][2] == 1,
+             "geom_loss: needs nested sub-voxel scales and a single pillar cell in z (got grid z = %d)", g.grid[0][2]);
   LossIO io;
   rc = fill(&io, a, cfg);
   if (rc) return rc;

@@ -2,6 +2,8 @@
 // (mmcv OptimizerHook grad_clip max_norm, torch clip_grad_norm_ semantics) + AdamW, with the
 // 1/world_size gradient averaging folded in.  No host synchronisation: the clip coefficient is
 // derived on the device from the partial sums.  HBM-bound elementwise work.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace {
@@ -79,8 +81,9 @@ extern "C" int geomae_adamw_step(float* params, const float* grads, float* exp_a
   int nblk = gm_div_up(n, (int64_t)TPB * 16);
   if (nblk > MAX_PARTIALS) nblk = MAX_PARTIALS;
   k_sumsq<<<nblk, TPB, 0, stream>>>(grads, n, partials);
-  const float bias1 = 1.0f - powf(beta1, (float)step);
-  const float bias2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  // bias corrections in double like torch.optim.AdamW (Python floats): fp32 powf is off by 5e-5 relative at step 1
+  const float bias1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bias2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   int ublk = gm_div_up(n, (int64_t)TPB * 4);
   if (ublk > GM_NUM_SMS * 8) ublk = GM_NUM_SMS * 8;
   k_adamw<<<ublk, TPB, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, n_decay, partials, nblk, grad_scale,

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__
     }
   }
   __syncthreads();
-  flush_tile(sO, meta, nq, out, DM, 0);
+  flush_tile(sO, meta, nq, out, DM, 0, (io_flags & 8) != 0);
   for (int idx = threadIdx.x; idx < nq * NH; idx += 256) lse[(int64_t)meta.tok[idx >> 3] * NH + (idx & 7)] = s_lse[idx];
 }
 

@@ -57,6 +57,13 @@ struct FwdArgs {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
+// operand tile / TMEM pre-load of this warp complete: one arrival per warp (the barriers expect NCOMP / 32 arrivals)
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(tc::smem_u32(dst)), "l"(src) : "memory");
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const FwdArgs a) {
   const bool chain = a.mode & 1, next = (a.mode & 2) != 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { tc::mbar_init(&a_ready[i], NCOMP); tc::mbar_init(&acc_full[i], 1); }
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&a_ready[i], NCOMP / 32); tc::mbar_init(&acc_full[i], 1); }
   }
   if (warp == 9) tc::tmem_alloc(tmem_slot, 512);
   if (threadIdx.x < NCOMP) {                       // parameters are never written by a kernel of this stream's chain
@@ -260,9 +267,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const FwdArgs a) {
       float v[64];
       cp_async_wait_all();
       if (chain) {
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        mbar_arrive(&a_ready[0]);
+        warp_arrive(&a_ready[0]);
       }
       compute_sync();                                // R (and A) complete for every thread
       if (chain) {
@@ -287,9 +292,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const FwdArgs a) {
         for (int c = 0; c < 64; ++c) v[c] = fmaf((v[c] - mean) * rstd, p_g1[c0 + c], p_be1[c0 + c]);     // y
 #pragma unroll
         for (int c = 0; c < 64; c += 8) *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        mbar_arrive(&a_ready[1]);
+        warp_arrive(&a_ready[1]);
         compute_sync();
         store_rows_f32(sR, a.s1, row0, m);           // saved pre-LN1 rows
         store_rows_op<2>(sA, a.y16, 128, row0, m);   // bf16 y: operand of the lin1 weight gradient
@@ -317,9 +320,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const FwdArgs a) {
             *reinterpret_cast<uint4*>(sG + (uint32_t)(col >> 6) * BLK + tc::swz(r, (col & 63) >> 3)) = pack8f(g8);
           }
           if (band == 1) {
-            tc::fence_async_smem();
-            tc::fence_before_sync();
-            mbar_arrive(&a_ready[2]);
+            warp_arrive(&a_ready[2]);
           }
           compute_sync();
           store_rows_st(sT, a.u16, 256, band * 128, row0, m);    // saved pre-GELU rows (bf16)
@@ -378,9 +379,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const FwdArgs a) {
         }
       }
       if (next) {
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        mbar_arrive(&a_ready[3]);
+        warp_arrive(&a_ready[3]);
       }
       compute_sync();                                // R is free
       const int ntile = tile + gridDim.x;
@@ -471,7 +470,7 @@ template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // LayerNorm backward of one row half held in v (= dz), xhat recomputed from the saved pre-LN row in R (overwritten in
-// place with dz * xhat for the d_gamma column sums).  On return v holds d(pre-LN row), dzc the untouched dz.
+// place with dz * xhat for the d_gamma column sums).  On return v holds d(pre-LN row), xh the untouched dz.
 __device__ __forceinline__ void ln_backward_row(float* v, float* xh, float* myR, const float* gamma, float mean, float rstd,
                                                 float2* red, int r, int hsel) {
   float p1 = 0.f, p2 = 0.f;
@@ -523,7 +522,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const BwdArgs a) {
   const bool up = a.mode & 1, chain = (a.mode & 2) != 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { tc::mbar_init(&a_ready[i], NCOMP); tc::mbar_init(&acc_full[i], 1); }
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&a_ready[i], NCOMP / 32); tc::mbar_init(&acc_full[i], 1); }
   }
   if (warp == 9) tc::tmem_alloc(tmem_slot, 512);
   if (threadIdx.x < NCOMP && chain) sPar[threadIdx.x] = threadIdx.x < 128 ? a.g2[threadIdx.x] : a.g1[threadIdx.x - 128];
@@ -652,17 +651,20 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const BwdArgs a) {
       if (up) load_band(sT, a.dqkv_up, 384, 256, row0, m);
       cp_commit();
     };
-    // column sums over the tile rows of R (fp32) and of the bf16 tile in A2
-    auto column_sums = [&](float& acc_r, float& acc_t) {
+    // column sums of R over this thread's 64 tile rows (two threads per column)
+    auto column_sum = [&](float& acc) {
       float s0 = 0.f, s1 = 0.f;
-      const uint32_t coff = (uint32_t)(cs_col & 7) * 2;
 #pragma unroll 8
-      for (int rr = cs_row0; rr < cs_row0 + 64; ++rr) {
+      for (int rr = cs_row0; rr < cs_row0 + 64; rr += 2) {
         s0 += sR[rr * R_LD + cs_col];
-        s1 += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sA2 + op_off(rr, cs_col >> 3) + coff));
+        s1 += sR[(rr + 1) * R_LD + cs_col];
       }
-      acc_r += s0;
-      acc_t += s1;
+      acc += s0 + s1;
+    };
+    // R <- v (this thread's half row)
+    auto put_row = [&](const float* v) {
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(myR + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
     };
     int it = 0;
     if ((int)blockIdx.x < n_tiles) { prefetch_early(blockIdx.x); prefetch_late(blockIdx.x); }
@@ -683,9 +685,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const BwdArgs a) {
         tmem_st32(t_lane + c0, v);                     // accumulator starts at ds1' (fp32 residual-gradient path)
         tmem_st32(t_lane + c0 + 32, v + 32);
         tmem_st_wait();
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        mbar_arrive(&a_ready[0]);
+        warp_arrive(&a_ready[0]);
       }
       compute_sync();                                  // every thread has read its R row
       if (chain) { load_rows_f32(a.s2, row0, m); cp_commit(); }
@@ -714,19 +714,18 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const BwdArgs a) {
       compute_sync();                                  // s2 in R, u sub-band 0 in the staging tile
       ln_backward_row(v, xh, myR, sPar + c0, st.x, st.y, sRed, r, hsel);       // v = ds2, xh = dz, R = dz * xhat2
 #pragma unroll
-      for (int c = 0; c < 64; c += 8) {
-        *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
-        *reinterpret_cast<uint4*>(sA2 + op_off(r, (c0 + c) >> 3)) = pack8f(xh + c);
-      }
+      for (int c = 0; c < 64; c += 8) *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
       tmem_st32(t_lane + c0, v);                       // dy accumulator starts at ds2
       tmem_st32(t_lane + c0 + 32, v + 32);
       tmem_st_wait();
-      tc::fence_async_smem();
-      tc::fence_before_sync();
-      mbar_arrive(&a_ready[1]);
+      warp_arrive(&a_ready[1]);
       compute_sync();
-      column_sums(acc_dg2, acc_db2);
+      column_sum(acc_dg2);                             // d_gamma2 += sum dz * xhat2
       store_rows_op<2>(sA, a.ds2_16, 128, row0, m);
+      compute_sync();
+      put_row(xh);
+      compute_sync();
+      column_sum(acc_db2);                             // d_beta2 += sum dz
       compute_sync();
       load_rows_f32(a.s1, row0, m);
       cp_commit();
@@ -757,9 +756,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const BwdArgs a) {
           *reinterpret_cast<uint4*>(sG + (uint32_t)sb * BLK + tc::swz(r, hsel * 4 + (c >> 3))) = pack8f(d8);
         }
         if (sb == 3) {
-          tc::fence_async_smem();
-          tc::fence_before_sync();
-          mbar_arrive(&a_ready[2]);
+          warp_arrive(&a_ready[2]);
         }
         compute_sync();                                // sub-band tile free again, du columns complete
       }
@@ -777,19 +774,17 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const BwdArgs a) {
       compute_sync();                                  // s1 in R, O rows in the staging tile; du16 copy-out finished
       ln_backward_row(v, xh, myR, sPar + 128 + c0, st.x, st.y, sRed, r, hsel);  // v = ds1, xh = dy, R = dy * xhat1
 #pragma unroll
-      for (int c = 0; c < 64; c += 8) {
-        *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
-        *reinterpret_cast<uint4*>(sA2 + op_off(r, (c0 + c) >> 3)) = pack8f(xh + c);
-      }
-      tc::fence_async_smem();
-      tc::fence_before_sync();
-      mbar_arrive(&a_ready[3]);
+      for (int c = 0; c < 64; c += 8) *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
+      warp_arrive(&a_ready[3]);
       compute_sync();
-      column_sums(acc_dg1, acc_db1);
+      column_sum(acc_dg1);                             // d_gamma1 += sum dy * xhat1
       store_rows_op<2>(sA, a.ds1_16, 128, row0, m);
       compute_sync();
-#pragma unroll
-      for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(myR + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      put_row(xh);
+      compute_sync();
+      column_sum(acc_db1);                             // d_beta1 += sum dy
+      compute_sync();
+      put_row(v);
       compute_sync();
       store_rows_f32(sR, a.ds1, row0, m);              // fp32 ds1: the residual-gradient term of the layer below
       compute_sync();

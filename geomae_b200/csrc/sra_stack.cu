@@ -79,6 +79,56 @@ int wgrad(const float* dY, int ldy, const float* X, int ldx, int n, float* dW, i
 
 }  // namespace
 
+// ---- bf16 mode: two launches per layer.  The stack prologue projects x_in into layer 0's q|k|v; then per layer the
+// window attention (sra_attention_tc.cu, bf16 in / bf16 out) and ONE chain kernel (sra_chain.cu) that runs out-proj + LN1
+// -> FFN -> LN2 and already the in-projection of the next layer.
+static int fused_forward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers, const geomae_sra_saved* saved,
+                  const float* x_in, void* stream) {
+  const int64_t n = c->n_tokens;
+  const double d = c->d_model, f = c->ffn;
+  for (int l = 0; l < n_layers; ++l)
+    GM_REQUIRE(saved[l].g && saved[l].xp && saved[l].xb, "sra_stack_forward: the bf16 path needs the g / xp / xb buffers of layer %d", l);
+  auto next_of = [&](geomae_chain_fwd_args& a, int l) {     // in-projection of layer l appended to the kernel
+    const geomae_sra_layer& N = layers[l];
+    a.p_in_proj_next = N.p_in_proj[0]; a.in_proj_b_next = N.in_proj_b;
+    a.pos_table = c->pos_table; a.tok_cell_next = c->shift[N.shift].tok_cell;
+    a.xp16_next = saved[l].xp; a.xb16_next = saved[l].xb; a.qkv16_next = saved[l].qkv;
+  };
+  const double in_flops = 2.0 * n * d * 3.0 * d, in_bytes = n * (2.0 * 2.0 * d + 2.0 * 3.0 * d) + 2.0 * 3.0 * d * d;
+  {
+    geomae_chain_fwd_args a{};
+    a.n_tokens = n; a.mode = 2; a.x = x_in;
+    next_of(a, 0);
+    Span span(0, in_flops, stream, 4.0 * n * d + in_bytes);
+    GM_TRY(geomae_sra_chain_fwd(&a, stream));
+  }
+  const float* x = x_in;
+  for (int l = 0; l < n_layers; ++l) {
+    const geomae_sra_layer& L = layers[l];
+    const geomae_sra_saved& S = saved[l];
+    const geomae_sra_windows& w = c->shift[L.shift];
+    {
+      Span span(2, 0.0, stream, n * (2.0 * 3.0 * d + 2.0 * d + 4.0 * c->n_heads));
+      GM_TRY(geomae_sra_attention_tc_fwd(S.qkv, n, c->n_heads, w.win_ptr, w.win_tok, w.tok_win, S.attn, S.lse, 1 | 8, stream));
+    }
+    geomae_chain_fwd_args a{};
+    const bool has_next = l + 1 < n_layers;
+    a.n_tokens = n; a.mode = has_next ? 3 : 1; a.x = x; a.attn = S.attn;
+    a.p_out_proj = L.p_out_proj[0]; a.p_lin1 = L.p_lin1[0]; a.p_lin2 = L.p_lin2[0];
+    a.out_proj_b = L.out_proj_b; a.lin1_b = L.lin1_b; a.lin2_b = L.lin2_b;
+    a.norm1_w = L.norm1_w; a.norm1_b = L.norm1_b; a.norm2_w = L.norm2_w; a.norm2_b = L.norm2_b; a.ln_eps = L.ln_eps;
+    a.s1 = S.s1; a.st1 = S.st1; a.s2 = S.s2; a.st2 = S.st2; a.z = S.z; a.y16 = S.y; a.u16 = S.u; a.g16 = S.g;
+    if (has_next) next_of(a, l + 1);
+    // algorithmic bytes: x + attn in; s1, s2, z (+ statistics), bf16 y, u, g out; bf16 weight images
+    const double bytes = n * (4.0 * d + 2.0 * d + 3.0 * 4.0 * d + 16.0 + 2.0 * d + 2.0 * 2.0 * f) + 2.0 * (d * d + 2.0 * d * f) +
+                         (has_next ? in_bytes : 0.0);
+    Span span(0, 2.0 * n * (d * d + 2.0 * d * f) + (has_next ? in_flops : 0.0), stream, bytes);
+    GM_TRY(geomae_sra_chain_fwd(&a, stream));
+    x = S.z;
+  }
+  return GEOMAE_OK;
+}
+
 extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers,
                                         const geomae_sra_saved* saved, const float* x_in, void* stream) {
   GM_REQUIRE(c && layers && saved && (x_in || c->n_tokens == 0), "sra_stack_forward: null argument");
@@ -100,11 +150,12 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
       for (int i = 0; i < 4; ++i) {
         GM_REQUIRE(ps[i][0] && ps[i][1], "sra_stack_forward: layer %d has no packed-weight scratch", l);
         W[k] = ws[i]; rows[k] = r[i]; cols[k] = cc[i]; hi[k] = ps[i][0]; lo[k] = ps[i][1];
-        if (++k == 64) { GM_TRY(geomae_pack_weights(k, W, rows, cols, hi, lo, stream)); k = 0; }
+        if (++k == 64) { GM_TRY(geomae_pack_weights(k, W, rows, cols, hi, p == 1 ? nullptr : lo, stream)); k = 0; }
       }
     }
-    if (k) GM_TRY(geomae_pack_weights(k, W, rows, cols, hi, lo, stream));
+    if (k) GM_TRY(geomae_pack_weights(k, W, rows, cols, hi, p == 1 ? nullptr : lo, stream));
   }
+  if (p == 1) return fused_forward(c, n_layers, layers, saved, x_in, stream);
   struct StableGuard { ~StableGuard() { gm_set_weights_stable(false); } } guard;
   gm_set_weights_stable(false);     // the first dense kernel directly follows the packing launch: no early weight fetch
   for (int l = 0; l < n_layers; ++l) {
@@ -176,6 +227,82 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
   const int b16 = p == 1 ? 1 : 0;     // see geomae_sra_stack_forward
   const int64_t set = scratch_floats(c);
   cudaEvent_t side_done[2] = {nullptr, nullptr};
+  if (p == 1) {
+    // ---- bf16 mode: per layer ONE chain kernel (in-proj backward of the layer above .. out-proj backward, sra_chain.cu),
+    // the attention backward, and ONE TMA-fed weight-gradient kernel (sra_wgrad.cu) on the side stream; a last chain
+    // launch turns layer 0's dqkv into the input gradient.  Scratch set (per layer parity), in floats per token:
+    // ds1 128 | dd 8 | ds2_16 64 | du16 128 | ds1_16 64 | dattn16 64 | dqkv16 192
+    struct Set { float *ds1, *dd; void *ds2_16, *du16, *ds1_16, *dattn16, *dqkv16; };
+    auto carve = [&](int parity) {
+      float* b = scratch + (int64_t)parity * set;
+      Set s;
+      s.ds1 = b; b += (int64_t)n * 128;
+      s.dd = b; b += (int64_t)n * 8;
+      s.ds2_16 = b; b += (int64_t)n * 64;
+      s.du16 = b; b += (int64_t)n * 128;
+      s.ds1_16 = b; b += (int64_t)n * 64;
+      s.dattn16 = b; b += (int64_t)n * 64;
+      s.dqkv16 = b;
+      return s;
+    };
+    const double dd_ = d, ff = f;
+    const double up_flops = 2.0 * n * 3.0 * dd_ * dd_, up_bytes = n * (2.0 * 3.0 * dd_ + 4.0 * dd_) + 2.0 * 3.0 * dd_ * dd_;
+    for (int l = n_layers - 1; l >= 0; --l) {
+      const geomae_sra_layer& L = layers[l];
+      const geomae_sra_saved& S = saved[l];
+      const geomae_sra_windows& w = c->shift[L.shift];
+      const Set cur = carve(l & 1);
+      const bool top = l == n_layers - 1;
+      if (side_done[l & 1]) GM_CUDA(cudaStreamWaitEvent(main, side_done[l & 1], 0));     // this set's last readers are done
+      geomae_chain_bwd_args a{};
+      a.n_tokens = n; a.mode = top ? 2 : 3;
+      if (top) a.dz_in = d_out;
+      else {
+        const Set above = carve((l + 1) & 1);
+        a.dqkv16_up = above.dqkv16; a.ds1_up = above.ds1; a.p_in_proj_up = layers[l + 1].p_in_proj[0];
+      }
+      a.s2 = S.s2; a.st2 = S.st2; a.s1 = S.s1; a.st1 = S.st1; a.u16 = S.u; a.attn16 = S.attn;
+      a.p_lin2 = L.p_lin2[0]; a.p_lin1 = L.p_lin1[0]; a.p_out_proj = L.p_out_proj[0];
+      a.norm2_w = L.norm2_w; a.norm1_w = L.norm1_w;
+      a.ds2_16 = cur.ds2_16; a.du16 = cur.du16; a.ds1_16 = cur.ds1_16; a.dattn16 = cur.dattn16; a.ds1 = cur.ds1; a.dd = cur.dd;
+      a.g_norm2_w = L.g_norm2_w; a.g_norm2_b = L.g_norm2_b; a.g_norm1_w = L.g_norm1_w; a.g_norm1_b = L.g_norm1_b;
+      {
+        // algorithmic bytes: dz (or dqkv' + ds1'), s2, s1, u, attn in; bf16 ds2, du, ds1, dattn + fp32 ds1 + D out; weights
+        const double bytes = (top ? 4.0 * n * dd_ : up_bytes) + n * (2.0 * 4.0 * dd_ + 16.0 + 2.0 * ff + 2.0 * dd_) +
+                             n * (3.0 * 2.0 * dd_ + 2.0 * ff + 4.0 * dd_ + 4.0 * c->n_heads) + 2.0 * (dd_ * dd_ + 2.0 * dd_ * ff);
+        Span span(0, 2.0 * n * (dd_ * dd_ + 2.0 * dd_ * ff) + (top ? 0.0 : up_flops), main, bytes);
+        GM_TRY(geomae_sra_chain_bwd(&a, main));
+      }
+      {
+        Span span(3, 0.0, main, n * (2.0 * 3.0 * dd_ + 2.0 * dd_ + 8.0 * c->n_heads + 2.0 * 3.0 * dd_));
+        GM_TRY(geomae_sra_attention_tc_bwd(S.qkv, S.attn, S.lse, (const float*)cur.dattn16, n, c->n_heads, w.win_ptr, w.win_tok,
+                                           w.tok_win, (float*)cur.dqkv16, cur.dd, 1 | 2 | 4, main));
+      }
+      GM_TRY(hand_off(main, side));
+      geomae_wgrad_layer_args g{};
+      g.n_tokens = n;
+      g.ds2_16 = cur.ds2_16; g.g16 = S.g; g.du16 = cur.du16; g.y16 = S.y; g.ds1_16 = cur.ds1_16; g.attn16 = S.attn;
+      g.dqkv16 = cur.dqkv16; g.xp16 = S.xp; g.xb16 = S.xb;
+      g.g_lin2_w = L.g_lin2_w; g.g_lin1_w = L.g_lin1_w; g.g_lin1_b = L.g_lin1_b; g.g_out_proj_w = L.g_out_proj_w;
+      g.g_in_proj_w = L.g_in_proj_w; g.g_in_proj_b = L.g_in_proj_b; g.g_lin2_b = L.g_lin2_b; g.g_out_proj_b = L.g_out_proj_b;
+      {
+        Span span(1, 2.0 * n * (3.0 * dd_ * dd_ + dd_ * dd_ + 2.0 * dd_ * ff), side, n * 2.0 * (6.0 * dd_ + 2.0 * ff + 3.0 * dd_) + 4.0 * (4.0 * dd_ * dd_ + 2.0 * dd_ * ff));
+        GM_TRY(geomae_sra_wgrad_layer(&g, side));
+      }
+      side_done[l & 1] = g_lanes.event();
+      GM_CUDA(cudaEventRecord(side_done[l & 1], side));
+    }
+    {
+      const Set s0 = carve(0);
+      geomae_chain_bwd_args a{};
+      a.n_tokens = n; a.mode = 1;
+      a.dqkv16_up = s0.dqkv16; a.ds1_up = s0.ds1; a.p_in_proj_up = layers[0].p_in_proj[0]; a.dx = d_in;
+      Span span(0, up_flops, main, up_bytes + 4.0 * n * dd_);
+      GM_TRY(geomae_sra_chain_bwd(&a, main));
+    }
+    GM_TRY(hand_off(side, main));   // join
+    return GEOMAE_OK;
+  }
   struct StableGuard { ~StableGuard() { gm_set_weights_stable(false); } } guard;
   gm_set_weights_stable(true);      // backward re-uses the images packed by the forward pass of this step
   for (int l = n_layers - 1; l >= 0; --l) {

@@ -28,11 +28,14 @@ class Augmentation:
 def draw_augmentation(rng: np.random.RandomState, rot_range=(-0.3925, 0.3925), scale_ratio_range=(0.95, 1.05),
                       flip_ratio_bev_horizontal=0.5, flip_ratio_bev_vertical=0.5) -> Augmentation:
     """The reference's draws in the reference's order: rotation (transforms_3d.py:679-680), scale (:728-730),
-    translation noise (:660, std 0 in the GeoMAE configs: drawn and discarded), then the two flip decisions
-    (RandomFlip3D.__call__, :143-152)."""
+    translation noise (:660, std 0 in the GeoMAE configs: drawn and discarded), then RandomFlip3D.__call__: first the
+    2-D flip draw of its mmdet base class (:138 -> mmdet 2.20 RandomFlip.__call__: one
+    ``np.random.choice(['horizontal', None], p=[r, 1 - r])``, drawn and discarded — there are no images on this path),
+    then the two BEV flip decisions (:143-152)."""
     rot = rng.uniform(rot_range[0], rot_range[1])
     scale = rng.uniform(scale_ratio_range[0], scale_ratio_range[1])
     rng.normal(scale=0.0, size=3)
+    rng.choice(2, p=[flip_ratio_bev_horizontal, 1.0 - flip_ratio_bev_horizontal])
     flip_h = bool(rng.rand() < flip_ratio_bev_horizontal)
     flip_v = bool(rng.rand() < flip_ratio_bev_vertical)
     return Augmentation(float(rot), float(scale), flip_h, flip_v)

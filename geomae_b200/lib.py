@@ -90,7 +90,7 @@ class SRALayer(C.Structure):
 
 
 class SRASaved(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("qkv", "attn", "lse", "s1", "st1", "y", "u", "s2", "st2", "z")]
+    _fields_ = [(k, C.c_void_p) for k in ("qkv", "attn", "lse", "s1", "st1", "y", "u", "s2", "st2", "z", "g", "xp", "xb")]
 
 
 class ChainFwdArgs(C.Structure):

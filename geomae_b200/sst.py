@@ -252,7 +252,7 @@ class SRAStack:
 def _carve(n, d, f, heads, n_layers, device):
     """One arena for everything a stack saves for backward; returns (arena, SRASaved array, last z view)."""
     sizes = [("qkv", 3 * d), ("attn", d), ("lse", heads), ("s1", d), ("st1", 2), ("y", d), ("u", f), ("s2", d),
-             ("st2", 2), ("z", d)]
+             ("st2", 2), ("z", d), ("g", f // 2), ("xp", d // 2), ("xb", d // 2)]     # last three: bf16 rows (bf16 mode)
     pad = lambda k: (k + 63) // 64 * 64  # noqa: E731
     per_layer = sum(pad(n * w) for _, w in sizes)
     arena = torch.empty(max(per_layer * n_layers, 1), dtype=torch.float32, device=device)
@@ -281,7 +281,7 @@ class _SRAStackFn(torch.autograd.Function):
         layers = stack._structs()
         c = stack.ctx(layout, table, n, precision)
         L.run("sra_stack_forward", C.byref(c), len(stack.layers), layers, saved, L.ptr(x), L.stream_ptr(x.device))
-        L.add_launches(5 * len(stack.layers) - 1)
+        L.add_launches((2 * len(stack.layers) + 1 if precision == 1 else 5 * len(stack.layers)) - 1 + 1)   # + weight packing
         ctx.save_for_backward(x, arena)
         ctx.stack, ctx.saved, ctx.layers, ctx.c, ctx.layout = stack, saved, layers, c, layout
         return z
@@ -298,7 +298,8 @@ class _SRAStackFn(torch.autograd.Function):
                               device=x.device)
         L.run("sra_stack_backward", C.byref(ctx.c), len(ctx.stack.layers), ctx.layers, ctx.saved, L.ptr(x), L.ptr(dz),
               L.ptr(dx), L.ptr(scratch), L.stream_ptr(x.device))
-        L.add_launches((9 if ctx.c.precision == 1 else 10) * len(ctx.stack.layers))    # + the top LayerNorm backward
+        nl = len(ctx.stack.layers)
+        L.add_launches(3 * nl if ctx.c.precision == 1 else 10 * nl)    # chain + attention + wgrad (+ final dx: the call itself)
         return dx, None, None, None, None
 
 
@@ -319,7 +320,7 @@ class _SRADualStackFn(torch.autograd.Function):
         la, lb = stack_a._structs(), stack_b._structs()
         c = stack_a.ctx(layout, table, n, precision)
         L.run("sra_stack2_forward", C.byref(c), nl, la, saved_a, lb, saved_b, L.ptr(x), L.stream_ptr(x.device))
-        L.add_launches(10 * nl - 1)
+        L.add_launches((2 * (2 * nl + 2) if precision == 1 else 2 * (5 * nl + 1)) - 1)
         ctx.save_for_backward(x, arena_a, arena_b)
         ctx.keep = (saved_a, saved_b, la, lb, c, layout, nl)
         return za, zb
@@ -335,7 +336,7 @@ class _SRADualStackFn(torch.autograd.Function):
                               device=x.device)
         L.run("sra_stack2_backward", C.byref(c), nl, la, saved_a, lb, saved_b, L.ptr(x), L.ptr(dza), L.ptr(dzb), L.ptr(dxa),
               L.ptr(dxb), L.ptr(scratch), L.stream_ptr(x.device))
-        L.add_launches((18 if c.precision == 1 else 20) * nl + 1)
+        L.add_launches((2 * (3 * nl + 1) if c.precision == 1 else 20 * nl + 2) - 1)
         return dxa + dxb, None, None, None, None, None
 
 

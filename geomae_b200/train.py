@@ -15,7 +15,7 @@ class FlatTrainer:
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, max_grad_norm=10.0,
                  no_decay_keys=("norm",)):
         self.model = model
-        named = list(model.named_parameters())
+        named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]     # frozen parameters stay outside
         decay = [(k, p) for k, p in named if not any(s in k for s in no_decay_keys)]
         no_decay = [(k, p) for k, p in named if any(s in k for s in no_decay_keys)]
         self.order = decay + no_decay
@@ -47,6 +47,33 @@ class FlatTrainer:
     def zero_grad(self):
         self.flat_grad.zero_()
 
+    def check_bindings(self):
+        """The fused backward passes accumulate into the flat gradient buffer through captured pointers: a
+        ``model.to()`` / ``.float()`` / ``zero_grad(set_to_none=True)`` after construction would silently detach them."""
+        off, align = 0, 64
+        base_p, base_g = self.flat_param.data_ptr(), self.flat_grad.data_ptr()
+        for k, p in self.order:
+            if p.data_ptr() != base_p + 4 * off or p.grad is None or p.grad.data_ptr() != base_g + 4 * off:
+                raise RuntimeError(f"FlatTrainer: parameter {k} no longer lives in the flat buffers (re-create the trainer "
+                                   "after moving / casting the model; never set .grad to None)")
+            off += (p.numel() + align - 1) // align * align
+
+    # ---- checkpoint / resume (mmcv CheckpointHook saves the optimizer every epoch, default_runtime.py:1,16-17)
+    def state_dict(self):
+        return dict(step_count=self.step_count, order=[k for k, _ in self.order], n=self.n, n_decay=self.n_decay,
+                    exp_avg=self.exp_avg.detach().cpu().clone(), exp_avg_sq=self.exp_avg_sq.detach().cpu().clone(),
+                    lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay,
+                    max_grad_norm=self.max_grad_norm)
+
+    def load_state_dict(self, sd):
+        if sd["order"] != [k for k, _ in self.order] or sd["n"] != self.n:
+            raise RuntimeError("FlatTrainer.load_state_dict: parameter order / sizes differ from the checkpoint")
+        self.step_count = int(sd["step_count"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr, self.betas, self.eps = sd["lr"], tuple(sd["betas"]), sd["eps"]
+        self.weight_decay, self.max_grad_norm = sd["weight_decay"], sd["max_grad_norm"]
+
     def optimizer_step(self, lr=None):
         self.step_count += 1
         L.run("adamw_step", 
@@ -57,6 +84,8 @@ class FlatTrainer:
 
     def train_step(self, points, ids=None, lr=None):
         """points: list of [N_i, C] CUDA tensors (one rank's samples).  Returns (total loss, loss dict)."""
+        if self.step_count == 0:
+            self.check_bindings()
         self.zero_grad()
         self.model.last_loss_vector = None
         losses = self.model.forward_train(points=points, img_metas=None, ids=ids)
@@ -73,3 +102,19 @@ class FlatTrainer:
         dev = self.flat_param.device
         pts = [p.to(dev, non_blocking=True) for p in host_points]
         return self.train_step(pts, ids=ids, lr=lr)
+
+
+def cyclic_lr(base_lr, it, max_iters, target_ratio=(100, 1e-3), cyclic_times=1, step_ratio_up=0.1):
+    """mmcv CyclicLrUpdaterHook as configured by configs/_base_/schedules/cosine_2x.py:10-15 (by_epoch=False, cosine
+    annealing): lr rises from base_lr to base_lr*target_ratio[0] over the first step_ratio_up of a cycle, then falls to
+    base_lr*target_ratio[1]; ``it`` counts iterations from 0."""
+    import math
+    period = max_iters // cyclic_times
+    up = int(step_ratio_up * period)
+    cur = it % period
+    if cur < up:
+        start, end, frac = 1.0, target_ratio[0], cur / up
+    else:
+        start, end, frac = target_ratio[0], target_ratio[1], (cur - up) / (period - up)
+    cos_out = math.cos(math.pi * frac) + 1.0
+    return base_lr * (end + 0.5 * (start - end) * cos_out)

@@ -282,7 +282,8 @@ int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* ls
  * replaces: nn.MultiheadAttention core inside WindowAttention.forward
  *           (models/sst/sst_basic_block.py:26-61) and its autograd backward. */
 /* io_flags: bit 0: qkv rows are bf16 [n, 3*d_model]; bit 1: d_out rows are bf16 (needs dd); bit 2: d_qkv is written
- * as bf16.  bf16 rows are moved with 16-byte cp.async copies (no registers, no conversion). */
+ * as bf16; bit 3 (forward): out is written as bf16 [n, d_model].  bf16 rows are moved with 16-byte cp.async copies
+ * (no registers, no conversion). */
 int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
                                 const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse, int32_t io_flags,
                                 void* stream);
@@ -396,6 +397,9 @@ typedef struct geomae_sra_saved {
   float* qkv;  /* [n,3d] */ float* attn; /* [n,d] */ float* lse; /* [n,heads] */
   float* s1;   /* [n,d] pre-LN1 */ float* st1; /* [n,2] */ float* y; /* [n,d] */
   float* u;    /* [n,f] pre-GELU */ float* s2; /* [n,d] pre-LN2 */ float* st2; /* [n,2] */ float* z; /* [n,d] output */
+  /* precision 1 (bf16 mode) stores qkv, attn, y, u as bf16 rows in the same buffers and additionally keeps the bf16
+   * operands of the weight-gradient kernel: g = gelu(u) [n,f], xp = x + pos, xb = x [n,d] (x = the layer's input). */
+  void* g; void* xp; void* xb;
 } geomae_sra_saved;
 
 /* Forward of n_layers EncoderLayers: layer l reads layer l-1's z (layer 0 reads x_in); 5 kernels per layer.

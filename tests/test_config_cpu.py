@@ -67,3 +67,14 @@ def test_checkpoint_compatibility_with_the_unmodified_reference_detector():
     det.load_state_dict(model.state_dict(), strict=True)
     for k, v in model.state_dict().items():
         assert torch.equal(v, ref_sd[k]), k
+
+
+def test_cyclic_lr_matches_the_schedule_of_cosine_2x():
+    """configs/_base_/schedules/cosine_2x.py:10-15: 1 -> 100x over the first 10 % of the run, then down to 1e-3x (cosine)."""
+    from geomae_b200.train import cyclic_lr
+    base, total = 1e-5, 1000
+    assert abs(cyclic_lr(base, 0, total) - base) < 1e-12
+    assert abs(cyclic_lr(base, 100, total) - 100 * base) < 1e-9
+    assert abs(cyclic_lr(base, 50, total) - base * (100 + 0.5 * (1 - 100) * 1.0)) < 1e-9      # half way up: cos(pi/2) + 1 = 1
+    assert abs(cyclic_lr(base, 999, total) - base * 1e-3) < base * 1e-3
+    assert all(cyclic_lr(base, i, total) >= cyclic_lr(base, i + 1, total) for i in range(100, 998))

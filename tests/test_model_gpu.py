@@ -298,3 +298,52 @@ def test_bf16_mode_stays_close():
     """Plain-bf16 tensor-core mode (the perf mode): not the parity gate, but it must track the fp32 result."""
     rep = run_parity("full_b2", loss_tol=2e-2, grad_tol=0.15, impl="tc1")
     print({k: f"{v[2]:.2e}" for k, v in rep.items()})
+
+
+def test_geometric_target_error_report():
+    """the three numbers behind the normal / curvature targets, measured on the full-config golden case
+    and written to gpurun_out/geom_target_errors.json: (i) target error on the well-conditioned pillars, the flipped /
+    degenerate fractions, (ii) loss parity with the kernel's normals substituted on the ill-conditioned set (the <=1e-4
+    gate of run_parity), (iii) the raw, unsubstituted loss_curv_around delta against the oracle's LAPACK normals."""
+    import json
+    import os
+    from geomae_b200.voxel import scatter_frames
+    case, cfg, frames, g = load_case("full_b2")
+    params = O.init_params(cfg, case["param_seed"])
+    pb = scatter_frames(geometry(cfg), [torch.from_numpy(f).to(DEV) for f in frames])
+    normal, curv, cov6, sing, pair = pb.geom_targets(want_debug=True)
+    normal, curv, sing = normal.cpu().numpy(), curv.cpu().numpy(), sing.cpu().numpy()
+    tgt = O.geometric_targets(frames, cfg, g["ids_mask"])
+    s = tgt["singular"]
+    well = (s[:, 1] - s[:, 2]) > 1e-3 * np.maximum(s[:, 0], 1e-12)
+    dot = (tgt["normal"] * normal).sum(-1)
+    flipped = well & (dot < 0)
+    aligned_err = np.abs(tgt["normal"] * np.sign(dot)[:, None] - normal).max(axis=1)
+    solid = s[:, 0] > 1e-6
+    curv_rel = np.abs(curv - tgt["curvature"]) / np.maximum(np.abs(tgt["curvature"]), 1e-12)
+    sing_rel = np.abs(sing - s) / np.maximum(s[:, :1], 1e-12)
+    q = lambda a, p: float(np.quantile(a, p)) if a.size else 0.0     # noqa: E731
+    # (ii) / (iii): the oracle's loss with its own normals, with sign-aligned + substituted normals, with the kernel's
+    aligned = np.where(well[:, None], tgt["normal"] * np.sign(dot)[:, None], normal)
+    loss = {}
+    for name, override in (("oracle_lapack_normals", None), ("aligned_and_substituted", aligned), ("kernel_normals", normal)):
+        with torch.no_grad():
+            losses, _, _ = O.forward_train(params, frames, cfg, g["ids_keep"], g["ids_mask"], normal_override=override)
+        loss[name] = float(losses["loss_curv_around"])
+    rep = dict(
+        case="full_b2", pillars=int(s.shape[0]),
+        well_conditioned_fraction=float(well.mean()), degenerate_fraction=float((~well).mean()),
+        sign_flipped_fraction_of_well=float(flipped.sum() / max(1, well.sum())),
+        normal_abs_err_well=dict(max=float(aligned_err[well].max()), p99=q(aligned_err[well], 0.99), median=q(aligned_err[well], 0.5)),
+        curvature_rel_err_solid=dict(max=float(curv_rel[solid].max()), p99=q(curv_rel[solid], 0.99), median=q(curv_rel[solid], 0.5)),
+        singular_rel_err=dict(max=float(sing_rel.max()), p99=q(sing_rel, 0.99)),
+        loss_curv_around=loss,
+        substituted_loss_rel_delta=abs(loss["kernel_normals"] - loss["aligned_and_substituted"]) / loss["aligned_and_substituted"],
+        raw_unsubstituted_loss_rel_delta=abs(loss["kernel_normals"] - loss["oracle_lapack_normals"]) / loss["oracle_lapack_normals"])
+    print(json.dumps(rep, indent=1))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "geom_target_errors.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+    assert rep["substituted_loss_rel_delta"] <= 1e-4
+    assert rep["normal_abs_err_well"]["p99"] <= 2e-3

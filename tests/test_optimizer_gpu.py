@@ -37,3 +37,37 @@ def test_flat_trainer_matches_torch_adamw():
         assert abs(float(tr.stats[0]) - float(norm)) <= 1e-5 * float(norm)
         for (k, a), (_, b) in zip(ref.named_parameters(), mine.named_parameters()):
             torch.testing.assert_close(b, a, rtol=2e-5, atol=2e-6, msg=k)
+
+
+def test_flat_trainer_checkpoint_resume_and_binding_check():
+    """state_dict / load_state_dict reproduce the run exactly; a detached parameter is reported, not silently skipped."""
+    from geomae_b200.train import FlatTrainer
+
+    def make():
+        torch.manual_seed(1)
+        m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.LayerNorm(32), torch.nn.Linear(32, 4)).cuda()
+        return m, FlatTrainer(m, lr=1e-2, max_grad_norm=1.0)
+
+    def step(m, tr, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        tr.zero_grad()
+        m(torch.randn(8, 16, device="cuda", generator=g)).pow(2).sum().backward()
+        tr.optimizer_step()
+
+    ma, ta = make()
+    for i in range(3):
+        step(ma, ta, i)
+    ckpt_model, ckpt_opt = {k: v.clone() for k, v in ma.state_dict().items()}, ta.state_dict()
+    for i in range(3, 6):
+        step(ma, ta, i)
+    mb, tb = make()
+    mb.load_state_dict(ckpt_model)          # copies in place: parameters stay views of the flat buffer
+    tb.load_state_dict(ckpt_opt)
+    tb.check_bindings()
+    for i in range(3, 6):
+        step(mb, tb, i)
+    for (k, a), (_, b) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert torch.equal(a, b), k
+    mb[0].weight.grad = None
+    with pytest.raises(RuntimeError, match="no longer lives"):
+        tb.check_bindings()

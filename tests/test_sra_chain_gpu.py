@@ -192,4 +192,4 @@ def test_chain_backward(n, mode):
     for key, ref in (("g_norm2_w", (dz * xh2).sum(0)), ("g_norm2_b", dz.sum(0)), ("g_norm1_w", (dy * xh1).sum(0)),
                      ("g_norm1_b", dy.sum(0))):
         d = (out[key] - ref).abs().max().item()
-        assert d <= 2e-2 * s + 1e-3, (key, d)
+        assert d <= 5e-3 * s + 1e-3, (key, d)
