@@ -9,11 +9,11 @@
 // issues tcgen05.mma (+ an N = 16 MMA against a constant "ones" block whose result column is the bias gradient),
 // the accumulator stays in TMEM over the whole token range and four warps flush it once with vector reductions.
 // The round-1 kernel re-staged fp32 rows through registers per slab (2-6 % tensor-pipe activity, 25 % of the step).
-#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma_host.cuh"
 
 namespace {
 
@@ -30,14 +30,6 @@ constexpr int NTHR = 192;
 struct Slab { int a_map, a_col, b_map, b_col; float* dW; int ldw; float* db; };
 struct WgArgs { int n_tiles; int tiles_per_cta; Slab slab[MAX_SLABS]; };
 struct WgMaps { CUtensorMap m[9]; };
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          tc::smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
-      : "memory");
-}
 
 __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tma(const __grid_constant__ WgMaps maps, const WgArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -81,10 +73,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tma(const __grid_constant__ W
         uint8_t* st = sm + slot * STAGE_BYTES;
         tc::mbar_wait(&empty[slot], ph ^ 1);
         tc::mbar_expect_tx(&full[slot], STAGE_BYTES);
-        tma_load_2d(st, ma, s.a_col, t * WT, &full[slot]);
-        tma_load_2d(st + BLK, ma, s.a_col + 64, t * WT, &full[slot]);
-        tma_load_2d(st + 2 * BLK, mb, s.b_col, t * WT, &full[slot]);
-        tma_load_2d(st + 3 * BLK, mb, s.b_col + 64, t * WT, &full[slot]);
+        tma::load_2d(st, ma, s.a_col, t * WT, &full[slot]);
+        tma::load_2d(st + BLK, ma, s.a_col + 64, t * WT, &full[slot]);
+        tma::load_2d(st + 2 * BLK, mb, s.b_col, t * WT, &full[slot]);
+        tma::load_2d(st + 3 * BLK, mb, s.b_col + 64, t * WT, &full[slot]);
       }
     }
   } else if (warp == 1) {
@@ -145,41 +137,6 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tma(const __grid_constant__ W
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda)
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// [128 tokens x 64 columns] bf16 boxes of a row-major [n, cols] tensor, 128-byte swizzle, rows past n read as zeros
-int make_map(CUtensorMap* map, const void* base, int64_t n, int cols) {
-  EncodeTiledFn fn = encode_fn();
-  GM_REQUIRE(fn, "sra_wgrad: cuTensorMapEncodeTiled is not available from this driver");
-  GM_REQUIRE(((uintptr_t)base & 15) == 0, "sra_wgrad: operand tensors must be 16-byte aligned");
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)n};
-  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  const cuuint32_t box[2] = {64, (cuuint32_t)WT};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  GM_REQUIRE(rc == CUDA_SUCCESS, "sra_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)rc);
-  return GEOMAE_OK;
-}
-
 }  // namespace
 
 extern "C" int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* p, void* stream) {
@@ -194,7 +151,7 @@ extern "C" int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* p, void* st
   const void* base[9] = {p->ds2_16, p->g16, p->du16, p->y16, p->ds1_16, p->attn16, p->dqkv16, p->xp16, p->xb16};
   const int cols[9] = {128, 256, 256, 128, 128, 128, 384, 128, 128};
   for (int i = 0; i < 9; ++i) {
-    const int rc = make_map(&maps.m[i], base[i], n, cols[i]);
+    const int rc = tma::make_map(&maps.m[i], base[i], n, cols[i], 2);
     if (rc) return rc;
   }
   WgArgs a;
