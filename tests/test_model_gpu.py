@@ -190,6 +190,62 @@ def test_sra_attention_tensor_core_kernel_bf16_rows(small):
         torch.testing.assert_close(b.grad.float(), a.grad, rtol=1e-2, atol=1e-3)
 
 
+def test_sra_attention_window_resident_kernel(small):
+    """All-bf16 window-resident attention (csrc/sra_attention_win.cu, the kernels of the fused bf16 path: one warp per
+    (window, head)) through the C ABI against the fp32 reference on the same bf16-rounded operands; also a synthetic
+    layout with full 144-token windows (9 x 9 tiles per head) and windows of every small length."""
+    from geomae_b200 import lib as L
+    from geomae_b200.windows import WindowLayout, WindowSpec
+    _, cfg, _, g, pb = small
+    spec = WindowSpec(cfg.window_shape, cfg.shifts)
+    all_rows = np.concatenate([g["ids_keep"], g["ids_mask"]])
+    gen = torch.Generator().manual_seed(3)
+
+    def layouts():
+        for n_rows in (37, len(all_rows)):
+            lay = WindowLayout.from_pillars(spec, pb, torch.from_numpy(all_rows[:n_rows]).to(DEV))
+            for s in (0, 1):
+                w = lay.shift(s)
+                yield n_rows, w["win_ptr"], w["win_tok"], w["tok_win"]
+        lens = list(range(1, 40)) + [144, 143, 129, 128, 127, 97, 64, 17, 16, 15, 1, 144]
+        n = sum(lens)
+        ptr = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32)
+        perm = torch.randperm(n, generator=gen)
+        tok_win = torch.empty(n, dtype=torch.int32)
+        tok_win[perm] = torch.repeat_interleave(torch.arange(len(lens)), torch.tensor(lens)).int()
+        yield n, ptr.to(DEV), perm.int().to(DEV), tok_win.to(DEV)
+
+    for n, win_ptr, win_tok, tok_win in layouts():
+        qkv16 = (torch.randn(n, 384, generator=gen) * 0.7).bfloat16()
+        dout16 = torch.randn(n, 128, generator=gen).bfloat16()
+        q = qkv16.float().requires_grad_(True)
+        ref = ref_attention(q, tok_win[:n].cpu().long(), 8)
+        ref.backward(dout16.float())
+        dd = (dout16.float() * ref.detach()).view(n, 8, 16).sum(-1).contiguous().to(DEV)
+        x, dy = qkv16.to(DEV), dout16.to(DEV)
+        out = torch.empty(n, 128, dtype=torch.bfloat16, device=DEV)
+        lse = torch.empty(n, 8, dtype=torch.float32, device=DEV)
+        dqkv = torch.zeros(n, 384, dtype=torch.bfloat16, device=DEV)
+        st = L.stream_ptr(DEV)
+        L.run("sra_attention_tc_fwd", L.ptr(x), n, 8, L.ptr(win_ptr), L.ptr(win_tok), L.ptr(tok_win), L.ptr(out), L.ptr(lse),
+              1 | 8, st)
+        L.run("sra_attention_tc_bwd", L.ptr(x), L.ptr(out), L.ptr(lse), L.ptr(dy), n, 8, L.ptr(win_ptr), L.ptr(win_tok),
+              L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4, st)
+        torch.cuda.synchronize()
+        for got, want, name in ((out.float().cpu(), ref.detach(), "out"), (dqkv.float().cpu(), q.grad, "d_qkv")):
+            assert torch.isfinite(got).all(), (name, n)
+            err = float((got - want).norm() / want.norm())
+            assert err < 1.2e-2, (name, n, err)
+            assert float((got - want).abs().max()) < 0.12, (name, n)
+        # log-sum-exp of the scaled scores, per (token, head)
+        tw = tok_win[:n].cpu().long()
+        k_all, q_all = qkv16.float()[:, 128:256].view(n, 8, 16), qkv16.float()[:, :128].view(n, 8, 16)
+        i = int(torch.randint(0, n, (1,), generator=gen))
+        peers = torch.where(tw == tw[i])[0]
+        want_lse = torch.logsumexp(torch.einsum("hd,khd->hk", q_all[i], k_all[peers]) * 0.25, dim=-1)
+        torch.testing.assert_close(lse[i].cpu(), want_lse, rtol=2e-3, atol=2e-3)
+
+
 def test_scatter_reduce_modes(small):
     from geomae_b200.voxel_encoder import scatter_reduce
     _, _, frames, _, pb = small
