@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--samples-per-gpu", type=int, default=0)     # 0: the workload's default (4 = data.samples_per_gpu)
     ap.add_argument("--sweeps", type=int, default=0)              # 0: the workload's default
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--length-bins", action="store_true", help="add the SRA window-length sweep (default for --workload dense)")
     ap.add_argument("--list-only", action="store_true",
                     help="profiler runs: W warm-up + K resident steps, then exit without the e2e / roofline / CPU legs")
     ap.add_argument("--sra-impl", default="tc1", choices=["tc1", "tc3", "glue"],
@@ -181,15 +182,16 @@ def sra_length_bin_sweep(dev, tens_peak, tokens=196608):
         dqkv = torch.empty_like(qkv)
         st = L.stream_ptr(dev)
 
-        def fwd():
+        def fwd(variant=0):
             L.run("sra_attention_tc_fwd", L.ptr(qkv), n, 8, L.ptr(win_ptr), L.ptr(win_tok), L.ptr(tok_win), L.ptr(attn),
-                  L.ptr(lse), 1 | 8, st)
+                  L.ptr(lse), 1 | 8 | variant, st)
 
-        def bwd():
+        def bwd(variant=0):
             L.run("sra_attention_tc_bwd", L.ptr(qkv), L.ptr(attn), L.ptr(lse), L.ptr(d_out), n, 8, L.ptr(win_ptr),
-                  L.ptr(win_tok), L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4, st)
+                  L.ptr(win_tok), L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4 | variant, st)
         res = dict(window_length=Lw, windows=nw, tokens=n)
-        for name, fn, fl in (("fwd", fwd, 64.0), ("bwd", bwd, 160.0)):
+        for name, fn, fl in (("fwd", fwd, 64.0), ("bwd", bwd, 160.0), ("fwd_window_resident", lambda: fwd(16), 64.0),
+                             ("bwd_window_resident", lambda: bwd(16), 160.0)):
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -478,7 +480,7 @@ def main():
         gpu_launches=launches, clocks=clocks, roofline=roof, kernel_families=fam_table, hbm_kernels=aux,
         kernel_ms_per_step={k: round(v[0] / K, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
         loss=last.get("loss_host"), loss_delta_vs_tc3=loss_delta)
-    if args.workload == "dense" and world == 1:
+    if (args.workload == "dense" or args.length_bins) and world == 1:
         line["sra_length_bins"] = sra_length_bin_sweep(dev, tens_peak)
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -112,94 +112,130 @@ __device__ __forceinline__ int window_count(const int32_t* __restrict__ win_tok,
   return __ldg(tok_win + __ldg(win_tok + n - 1)) + 1;     // the last CSR position belongs to the last window
 }
 
+constexpr int CHUNKS = 5;           // a window has at most 9 16-row tiles: 5 chunks of 2
+
+// one 16-query tile against one 16-key block: scores, online softmax update, O += P V
+struct FwdTile {
+  float mx0 = -INFINITY, mx1 = -INFINITY, ls0 = 0.f, ls1 = 0.f;
+  float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+};
+__device__ __forceinline__ void fwd_block(FwdTile& f, const uint32_t (&qa)[4], const uint8_t* sK, const uint8_t* sV, int kb,
+                                          int L, bool last_padded) {
+  const int t = threadIdx.x & 3;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t b0, b1;
+  ldb(b0, b1, sK, kb * 16);
+  mma16816(s0, qa, b0, b1);
+  ldb(b0, b1, sK, kb * 16 + 8);
+  mma16816(s1, qa, b0, b1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s0[i] *= QSCALE; s1[i] *= QSCALE; }
+  if (last_padded) {                                     // padding keys of the window's last block
+    const int k0 = kb * 16 + 2 * t;
+    if (k0 >= L) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
+    if (k0 + 1 >= L) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
+    if (k0 + 8 >= L) { s1[0] = -INFINITY; s1[2] = -INFINITY; }
+    if (k0 + 9 >= L) { s1[1] = -INFINITY; s1[3] = -INFINITY; }
+  }
+  float m0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
+  float m1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  const float n0 = fmaxf(f.mx0, m0), n1 = fmaxf(f.mx1, m1);       // finite: key 0 of block 0 is always a real key
+  const float c0 = ex2(f.mx0 - n0), c1 = ex2(f.mx1 - n1);
+  f.mx0 = n0; f.mx1 = n1;
+  const float p00 = ex2(s0[0] - n0), p01 = ex2(s0[1] - n0), p02 = ex2(s1[0] - n0), p03 = ex2(s1[1] - n0);
+  const float p10 = ex2(s0[2] - n1), p11 = ex2(s0[3] - n1), p12 = ex2(s1[2] - n1), p13 = ex2(s1[3] - n1);
+  f.ls0 = f.ls0 * c0 + ((p00 + p01) + (p02 + p03));
+  f.ls1 = f.ls1 * c1 + ((p10 + p11) + (p12 + p13));
+  f.o0[0] *= c0; f.o0[1] *= c0; f.o1[0] *= c0; f.o1[1] *= c0;
+  f.o0[2] *= c1; f.o0[3] *= c1; f.o1[2] *= c1; f.o1[3] *= c1;
+  const uint32_t pa[4] = {pack_bf16(p00, p01), pack_bf16(p10, p11), pack_bf16(p02, p03), pack_bf16(p12, p13)};
+  uint32_t vb[4];
+  ldsm_bt(vb, sV, kb * 16);
+  mma16816(f.o0, pa, vb[0], vb[1]);
+  mma16816(f.o1, pa, vb[2], vb[3]);
+}
+__device__ __forceinline__ void fwd_store(FwdTile& f, int mt, int L, const int32_t* sTok, int h, __nv_bfloat16* out, float* lse) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float ls0 = f.ls0, ls1 = f.ls1;
+  ls0 += __shfl_xor_sync(0xffffffffu, ls0, 1); ls0 += __shfl_xor_sync(0xffffffffu, ls0, 2);
+  ls1 += __shfl_xor_sync(0xffffffffu, ls1, 1); ls1 += __shfl_xor_sync(0xffffffffu, ls1, 2);
+  const float i0 = 1.0f / ls0, i1 = 1.0f / ls1;
+  const int r0 = mt * 16 + g, r1 = r0 + 8;
+  if (r0 < L) {
+    const int64_t tok = sTok[r0];
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + tok * 128 + h * 16) + t;
+    o[0] = pack_bf16(f.o0[0] * i0, f.o0[1] * i0);
+    o[4] = pack_bf16(f.o1[0] * i0, f.o1[1] * i0);
+    if (t == 0) lse[tok * NH + h] = (f.mx0 + log2f(ls0)) * 0.6931471805599453f;
+  }
+  if (r1 < L) {
+    const int64_t tok = sTok[r1];
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + tok * 128 + h * 16) + t;
+    o[0] = pack_bf16(f.o0[2] * i1, f.o0[3] * i1);
+    o[4] = pack_bf16(f.o1[2] * i1, f.o1[3] * i1);
+    if (t == 0) lse[tok * NH + h] = (f.mx1 + log2f(ls1)) * 0.6931471805599453f;
+  }
+}
+
+// Work item = (window, chunk of two 16-query tiles): the largest window (9 tiles) is five items, so no CTA is stuck
+// behind an 81-block chain; the two tiles of a chunk run interleaved (two independent MMA -> softmax -> MMA chains).
 __global__ void __launch_bounds__(256) k_sra_win_fwd(const __nv_bfloat16* __restrict__ qkv, int n,
                                                      const int32_t* __restrict__ win_ptr,
                                                      const int32_t* __restrict__ win_tok,
                                                      const int32_t* __restrict__ tok_win, __nv_bfloat16* __restrict__ out,
                                                      float* __restrict__ lse) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
   WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[h];
   gm_pdl_wait();
   gm_pdl_trigger();
   const int W = window_count(win_tok, tok_win, n);
-  for (int w = blockIdx.x; w < W; w += gridDim.x) {
-    const int beg = __ldg(win_ptr + w), L = __ldg(win_ptr + w + 1) - beg;
+  const int mt0 = blockIdx.y * 2;                        // this CTA's chunk of two query tiles, for every window it visits
+  // 32 windows per round: one batched read of their extents, then only the windows that HAVE this chunk are visited
+  for (int base = blockIdx.x; base < W; base += gridDim.x * 32) {
+    const int wl = base + lane * gridDim.x;
+    int beg_l = 0, len_l = 0;
+    if (wl < W) { beg_l = __ldg(win_ptr + wl); len_l = __ldg(win_ptr + wl + 1) - beg_l; }
+    unsigned todo = __ballot_sync(0xffffffffu, ((len_l + 15) >> 4) > mt0);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int beg = __shfl_sync(0xffffffffu, beg_l, src), L = __shfl_sync(0xffffffffu, len_l, src);
     const int T = (L + 15) >> 4, Lpad = T * 16;
-    __syncwarp();                                        // previous window's slabs fully consumed
+    const bool two = mt0 + 1 < T;
+    __syncwarp();                                        // previous item's slabs fully consumed
     for (int i = lane; i < Lpad; i += 32) ws.tok[i] = i < L ? __ldg(win_tok + beg + i) : 0;
     __syncwarp();
+    uint32_t qa[4], qb[4];
+    lda_global(qa, qkv, 384, h * 16, ws.tok, mt0 * 16, L);
+    lda_global(qb, qkv, 384, h * 16, ws.tok, (mt0 + 1) * 16, two ? L : 0);
     stage_slab(ws.x, qkv, 384, 128 + h * 16, ws.tok, L, Lpad);
     stage_slab(ws.y, qkv, 384, 256 + h * 16, ws.tok, L, Lpad);
-    uint32_t qa[4], qn[4];
-    lda_global(qa, qkv, 384, h * 16, ws.tok, 0, L);
     __syncwarp();
-    for (int mt = 0; mt < T; ++mt) {
-      if (mt + 1 < T) lda_global(qn, qkv, 384, h * 16, ws.tok, (mt + 1) * 16, L);     // next tile's Q in flight
-      float mx0 = -INFINITY, mx1 = -INFINITY, ls0 = 0.f, ls1 = 0.f;
-      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    FwdTile fa, fb;
+    const bool padded = Lpad != L;
+    if (two) {
       for (int kb = 0; kb < T; ++kb) {
-        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t b0, b1;
-        ldb(b0, b1, ws.x, kb * 16);
-        mma16816(s0, qa, b0, b1);
-        ldb(b0, b1, ws.x, kb * 16 + 8);
-        mma16816(s1, qa, b0, b1);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { s0[i] *= QSCALE; s1[i] *= QSCALE; }
-        if (kb == T - 1 && Lpad != L) {                  // padding keys of the last block
-          const int k0 = kb * 16 + 2 * t;
-          if (k0 >= L) { s0[0] = -INFINITY; s0[2] = -INFINITY; }
-          if (k0 + 1 >= L) { s0[1] = -INFINITY; s0[3] = -INFINITY; }
-          if (k0 + 8 >= L) { s1[0] = -INFINITY; s1[2] = -INFINITY; }
-          if (k0 + 9 >= L) { s1[1] = -INFINITY; s1[3] = -INFINITY; }
-        }
-        float m0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
-        float m1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-        const float n0 = fmaxf(mx0, m0), n1 = fmaxf(mx1, m1);     // finite: key 0 of block 0 is always a real key
-        const float c0 = ex2(mx0 - n0), c1 = ex2(mx1 - n1);
-        mx0 = n0; mx1 = n1;
-        const float p00 = ex2(s0[0] - n0), p01 = ex2(s0[1] - n0), p02 = ex2(s1[0] - n0), p03 = ex2(s1[1] - n0);
-        const float p10 = ex2(s0[2] - n1), p11 = ex2(s0[3] - n1), p12 = ex2(s1[2] - n1), p13 = ex2(s1[3] - n1);
-        ls0 = ls0 * c0 + ((p00 + p01) + (p02 + p03));
-        ls1 = ls1 * c1 + ((p10 + p11) + (p12 + p13));
-        o0[0] *= c0; o0[1] *= c0; o1[0] *= c0; o1[1] *= c0;
-        o0[2] *= c1; o0[3] *= c1; o1[2] *= c1; o1[3] *= c1;
-        const uint32_t pa[4] = {pack_bf16(p00, p01), pack_bf16(p10, p11), pack_bf16(p02, p03), pack_bf16(p12, p13)};
-        uint32_t vb[4];
-        ldsm_bt(vb, ws.y, kb * 16);
-        mma16816(o0, pa, vb[0], vb[1]);
-        mma16816(o1, pa, vb[2], vb[3]);
+        const bool lp = padded && kb == T - 1;
+        fwd_block(fa, qa, ws.x, ws.y, kb, L, lp);
+        fwd_block(fb, qb, ws.x, ws.y, kb, L, lp);
       }
-      ls0 += __shfl_xor_sync(0xffffffffu, ls0, 1); ls0 += __shfl_xor_sync(0xffffffffu, ls0, 2);
-      ls1 += __shfl_xor_sync(0xffffffffu, ls1, 1); ls1 += __shfl_xor_sync(0xffffffffu, ls1, 2);
-      const float i0 = 1.0f / ls0, i1 = 1.0f / ls1;
-      const int r0 = mt * 16 + g, r1 = r0 + 8;
-      if (r0 < L) {
-        const int64_t tok = ws.tok[r0];
-        uint32_t* o = reinterpret_cast<uint32_t*>(out + tok * 128 + h * 16) + t;
-        o[0] = pack_bf16(o0[0] * i0, o0[1] * i0);
-        o[4] = pack_bf16(o1[0] * i0, o1[1] * i0);
-        if (t == 0) lse[tok * NH + h] = (mx0 + log2f(ls0)) * 0.6931471805599453f;
-      }
-      if (r1 < L) {
-        const int64_t tok = ws.tok[r1];
-        uint32_t* o = reinterpret_cast<uint32_t*>(out + tok * 128 + h * 16) + t;
-        o[0] = pack_bf16(o0[2] * i1, o0[3] * i1);
-        o[4] = pack_bf16(o1[2] * i1, o1[3] * i1);
-        if (t == 0) lse[tok * NH + h] = (mx1 + log2f(ls1)) * 0.6931471805599453f;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) qa[i] = qn[i];
+      fwd_store(fa, mt0, L, ws.tok, h, out, lse);
+      fwd_store(fb, mt0 + 1, L, ws.tok, h, out, lse);
+    } else {
+      for (int kb = 0; kb < T; ++kb) fwd_block(fa, qa, ws.x, ws.y, kb, L, padded && kb == T - 1);
+      fwd_store(fa, mt0, L, ws.tok, h, out, lse);
     }
+  }
   }
 }
 
-// Backward.  Pass A: queries as rows -> dQ (K, V staged).  Pass B: keys as rows -> dK, dV (Q, dO staged).
+// Backward.  Pass A: queries as rows -> dQ (K, V staged).  Pass B: keys as rows -> dK, dV (Q, dO staged).  The two passes
+// of a window are independent work items.
 __global__ void __launch_bounds__(256) k_sra_win_bwd(const __nv_bfloat16* __restrict__ qkv,
                                                      const float* __restrict__ lse, const __nv_bfloat16* __restrict__ d_out,
                                                      const float* __restrict__ dd, int n,
@@ -212,9 +248,20 @@ __global__ void __launch_bounds__(256) k_sra_win_bwd(const __nv_bfloat16* __rest
   gm_pdl_wait();
   gm_pdl_trigger();
   const int W = window_count(win_tok, tok_win, n);
-  for (int w = blockIdx.x; w < W; w += gridDim.x) {
-    const int beg = __ldg(win_ptr + w), L = __ldg(win_ptr + w + 1) - beg;
+  // work item = (window, chunk of two 16-row tiles, pass): blockIdx.y = pass * CHUNKS + chunk, windows as in k_sra_win_fwd
+  const bool pass_b = (int)blockIdx.y >= CHUNKS;
+  const int t_lo = ((int)blockIdx.y - (pass_b ? CHUNKS : 0)) * 2;
+  for (int base = blockIdx.x; base < W; base += gridDim.x * 32) {
+    const int wl = base + lane * gridDim.x;
+    int beg_l = 0, len_l = 0;
+    if (wl < W) { beg_l = __ldg(win_ptr + wl); len_l = __ldg(win_ptr + wl + 1) - beg_l; }
+    unsigned todo = __ballot_sync(0xffffffffu, ((len_l + 15) >> 4) > t_lo);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int beg = __shfl_sync(0xffffffffu, beg_l, src), L = __shfl_sync(0xffffffffu, len_l, src);
     const int T = (L + 15) >> 4, Lpad = T * 16;
+    const int t_hi = min(t_lo + 2, T);
     __syncwarp();
     for (int i = lane; i < Lpad; i += 32) {
       const int tok = i < L ? __ldg(win_tok + beg + i) : 0;
@@ -223,11 +270,12 @@ __global__ void __launch_bounds__(256) k_sra_win_bwd(const __nv_bfloat16* __rest
       ws.dd[i] = i < L ? __ldg(dd + (int64_t)tok * NH + h) : 0.f;
     }
     __syncwarp();
+    if (!pass_b) {
     // ------------------------------------------------------------ pass A: dQ
     stage_slab(ws.x, qkv, 384, 128 + h * 16, ws.tok, L, Lpad);      // K
     stage_slab(ws.y, qkv, 384, 256 + h * 16, ws.tok, L, Lpad);      // V
     __syncwarp();
-    for (int mt = 0; mt < T; ++mt) {
+    for (int mt = t_lo; mt < t_hi; ++mt) {
       uint32_t qa[4], ga[4];
       lda_global(qa, qkv, 384, h * 16, ws.tok, mt * 16, L);
       lda_global(ga, d_out, 128, h * 16, ws.tok, mt * 16, L);
@@ -274,12 +322,12 @@ __global__ void __launch_bounds__(256) k_sra_win_bwd(const __nv_bfloat16* __rest
         o[4] = pack_bf16(a1[2] * 0.25f, a1[3] * 0.25f);
       }
     }
-    __syncwarp();
+    } else {
     // ------------------------------------------------------------ pass B: dK, dV (rows = keys, columns = queries)
     stage_slab(ws.x, qkv, 384, h * 16, ws.tok, L, Lpad);            // Q
     stage_slab(ws.y, d_out, 128, h * 16, ws.tok, L, Lpad);          // dO
     __syncwarp();
-    for (int kt = 0; kt < T; ++kt) {
+    for (int kt = t_lo; kt < t_hi; ++kt) {
       uint32_t ka[4], va[4];
       lda_global(ka, qkv, 384, 128 + h * 16, ws.tok, kt * 16, L);
       lda_global(va, qkv, 384, 256 + h * 16, ws.tok, kt * 16, L);
@@ -332,6 +380,8 @@ __global__ void __launch_bounds__(256) k_sra_win_bwd(const __nv_bfloat16* __rest
         o[68] = pack_bf16(dv1[2], dv1[3]);
       }
     }
+    }
+  }
   }
 }
 
@@ -347,7 +397,7 @@ int gm_sra_win_fwd(const void* qkv, int64_t n, const int32_t* win_ptr, const int
     GM_CUDA(cudaFuncSetAttribute(k_sra_win_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM));
     configured = true;
   }
-  GM_CUDA(gm_launch_pdl(k_sra_win_fwd, dim3(GM_NUM_SMS * 3), dim3(256), (size_t)WIN_SMEM, st, (const __nv_bfloat16*)qkv, (int)n,
+  GM_CUDA(gm_launch_pdl(k_sra_win_fwd, dim3(GM_NUM_SMS * 3, CHUNKS), dim3(256), (size_t)WIN_SMEM, st, (const __nv_bfloat16*)qkv, (int)n,
                         win_ptr, win_tok, tok_win, (__nv_bfloat16*)out, lse));
   return GEOMAE_OK;
 }
@@ -359,7 +409,7 @@ int gm_sra_win_bwd(const void* qkv, const float* lse, const void* d_out, const f
     GM_CUDA(cudaFuncSetAttribute(k_sra_win_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM));
     configured = true;
   }
-  GM_CUDA(gm_launch_pdl(k_sra_win_bwd, dim3(GM_NUM_SMS * 3), dim3(256), (size_t)WIN_SMEM, st, (const __nv_bfloat16*)qkv, lse,
+  GM_CUDA(gm_launch_pdl(k_sra_win_bwd, dim3(GM_NUM_SMS * 3, 2 * CHUNKS), dim3(256), (size_t)WIN_SMEM, st, (const __nv_bfloat16*)qkv, lse,
                         (const __nv_bfloat16*)d_out, dd, (int)n, win_ptr, win_tok, tok_win, (__nv_bfloat16*)d_qkv));
   return GEOMAE_OK;
 }

@@ -228,9 +228,9 @@ def test_sra_attention_window_resident_kernel(small):
         dqkv = torch.zeros(n, 384, dtype=torch.bfloat16, device=DEV)
         st = L.stream_ptr(DEV)
         L.run("sra_attention_tc_fwd", L.ptr(x), n, 8, L.ptr(win_ptr), L.ptr(win_tok), L.ptr(tok_win), L.ptr(out), L.ptr(lse),
-              1 | 8, st)
+              1 | 8 | 16, st)
         L.run("sra_attention_tc_bwd", L.ptr(x), L.ptr(out), L.ptr(lse), L.ptr(dy), n, 8, L.ptr(win_ptr), L.ptr(win_tok),
-              L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4, st)
+              L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4 | 16, st)
         torch.cuda.synchronize()
         for got, want, name in ((out.float().cpu(), ref.detach(), "out"), (dqkv.float().cpu(), q.grad, "d_qkv")):
             assert torch.isfinite(got).all(), (name, n)
