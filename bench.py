@@ -182,16 +182,15 @@ def sra_length_bin_sweep(dev, tens_peak, tokens=196608):
         dqkv = torch.empty_like(qkv)
         st = L.stream_ptr(dev)
 
-        def fwd(variant=0):
+        def fwd():
             L.run("sra_attention_tc_fwd", L.ptr(qkv), n, 8, L.ptr(win_ptr), L.ptr(win_tok), L.ptr(tok_win), L.ptr(attn),
-                  L.ptr(lse), 1 | 8 | variant, st)
+                  L.ptr(lse), 1 | 8, st)
 
-        def bwd(variant=0):
+        def bwd():
             L.run("sra_attention_tc_bwd", L.ptr(qkv), L.ptr(attn), L.ptr(lse), L.ptr(d_out), n, 8, L.ptr(win_ptr),
-                  L.ptr(win_tok), L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4 | variant, st)
+                  L.ptr(win_tok), L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4, st)
         res = dict(window_length=Lw, windows=nw, tokens=n)
-        for name, fn, fl in (("fwd", fwd, 64.0), ("bwd", bwd, 160.0), ("fwd_window_resident", lambda: fwd(16), 64.0),
-                             ("bwd_window_resident", lambda: bwd(16), 160.0)):
+        for name, fn, fl in (("fwd", fwd, 64.0), ("bwd", bwd, 160.0)):
             fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -534,12 +534,6 @@ int launch_bwd(const float* qkv, const float* out, const float* lse, const float
 
 }  // namespace
 
-// window-resident all-bf16 kernels (sra_attention_win.cu)
-int gm_sra_win_fwd(const void* qkv, int64_t n, const int32_t* win_ptr, const int32_t* win_tok, const int32_t* tok_win,
-                   void* out, float* lse, cudaStream_t st);
-int gm_sra_win_bwd(const void* qkv, const float* lse, const void* d_out, const float* dd, int64_t n, const int32_t* win_ptr,
-                   const int32_t* win_tok, const int32_t* tok_win, void* d_qkv, cudaStream_t st);
-
 extern "C" int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
                                            const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse,
                                            int32_t io_flags, void* stream) {
@@ -548,8 +542,6 @@ extern "C" int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, i
   GM_REQUIRE(qkv && win_ptr && win_tok && tok_win && out && lse, "sra_attention_tc_fwd: null argument");
   GM_REQUIRE(n_tokens < (int64_t)1 << 31, "sra_attention_tc: too many tokens");
   const int n = (int)n_tokens;
-  if ((io_flags & 25) == 25)    // bit 4 + bf16 in / out: the window-resident variant (one warp per (window, head))
-    return gm_sra_win_fwd(qkv, n_tokens, win_ptr, win_tok, tok_win, out, lse, (cudaStream_t)stream);
   // small token sets (the encoder sees 30 % of the pillars): 32-query CTAs so the grid still covers the SMs
   if (gm_div_up(n, 64) < 2 * GM_NUM_SMS)
     return launch_fwd<32>(qkv, n, win_ptr, win_tok, tok_win, out, lse, io_flags, (cudaStream_t)stream);
@@ -566,8 +558,6 @@ extern "C" int geomae_sra_attention_tc_bwd(const float* qkv, const float* out, c
   GM_REQUIRE(!(io_flags & 2) || dd, "sra_attention_tc_bwd: a bf16 d_out needs the precomputed D = dO.O (dd)");
   GM_REQUIRE(n_tokens < (int64_t)1 << 31, "sra_attention_tc: too many tokens");
   const int n = (int)n_tokens;
-  if ((io_flags & 23) == 23)    // bit 4 + everything bf16 (and D given): the window-resident variant
-    return gm_sra_win_bwd(qkv, lse, d_out, dd, n_tokens, win_ptr, win_tok, tok_win, d_qkv, (cudaStream_t)stream);
   if (gm_div_up(n, 64) < GM_NUM_SMS)
     return launch_bwd<32>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags, (cudaStream_t)stream);
   return launch_bwd<64>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags, (cudaStream_t)stream);

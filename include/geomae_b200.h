@@ -283,9 +283,7 @@ int geomae_sra_attention_bwd(const float* qkv, const float* out, const float* ls
  *           (models/sst/sst_basic_block.py:26-61) and its autograd backward. */
 /* io_flags: bit 0: qkv rows are bf16 [n, 3*d_model]; bit 1: d_out rows are bf16 (needs dd); bit 2: d_qkv is written
  * as bf16; bit 3 (forward): out is written as bf16 [n, d_model].  bf16 rows are moved with 16-byte cp.async copies
- * (no registers, no conversion).  bit 4 (with all-bf16 operands): the window-resident variant, one warp per
- * (window, head) with the window's K / V slices in a private shared-memory slab (csrc/sra_attention_win.cu).  Opt-in:
- * the per-length comparison of the two variants is bench.py's `sra_length_bins` table (profiles/). */
+ * (no registers, no conversion). */
 int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, int32_t n_heads, const int32_t* win_ptr,
                                 const int32_t* win_tok, const int32_t* tok_win, float* out, float* lse, int32_t io_flags,
                                 void* stream);

@@ -190,10 +190,10 @@ def test_sra_attention_tensor_core_kernel_bf16_rows(small):
         torch.testing.assert_close(b.grad.float(), a.grad, rtol=1e-2, atol=1e-3)
 
 
-def test_sra_attention_window_resident_kernel(small):
-    """All-bf16 window-resident attention (csrc/sra_attention_win.cu, the kernels of the fused bf16 path: one warp per
-    (window, head)) through the C ABI against the fp32 reference on the same bf16-rounded operands; also a synthetic
-    layout with full 144-token windows (9 x 9 tiles per head) and windows of every small length."""
+def test_sra_attention_all_bf16_operands(small):
+    """The attention kernels exactly as the fused bf16 path calls them (bf16 q|k|v in, bf16 O out, bf16 dO in with the
+    precomputed D term, bf16 dqkv out) through the C ABI against the fp32 reference on the same bf16-rounded operands;
+    also a synthetic layout with full 144-token windows and windows of every small length."""
     from geomae_b200 import lib as L
     from geomae_b200.windows import WindowLayout, WindowSpec
     _, cfg, _, g, pb = small
@@ -228,9 +228,9 @@ def test_sra_attention_window_resident_kernel(small):
         dqkv = torch.zeros(n, 384, dtype=torch.bfloat16, device=DEV)
         st = L.stream_ptr(DEV)
         L.run("sra_attention_tc_fwd", L.ptr(x), n, 8, L.ptr(win_ptr), L.ptr(win_tok), L.ptr(tok_win), L.ptr(out), L.ptr(lse),
-              1 | 8 | 16, st)
+              1 | 8, st)
         L.run("sra_attention_tc_bwd", L.ptr(x), L.ptr(out), L.ptr(lse), L.ptr(dy), n, 8, L.ptr(win_ptr), L.ptr(win_tok),
-              L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4 | 16, st)
+              L.ptr(tok_win), L.ptr(dqkv), L.ptr(dd), 1 | 2 | 4, st)
         torch.cuda.synchronize()
         for got, want, name in ((out.float().cpu(), ref.detach(), "out"), (dqkv.float().cpu(), q.grad, "d_qkv")):
             assert torch.isfinite(got).all(), (name, n)
