@@ -267,7 +267,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a hang must not eat the box
     torch.backends.cuda.matmul.allow_tf32 = False        # the reference trains fp32 with TF32 off (tools/train.py:24-25)
     torch.backends.cudnn.allow_tf32 = False
 
@@ -373,6 +374,22 @@ def main():
     ms_e2e = timed_loop(step_host, K)
     sampler.mark()
     barrier()
+    # bf16-mode vs parity-mode (bf16x3 + fp32 attention) loss on one identical batch, same weights, same mask split
+    loss_delta = None
+    if args.sra_impl != "tc3":      # every rank runs it: the VFE's synchronised BatchNorm is a collective
+        with torch.no_grad():
+            tg = model.last_targets
+            ids = (tg["ids_keep"], tg["ids_mask"])
+            batch = resident[(K - 1) % len(resident)]
+            out = {}
+            for impl in (args.sra_impl, "tc3"):
+                model.set_impl(impl)
+                model.forward_train(points=batch, img_metas=None, ids=ids)
+                out[impl] = model.last_loss_vector.double().sum().item() if getattr(model, "last_loss_vector", None) is not None else None
+            model.set_impl(args.sra_impl)
+        if out[args.sra_impl] is not None and out["tc3"]:
+            loss_delta = dict(loss=out[args.sra_impl], loss_tc3=out["tc3"],
+                              rel=abs(out[args.sra_impl] - out["tc3"]) / abs(out["tc3"]))
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -445,22 +462,6 @@ def main():
                          "instrumented pass over the same K steps; launches of concurrent streams overlap, so family "
                          "shares can add up to more than 1; the ncu launch list of the same command is under profiles/",
                     share_of_step=prof_ms[top] / ms_prof, instrumented_ms_per_step=ms_prof / K)
-    # bf16-mode vs parity-mode (bf16x3 + fp32 attention) loss on one identical batch, same weights, same mask split
-    loss_delta = None
-    if args.sra_impl != "tc3":
-        with torch.no_grad():
-            tg = model.last_targets
-            ids = (tg["ids_keep"], tg["ids_mask"])
-            batch = resident[(K - 1) % len(resident)]
-            out = {}
-            for impl in (args.sra_impl, "tc3"):
-                model.set_impl(impl)
-                model.forward_train(points=batch, img_metas=None, ids=ids)
-                out[impl] = model.last_loss_vector.double().sum().item() if getattr(model, "last_loss_vector", None) is not None else None
-            model.set_impl(args.sra_impl)
-        if out[args.sra_impl] is not None and out["tc3"]:
-            loss_delta = dict(loss=out[args.sra_impl], loss_tc3=out["tc3"],
-                              rel=abs(out[args.sra_impl] - out["tc3"]) / abs(out["tc3"]))
     aux = hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src)
     line = dict(
         metric=METRIC, value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=K, warmup=W,

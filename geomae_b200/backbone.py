@@ -193,6 +193,10 @@ class MultiMAESSTSPChoose(nn.Module):
     def forward_decoder(self, visible_voxel_feat, coors, coors_mask, batch_size, pillar_batch=None, rows_keep=None,
                         rows_mask=None):
         n_vis = coors.shape[0]
+        hook = getattr(self, "encoder_output_hook", None)
+        if hook is not None and visible_voxel_feat.requires_grad:
+            # fires in backward once every decoder / head gradient has been queued (FlatTrainer: early all-reduce bucket)
+            visible_voxel_feat.register_hook(lambda g: (hook(g), None)[1])
         tokens = torch.cat([visible_voxel_feat, self.mask_token.repeat(coors_mask.shape[0], 1)], dim=0)
         all_coors = torch.cat([coors, coors_mask], dim=0)
         rows = torch.cat([rows_keep, rows_mask]) if pillar_batch is not None else None

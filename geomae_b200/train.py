@@ -12,19 +12,32 @@ from . import lib as L
 
 
 class FlatTrainer:
+    # parameters whose gradients are complete once the backward pass has left the decoders (they are all-reduced while
+    # the encoder / VFE backward still runs); everything else goes with the second bucket after backward
+    EARLY_KEYS = ("backbone.decoder_", "backbone.cls_pred_")
+
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, max_grad_norm=10.0,
                  no_decay_keys=("norm",)):
         self.model = model
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]     # frozen parameters stay outside
-        decay = [(k, p) for k, p in named if not any(s in k for s in no_decay_keys)]
-        no_decay = [(k, p) for k, p in named if any(s in k for s in no_decay_keys)]
-        self.order = decay + no_decay
+        is_nd = lambda k: any(s in k for s in no_decay_keys)                        # noqa: E731
+        is_early = lambda k: k.startswith(self.EARLY_KEYS)                           # noqa: E731
+        groups = [[(k, p) for k, p in named if not is_nd(k) and is_early(k)],        # decay, early
+                  [(k, p) for k, p in named if not is_nd(k) and not is_early(k)],    # decay, late
+                  [(k, p) for k, p in named if is_nd(k) and not is_early(k)],        # no decay, late
+                  [(k, p) for k, p in named if is_nd(k) and is_early(k)]]            # no decay, early
+        self.order = [kp for g in groups for kp in g]
         align = 64      # floats: every tensor starts 256-byte aligned (the kernels use 128-bit accesses)
 
         def padded(p):
             return (p.numel() + align - 1) // align * align
-        self.n_decay = sum(padded(p) for _, p in decay)
-        self.n = sum(padded(p) for _, p in self.order)
+        sizes = [sum(padded(p) for _, p in g) for g in groups]
+        self.n_decay = sizes[0] + sizes[1]
+        self.n = sum(sizes)
+        # flat layout [decay early | decay late | no-decay late | no-decay early]: the decayed prefix the optimiser kernel
+        # needs, the late bucket contiguous, the early bucket = the two ends
+        self.early_ranges = [(0, sizes[0]), (self.n - sizes[3], self.n)]
+        self.late_range = (sizes[0], self.n - sizes[3])
         self.n_params = sum(p.numel() for _, p in self.order)
         dev = named[0][1].device
         self.flat_param = torch.zeros(self.n, dtype=torch.float32, device=dev)
@@ -91,9 +104,24 @@ class FlatTrainer:
         losses = self.model.forward_train(points=points, img_metas=None, ids=ids)
         vec = getattr(self.model, "last_loss_vector", None)
         total = vec.sum() if vec is not None else sum(losses.values())     # one reduction instead of six adds
+        pending = []
+        if self.world > 1:
+            # bucket 1 (decoders + heads) starts its all-reduce from inside backward, as soon as the gradient reaching the
+            # encoder output exists: NCCL runs it on its own stream under the encoder / VFE backward
+            def early(_grad):
+                for a, b in self.early_ranges:
+                    if b > a:
+                        pending.append(dist.all_reduce(self.flat_grad[a:b], async_op=True))
+            self.model.backbone.encoder_output_hook = early
         total.backward()
         if self.world > 1:
-            dist.all_reduce(self.flat_grad)          # the single gradient collective (sum; 1/world folded below)
+            self.model.backbone.encoder_output_hook = None
+            if not pending:                          # the hook never fired (model without the backbone hook point)
+                early(None)
+            a, b = self.late_range
+            pending.append(dist.all_reduce(self.flat_grad[a:b], async_op=True))
+            for w in pending:
+                w.wait()                             # stream-level wait: the optimiser kernel is ordered after NCCL
         self.optimizer_step(lr)
         return total.detach(), losses
 

@@ -78,3 +78,35 @@ def test_cyclic_lr_matches_the_schedule_of_cosine_2x():
     assert abs(cyclic_lr(base, 50, total) - base * (100 + 0.5 * (1 - 100) * 1.0)) < 1e-9      # half way up: cos(pi/2) + 1 = 1
     assert abs(cyclic_lr(base, 999, total) - base * 1e-3) < base * 1e-3
     assert all(cyclic_lr(base, i, total) >= cyclic_lr(base, i + 1, total) for i in range(100, 998))
+
+
+def test_flat_trainer_layout_buckets():
+    """Flat layout [decay early | decay late | no-decay late | no-decay early]: decayed prefix, contiguous late bucket,
+    every parameter inside exactly one bucket (the early bucket is all-reduced from inside backward)."""
+    import torch
+    from geomae_b200.train import FlatTrainer
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = torch.nn.Module()
+            self.backbone.decoder_pred_top = torch.nn.Linear(8, 3)
+            self.backbone.decoder_centroid_blocks = torch.nn.ModuleList([torch.nn.Linear(8, 8), torch.nn.LayerNorm(8)])
+            self.backbone.decoder_centroid_blocks[1].register_parameter("norm_w", torch.nn.Parameter(torch.ones(8)))
+            self.backbone.encoder_blocks = torch.nn.ModuleList([torch.nn.Linear(8, 8)])
+            self.backbone.norm1 = torch.nn.LayerNorm(8)
+            self.voxel_encoder = torch.nn.Linear(5, 8)
+    net = Net()
+    tr = FlatTrainer(net)
+    (a0, a1), (b0, b1) = tr.early_ranges
+    l0, l1 = tr.late_range
+    assert a0 == 0 and a1 == l0 and l1 == b0 and b1 == tr.n and l0 <= tr.n_decay <= l1
+    off = 0
+    for k, p in tr.order:
+        early = k.startswith(FlatTrainer.EARLY_KEYS)
+        inside_early = (a0 <= off < a1) or (b0 <= off < b1)
+        assert early == inside_early, k
+        assert ("norm" in k) == (off >= tr.n_decay), k
+        assert p.data_ptr() == tr.flat_param.data_ptr() + 4 * off
+        off += (p.numel() + 63) // 64 * 64
+    assert off == tr.n

@@ -377,6 +377,7 @@ def test_geometric_target_error_report():
     aligned_err = np.abs(tgt["normal"] * np.sign(dot)[:, None] - normal).max(axis=1)
     solid = s[:, 0] > 1e-6
     curv_rel = np.abs(curv - tgt["curvature"]) / np.maximum(np.abs(tgt["curvature"]), 1e-12)
+    curv_abs = np.abs(curv - tgt["curvature"])          # curvature components are fractions of 1 (they sum to 1)
     sing_rel = np.abs(sing - s) / np.maximum(s[:, :1], 1e-12)
     q = lambda a, p: float(np.quantile(a, p)) if a.size else 0.0     # noqa: E731
     # (ii) / (iii): the oracle's loss with its own normals, with sign-aligned + substituted normals, with the kernel's
@@ -391,7 +392,11 @@ def test_geometric_target_error_report():
         well_conditioned_fraction=float(well.mean()), degenerate_fraction=float((~well).mean()),
         sign_flipped_fraction_of_well=float(flipped.sum() / max(1, well.sum())),
         normal_abs_err_well=dict(max=float(aligned_err[well].max()), p99=q(aligned_err[well], 0.99), median=q(aligned_err[well], 0.5)),
-        curvature_rel_err_solid=dict(max=float(curv_rel[solid].max()), p99=q(curv_rel[solid], 0.99), median=q(curv_rel[solid], 0.5)),
+        curvature_abs_err_solid=dict(max=float(curv_abs[solid].max()), p99=q(curv_abs[solid], 0.99), median=q(curv_abs[solid], 0.5)),
+        curvature_abs_err_all=dict(max=float(curv_abs.max()), p99=q(curv_abs, 0.99)),
+        curvature_rel_err_solid=dict(max=float(curv_rel[solid].max()), p99=q(curv_rel[solid], 0.99), median=q(curv_rel[solid], 0.5),
+                                     note="relative error of components that are ~1e-9/sum (rank-deficient neighbourhoods) is "
+                                          "noise against the reference's own 1e-9 floor; see the absolute figures"),
         singular_rel_err=dict(max=float(sing_rel.max()), p99=q(sing_rel, 0.99)),
         loss_curv_around=loss,
         substituted_loss_rel_delta=abs(loss["kernel_normals"] - loss["aligned_and_substituted"]) / loss["aligned_and_substituted"],
@@ -402,4 +407,5 @@ def test_geometric_target_error_report():
     with open(os.path.join(out_dir, "geom_target_errors.json"), "w") as f:
         json.dump(rep, f, indent=1)
     assert rep["substituted_loss_rel_delta"] <= 1e-4
-    assert rep["normal_abs_err_well"]["p99"] <= 2e-3
+    assert rep["normal_abs_err_well"]["max"] <= 1e-4          # the north star's fp32 target tolerance
+    assert rep["singular_rel_err"]["max"] <= 1e-4

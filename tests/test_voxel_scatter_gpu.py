@@ -74,7 +74,7 @@ def check_against_oracle(cfg, frames, ids_mask=None, atol=3e-6, min_well_frac=0.
     # centroid ulps at |x|~50 m (4e-6) over offsets ~0.1 m: ~1e-4 relative; (4e-6)^2-sized entries are noise
     assert (np.abs(cov - tgt["cov"]) <= 3e-4 * scale + 1e-9).all()
     s_ref = tgt["singular"]
-    np.testing.assert_allclose(sing.cpu().numpy(), s_ref, rtol=5e-4, atol=2e-5 * s_ref.max())
+    np.testing.assert_allclose(sing.cpu().numpy(), s_ref, rtol=1e-4, atol=2e-5 * s_ref.max())      # measured: 1e-5 of s0
     # curvature = (S + 1e-9) / sum: where the moments are at the level of the centroids' rounding noise
     # ((4e-6 m)^2 per point, summation order differs between the float atomics and the CPU loop) the ratio against
     # the 1e-9 floor is noise-dominated; hold those pillars to a loose bound and the rest to the tight one
@@ -84,7 +84,8 @@ def check_against_oracle(cfg, frames, ids_mask=None, atol=3e-6, min_well_frac=0.
     well = (s_ref[:, 1] - s_ref[:, 2]) > 1e-3 * np.maximum(s_ref[:, 0], 1e-12)
     mine = align_sign(tgt["normal"], normal.cpu().numpy())
     assert well.sum() >= min_well_frac * v
-    assert not well.any() or np.abs(mine[well] - tgt["normal"][well]).max() < 2e-3
+    # measured on the full-config case (profiles/r02_geom_target_errors.json): max 2.7e-5, p99 1.2e-5
+    assert not well.any() or np.abs(mine[well] - tgt["normal"][well]).max() < 1e-4
     nn = normal.cpu().numpy()
     np.testing.assert_allclose(np.linalg.norm(nn, axis=1), 1.0, atol=1e-5)
     # residual check on ALL pillars incl. degenerate ones: C n = lambda_min n
