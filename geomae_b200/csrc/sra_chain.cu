@@ -50,7 +50,7 @@ constexpr int OFF_BAR = OFF_RED + 2 * CT * 4 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "forward chain: shared memory over the 227 KB limit");
 
-enum { FX, FATTN, FS1, FS2, FZ, FY16, FU16, FG16, FXP, FXB, FQKV, F_MAPS };
+enum { FX, FATTN, FXH1, FXH2, FZ, FU16, FG16, FXB, FQKV, F_MAPS };
 struct FwdMaps { CUtensorMap m[F_MAPS]; };
 struct FwdArgs {
   int n; int mode;
@@ -338,11 +338,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const __grid_constant
           v[4 * k] += b4.x + xr.x; v[4 * k + 1] += b4.y + xr.y; v[4 * k + 2] += b4.z + xr.z; v[4 * k + 3] += b4.w + xr.w;
         }
         float mean, rstd;
-        row_stats(v, sRed, r, cq, a.eps, mean, rstd);
-        put_row(sR, cq, r, v);                       // s1 over x, in place
+        row_stats(v, sRed, r, cq, a.eps, mean, rstd);          // (its barriers: every thread has read its x row)
         if (cq == 0 && grow < a.n) *reinterpret_cast<float2*>(a.st1 + 2 * (int64_t)grow) = make_float2(mean, rstd);
 #pragma unroll
-        for (int c = 0; c < CW; ++c) v[c] = fmaf((v[c] - mean) * rstd, p_g1[c0 + c], p_be1[c0 + c]);     // y
+        for (int c = 0; c < CW; ++c) v[c] = (v[c] - mean) * rstd;                                       // xhat1
+#pragma unroll
+        for (int c = 0; c < CW; c += 8)               // saved for the backward (bf16): staged in the lower half of R
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sR) + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) v[c] = fmaf(v[c], p_g1[c0 + c], p_be1[c0 + c]);                    // y
 #pragma unroll
         for (int c = 0; c < CW; c += 8) *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
 #pragma unroll
@@ -352,20 +356,17 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const __grid_constant
         warp_arrive(&a_ready[1]);
         compute_sync();
         if (t0) {
-          store_f32(sR, &maps.m[FS1], row0);         // saved pre-LN1 rows
-          store_b16<2>(sA, &maps.m[FY16], 0, row0);  // bf16 y: operand of the lin1 weight gradient
+          store_b16<2>(reinterpret_cast<uint8_t*>(sR), &maps.m[FXH1], 0, row0);       // xhat1: LN1 backward + lin1 weight gradient
           tma::store_commit();
         }
-        // ---------------- E2: u = acc + b1 ; g = gelu(u)   (two 128-column bands; u staged in T, then in R)
+        // ---------------- E2: u = acc + b1 ; g = gelu(u)   (two 128-column bands; u staged in T, then in the upper half of R)
         stamp();                                     // 3: E1 done
         tc::mbar_wait(&acc_full[1], par);
         tc::fence_after_sync();
         stamp();                                     // 4: FFN1 accumulators complete
-        if (t0) tma::store_wait_read();              // A (y16) and R (s1) have been read: G and R may be overwritten
-        compute_sync();
 #pragma unroll 1
         for (int band = 0; band < 2; ++band) {
-          uint8_t* ust = band == 0 ? sT : reinterpret_cast<uint8_t*>(sR);
+          uint8_t* ust = band == 0 ? sT : reinterpret_cast<uint8_t*>(sR) + 2 * BLK;
           tc::tmem_ld32(t_lane + 128 + band * 128 + c0, v);
           tc::tmem_ld_wait();
 #pragma unroll
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const __grid_constant
         compute_sync();
         if (t0) {
           store_b16<2>(sT, &maps.m[FU16], 0, row0);                                   // saved pre-GELU rows (bf16)
-          store_b16<2>(reinterpret_cast<uint8_t*>(sR), &maps.m[FU16], 128, row0);
+          store_b16<2>(reinterpret_cast<uint8_t*>(sR) + 2 * BLK, &maps.m[FU16], 128, row0);
           store_b16<4>(sG, &maps.m[FG16], 0, row0);                                   // bf16 gelu(u): lin2 weight-gradient operand
           tma::store_commit();
         }
@@ -396,22 +397,19 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const __grid_constant
         stamp();                                     // 6: FFN2 accumulators complete
         tc::tmem_ld32(t_lane + c0, v);
         tc::tmem_ld_wait();
-        if (t0) tma::store_wait_read();              // R (u band 1), T, G have been read (the barrier is inside row_stats)
+        if (t0) tma::store_wait_read();              // R, T, G have been read by their stores (the barrier is inside row_stats)
         row_stats(v, sRed, r, cq, a.eps, mean, rstd);
-        put_row(sR, cq, r, v);
         if (cq == 0 && grow < a.n) *reinterpret_cast<float2*>(a.st2 + 2 * (int64_t)grow) = make_float2(mean, rstd);
-        publish_sync();
-        if (t0) {
-          store_f32(sR, &maps.m[FS2], row0);         // saved pre-LN2 rows
-          tma::store_commit();
-        }
 #pragma unroll
-        for (int c = 0; c < CW; ++c) v[c] = fmaf((v[c] - mean) * rstd, p_g2[c0 + c], p_be2[c0 + c]);     // z
-        if (t0) tma::store_wait_read();
-        compute_sync();
+        for (int c = 0; c < CW; ++c) v[c] = (v[c] - mean) * rstd;                                       // xhat2
+#pragma unroll
+        for (int c = 0; c < CW; c += 8) *reinterpret_cast<uint4*>(sT + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) v[c] = fmaf(v[c], p_g2[c0 + c], p_be2[c0 + c]);                    // z
         put_row(sR, cq, r, v);
         publish_sync();
         if (t0) {
+          store_b16<2>(sT, &maps.m[FXH2], 0, row0);  // xhat2: LN2 backward + the next layer's in-projection weight gradient
           store_f32(sR, &maps.m[FZ], row0);          // the layer output (next layer's residual input)
           tma::store_commit();
         }
@@ -437,9 +435,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const __grid_constant
         }
         warp_arrive(&a_ready[3]);
         compute_sync();
-        if (t0) {
-          store_b16<2>(sA, &maps.m[FXP], 0, row0);   // operands of the next layer's in-projection weight gradient
-          store_b16<2>(sA2, &maps.m[FXB], 0, row0);
+        if (t0 && !chain) {
+          store_b16<2>(sA2, &maps.m[FXB], 0, row0);  // bf16 copy of the stack input: operand of layer 0's in-projection weight gradient
           tma::store_commit();
         }
         stamp();                                     // 8: next-layer operands done
@@ -451,10 +448,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_fwd(const __grid_constant
         for (int band = 0; band < 3; ++band) {
           tc::tmem_ld32(t_lane + 128 + band * 128 + c0, v);
           tc::tmem_ld_wait();
-          if (band > 0) {
-            if (t0) tma::store_wait_read();          // the previous band has left T
-            compute_sync();
-          }
+          if (t0) tma::store_wait_read();            // xhat2 / the previous band has left T
+          compute_sync();
 #pragma unroll
           for (int c = 0; c < CW; c += 8) {
             float o8[8];
@@ -505,7 +500,7 @@ constexpr int B_OFF_BAR = B_OFF_RED + CT * 4 * 8;
 constexpr int B_SMEM_BYTES = B_OFF_BAR + 256 + 1024;
 static_assert(B_SMEM_BYTES <= 232448, "backward chain: shared memory over the 227 KB limit");
 
-enum { BDIN, BDQKV, BS2, BS1, BU16, BATTN, BDS2, BDU, BDS1H, BDS1, BDO, BDX, B_MAPS };
+enum { BDIN, BDQKV, BXH2, BXH1, BU16, BATTN, BDS2, BDU, BDS1H, BDS1, BDO, BDX, B_MAPS };
 struct BwdMaps { CUtensorMap m[B_MAPS]; };
 struct BwdArgs {
   int n; int mode;
@@ -515,39 +510,55 @@ struct BwdArgs {
   float *d_g2, *d_be2, *d_g1, *d_be1;
 };
 
-// LayerNorm backward of one 32-column group of a row held in v (= dz), xhat recomputed from the saved pre-LN row in R
-// (overwritten in place with dz * xhat for the d_gamma column sums).  On return v holds d(pre-LN row), xh the untouched dz.
-__device__ __forceinline__ void ln_backward_row(float* v, float* xh, float* sR, const float* gamma, float mean, float rstd,
-                                                float2* red, int r, int cq) {
+// Column sums over the 32 rows of a warp of 32 per-lane values: after five exchange-and-halve stages lane l holds the sum
+// over the warp's rows of column l (62 selects + 31 shuffles + 31 adds, no shared memory, no barrier).
+__device__ __forceinline__ float warp_column_sums(float* a) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) {
+    const bool up = (lane & k) != 0;
+#pragma unroll
+    for (int i = 0; i < k; ++i) {
+      const float send = up ? a[i] : a[i + k];
+      const float keep = up ? a[i + k] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, k);
+    }
+  }
+  return a[0];
+}
+
+// LayerNorm backward of one 32-column group of a row: v = dz in, d(pre-LN row) out; xhat comes from the saved bf16 tile.
+// acc_dg / acc_db (lane l = column c0 + l) accumulate this warp's share of d_gamma = sum dz xhat and d_beta = sum dz.
+__device__ __forceinline__ void ln_backward_row(float* v, const uint8_t* xh_tile, const float* gamma, float rstd, float2* red,
+                                                int r, int cq, float& acc_dg, float& acc_db) {
+  const int c0 = cq * CW;
+  float xh[CW], t[CW];
   float p1a = 0.f, p1b = 0.f, p2a = 0.f, p2b = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float4* cell = rq(sR, cq, r, k);
-    const float4 s4 = *cell;
-    const float4 g4 = *reinterpret_cast<const float4*>(gamma + 4 * k);
-    const float s[4] = {s4.x, s4.y, s4.z, s4.w}, gm[4] = {g4.x, g4.y, g4.z, g4.w};
-    float t[4];
+  for (int c = 0; c < CW; c += 8) {
+    const uint4 x4 = *reinterpret_cast<const uint4*>(xh_tile + op_off(r, (c0 + c) >> 3));
+    const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&x4);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int c = 4 * k + e;
-      xh[c] = (s[e] - mean) * rstd;
-      const float g = v[c] * gm[e];
-      if (e & 1) { p1b += g; p2b = fmaf(g, xh[c], p2b); }
-      else { p1a += g; p2a = fmaf(g, xh[c], p2a); }
-      t[e] = v[c] * xh[c];
+      const float2 xf = __bfloat1622float2(x2[e]);
+      xh[c + 2 * e] = xf.x; xh[c + 2 * e + 1] = xf.y;
+      const float g0 = v[c + 2 * e] * gamma[c + 2 * e], g1 = v[c + 2 * e + 1] * gamma[c + 2 * e + 1];
+      p1a += g0; p1b += g1;
+      p2a = fmaf(g0, xf.x, p2a); p2b = fmaf(g1, xf.y, p2b);
     }
-    *cell = make_float4(t[0], t[1], t[2], t[3]);
   }
   red[r * 4 + cq] = make_float2(p1a + p1b, p2a + p2b);
+#pragma unroll
+  for (int c = 0; c < CW; ++c) t[c] = v[c] * xh[c];
+  acc_dg += warp_column_sums(t);
+#pragma unroll
+  for (int c = 0; c < CW; ++c) t[c] = v[c];
+  acc_db += warp_column_sums(t);
   compute_sync();
   const float4 ra = *reinterpret_cast<const float4*>(red + r * 4), rb = *reinterpret_cast<const float4*>(red + r * 4 + 2);
   const float m1 = ((ra.x + ra.z) + (rb.x + rb.z)) * (1.0f / 128.f), m2 = ((ra.y + ra.w) + (rb.y + rb.w)) * (1.0f / 128.f);
 #pragma unroll
-  for (int c = 0; c < CW; ++c) {
-    const float dzv = v[c];
-    v[c] = rstd * (dzv * gamma[c] - m1 - xh[c] * m2);
-    xh[c] = dzv;                                      // keep dz for the d_beta column sums
-  }
+  for (int c = 0; c < CW; ++c) v[c] = rstd * (v[c] * gamma[c] - m1 - xh[c] * m2);
 }
 
 __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant__ BwdMaps maps, const BwdArgs a) {
@@ -566,7 +577,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
   uint64_t* a_ready = w_empty + RING;      // [4]: 0 dqkv' bands (+ ds1' pre-load), 1 ds2, 2 du (+ ds2 pre-load), 3 ds1
   uint64_t* acc_full = a_ready + 4;        // [4]: 0 dz, 1 du_pre, 2 dy, 3 dO
   uint64_t* in_full = acc_full + 4;        // ds1' / dz rows and the dqkv' bands
-  uint64_t* r_full = in_full + 1;          // s2, then s1, in R (two uses per tile)
+  uint64_t* r_full = in_full + 1;          // the bf16 xhat2 | xhat1 tiles in R (once per tile)
   uint64_t* u_full = r_full + 1;           // u bands, then O rows (two uses per tile)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -654,10 +665,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
     const int c0 = cq * CW;
     const bool t0 = threadIdx.x == 0;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
-    const int cs_col = threadIdx.x & 127, cs_row0 = (threadIdx.x >> 7) * 32;     // column-sum ownership: 4 threads / column
-    const uint8_t* cs_base = reinterpret_cast<const uint8_t*>(sR) + (cs_col >> 5) * BLK + (cs_col & 3) * 4;
-    const int cs_k = (cs_col & 31) >> 2;
-    float acc_dg2 = 0.f, acc_db2 = 0.f, acc_dg1 = 0.f, acc_db1 = 0.f;
+    float acc_dg2 = 0.f, acc_db2 = 0.f, acc_dg1 = 0.f, acc_db1 = 0.f;     // lane l: column c0 + l, this warp's 32 rows of every tile
     auto issue_inputs = [&](int tile) {                // ds1' (or dz) -> R, the three dqkv' bands -> A, A2, T
       const int row0 = tile * CT;
       tc::mbar_expect_tx(in_full, (up ? 10 : 4) * BLK);
@@ -668,18 +676,6 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
         load_b16<2>(sT, &maps.m[BDQKV], 256, row0, in_full);
       }
     };
-    // column sums of R over this thread's 32 tile rows
-    auto column_sum = [&](float& acc) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int rr = cs_row0; rr < cs_row0 + 32; rr += 4) {
-        s0 += *reinterpret_cast<const float*>(cs_base + tc::swz(rr, cs_k));
-        s1 += *reinterpret_cast<const float*>(cs_base + tc::swz(rr + 1, cs_k));
-        s2 += *reinterpret_cast<const float*>(cs_base + tc::swz(rr + 2, cs_k));
-        s3 += *reinterpret_cast<const float*>(cs_base + tc::swz(rr + 3, cs_k));
-      }
-      acc += (s0 + s1) + (s2 + s3);
-    };
     int it = 0;
     if (t0) issue_inputs(blockIdx.x);
     cp_wait_all();                                     // LayerNorm weights
@@ -688,7 +684,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
       const int row0 = tile * CT;
       const int grow = row0 + r;
       const int ntile = tile + gridDim.x;
-      float v[CW], xh[CW];
+      float v[CW];
       tc::mbar_wait(in_full, par);                     // R = ds1' (or dz), dqkv' bands on chip
       get_row(sR, cq, r, v);
       if (up) {
@@ -697,9 +693,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
         warp_arrive(&a_ready[0]);
       }
       compute_sync();                                  // every thread has read its R row (and sees the parameters)
-      if (chain && t0) {
+      if (chain && t0) {                               // bf16 xhat2 -> lower half of R, xhat1 -> upper half
         tc::mbar_expect_tx(r_full, 4 * BLK);
-        load_f32(sR, &maps.m[BS2], row0, r_full);
+        load_b16<2>(reinterpret_cast<uint8_t*>(sR), &maps.m[BXH2], 0, row0, r_full);
+        load_b16<2>(reinterpret_cast<uint8_t*>(sR) + 2 * BLK, &maps.m[BXH1], 0, row0, r_full);
       }
       if (up) {
         tc::mbar_wait(&acc_full[0], par);
@@ -726,9 +723,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
         load_b16<2>(sT, &maps.m[BU16], 0, row0, u_full);
         load_b16<2>(sA2, &maps.m[BU16], 128, row0, u_full);
       }
-      float2 st = grow < a.n ? __ldg(reinterpret_cast<const float2*>(a.st2 + 2 * (int64_t)grow)) : make_float2(0.f, 0.f);
-      tc::mbar_wait(r_full, 0);                        // s2 in R
-      ln_backward_row(v, xh, sR, sPar + c0, st.x, st.y, sRed, r, cq);          // v = ds2, xh = dz, R = dz * xhat2
+      float rstd = grow < a.n ? __ldg(a.st2 + 2 * (int64_t)grow + 1) : 0.f;
+      tc::mbar_wait(r_full, par);                      // xhat tiles in R
+      ln_backward_row(v, reinterpret_cast<const uint8_t*>(sR), sPar + c0, rstd, sRed, r, cq, acc_dg2, acc_db2);       // v = ds2
 #pragma unroll
       for (int c = 0; c < CW; c += 8) *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
       tmem_st32(t_lane + c0, v);                       // dy accumulator starts at ds2
@@ -739,24 +736,16 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
         store_b16<2>(sA, &maps.m[BDS2], 0, row0);      // bf16 ds2: operand of the lin2 weight gradient
         tma::store_commit();
       }
-      column_sum(acc_dg2);                             // d_gamma2 += sum dz * xhat2
-      compute_sync();
-      put_row(sR, cq, r, xh);
-      compute_sync();
-      column_sum(acc_db2);                             // d_beta2 += sum dz
-      if (t0) tma::store_wait_read();                  // A (ds2) has been read: du may be written over it
-      compute_sync();
-      if (t0) {
-        tc::mbar_expect_tx(r_full, 4 * BLK);
-        load_f32(sR, &maps.m[BS1], row0, r_full);
-      }
       // ---------------- du = (ds2 W2) * gelu'(u): two 128-column bands, 32 columns per thread
       tc::mbar_wait(&acc_full[1], par);
       tc::fence_after_sync();
       tc::mbar_wait(u_full, 0);
+      if (t0) tma::store_wait_read();                  // A (ds2) has been read: du may be written over it
+      compute_sync();
 #pragma unroll 1
       for (int band = 0; band < 2; ++band) {
-        tc::tmem_ld32(t_lane + 128 + band * 128 + c0, xh);
+        float w[CW];
+        tc::tmem_ld32(t_lane + 128 + band * 128 + c0, w);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < CW; c += 8) {
@@ -768,8 +757,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 uf = __bfloat1622float2(u2[e]);
-            d8[2 * e] = xh[c + 2 * e] * gelu_grad_f(uf.x);
-            d8[2 * e + 1] = xh[c + 2 * e + 1] * gelu_grad_f(uf.y);
+            d8[2 * e] = w[c + 2 * e] * gelu_grad_f(uf.x);
+            d8[2 * e + 1] = w[c + 2 * e + 1] * gelu_grad_f(uf.y);
           }
           *reinterpret_cast<uint4*>(gdst) = pack8f(d8);
         }
@@ -787,27 +776,16 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
       tc::fence_after_sync();
       tc::tmem_ld32(t_lane + c0, v);
       tc::tmem_ld_wait();
-      st = grow < a.n ? __ldg(reinterpret_cast<const float2*>(a.st1 + 2 * (int64_t)grow)) : make_float2(0.f, 0.f);
-      tc::mbar_wait(r_full, 1);                        // s1 in R
+      rstd = grow < a.n ? __ldg(a.st1 + 2 * (int64_t)grow + 1) : 0.f;
       if (t0) tma::store_wait_read();                  // G (du) has been read (the barrier is inside ln_backward_row)
-      ln_backward_row(v, xh, sR, sPar + 128 + c0, st.x, st.y, sRed, r, cq);     // v = ds1, xh = dy, R = dy * xhat1
+      ln_backward_row(v, reinterpret_cast<const uint8_t*>(sR) + 2 * BLK, sPar + 128 + c0, rstd, sRed, r, cq, acc_dg1, acc_db1);   // v = ds1
 #pragma unroll
       for (int c = 0; c < CW; c += 8) *reinterpret_cast<uint4*>(sA + op_off(r, (c0 + c) >> 3)) = pack8f(v + c);
       warp_arrive(&a_ready[3]);
-      compute_sync();
-      if (t0) {
-        store_b16<2>(sA, &maps.m[BDS1H], 0, row0);     // bf16 ds1: operand of the out_proj weight gradient
-        tma::store_commit();
-      }
-      column_sum(acc_dg1);                             // d_gamma1 += sum dy * xhat1
-      compute_sync();
-      put_row(sR, cq, r, xh);
-      compute_sync();
-      column_sum(acc_db1);                             // d_beta1 += sum dy
-      compute_sync();
-      put_row(sR, cq, r, v);
+      put_row(sR, cq, r, v);                           // (every thread read its xhat values before the barrier above)
       publish_sync();
       if (t0) {
+        store_b16<2>(sA, &maps.m[BDS1H], 0, row0);     // bf16 ds1: operand of the out_proj weight gradient
         store_f32(sR, &maps.m[BDS1], row0);            // fp32 ds1: the residual-gradient term of the layer below
         tma::store_commit();
       }
@@ -849,10 +827,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_sra_chain_bwd(const __grid_constant
     }
     if (t0) tma::store_wait_all();
     if (chain) {
-      atomicAdd(a.d_g2 + cs_col, acc_dg2);
-      atomicAdd(a.d_be2 + cs_col, acc_db2);
-      atomicAdd(a.d_g1 + cs_col, acc_dg1);
-      atomicAdd(a.d_be1 + cs_col, acc_db1);
+      atomicAdd(a.d_g2 + c0 + lane, acc_dg2);
+      atomicAdd(a.d_be2 + c0 + lane, acc_db2);
+      atomicAdd(a.d_g1 + c0 + lane, acc_dg1);
+      atomicAdd(a.d_be1 + c0 + lane, acc_db1);
     }
     tc::fence_before_sync();
   }
@@ -886,30 +864,26 @@ extern "C" int geomae_sra_chain_fwd(const geomae_chain_fwd_args* p, void* stream
   GM_REQUIRE(p->x, "sra_chain_fwd: x is null");
   if (chain)
     GM_REQUIRE(p->attn && p->p_out_proj && p->p_lin1 && p->p_lin2 && p->out_proj_b && p->lin1_b && p->lin2_b &&
-                   p->norm1_w && p->norm1_b && p->norm2_w && p->norm2_b && p->s1 && p->st1 && p->s2 && p->st2 && p->z &&
-                   p->y16 && p->u16 && p->g16,
+                   p->norm1_w && p->norm1_b && p->norm2_w && p->norm2_b && p->xh1_16 && p->st1 && p->xh2_16 && p->st2 && p->z &&
+                   p->u16 && p->g16,
                "sra_chain_fwd: the layer chain needs attn, packed weights, biases, norms and every saved-tensor buffer");
   if (next)
-    GM_REQUIRE(p->p_in_proj_next && p->in_proj_b_next && p->pos_table && p->tok_cell_next && p->xp16_next &&
-                   p->xb16_next && p->qkv16_next,
+    GM_REQUIRE(p->p_in_proj_next && p->in_proj_b_next && p->pos_table && p->tok_cell_next && p->qkv16_next && (chain || p->xb16),
                "sra_chain_fwd: the next in-projection needs packed weights, bias, position table, cells and outputs");
   const int64_t n = p->n_tokens;
   FwdMaps maps;
   GM_MAP(maps.m[FX], p->x, 128, 4);
   if (chain) {
     GM_MAP(maps.m[FATTN], p->attn, 128, 2);
-    GM_MAP(maps.m[FS1], p->s1, 128, 4);
-    GM_MAP(maps.m[FS2], p->s2, 128, 4);
+    GM_MAP(maps.m[FXH1], p->xh1_16, 128, 2);
+    GM_MAP(maps.m[FXH2], p->xh2_16, 128, 2);
     GM_MAP(maps.m[FZ], p->z, 128, 4);
-    GM_MAP(maps.m[FY16], p->y16, 128, 2);
     GM_MAP(maps.m[FU16], p->u16, 256, 2);
     GM_MAP(maps.m[FG16], p->g16, 256, 2);
+  } else {
+    GM_MAP(maps.m[FXB], p->xb16, 128, 2);
   }
-  if (next) {
-    GM_MAP(maps.m[FXP], p->xp16_next, 128, 2);
-    GM_MAP(maps.m[FXB], p->xb16_next, 128, 2);
-    GM_MAP(maps.m[FQKV], p->qkv16_next, 384, 2);
-  }
+  if (next) GM_MAP(maps.m[FQKV], p->qkv16_next, 384, 2);
   FwdArgs a;
   a.n = (int)n; a.mode = p->mode;
   a.Wo = (const uint8_t*)p->p_out_proj; a.W1 = (const uint8_t*)p->p_lin1; a.W2 = (const uint8_t*)p->p_lin2;
@@ -939,7 +913,7 @@ extern "C" int geomae_sra_chain_bwd(const geomae_chain_bwd_args* p, void* stream
   if (up) GM_REQUIRE(p->dqkv16_up && p->ds1_up && p->p_in_proj_up, "sra_chain_bwd: the in-projection backward needs dqkv, ds1 and packed weights of the layer above");
   else GM_REQUIRE(p->dz_in, "sra_chain_bwd: dz_in is null");
   if (chain)
-    GM_REQUIRE(p->s2 && p->st2 && p->s1 && p->st1 && p->u16 && p->attn16 && p->p_lin2 && p->p_lin1 && p->p_out_proj &&
+    GM_REQUIRE(p->xh2_16 && p->st2 && p->xh1_16 && p->st1 && p->u16 && p->attn16 && p->p_lin2 && p->p_lin1 && p->p_out_proj &&
                    p->norm2_w && p->norm1_w && p->ds2_16 && p->du16 && p->ds1_16 && p->dattn16 && p->ds1 && p->dd &&
                    p->g_norm2_w && p->g_norm2_b && p->g_norm1_w && p->g_norm1_b,
                "sra_chain_bwd: the layer chain needs every saved tensor, packed weight, output and gradient buffer");
@@ -949,8 +923,8 @@ extern "C" int geomae_sra_chain_bwd(const geomae_chain_bwd_args* p, void* stream
   GM_MAP(maps.m[BDIN], up ? p->ds1_up : p->dz_in, 128, 4);
   if (up) GM_MAP(maps.m[BDQKV], p->dqkv16_up, 384, 2);
   if (chain) {
-    GM_MAP(maps.m[BS2], p->s2, 128, 4);
-    GM_MAP(maps.m[BS1], p->s1, 128, 4);
+    GM_MAP(maps.m[BXH2], p->xh2_16, 128, 2);
+    GM_MAP(maps.m[BXH1], p->xh1_16, 128, 2);
     GM_MAP(maps.m[BU16], p->u16, 256, 2);
     GM_MAP(maps.m[BATTN], p->attn16, 128, 2);
     GM_MAP(maps.m[BDS2], p->ds2_16, 128, 2);

@@ -86,18 +86,21 @@ static int fused_forward(const geomae_sra_ctx* c, int32_t n_layers, const geomae
                   const float* x_in, void* stream) {
   const int64_t n = c->n_tokens;
   const double d = c->d_model, f = c->ffn;
-  for (int l = 0; l < n_layers; ++l)
-    GM_REQUIRE(saved[l].g && saved[l].xp && saved[l].xb, "sra_stack_forward: the bf16 path needs the g / xp / xb buffers of layer %d", l);
+  for (int l = 0; l < n_layers; ++l) GM_REQUIRE(saved[l].g, "sra_stack_forward: the bf16 path needs the g buffer of layer %d", l);
+  GM_REQUIRE(saved[0].xb && c->pos16[0] && (c->pos16[1] || !c->shift[1].tok_cell),
+             "sra_stack_forward: the bf16 path needs saved[0].xb and the pos16 scratch of every shift");
+  for (int sft = 0; sft < 2; ++sft)      // gathered bf16 position rows per shift: operands of the in-projection weight gradients
+    if (c->shift[sft].tok_cell) GM_TRY(geomae_pos_rows_bf16(c->pos_table, c->shift[sft].tok_cell, n, c->pos16[sft], stream));
   auto next_of = [&](geomae_chain_fwd_args& a, int l) {     // in-projection of layer l appended to the kernel
     const geomae_sra_layer& N = layers[l];
     a.p_in_proj_next = N.p_in_proj[0]; a.in_proj_b_next = N.in_proj_b;
     a.pos_table = c->pos_table; a.tok_cell_next = c->shift[N.shift].tok_cell;
-    a.xp16_next = saved[l].xp; a.xb16_next = saved[l].xb; a.qkv16_next = saved[l].qkv;
+    a.qkv16_next = saved[l].qkv;
   };
-  const double in_flops = 2.0 * n * d * 3.0 * d, in_bytes = n * (2.0 * 2.0 * d + 2.0 * 3.0 * d) + 2.0 * 3.0 * d * d;
+  const double in_flops = 2.0 * n * d * 3.0 * d, in_bytes = n * (2.0 * 3.0 * d) + 2.0 * 3.0 * d * d;
   {
     geomae_chain_fwd_args a{};
-    a.n_tokens = n; a.mode = 2; a.x = x_in;
+    a.n_tokens = n; a.mode = 2; a.x = x_in; a.xb16 = saved[0].xb;
     next_of(a, 0);
     Span span(0, in_flops, stream, 4.0 * n * d + in_bytes);
     GM_TRY(geomae_sra_chain_fwd(&a, stream));
@@ -117,10 +120,10 @@ static int fused_forward(const geomae_sra_ctx* c, int32_t n_layers, const geomae
     a.p_out_proj = L.p_out_proj[0]; a.p_lin1 = L.p_lin1[0]; a.p_lin2 = L.p_lin2[0];
     a.out_proj_b = L.out_proj_b; a.lin1_b = L.lin1_b; a.lin2_b = L.lin2_b;
     a.norm1_w = L.norm1_w; a.norm1_b = L.norm1_b; a.norm2_w = L.norm2_w; a.norm2_b = L.norm2_b; a.ln_eps = L.ln_eps;
-    a.s1 = S.s1; a.st1 = S.st1; a.s2 = S.s2; a.st2 = S.st2; a.z = S.z; a.y16 = S.y; a.u16 = S.u; a.g16 = S.g;
+    a.xh1_16 = S.s1; a.st1 = S.st1; a.xh2_16 = S.s2; a.st2 = S.st2; a.z = S.z; a.u16 = S.u; a.g16 = S.g;
     if (has_next) next_of(a, l + 1);
-    // algorithmic bytes: x + attn in; s1, s2, z (+ statistics), bf16 y, u, g out; bf16 weight images
-    const double bytes = n * (4.0 * d + 2.0 * d + 3.0 * 4.0 * d + 16.0 + 2.0 * d + 2.0 * 2.0 * f) + 2.0 * (d * d + 2.0 * d * f) +
+    // algorithmic bytes: x + attn in; z (+ statistics), bf16 xhat1, xhat2, u, g out; bf16 weight images
+    const double bytes = n * (4.0 * d + 2.0 * d + 4.0 * d + 16.0 + 2.0 * 2.0 * d + 2.0 * 2.0 * f) + 2.0 * (d * d + 2.0 * d * f) +
                          (has_next ? in_bytes : 0.0);
     Span span(0, 2.0 * n * (d * d + 2.0 * d * f) + (has_next ? in_flops : 0.0), stream, bytes);
     GM_TRY(geomae_sra_chain_fwd(&a, stream));
@@ -261,14 +264,14 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
         const Set above = carve((l + 1) & 1);
         a.dqkv16_up = above.dqkv16; a.ds1_up = above.ds1; a.p_in_proj_up = layers[l + 1].p_in_proj[0];
       }
-      a.s2 = S.s2; a.st2 = S.st2; a.s1 = S.s1; a.st1 = S.st1; a.u16 = S.u; a.attn16 = S.attn;
+      a.xh2_16 = S.s2; a.st2 = S.st2; a.xh1_16 = S.s1; a.st1 = S.st1; a.u16 = S.u; a.attn16 = S.attn;
       a.p_lin2 = L.p_lin2[0]; a.p_lin1 = L.p_lin1[0]; a.p_out_proj = L.p_out_proj[0];
       a.norm2_w = L.norm2_w; a.norm1_w = L.norm1_w;
       a.ds2_16 = cur.ds2_16; a.du16 = cur.du16; a.ds1_16 = cur.ds1_16; a.dattn16 = cur.dattn16; a.ds1 = cur.ds1; a.dd = cur.dd;
       a.g_norm2_w = L.g_norm2_w; a.g_norm2_b = L.g_norm2_b; a.g_norm1_w = L.g_norm1_w; a.g_norm1_b = L.g_norm1_b;
       {
-        // algorithmic bytes: dz (or dqkv' + ds1'), s2, s1, u, attn in; bf16 ds2, du, ds1, dattn + fp32 ds1 + D out; weights
-        const double bytes = (top ? 4.0 * n * dd_ : up_bytes) + n * (2.0 * 4.0 * dd_ + 16.0 + 2.0 * ff + 2.0 * dd_) +
+        // algorithmic bytes: dz (or dqkv' + ds1'), bf16 xhat2, xhat1, u, attn in; bf16 ds2, du, ds1, dattn + fp32 ds1 + D out; weights
+        const double bytes = (top ? 4.0 * n * dd_ : up_bytes) + n * (2.0 * 2.0 * dd_ + 16.0 + 2.0 * ff + 2.0 * dd_) +
                              n * (3.0 * 2.0 * dd_ + 2.0 * ff + 4.0 * dd_ + 4.0 * c->n_heads) + 2.0 * (dd_ * dd_ + 2.0 * dd_ * ff);
         Span span(0, 2.0 * n * (dd_ * dd_ + 2.0 * dd_ * ff) + (top ? 0.0 : up_flops), main, bytes);
         GM_TRY(geomae_sra_chain_bwd(&a, main));
@@ -281,8 +284,11 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
       GM_TRY(hand_off(main, side));
       geomae_wgrad_layer_args g{};
       g.n_tokens = n;
-      g.ds2_16 = cur.ds2_16; g.g16 = S.g; g.du16 = cur.du16; g.y16 = S.y; g.ds1_16 = cur.ds1_16; g.attn16 = S.attn;
-      g.dqkv16 = cur.dqkv16; g.xp16 = S.xp; g.xb16 = S.xb;
+      g.ds2_16 = cur.ds2_16; g.g16 = S.g; g.du16 = cur.du16; g.xh1_16 = S.s1; g.ds1_16 = cur.ds1_16; g.attn16 = S.attn;
+      g.dqkv16 = cur.dqkv16; g.pos16 = c->pos16[L.shift];
+      g.norm1_w = L.norm1_w; g.norm1_b = L.norm1_b;
+      if (l == 0) { g.xin16 = saved[0].xb; g.in_scale = g.in_shift = nullptr; }             // the stack input itself
+      else { g.xin16 = saved[l - 1].s2; g.in_scale = layers[l - 1].norm2_w; g.in_shift = layers[l - 1].norm2_b; }   // x = LN2 of the layer below
       g.g_lin2_w = L.g_lin2_w; g.g_lin1_w = L.g_lin1_w; g.g_lin1_b = L.g_lin1_b; g.g_out_proj_w = L.g_out_proj_w;
       g.g_in_proj_w = L.g_in_proj_w; g.g_in_proj_b = L.g_in_proj_b; g.g_lin2_b = L.g_lin2_b; g.g_out_proj_b = L.g_out_proj_b;
       {

@@ -1,5 +1,10 @@
 // Weight gradients of one SRA EncoderLayer in ONE launch, fed by TMA (bf16 mode):
 //   dW2  += ds2^T gelu(u)      dW1 += du^T y  (+ db1)      dWo += ds1^T O      dWin += dqkv^T (x+pos | x)  (+ dbin)
+// The LayerNorm outputs y = xhat1*g1 + b1 and x = xhat2'*g2' + b2' (' = the layer below) are never stored: the chain
+// kernels save only the bf16 xhat tiles the LayerNorm backward needs anyway, and because the affine map is per COLUMN of
+// the operand it moves into the flush:  dY^T (xhat*g + b) = g[n] * (dY^T xhat)[m][n] + (sum_tok dY)[m] * b[n],  the second
+// factor being the bias-gradient column this kernel accumulates anyway.  The position term of the q|k rows,
+// dqk^T pos[cell], is two more slabs against the gathered position rows (one bf16 tensor per token set and shift).
 // i.e. the weight / bias gradient GEMMs autograd runs for nn.Linear / nn.MultiheadAttention in
 // models/sst/sst_basic_block.py:55,94-100.  Every operand is a token-major bf16 tensor [n, C] that the forward /
 // backward chain kernels saved; dW = dY^T X contracts over TOKENS, so both MMA operands are MN-major views of
@@ -24,10 +29,10 @@ constexpr int STAGE_BYTES = 4 * BLK;          // dY box pair + X box pair
 constexpr int OFF_ONES = STAGES * STAGE_BYTES;
 constexpr int OFF_BAR = OFF_ONES + BLK;
 constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-constexpr int MAX_SLABS = 8;
+constexpr int MAX_SLABS = 10;
 constexpr int NTHR = 192;
 
-struct Slab { int a_map, a_col, b_map, b_col; float* dW; int ldw; float* db; };
+struct Slab { int a_map, a_col, b_map, b_col; float* dW; int ldw; float* db; const float* scale; const float* shift; };
 struct WgArgs { int n_tiles; int tiles_per_cta; Slab slab[MAX_SLABS]; };
 struct WgMaps { CUtensorMap m[9]; };
 
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tma(const __grid_constant__ W
       const uint32_t idesc = tc::make_idesc_bf16(128, 128, 1, 1);
       const uint32_t idesc_b = tc::make_idesc_bf16(128, 16, 1, 1);
       const uint32_t ones = tc::smem_u32(sOnes);
-      const bool bias = s.db != nullptr;
+      const bool bias = s.db != nullptr || s.shift != nullptr;
       uint32_t cnt = 0;
       for (int t = tile_begin; t < tile_end; ++t, ++cnt) {
         const uint32_t slot = cnt % STAGES, ph = (cnt / STAGES) & 1;
@@ -104,29 +109,36 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tma(const __grid_constant__ W
       tc::mma_commit(acc_bar);
     }
   } else {
-    // ---- epilogue warps 2..5: TMEM lane quarter warp % 4 -> dW rows, one vector reduction per 4 columns
+    // ---- epilogue warps 2..5: TMEM lane quarter warp % 4 -> dW rows, one vector reduction per 4 columns;
+    // out = scale[n] * acc[m][n] + colsum[m] * shift[n] when the operand was a LayerNorm's xhat (see the file header)
     tc::mbar_wait(acc_bar, 0);
     tc::fence_after_sync();
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     float* o = s.dW + (int64_t)m * s.ldw;
+    float colsum = 0.f;
+    if (s.db || s.shift) {
+      float v[32];
+      tc::tmem_ld32(t_lane + 128, v);
+      tc::tmem_ld_wait();
+      colsum = v[0];
+      if (s.db) atomicAdd(s.db + m, colsum);
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
       float v[32];
       tc::tmem_ld32(t_lane + c0, v);
       tc::tmem_ld_wait();
+      if (s.scale) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], __ldg(s.scale + c0 + c), colsum * __ldg(s.shift + c0 + c));
+      }
 #pragma unroll
       for (int c = 0; c < 32; c += 4)
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + c0 + c), "f"(v[c]), "f"(v[c + 1]),
                      "f"(v[c + 2]), "f"(v[c + 3])
                      : "memory");
-    }
-    if (s.db) {
-      float v[32];
-      tc::tmem_ld32(t_lane + 128, v);
-      tc::tmem_ld_wait();
-      atomicAdd(s.db + m, v[0]);
     }
     tc::fence_before_sync();
   }
@@ -137,18 +149,43 @@ __global__ void __launch_bounds__(NTHR, 1) k_wgrad_tma(const __grid_constant__ W
   }
 }
 
+// out[i, :] = bf16(pos_table[tok_cell[i], :]) — the position rows of a token set and shift, gathered once per step
+__global__ void __launch_bounds__(256) k_pos_rows(const float* __restrict__ table, const int32_t* __restrict__ cell, int n,
+                                                  __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(table + (int64_t)__ldg(cell + i) * 128) + lane);
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(out + (int64_t)i * 128)[lane] =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+}
+
 }  // namespace
+
+extern "C" int geomae_pos_rows_bf16(const float* pos_table, const int32_t* tok_cell, int64_t n_tokens, void* out16, void* stream) {
+  GM_REQUIRE(n_tokens >= 0 && n_tokens < ((int64_t)1 << 31), "pos_rows_bf16: bad token count");
+  if (n_tokens == 0) return GEOMAE_OK;
+  GM_REQUIRE(pos_table && tok_cell && out16, "pos_rows_bf16: null argument");
+  int blocks = gm_div_up(n_tokens, 8);
+  if (blocks > GM_NUM_SMS * 8) blocks = GM_NUM_SMS * 8;
+  k_pos_rows<<<blocks, 256, 0, (cudaStream_t)stream>>>(pos_table, tok_cell, (int)n_tokens, (__nv_bfloat16*)out16);
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
 
 extern "C" int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* p, void* stream) {
   GM_REQUIRE(p, "sra_wgrad_layer: null argument");
   GM_REQUIRE(p->n_tokens >= 0 && p->n_tokens < ((int64_t)1 << 31) - 256, "sra_wgrad_layer: bad token count");
   if (p->n_tokens == 0) return GEOMAE_OK;
-  GM_REQUIRE(p->ds2_16 && p->g16 && p->du16 && p->y16 && p->ds1_16 && p->attn16 && p->dqkv16 && p->xp16 && p->xb16,
+  GM_REQUIRE(p->ds2_16 && p->g16 && p->du16 && p->xh1_16 && p->ds1_16 && p->attn16 && p->dqkv16 && p->xin16 && p->pos16,
              "sra_wgrad_layer: null operand tensor");
-  GM_REQUIRE(p->g_lin2_w && p->g_lin1_w && p->g_out_proj_w && p->g_in_proj_w, "sra_wgrad_layer: null gradient buffer");
+  GM_REQUIRE(p->g_lin2_w && p->g_lin1_w && p->g_out_proj_w && p->g_in_proj_w && p->norm1_w && p->norm1_b,
+             "sra_wgrad_layer: null gradient buffer / LayerNorm-1 parameters");
+  GM_REQUIRE((p->in_scale == nullptr) == (p->in_shift == nullptr), "sra_wgrad_layer: in_scale and in_shift go together");
   const int64_t n = p->n_tokens;
   WgMaps maps;
-  const void* base[9] = {p->ds2_16, p->g16, p->du16, p->y16, p->ds1_16, p->attn16, p->dqkv16, p->xp16, p->xb16};
+  const void* base[9] = {p->ds2_16, p->g16, p->du16, p->xh1_16, p->ds1_16, p->attn16, p->dqkv16, p->xin16, p->pos16};
   const int cols[9] = {128, 256, 256, 128, 128, 128, 384, 128, 128};
   for (int i = 0; i < 9; ++i) {
     const int rc = tma::make_map(&maps.m[i], base[i], n, cols[i], 2);
@@ -156,19 +193,22 @@ extern "C" int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* p, void* st
   }
   WgArgs a;
   a.n_tiles = gm_div_up(n, WT);
-  int splits = GM_NUM_SMS / MAX_SLABS;                  // 18 token ranges x 8 slabs = 144 CTAs
+  int splits = GM_NUM_SMS / MAX_SLABS;                  // 14 token ranges x 10 slabs = 140 CTAs
   if (splits > a.n_tiles) splits = a.n_tiles;
   a.tiles_per_cta = gm_div_up(a.n_tiles, splits);
   splits = gm_div_up(a.n_tiles, a.tiles_per_cta);
-  // slab = [128 dY columns] x [128 X columns]:            dY map, col, X map, col, dW,                 ld, db
-  a.slab[0] = Slab{0, 0, 1, 0, p->g_lin2_w, 256, p->g_lin2_b};                        // dW2[:, 0:128]   = ds2^T g[:, 0:128]
-  a.slab[1] = Slab{0, 0, 1, 128, p->g_lin2_w + 128, 256, nullptr};                // dW2[:, 128:256]
-  a.slab[2] = Slab{2, 0, 3, 0, p->g_lin1_w, 128, p->g_lin1_b};                    // dW1[0:128]      = du[:, 0:128]^T y
-  a.slab[3] = Slab{2, 128, 3, 0, p->g_lin1_w + 128 * 128, 128, p->g_lin1_b ? p->g_lin1_b + 128 : nullptr};
-  a.slab[4] = Slab{4, 0, 5, 0, p->g_out_proj_w, 128, p->g_out_proj_b};                    // dWo             = ds1^T O
-  a.slab[5] = Slab{6, 0, 7, 0, p->g_in_proj_w, 128, p->g_in_proj_b};              // dWin[q rows]    = dq^T (x + pos)
-  a.slab[6] = Slab{6, 128, 7, 0, p->g_in_proj_w + 128 * 128, 128, p->g_in_proj_b ? p->g_in_proj_b + 128 : nullptr};
-  a.slab[7] = Slab{6, 256, 8, 0, p->g_in_proj_w + 256 * 128, 128, p->g_in_proj_b ? p->g_in_proj_b + 256 : nullptr};
+  float* bi = p->g_in_proj_b;
+  // slab = [128 dY columns] x [128 X columns]:  dY map, col, X map, col, dW, ld, db, scale, shift
+  a.slab[0] = Slab{0, 0, 1, 0, p->g_lin2_w, 256, p->g_lin2_b, nullptr, nullptr};              // dW2[:, 0:128] = ds2^T g[:, 0:128]
+  a.slab[1] = Slab{0, 0, 1, 128, p->g_lin2_w + 128, 256, nullptr, nullptr, nullptr};          // dW2[:, 128:256]
+  a.slab[2] = Slab{2, 0, 3, 0, p->g_lin1_w, 128, p->g_lin1_b, p->norm1_w, p->norm1_b};        // dW1[0:128] = du[:, 0:128]^T y
+  a.slab[3] = Slab{2, 128, 3, 0, p->g_lin1_w + 128 * 128, 128, p->g_lin1_b ? p->g_lin1_b + 128 : nullptr, p->norm1_w, p->norm1_b};
+  a.slab[4] = Slab{4, 0, 5, 0, p->g_out_proj_w, 128, p->g_out_proj_b, nullptr, nullptr};      // dWo = ds1^T O
+  a.slab[5] = Slab{6, 0, 7, 0, p->g_in_proj_w, 128, bi, p->in_scale, p->in_shift};            // dWin[q rows] = dq^T x
+  a.slab[6] = Slab{6, 128, 7, 0, p->g_in_proj_w + 128 * 128, 128, bi ? bi + 128 : nullptr, p->in_scale, p->in_shift};
+  a.slab[7] = Slab{6, 256, 7, 0, p->g_in_proj_w + 256 * 128, 128, bi ? bi + 256 : nullptr, p->in_scale, p->in_shift};
+  a.slab[8] = Slab{6, 0, 8, 0, p->g_in_proj_w, 128, nullptr, nullptr, nullptr};               // += dq^T pos[cell]
+  a.slab[9] = Slab{6, 128, 8, 0, p->g_in_proj_w + 128 * 128, 128, nullptr, nullptr, nullptr}; // += dk^T pos[cell]
   static bool configured = false;
   if (!configured) {
     GM_CUDA(cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -142,17 +142,20 @@ def sra_chain_fwd(x, *, attn=None, layer=None, next_in_proj=None, pos_table=None
                            ("g2", "norm2_w"), ("be2", "norm2_b")):
             setattr(a, field, layer[key].data_ptr())
         a.ln_eps = layer["eps"]
-        out.update(s1=f32(n, 128), st1=f32(n, 2), s2=f32(n, 128), st2=f32(n, 2), z=f32(n, 128), y16=b16(n, 128),
-                   u16=b16(n, 256), g16=b16(n, 256))
-        for k in ("s1", "st1", "s2", "st2", "z", "y16", "u16", "g16"):
+        out.update(st1=f32(n, 2), st2=f32(n, 2), z=f32(n, 128), xh1_16=b16(n, 128), xh2_16=b16(n, 128), u16=b16(n, 256),
+                   g16=b16(n, 256))
+        for k in ("st1", "st2", "z", "xh1_16", "xh2_16", "u16", "g16"):
             setattr(a, k, out[k].data_ptr())
+    else:
+        out.update(xb16=b16(n, 128))
+        a.xb16 = out["xb16"].data_ptr()
     if next_in_proj is not None:
         Win, bin_ = next_in_proj
         img = pack_weight(Win, want_lo=False)[0]
         keep.append(img)
         a.p_in_proj_next, a.in_proj_b_next = img.data_ptr(), bin_.data_ptr()
         a.pos_table, a.tok_cell_next = pos_table.data_ptr(), tok_cell_next.data_ptr()
-        out.update(xp16=b16(n, 128), xb16=b16(n, 128), qkv16=b16(n, 384))
-        a.xp16_next, a.xb16_next, a.qkv16_next = out["xp16"].data_ptr(), out["xb16"].data_ptr(), out["qkv16"].data_ptr()
+        out.update(qkv16=b16(n, 384))
+        a.qkv16_next = out["qkv16"].data_ptr()
     L.run("sra_chain_fwd", C.byref(a), L.stream_ptr(dev))
     return out

@@ -74,7 +74,7 @@ class SRAWindows(C.Structure):
 
 class SRACtx(C.Structure):
     _fields_ = [("n_tokens", C.c_int64), ("d_model", C.c_int32), ("n_heads", C.c_int32), ("ffn", C.c_int32),
-                ("precision", C.c_int32), ("pos_table", C.c_void_p), ("shift", SRAWindows * 2)]
+                ("precision", C.c_int32), ("pos_table", C.c_void_p), ("shift", SRAWindows * 2), ("pos16", C.c_void_p * 2)]
 
 
 _LAYER_PARAMS = ["in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
@@ -98,20 +98,20 @@ class ChainFwdArgs(C.Structure):
                 [(k, C.c_void_p) for k in ("p_out_proj", "p_lin1", "p_lin2", "p_in_proj_next", "out_proj_b", "lin1_b",
                                            "lin2_b", "in_proj_b_next", "norm1_w", "norm1_b", "norm2_w", "norm2_b")] +
                 [("ln_eps", C.c_float), ("pos_table", C.c_void_p), ("tok_cell_next", C.c_void_p)] +
-                [(k, C.c_void_p) for k in ("s1", "st1", "s2", "st2", "z", "y16", "u16", "g16", "xp16_next",
-                                           "xb16_next", "qkv16_next")])
+                [(k, C.c_void_p) for k in ("st1", "st2", "z", "xh1_16", "xh2_16", "u16", "g16", "xb16", "qkv16_next")])
 
 
 class WgradLayerArgs(C.Structure):
     _fields_ = [("n_tokens", C.c_int64)] + [(k, C.c_void_p) for k in (
-        "ds2_16", "g16", "du16", "y16", "ds1_16", "attn16", "dqkv16", "xp16", "xb16", "g_lin2_w", "g_lin1_w", "g_lin1_b",
-        "g_out_proj_w", "g_in_proj_w", "g_in_proj_b", "g_lin2_b", "g_out_proj_b")]
+        "ds2_16", "g16", "du16", "xh1_16", "ds1_16", "attn16", "dqkv16", "xin16", "pos16", "norm1_w", "norm1_b", "in_scale",
+        "in_shift", "g_lin2_w", "g_lin1_w", "g_lin1_b", "g_out_proj_w", "g_in_proj_w", "g_in_proj_b", "g_lin2_b",
+        "g_out_proj_b")]
 
 
 class ChainBwdArgs(C.Structure):
     _fields_ = ([("n_tokens", C.c_int64), ("mode", C.c_int32)] +
                 [(k, C.c_void_p) for k in (
-                    "dqkv16_up", "ds1_up", "p_in_proj_up", "dz_in", "s2", "st2", "s1", "st1", "u16", "attn16", "p_lin2",
+                    "dqkv16_up", "ds1_up", "p_in_proj_up", "dz_in", "xh2_16", "st2", "xh1_16", "st1", "u16", "attn16", "p_lin2",
                     "p_lin1", "p_out_proj", "norm2_w", "norm1_w", "ds2_16", "du16", "ds1_16", "dattn16", "ds1", "dd", "dx",
                     "g_norm2_w", "g_norm2_b", "g_norm1_w", "g_norm1_b")])
 
@@ -182,6 +182,7 @@ class _Sigs:
                                   C.POINTER(SRALayer), C.POINTER(SRASaved), _p, _p, _p, _p, _p, _p, _p]
     geomae_sra_chain_fwd = [C.POINTER(ChainFwdArgs), _p]
     geomae_sra_chain_bwd = [C.POINTER(ChainBwdArgs), _p]
+    geomae_pos_rows_bf16 = [_p, _p, _i64, _p, _p]
     geomae_sra_wgrad_layer = [C.POINTER(WgradLayerArgs), _p]
     geomae_layernorm_bwd = [_p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]
     geomae_geom_loss_fwd = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), C.POINTER(LossArgs), _p, _p, _p, _p]

@@ -243,6 +243,13 @@ class SRAStack:
             w = layout.shift(s)
             c.shift[s].win_ptr, c.shift[s].win_tok = w["win_ptr"].data_ptr(), w["win_tok"].data_ptr()
             c.shift[s].tok_win, c.shift[s].tok_cell = w["tok_win"].data_ptr(), w["tok_cell"].data_ptr()
+        if precision == 1:      # gathered bf16 position rows per shift (filled by the forward executor), kept on the layout
+            pos16 = layout.__dict__.setdefault("_pos16", {})
+            key = (n, table.data_ptr())
+            if key not in pos16:
+                pos16[key] = torch.empty((layout.spec.n_shifts, max(n, 1), c.d_model), dtype=torch.bfloat16, device=table.device)
+            for s in range(layout.spec.n_shifts):
+                c.pos16[s] = pos16[key][s].data_ptr()
         return c
 
     def __call__(self, x, layout, table, precision):

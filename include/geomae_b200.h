@@ -375,6 +375,7 @@ typedef struct geomae_sra_ctx {
   int64_t n_tokens; int32_t d_model; int32_t n_heads; int32_t ffn; int32_t precision;   /* 1 bf16, 3 bf16x3 */
   const float* pos_table;             /* [win_x*win_y, d_model] */
   geomae_sra_windows shift[2];
+  void* pos16[2];                     /* precision 1: scratch [n_tokens, d_model] bf16 per shift (gathered position rows) */
 } geomae_sra_ctx;
 
 /* Parameters (and their fp32 gradient accumulators) of one EncoderLayer, reference names in comments. */
@@ -397,8 +398,8 @@ typedef struct geomae_sra_saved {
   float* qkv;  /* [n,3d] */ float* attn; /* [n,d] */ float* lse; /* [n,heads] */
   float* s1;   /* [n,d] pre-LN1 */ float* st1; /* [n,2] */ float* y; /* [n,d] */
   float* u;    /* [n,f] pre-GELU */ float* s2; /* [n,d] pre-LN2 */ float* st2; /* [n,2] */ float* z; /* [n,d] output */
-  /* precision 1 (bf16 mode) stores qkv, attn, y, u as bf16 rows in the same buffers and additionally keeps the bf16
-   * operands of the weight-gradient kernel: g = gelu(u) [n,f], xp = x + pos, xb = x [n,d] (x = the layer's input). */
+  /* precision 1 (bf16 mode): qkv, attn, u hold bf16 rows; s1 / s2 hold the bf16 NORMALISED rows xhat1 / xhat2 (y is
+   * not stored); g = gelu(u) [n,f] bf16; xb (layer 0 only) = bf16 copy of the stack input; xp is unused. */
   void* g; void* xp; void* xb;
 } geomae_sra_saved;
 
@@ -433,10 +434,12 @@ int geomae_sra_stack2_backward(const geomae_sra_ctx* ctx, int32_t n_layers, cons
  * (csrc/sra_chain.cu):  s1 = x + attn Wo^T + bo ; y = LN1(s1) ; u = y W1^T + b1 ; g = gelu(u) ; s2 = y + g W2^T + b2 ;
  * z = LN2(s2) ; and (mode bit 1) the in-projection of the NEXT layer, q|k = (z + pos) Wqk^T + b, v = z Wv^T + b.
  * mode: bit 0 = this layer's chain, bit 1 = next in-projection (mode 2 alone = in-projection of x: the stack prologue).
- * p_*: packed bf16 "hi" images from geomae_pack_weights.  bf16 tensors are row-major [n, cols]:
- *   attn [n,128] (attention output), y16 [n,128], u16 [n,256] (pre-GELU), g16 [n,256] (gelu(u)),
- *   xp16_next / xb16_next [n,128] (z + pos / z, the operands of the next layer's in-projection weight gradient),
- *   qkv16_next [n,384].  fp32: s1, s2 [n,128] pre-LayerNorm rows, st1, st2 [n,2] (mean, rstd), z [n,128].
+ * p_*: packed bf16 "hi" images from geomae_pack_weights.  Saved for the backward, bf16 row-major [n, cols]:
+ *   xh1_16, xh2_16 [n,128] = the NORMALISED rows (s - mean) * rstd of the two LayerNorms (their outputs y, z are
+ *   affine in them per column, so neither y nor the pre-LN rows are stored), u16 [n,256] (pre-GELU), g16 [n,256]
+ *   (gelu(u)), qkv16_next [n,384]; fp32: st1, st2 [n,2] (mean, rstd), z [n,128] (the residual stream stays fp32).
+ *   xb16 [n,128] (mode 2 only): bf16 copy of x, the operand of layer 0's in-projection weight gradient.
+ * attn [n,128] bf16 = the attention output.  Every tile tensor moves by TMA box loads / stores.
  * replaces: out_proj of nn.MultiheadAttention + EncoderLayer.forward (models/sst/sst_basic_block.py:55,85-102) and
  *           the in_proj of the next layer's WindowAttention (:41-55) — library GEMMs + ~8 elementwise kernels. */
 typedef struct geomae_chain_fwd_args {
@@ -445,15 +448,16 @@ typedef struct geomae_chain_fwd_args {
   const void *p_out_proj, *p_lin1, *p_lin2, *p_in_proj_next;
   const float *out_proj_b, *lin1_b, *lin2_b, *in_proj_b_next, *norm1_w, *norm1_b, *norm2_w, *norm2_b; float ln_eps;
   const float* pos_table; const int32_t* tok_cell_next;
-  float *s1, *st1, *s2, *st2, *z;
-  void *y16, *u16, *g16, *xp16_next, *xb16_next, *qkv16_next;
+  float *st1, *st2, *z;
+  void *xh1_16, *xh2_16, *u16, *g16, *xb16, *qkv16_next;
 } geomae_chain_fwd_args;
 
 int geomae_sra_chain_fwd(const geomae_chain_fwd_args* args, void* stream);
 
 /* Backward of the same chain (k_sra_chain_bwd), gradients flowing DOWN through one EncoderLayer per 128-token tile:
  *   mode bit 0: dz = dqkv16_up Win_up + ds1_up  (in-projection backward of the layer ABOVE; else dz = dz_in, fp32)
- *   mode bit 1: ds2 = LN2-bwd(dz) ; du = (ds2 W2) gelu'(u) ; dy = du W1 + ds2 ; ds1 = LN1-bwd(dy) ; dattn = ds1 Wo ;
+ *   mode bit 1: ds2 = LN2-bwd(dz; xh2_16, st2) ; du = (ds2 W2) gelu'(u) ; dy = du W1 + ds2 ; ds1 = LN1-bwd(dy; xh1_16, st1) ;
+ *               dattn = ds1 Wo ;
  *               dd[n,8] = per-head dot(dattn, attn)  (the attention backward's row term D)
  *   mode 1 alone writes dx = dz (the input gradient of the stack's first layer).
  * Outputs: ds2_16, ds1_16, dattn16 [n,128], du16 [n,256] bf16 (operands of geomae_sra_wgrad_layer and of the attention
@@ -464,7 +468,7 @@ int geomae_sra_chain_fwd(const geomae_chain_fwd_args* args, void* stream);
 typedef struct geomae_chain_bwd_args {
   int64_t n_tokens; int32_t mode;
   const void* dqkv16_up; const float* ds1_up; const void* p_in_proj_up; const float* dz_in;
-  const float *s2, *st2, *s1, *st1; const void *u16, *attn16;
+  const void* xh2_16; const float* st2; const void* xh1_16; const float* st1; const void *u16, *attn16;
   const void *p_lin2, *p_lin1, *p_out_proj; const float *norm2_w, *norm1_w;
   void *ds2_16, *du16, *ds1_16, *dattn16; float *ds1, *dd, *dx;
   float *g_norm2_w, *g_norm2_b, *g_norm1_w, *g_norm1_b;
@@ -474,17 +478,25 @@ int geomae_sra_chain_bwd(const geomae_chain_bwd_args* args, void* stream);
 
 /* Weight / bias gradients of one EncoderLayer in ONE TMA-fed tcgen05 launch (csrc/sra_wgrad.cu), accumulated (+=)
  * with vector reductions:  g_lin2_w [128,256] += ds2^T g ; g_lin1_w [256,128] += du^T y, g_lin1_b += colsum du ;
- * g_out_proj_w [128,128] += ds1^T attn ; g_in_proj_w [384,128] += dq|dk ^T xp, dv^T xb ; g_in_proj_b += colsum dqkv ;
+ * g_out_proj_w [128,128] += ds1^T attn ; g_in_proj_w [384,128] += dq|dk ^T (x + pos), dv^T x ; g_in_proj_b += colsum dqkv ;
  * g_lin2_b += colsum ds2 ; g_out_proj_b += colsum ds1.
- * Operands are bf16 row-major: ds2_16, y16, ds1_16, attn16, xp16, xb16 [n,128]; g16, du16 [n,256]; dqkv16 [n,384]
- * (16-byte aligned).  Bias buffers may be NULL.
+ * Operands are bf16 row-major (16-byte aligned): ds2_16, ds1_16, attn16 [n,128]; g16, du16 [n,256]; dqkv16 [n,384];
+ *   xh1_16 [n,128]: y = xh1 * norm1_w + norm1_b is applied in the flush (per-column scale + rank-1 term);
+ *   xin16 [n,128] with in_scale / in_shift: the layer input x = xin * in_scale + in_shift (the xhat2 tile and norm2
+ *   parameters of the layer below), or x itself with in_scale = in_shift = NULL (first layer of a stack);
+ *   pos16 [n,128]: the gathered position rows of this layer's shift (geomae_pos_rows_bf16).
+ * Bias buffers may be NULL.
  * replaces: the weight-gradient GEMMs + bias column sums autograd runs for linear1 / linear2 / out_proj / in_proj
  *           of models/sst/sst_basic_block.py:55,94-100. */
 typedef struct geomae_wgrad_layer_args {
   int64_t n_tokens;
-  const void *ds2_16, *g16, *du16, *y16, *ds1_16, *attn16, *dqkv16, *xp16, *xb16;
+  const void *ds2_16, *g16, *du16, *xh1_16, *ds1_16, *attn16, *dqkv16, *xin16, *pos16;
+  const float *norm1_w, *norm1_b, *in_scale, *in_shift;
   float *g_lin2_w, *g_lin1_w, *g_lin1_b, *g_out_proj_w, *g_in_proj_w, *g_in_proj_b, *g_lin2_b, *g_out_proj_b;
 } geomae_wgrad_layer_args;
+
+/* out16[i, :] = bf16(pos_table[tok_cell[i], :]), [n,128]: once per token set and shift. */
+int geomae_pos_rows_bf16(const float* pos_table, const int32_t* tok_cell, int64_t n_tokens, void* out16, void* stream);
 
 int geomae_sra_wgrad_layer(const geomae_wgrad_layer_args* args, void* stream);
 

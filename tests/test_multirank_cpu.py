@@ -66,8 +66,8 @@ def test_sync_bn_and_grad_allreduce_two_ranks():
 
 def test_frame_sharding_is_disjoint_and_seeded():
     from bench import make_batches
-    a = make_batches(0, 1, 2, 1)[0]
-    b = make_batches(1, 1, 2, 1)[0]
-    a2 = make_batches(0, 1, 2, 1)[0]
+    a = make_batches(0, 1, 2, dict(sweeps=1))[0]
+    b = make_batches(1, 1, 2, dict(sweeps=1))[0]
+    a2 = make_batches(0, 1, 2, dict(sweeps=1))[0]
     assert all((x == y).all() for x, y in zip(a, a2))                 # deterministic per rank
     assert not any(x.shape == y.shape and (x == y).all() for x in a for y in b)   # ranks see different frames
