@@ -229,8 +229,31 @@ class DynamicScatterVFE(nn.Module):
                         and x.norm.momentum is not None for x in l)
                 and getattr(self, "fused", True))
 
-    def forward(self, pb: PillarBatch, return_inv=False):
-        """-> voxel_feats [V, C_out], voxel_coors [V,4] int32 (b,z,y,x) sorted (, point->pillar map)."""
+    def _pillars_from(self, features, coors):
+        """PillarBatch for the reference call form ``forward(features [P,C], coors [P,4] (b,z,y,x))``
+        (voxel_encoders/voxel_encoder.py:358-364): ``coors`` must be the dynamic voxelisation of ``features`` at this
+        encoder's own voxel size / range (what the detector passes); only its batch column is read here — the fused
+        scatter recomputes the coordinates bit-exactly and returns the same sorted pillar list as torch.unique(coors)."""
+        from .voxel import VoxelGeometry
+        L.require_cuda(features, "features")
+        if coors.shape[0] != features.shape[0] or coors.shape[1] != 4:
+            raise RuntimeError("DynamicScatterVFE: coors must be [P, 4] (batch, z, y, x) rows of the points")
+        n_frames = int(coors[-1, 0]) + 1 if coors.shape[0] else 1          # compat path: one host read
+        geom = self.__dict__.get("_geom")
+        if geom is None:
+            vs = (self.vx, self.vy, self.vz)
+            geom = self.__dict__["_geom"] = VoxelGeometry(tuple(self.point_cloud_range), vs, vs, vs, (1, 1, 1), (1, 1, 1))
+        counts = torch.bincount(coors[:, 0].long(), minlength=n_frames)
+        offsets = torch.zeros(n_frames + 1, dtype=torch.int32, device=features.device)
+        offsets[1:] = torch.cumsum(counts, 0).int()
+        return PillarBatch(geom, features.float().contiguous(), offsets, n_frames).run()
+
+    def forward(self, pb, coors=None, points=None, img_feats=None, img_metas=None, return_inv=False):
+        """-> voxel_feats [V, C_out], voxel_coors [V,4] int32 (b,z,y,x) sorted (, point->pillar map).
+        ``pb``: the PillarBatch of the fused scatter stage (hot path), or the reference's ``features`` tensor together
+        with ``coors`` (voxel_encoder.py:358-364)."""
+        if isinstance(pb, torch.Tensor):
+            pb = self._pillars_from(pb, coors)
         if self._can_fuse(pb):       # the GeoMAE configuration in training: fused kernels (csrc/vfe_fused.cu)
             voxel_feats = _FusedVFEFn.apply(self.vfe_layers[0].linear.weight, self, pb, self.tc_precision)
             coors = pb.pillar_coors[:pb.n_pillars]

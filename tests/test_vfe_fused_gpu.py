@@ -107,3 +107,25 @@ def test_fused_equals_reference_form_sync_bn_two_ranks():
         p.join(timeout=60)
     for rank, msg in sorted(res):
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_reference_call_form_features_coors():
+    """DynamicScatterVFE.forward(features, coors) — the reference's signature (voxel_encoders/voxel_encoder.py:358-364) —
+    equals the PillarBatch call: same pillar order (= torch.unique(coors, dim=0)), same features."""
+    from geomae_b200.voxel import Voxelization
+    cfg, vfe = _build(3)
+    frames = _frames((31, 32))
+    m = cfg.model
+    vox = Voxelization(**m["voxel_layer"])
+    coors = torch.cat([torch.nn.functional.pad(vox(f), (1, 0), value=i) for i, f in enumerate(frames)])
+    feats = torch.cat(frames)
+    vfe.tc_precision = 3
+    out_ref, coors_ref = vfe(feats, coors)
+    from geomae_b200.voxel import VoxelGeometry, scatter_frames
+    geom = VoxelGeometry(tuple(m["voxel_layer"]["point_cloud_range"]), tuple(m["voxel_layer"]["voxel_size"]),
+                         tuple(m["sub_voxel_layer_med"]["voxel_size"]), tuple(m["sub_voxel_layer_low"]["voxel_size"]),
+                         tuple(m["sub_voxel_ratio_med"]), tuple(m["sub_voxel_ratio_low"]))
+    out_pb, coors_pb = vfe(scatter_frames(geom, frames))
+    assert torch.equal(coors_ref, coors_pb)
+    assert torch.equal(coors_ref.long(), torch.unique(coors.long(), dim=0))
+    torch.testing.assert_close(out_ref, out_pb, rtol=1e-5, atol=1e-6)
