@@ -34,6 +34,12 @@ constexpr float QSCALE = 0.25f * LOG2E;     // 1/sqrt(head_dim), exp2 domain
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// exp2 on the special-function unit: one MUFU.EX2 (exp2f without fast-math adds a denormal-range rescale per call)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -272,6 +278,9 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__
           lda(qa, sQ, r0, h * 16);
           const int b0 = meta.beg[r0 + g] - c0, e0 = meta.end[r0 + g] - c0;
           const int b1 = meta.beg[r0 + g + 8] - c0, e1 = meta.end[r0 + g + 8] - c0;
+          // all 16 rows of the m-tile valid and in ONE window [wb, we) (chunk-relative): interior key blocks need no mask
+          const bool one_window = r0 + 15 < nq && meta.beg[r0] == meta.beg[r0 + 15];
+          const int wb = meta.beg[r0] - c0, we = meta.end[r0] - c0;
           for (int kb = j_lo >> 4; kb * 16 < j_hi; ++kb) {
             float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t kb0, kb1;
@@ -280,14 +289,19 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__
             ldb(kb0, kb1, sK, kb * 16 + 8, h * 16);
             mma16816(s1, qa, kb0, kb1);
             const int k0 = kb * 16 + 2 * t, k1 = k0 + 8;       // scores -> exp2 domain (scale 1/sqrt(hd) * log2 e), window mask
-            s0[0] = (k0 >= b0 && k0 < e0) ? s0[0] * QSCALE : -INFINITY;
-            s0[1] = (k0 + 1 >= b0 && k0 + 1 < e0) ? s0[1] * QSCALE : -INFINITY;
-            s1[0] = (k1 >= b0 && k1 < e0) ? s1[0] * QSCALE : -INFINITY;
-            s1[1] = (k1 + 1 >= b0 && k1 + 1 < e0) ? s1[1] * QSCALE : -INFINITY;
-            s0[2] = (k0 >= b1 && k0 < e1) ? s0[2] * QSCALE : -INFINITY;
-            s0[3] = (k0 + 1 >= b1 && k0 + 1 < e1) ? s0[3] * QSCALE : -INFINITY;
-            s1[2] = (k1 >= b1 && k1 < e1) ? s1[2] * QSCALE : -INFINITY;
-            s1[3] = (k1 + 1 >= b1 && k1 + 1 < e1) ? s1[3] * QSCALE : -INFINITY;
+            if (one_window && kb * 16 >= wb && kb * 16 + 16 <= we) {   // whole block inside the tile's single window: no mask
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { s0[i] *= QSCALE; s1[i] *= QSCALE; }
+            } else {
+              s0[0] = (k0 >= b0 && k0 < e0) ? s0[0] * QSCALE : -INFINITY;
+              s0[1] = (k0 + 1 >= b0 && k0 + 1 < e0) ? s0[1] * QSCALE : -INFINITY;
+              s1[0] = (k1 >= b0 && k1 < e0) ? s1[0] * QSCALE : -INFINITY;
+              s1[1] = (k1 + 1 >= b0 && k1 + 1 < e0) ? s1[1] * QSCALE : -INFINITY;
+              s0[2] = (k0 >= b1 && k0 < e1) ? s0[2] * QSCALE : -INFINITY;
+              s0[3] = (k0 + 1 >= b1 && k0 + 1 < e1) ? s0[3] * QSCALE : -INFINITY;
+              s1[2] = (k1 >= b1 && k1 < e1) ? s1[2] * QSCALE : -INFINITY;
+              s1[3] = (k1 + 1 >= b1 && k1 + 1 < e1) ? s1[3] * QSCALE : -INFINITY;
+            }
             float m0 = fmaxf(fmaxf(s0[0], s0[1]), fmaxf(s1[0], s1[1]));
             float m1 = fmaxf(fmaxf(s0[2], s0[3]), fmaxf(s1[2], s1[3]));
             m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
@@ -296,10 +310,10 @@ __global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__
             m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
             const float n0 = fmaxf(mx[mt][0], m0), n1 = fmaxf(mx[mt][1], m1);
             const float u0 = n0 == -INFINITY ? 0.f : n0, u1 = n1 == -INFINITY ? 0.f : n1;
-            const float c0f = exp2f(mx[mt][0] - u0), c1f = exp2f(mx[mt][1] - u1);
+            const float c0f = ex2(mx[mt][0] - u0), c1f = ex2(mx[mt][1] - u1);
             mx[mt][0] = n0; mx[mt][1] = n1;
-            const float p00 = exp2f(s0[0] - u0), p01 = exp2f(s0[1] - u0), p02 = exp2f(s1[0] - u0), p03 = exp2f(s1[1] - u0);
-            const float p10 = exp2f(s0[2] - u1), p11 = exp2f(s0[3] - u1), p12 = exp2f(s1[2] - u1), p13 = exp2f(s1[3] - u1);
+            const float p00 = ex2(s0[0] - u0), p01 = ex2(s0[1] - u0), p02 = ex2(s1[0] - u0), p03 = ex2(s1[1] - u0);
+            const float p10 = ex2(s0[2] - u1), p11 = ex2(s0[3] - u1), p12 = ex2(s1[2] - u1), p13 = ex2(s1[3] - u1);
             ls[mt][0] = ls[mt][0] * c0f + ((p00 + p01) + (p02 + p03));
             ls[mt][1] = ls[mt][1] * c1f + ((p10 + p11) + (p12 + p13));
             o0[mt][0] *= c0f; o0[mt][1] *= c0f; o1[mt][0] *= c0f; o1[mt][1] *= c0f;
@@ -412,6 +426,8 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
           lda(fb, sB, r0, h * 16);
           const int b0 = meta.beg[r0 + g] - c0, e0 = meta.end[r0 + g] - c0;
           const int b1 = meta.beg[r0 + g + 8] - c0, e1 = meta.end[r0 + g + 8] - c0;
+          const bool one_window = r0 + 15 < nq && meta.beg[r0] == meta.beg[r0 + 15];
+          const int wb = meta.beg[r0] - c0, we = meta.end[r0] - c0;
           float lr0 = 0.f, lr1 = 0.f, dr0 = 0.f, dr1 = 0.f;
           if (!AS_KEYS) {                  // LSE and D belong to the ROWS (queries) of this m-tile
             lr0 = sL[(r0 + g) * NH + h]; lr1 = sL[(r0 + g + 8) * NH + h];
@@ -436,6 +452,7 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
               dc[0] = sDd[k0 * NH + h]; dc[1] = sDd[(k0 + 1) * NH + h]; dc[2] = sDd[k1 * NH + h]; dc[3] = sDd[(k1 + 1) * NH + h];
             }
             const int kk[4] = {k0, k0 + 1, k1, k1 + 1};
+            const bool inside = one_window && kb * 16 >= wb && kb * 16 + 16 <= we;    // warp-uniform: no per-element mask
             const float sc[2][4] = {{s0[0], s0[1], s1[0], s1[1]}, {s0[2], s0[3], s1[2], s1[3]}};
             const float dp[2][4] = {{q0[0], q0[1], q1[0], q1[1]}, {q0[2], q0[3], q1[2], q1[3]}};
             float pr[2][4], dsv[2][4];
@@ -444,10 +461,10 @@ __device__ __forceinline__ void sra_bwd_body(uint8_t* smem, RowMeta& meta, const
               const int bb = r ? b1 : b0, ee = r ? e1 : e0;
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const bool valid = kk[c] >= bb && kk[c] < ee;
+                const bool valid = inside || (kk[c] >= bb && kk[c] < ee);
                 const float lz = AS_KEYS ? lc[c] : (r ? lr1 : lr0);
                 const float dz = AS_KEYS ? dc[c] : (r ? dr1 : dr0);
-                const float p = valid ? exp2f(fmaf(sc[r][c], QSCALE, -lz)) : 0.f;
+                const float p = valid ? ex2(fmaf(sc[r][c], QSCALE, -lz)) : 0.f;
                 pr[r][c] = p;
                 dsv[r][c] = valid ? p * (dp[r][c] - dz) : 0.f;   // dS = P * (dP - D)
               }
