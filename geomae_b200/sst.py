@@ -211,7 +211,22 @@ class SRAStack:
             self._packed = torch.empty(per_layer * len(self.layers), dtype=torch.uint8, device=device)
         return self._packed
 
+    def _fingerprint(self):
+        """Cheap identity of everything `_structs` captures by pointer: the parameters and gradient accumulators of the
+        first and last layer (FlatTrainer keeps all of them in two flat buffers, so they move together) + the arena."""
+        a, b = self.layers[0].norm1.weight, self.layers[-1].linear2.weight
+        return (a.data_ptr(), 0 if a.grad is None else a.grad.data_ptr(), b.data_ptr(),
+                0 if b.grad is None else b.grad.data_ptr(), 0 if self._packed is None else self._packed.data_ptr())
+
     def _structs(self):
+        cached = self.__dict__.get("_struct_cache")
+        if cached is not None and cached[0] == self._fingerprint():
+            return cached[1]
+        arr = self._build_structs()
+        self._struct_cache = (self._fingerprint(), arr)
+        return arr
+
+    def _build_structs(self):
         import ctypes as C
         arr = (L.SRALayer * len(self.layers))()
         for s, layer, shift in zip(arr, self.layers, self.shifts):

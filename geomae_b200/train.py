@@ -99,6 +99,13 @@ class FlatTrainer:
         """points: list of [N_i, C] CUDA tensors (one rank's samples).  Returns (total loss, loss dict)."""
         if self.step_count == 0:
             self.check_bindings()
+        prev = L.pin_stream(self.flat_param.device)
+        try:
+            return self._train_step(points, ids, lr)
+        finally:
+            L.unpin_stream(prev)
+
+    def _train_step(self, points, ids, lr):
         self.zero_grad()
         self.model.last_loss_vector = None
         losses = self.model.forward_train(points=points, img_metas=None, ids=ids)
