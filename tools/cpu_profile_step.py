@@ -14,4 +14,4 @@ torch.cuda.synchronize()
 pr = cProfile.Profile(); pr.enable()
 for _ in range(20): tr.train_step(frames)
 pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("tottime").print_stats(45)
+st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats("geomae_b200|built-in method torch|method .* of .torch", 60)
