@@ -120,6 +120,68 @@ __global__ void __launch_bounds__(256) k_win_fill(VoxGeom g, WinGeom w, const ui
   }
 }
 
+// Region batching with voxel drop (middle_encoders/sst_input_layer.py:211-275).  One warp per candidate window of
+// ONE shift: the window's live tokens are counted (n), the bucket with lower < n <= upper gives the level and the
+// token budget, and when n exceeds the budget the `budget` tokens with the smallest key survive.  key = token index
+// (seed 0: what the reference keeps with shuffle_voxels=False and a stable sort) or a hash of (seed, token)
+// (shuffle_voxels=True: a uniformly random subset, which is all the reference's randperm + sort provides).
+// A window that matches no bucket keeps nothing and reports level -1 (:219-228 leave target 0 / level -1).
+struct DropLevels {
+  int n;
+  int max_tokens[8], lower[8], upper[8];
+};
+constexpr int DROP_MAX_CELLS = 1024;
+
+__device__ __forceinline__ uint32_t drop_key(uint64_t seed, int tok) {
+  if (seed == 0) return (uint32_t)tok;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(tok + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+
+__global__ void __launch_bounds__(128) k_win_drop(VoxGeom g, WinGeom w, DropLevels lv, int shift, uint64_t seed,
+                                                  const uint32_t* __restrict__ bitmap,
+                                                  const int32_t* __restrict__ word_rank,
+                                                  const int32_t* __restrict__ tok_of_pillar, uint8_t* alive,
+                                                  int32_t* level /* this shift */) {
+  __shared__ int s_tok[4][DROP_MAX_CELLS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int cand = blockIdx.x * 4 + wib;
+  if (cand >= w.n_cand) return;
+  const int cells = w.win_x * w.win_y;
+  int n = 0;
+  for (int c0 = 0; c0 < cells; c0 += 32) {
+    const int c = c0 + lane;
+    int tok = c < cells ? probe(g, w, bitmap, word_rank, tok_of_pillar, shift, cand, c) : -1;
+    if (tok >= 0 && !alive[tok]) tok = -1;
+    const uint32_t m = __ballot_sync(0xffffffffu, tok >= 0);
+    if (tok >= 0) s_tok[wib][n + __popc(m & ((1u << lane) - 1u))] = tok;
+    n += __popc(m);
+  }
+  if (n == 0) return;
+  __syncwarp();
+  int lvl = -1, budget = 0;
+  for (int l = 0; l < lv.n; ++l)   // later buckets override earlier ones, as the reference's loop of masked writes does
+    if (n > lv.lower[l] && n <= lv.upper[l]) { lvl = l; budget = lv.max_tokens[l]; }
+  for (int i = lane; i < n; i += 32) {
+    const int tok = s_tok[wib][i];
+    bool keep = budget >= n;
+    if (!keep && budget > 0) {
+      const uint32_t key = drop_key(seed, tok);
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const int tj = s_tok[wib][j];
+        const uint32_t kj = drop_key(seed, tj);
+        rank += (kj < key || (kj == key && tj < tok)) ? 1 : 0;
+      }
+      keep = rank < budget;
+    }
+    level[tok] = lvl;
+    if (!keep) alive[tok] = 0;
+  }
+}
+
 __global__ void k_token_map(const int64_t* __restrict__ rows, int64_t n, int32_t* tok_of_pillar) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) tok_of_pillar[rows[i]] = (int32_t)i;
@@ -208,6 +270,39 @@ extern "C" int geomae_window_csr(const geomae_voxel_cfg* cfg, const geomae_windo
     k_win_fill<<<grid, 256, 0, stream>>>(g, w, io->bitmap, io->word_rank, tok_of_pillar, out->cand_count,
                                          out->cand_tok_off, out->cand_win_idx, n_tokens, out->win_tok, out->tok_cell,
                                          out->tok_win, out->tok_pos);
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
+
+extern "C" int geomae_window_drop(const geomae_voxel_cfg* cfg, const geomae_window_cfg* wcfg,
+                                  const geomae_scatter_io* io, const int32_t* tok_of_pillar, int64_t n_tokens,
+                                  int32_t n_levels, const int32_t* max_tokens, const int32_t* lower,
+                                  const int32_t* upper, uint64_t seed, uint8_t* keep, int32_t* level, void* stream_) {
+  GM_REQUIRE(cfg && wcfg && io && tok_of_pillar && max_tokens && lower && upper && keep && level,
+             "window_drop: null argument");
+  GM_REQUIRE(n_levels >= 1 && n_levels <= 8, "window_drop: 1..8 drop levels, got %d", n_levels);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VoxGeom g;
+  int rc = gm_make_geom(cfg, io->n_frames, &g);
+  if (rc) return rc;
+  WinGeom w;
+  rc = make_win_geom(g, wcfg, io->n_frames, &w);
+  if (rc) return rc;
+  GM_REQUIRE(w.win_x * w.win_y <= DROP_MAX_CELLS, "window_drop: window of %d cells > %d", w.win_x * w.win_y,
+             DROP_MAX_CELLS);
+  DropLevels lv;
+  lv.n = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    lv.max_tokens[l] = max_tokens[l];
+    lv.lower[l] = lower[l];
+    lv.upper[l] = upper[l];
+  }
+  if (n_tokens == 0) return GEOMAE_OK;
+  GM_CUDA(cudaMemsetAsync(keep, 1, (size_t)n_tokens, stream));
+  // shift 1 buckets the survivors of shift 0 (sst_input_layer.py:252-262); a token leaves if either shift drops it
+  for (int s = 0; s < w.n_shifts; ++s)
+    k_win_drop<<<gm_div_up(w.n_cand, 4), 128, 0, stream>>>(g, w, lv, s, seed, io->bitmap, io->word_rank,
+                                                           tok_of_pillar, keep, level + (int64_t)s * n_tokens);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
 }

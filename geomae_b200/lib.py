@@ -164,6 +164,10 @@ class _Sigs:
     geomae_token_map = [_p, _i64, _p, _i64, _p]
     geomae_window_csr = [C.POINTER(VoxelCfg), C.POINTER(WindowCfg), C.POINTER(ScatterIO), _p, _i64,
                          C.POINTER(WindowIO), _p]
+    geomae_window_drop = [C.POINTER(VoxelCfg), C.POINTER(WindowCfg), C.POINTER(ScatterIO), _p, _i64, _i32,
+                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint64, _p, _p, _p]
+    geomae_recover_bev = [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]
+    geomae_recover_bev_bwd = [_p, _p, _i64, _i32, _i32, _i32, _p, _p]
     geomae_pos_table = [_i32, _i32, _i32, C.c_float, _p, _p]
     geomae_vfe_decorate = [_p, _i64, _i32, _p, _p, _p, _f3, _f3, _p, _p]
     geomae_scatter_reduce_fwd = [_p, _i64, _i32, _p, _p, _i64, _i32, _p, _p, _p]
@@ -212,7 +216,7 @@ _calls = {}         # name -> number of C-ABI calls (bench.py reports kernel lau
 
 # kernels launched per C-ABI call (upper bound for the optional ones), for the gpu_launches claim
 LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=9, augment_filter=3, geom_targets=1, dense_targets=1, coors_bitmap=4,
-                         token_map=1, window_csr=3, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
+                         token_map=1, window_csr=3, window_drop=2, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
                          scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=2, sra_attention_tc_fwd=1,
                          sra_attention_tc_bwd=1, adamw_step=2,
                          tc_linear=1, tc_wgrad=1, layernorm_bwd=1, geom_loss_fwd=3, geom_loss_bwd=1)

@@ -50,3 +50,30 @@ class NaiveSyncBatchNorm1d(nn.BatchNorm1d):
 
 NORM_LAYERS.register_module("BN1d")(nn.BatchNorm1d)
 NORM_LAYERS.register_module("BN")(nn.BatchNorm1d)
+
+
+@NORM_LAYERS.register_module("naiveSyncBN2d")
+class NaiveSyncBatchNorm2d(nn.BatchNorm2d):
+    """mmdet3d/ops/norm.py:89-144 — the 4-D twin of naiveSyncBN1d (statistics over N, H, W; equal rank weights)."""
+
+    def forward(self, x):
+        if x.dtype != torch.float32:
+            raise RuntimeError(f"input should be in float32 type, got {x.dtype}")
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1 or not self.training:
+            return super().forward(x)
+        if x.shape[0] == 0:
+            raise RuntimeError("SyncBN does not support empty inputs")
+        c = x.shape[1]
+        mean = x.mean(dim=[0, 2, 3])
+        meansqr = (x * x).mean(dim=[0, 2, 3])
+        vec = _AllReduceSum.apply(torch.cat([mean, meansqr])) * (1.0 / dist.get_world_size())
+        mean, meansqr = torch.split(vec, c)
+        var = meansqr - mean * mean
+        with torch.no_grad():
+            self.running_mean += self.momentum * (mean.detach() - self.running_mean)
+            self.running_var += self.momentum * (var.detach() - self.running_var)
+        scale = self.weight * torch.rsqrt(var + self.eps)
+        return x * scale.view(1, -1, 1, 1) + (self.bias - mean * scale).view(1, -1, 1, 1)
+
+
+NORM_LAYERS.register_module("BN2d")(nn.BatchNorm2d)

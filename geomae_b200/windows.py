@@ -15,6 +15,26 @@ from . import lib as L
 from .voxel import PillarBatch, VoxelGeometry
 
 
+def coors_bitmap(geom: VoxelGeometry, coors: torch.Tensor, batch_size: int):
+    """Occupancy bitmap + ranks of explicit token rows ``coors [n,4] = (b,z,y,x)``: (ScatterIO view, tok_of_pillar,
+    buffers to keep alive) — what the window kernels need when no scatter result is at hand."""
+    L.require_cuda(coors, "coors")
+    dev = coors.device
+    coors = coors.to(torch.int32).contiguous()
+    n = coors.shape[0]
+    gx, gy, _ = geom.grid
+    n_words = (batch_size * gx * gy + 31) // 32
+    i32 = dict(dtype=torch.int32, device=dev)
+    bitmap, word_rank = torch.empty(n_words, **i32), torch.empty(n_words, **i32)
+    scan_tmp, counts = torch.empty(3 * 16384, **i32), torch.zeros(4, **i32)
+    tok_of_pillar = torch.empty(max(n, 1), **i32)
+    L.run("coors_bitmap", C.byref(geom.cstruct), L.ptr(coors), n, batch_size, L.ptr(bitmap), L.ptr(word_rank),
+          L.ptr(scan_tmp), L.ptr(counts), L.ptr(tok_of_pillar), L.stream_ptr(dev))
+    io = L.ScatterIO()
+    io.n_frames, io.bitmap, io.word_rank = batch_size, L.ptr(bitmap), L.ptr(word_rank)
+    return io, tok_of_pillar, (bitmap, word_rank, scan_tmp, counts, tok_of_pillar, coors)
+
+
 class WindowSpec:
     """window_shape + shifts_list of the backbone config (…6x_1e-5.py:15,57)."""
 
@@ -77,26 +97,12 @@ class WindowLayout:
     @classmethod
     def from_coors(cls, spec, geom: VoxelGeometry, coors: torch.Tensor, batch_size: int):
         """Token i sits at ``coors[i] = (b,z,y,x)`` (unique cells), the reference's call form."""
-        L.require_cuda(coors, "coors")
-        dev = coors.device
-        coors = coors.to(torch.int32).contiguous()
+        io, tok_of_pillar, keep = coors_bitmap(geom, coors, batch_size)
         n = coors.shape[0]
-        self = cls(spec, geom, batch_size, n, dev)
-        gx, gy, _ = geom.grid
-        n_words = (batch_size * gx * gy + 31) // 32
-        i32 = dict(dtype=torch.int32, device=dev)
-        bitmap, word_rank = torch.empty(n_words, **i32), torch.empty(n_words, **i32)
-        scan_tmp, counts = torch.empty(3 * 16384, **i32), torch.zeros(4, **i32)
-        tok_of_pillar = torch.empty(max(n, 1), **i32)
-        s = L.stream_ptr(dev)
-        L.run("coors_bitmap", C.byref(geom.cstruct), L.ptr(coors), n, batch_size, L.ptr(bitmap),
-                                            L.ptr(word_rank), L.ptr(scan_tmp), L.ptr(counts),
-                                            L.ptr(tok_of_pillar), s)
-        io = L.ScatterIO()
-        io.n_frames, io.bitmap, io.word_rank = batch_size, L.ptr(bitmap), L.ptr(word_rank)
+        self = cls(spec, geom, batch_size, n, coors.device)
         L.run("window_csr", C.byref(geom.cstruct), C.byref(spec.cstruct), C.byref(io),
-                                          L.ptr(tok_of_pillar), n, C.byref(self.io), s)
-        self._keep = (bitmap, word_rank, scan_tmp, counts, tok_of_pillar, coors)
+                                          L.ptr(tok_of_pillar), n, C.byref(self.io), L.stream_ptr(coors.device))
+        self._keep = keep
         return self
 
     def shift(self, i: int):

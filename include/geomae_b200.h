@@ -182,6 +182,26 @@ int geomae_token_map(const int64_t* rows, int64_t n_tokens, int32_t* tok_of_pill
 int geomae_window_csr(const geomae_voxel_cfg* cfg, const geomae_window_cfg* wcfg, const geomae_scatter_io* io,
                       const int32_t* tok_of_pillar, int64_t n_tokens, const geomae_window_io* out, void* stream);
 
+/* Region batching with voxel drop for one token set, both shifts: keep[t] = 1 when token t survives, level[s][t] =
+ * drop level of t's shift-s window (-1: no bucket matched, the token is dropped).  A window with n live tokens takes
+ * the level l with lower[l] < n <= upper[l] and keeps max_tokens[l] of them; shift 1 buckets the survivors of
+ * shift 0.  seed 0 keeps the lowest token indices (the reference with shuffle_voxels=False), any other seed a
+ * uniformly random subset (shuffle_voxels=True).  max_tokens / lower / upper are HOST arrays [n_levels <= 8].
+ * replaces: SSTInputLayer.drop_single_shift / get_voxel_keep_inds (middle_encoders/sst_input_layer.py:211-275)
+ *           and the shuffle at :66-74. */
+int geomae_window_drop(const geomae_voxel_cfg* cfg, const geomae_window_cfg* wcfg, const geomae_scatter_io* io,
+                       const int32_t* tok_of_pillar, int64_t n_tokens, int32_t n_levels, const int32_t* max_tokens,
+                       const int32_t* lower, const int32_t* upper, uint64_t seed, uint8_t* keep /*[n_tokens]*/,
+                       int32_t* level /*[n_shifts, n_tokens]*/, void* stream);
+
+/* canvas[b, c, y, x] = feat[i, c] for coors[i] = (b, z, y, x), zero elsewhere; canvas [n_frames, channels, ny, nx]
+ * is cleared here.  _bwd gathers d_feat[i, c] = d_canvas[b, c, y, x].
+ * replaces: SSTSecondPretrainedv1.recover_bev (backbones/sst_second_pretrained_v1.py:246-276). */
+int geomae_recover_bev(const float* feat, const int32_t* coors, int64_t n, int32_t channels, int32_t n_frames,
+                       int32_t ny, int32_t nx, float* canvas, void* stream);
+int geomae_recover_bev_bwd(const float* d_canvas, const int32_t* coors, int64_t n, int32_t channels, int32_t ny,
+                           int32_t nx, float* d_feat, void* stream);
+
 /* [win_x*win_y, d_model] sinusoidal position table, row = cx*win_y + cy.
  * replaces: MultiMAESSTSPChoose.get_pos_embed (…top_only.py:361-399). */
 int geomae_pos_table(int32_t win_x, int32_t win_y, int32_t d_model, float temperature, float* table, void* stream);

@@ -403,13 +403,15 @@ def pos_embed_table(cfg: PathConfig) -> torch.Tensor:
 class WindowLayout:
     """get_voxel_info (backbones/…top_only.py:143-196) for one token set: both shifts."""
 
-    def __init__(self, coors: np.ndarray, cfg: PathConfig):
+    def __init__(self, coors: np.ndarray, cfg: PathConfig, levels=None):
+        """levels: per-shift drop levels decided elsewhere (SSTInputLayer, after its voxel drop) instead of the
+        backbone's own bucketing."""
         self.cfg, self.n = cfg, coors.shape[0]
         table = pos_embed_table(cfg)
         self.shifts = []
         for s in range(len(cfg.shifts)):
             win, ciw = window_partition(coors, cfg, s)
-            lvl, cnt = window_levels(win, cfg)
+            lvl, cnt = window_levels(win, cfg) if levels is None else (levels[s], np.bincount(win)[win])
             inds = flat2win_indices(win, lvl, cfg)
             pos_flat = table[torch.from_numpy(ciw[:, 0] * cfg.window_shape[1] + ciw[:, 1])]
             self.shifts.append(dict(win=win, ciw=ciw, lvl=lvl, cnt=cnt, inds=inds, pos=pos_flat))
@@ -621,3 +623,115 @@ def augment_filter(frames, params, pc_range):
         g[:, 0], g[:, 1], g[:, 2] = xr, yr, zr
         out.append(np.ascontiguousarray(g[keep]))
     return out
+
+
+# ---------------------------------------------------------------------------
+# N1  fine-tune consumer: SSTInputLayer (voxel drop) + SSTSecondPretrainedv1
+# ---------------------------------------------------------------------------
+def inner_win_inds_stable(win: np.ndarray):
+    """get_inner_win_inds (middle_encoders/sst_input_layer.py:135-171) with a STABLE sort: a voxel's rank inside its
+    window is its order of appearance.  The reference calls torch.sort without stable=True, so which voxel gets
+    which rank is implementation-defined there (its docstring says so); every choice is a valid instance."""
+    order = np.argsort(win, kind="stable")
+    srt = win[order]
+    inner = np.empty(win.size, np.int64)
+    inner[order] = np.arange(win.size) - np.searchsorted(srt, srt, side="left")
+    return inner
+
+
+def input_layer_drop(coors: np.ndarray, cfg: PathConfig, inner_fn=inner_win_inds_stable):
+    """middle_encoders/sst_input_layer.py:51-103 with shuffle_voxels=False: region grouping (:335-366), drop per
+    shift (:211-236; bucket rule lower < n <= upper, :222; the voxels ranked below the budget stay), shift 1 on the
+    survivors of shift 0 (:252-262).  ``inner_fn`` supplies the in-window rank (make_golden_n1 plugs in the
+    reference's own get_inner_win_inds to pin everything else bit-exactly).
+    -> (voxel_keep_inds, [level_shift0, level_shift1] of the kept voxels)."""
+    def single(win):
+        cnt = np.bincount(win)[win]
+        inner = inner_fn(win)
+        target = np.zeros(win.size, np.int64)
+        lvl = np.full(win.size, -1, np.int64)
+        for dl, info in cfg.drop_info.items():
+            lo, hi = info["drop_range"]
+            m = (cnt > lo) & (cnt <= hi)
+            target[m], lvl[m] = info["max_tokens"], dl
+        return inner < target, lvl
+
+    keep = np.arange(coors.shape[0])
+    keep0, lvl0 = single(window_partition(coors, cfg, 0)[0])
+    keep, lvl0 = keep[keep0], lvl0[keep0]
+    if len(cfg.shifts) == 1:
+        return keep, [lvl0]
+    keep1, lvl1 = single(window_partition(coors, cfg, 1)[0][keep0])
+    return keep[keep1], [lvl0[keep1], lvl1[keep1]]
+
+
+def recover_bev(feat: torch.Tensor, coors: np.ndarray, batch_size: int, ny: int, nx: int):
+    """backbones/sst_second_pretrained_v1.py:246-276 -> [B, C, ny, nx]."""
+    c = feat.shape[1]
+    canvas = feat.new_zeros((batch_size, c, ny * nx))
+    b = torch.from_numpy(coors[:, 0].astype(np.int64))
+    at = torch.from_numpy((coors[:, 2].astype(np.int64) * nx + coors[:, 3]))
+    canvas = _bev_put(canvas, b, at, feat)
+    return canvas.view(batch_size, c, ny, nx)
+
+
+def _bev_put(canvas, b, at, feat):
+    flat = canvas.permute(0, 2, 1).reshape(-1, canvas.shape[1])
+    flat = flat.index_put((b * canvas.shape[2] + at,), feat)
+    return flat.view(canvas.shape[0], canvas.shape[2], canvas.shape[1]).permute(0, 2, 1).contiguous()
+
+
+def second_stages(params, x, layer_nums, strides, eps, prefix="backbone.conv_blocks."):
+    """backbones/sst_second_pretrained_v1.py:137-166,208-213: per stage a strided 3x3 conv + BN + ReLU followed by
+    layer_num x (3x3 conv + BN + ReLU); BN in training mode (batch statistics), no conv bias."""
+    outs = []
+    for i, (n, stride) in enumerate(zip(layer_nums, strides)):
+        for j in range(n + 1):
+            w = params[f"{prefix}{i}.{3 * j}.weight"]
+            x = F.conv2d(x, w, None, stride=stride if j == 0 else 1, padding=1)
+            x = F.batch_norm(x, None, None, params[f"{prefix}{i}.{3 * j + 1}.weight"],
+                             params[f"{prefix}{i}.{3 * j + 1}.bias"], training=True, eps=eps)
+            x = F.relu(x)
+        outs.append(x)
+    return outs
+
+
+def sst_second_forward(params, voxel_feat, coors, batch_size, cfg: PathConfig, n_blocks, output_shape, layer_nums,
+                       strides, bn_eps=1e-3):
+    """SSTInputLayer.forward + SSTSecondPretrainedv1.forward (:170-214) on pillar rows ``coors`` (b,z,y,x)."""
+    keep, levels = input_layer_drop(coors, cfg)
+    x, kept = voxel_feat[torch.from_numpy(keep)], coors[keep]
+    layout = WindowLayout(kept, cfg, levels=levels)
+    for i in range(n_blocks):
+        x = shift_block(params, f"backbone.encoder_blocks.{i}.", x, layout, cfg)
+    canvas = recover_bev(x, kept, batch_size, *output_shape)
+    return keep, levels, layout, x, second_stages(params, canvas, layer_nums, strides, bn_eps)
+
+
+def init_params_second(cfg: PathConfig, n_blocks, conv_in, conv_out, layer_nums, seed=0):
+    """Random parameters with SSTSecondPretrainedv1's names and shapes."""
+    g = torch.Generator().manual_seed(seed)
+    d, f = cfg.d_model, cfg.ffn
+    p = {}
+
+    def uni(bound, *shape):
+        return (torch.rand(*shape, generator=g) * 2 - 1) * bound
+    for i in range(n_blocks):
+        for j in range(2):
+            k = f"backbone.encoder_blocks.{i}.encoder_list.{j}."
+            p[k + "win_attn.self_attn.in_proj_weight"] = uni(math.sqrt(6.0 / (4 * d)), 3 * d, d)
+            p[k + "win_attn.self_attn.in_proj_bias"] = uni(0.05, 3 * d)
+            p[k + "win_attn.self_attn.out_proj.weight"] = uni(math.sqrt(3.0 / d), d, d)
+            p[k + "win_attn.self_attn.out_proj.bias"] = uni(0.05, d)
+            p[k + "linear1.weight"], p[k + "linear1.bias"] = uni(math.sqrt(6.0 / (d + f)), f, d), uni(0.05, f)
+            p[k + "linear2.weight"], p[k + "linear2.bias"] = uni(math.sqrt(6.0 / (d + f)), d, f), uni(0.05, d)
+            for nrm in ("norm1", "norm2"):
+                p[k + nrm + ".weight"], p[k + nrm + ".bias"] = 1 + uni(0.05, d), uni(0.05, d)
+    cin = [conv_in, *conv_out[:-1]]
+    for i, n in enumerate(layer_nums):
+        for j in range(n + 1):
+            ci = cin[i] if j == 0 else conv_out[i]
+            p[f"backbone.conv_blocks.{i}.{3 * j}.weight"] = uni(math.sqrt(2.0 / (ci * 9)), conv_out[i], ci, 3, 3)
+            p[f"backbone.conv_blocks.{i}.{3 * j + 1}.weight"] = 1 + uni(0.05, conv_out[i])
+            p[f"backbone.conv_blocks.{i}.{3 * j + 1}.bias"] = uni(0.05, conv_out[i])
+    return p

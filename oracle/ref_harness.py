@@ -367,6 +367,34 @@ def load_pipeline_loading():
     return env["loading"]
 
 
+def load_finetune_consumer():
+    """The reference's SSTInputLayer (middle_encoders/sst_input_layer.py) and SSTSecondPretrainedv1
+    (backbones/sst_second_pretrained_v1.py) loaded by path on top of install(); mmcv's build_conv_layer is the one
+    absent piece (restated: ``nn.Conv2d`` with the cfg's extra keys, which is all the 'Conv2d' type does).
+    -> (SSTInputLayer class, SSTSecondPretrainedv1 class)."""
+    env = install()
+    if "finetune" in env:
+        return env["finetune"]
+
+    def build_conv_layer(cfg, *args, **kwargs):
+        cfg = dict(cfg or dict(type="Conv2d"))
+        assert cfg.pop("type") == "Conv2d"
+        return nn.Conv2d(*args, **kwargs, **cfg)
+    sys.modules["mmcv.cnn"].build_conv_layer = build_conv_layer
+
+    def load(dotted, rel):
+        spec = importlib.util.spec_from_file_location(dotted, os.path.join(REF_ROOT, "mmdet3d", rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[dotted] = m
+        spec.loader.exec_module(m)
+        return m
+    _pkg("mmdet3d.models.middle_encoders")
+    inp = load("mmdet3d.models.middle_encoders.sst_input_layer", "models/middle_encoders/sst_input_layer.py")
+    bb = load("mmdet3d.models.backbones.sst_second_pretrained_v1", "models/backbones/sst_second_pretrained_v1.py")
+    env["finetune"] = (inp.SSTInputLayer, bb.SSTSecondPretrainedv1)
+    return env["finetune"]
+
+
 def load_config_model(config_rel: str = MAE_CONFIG) -> dict:
     """exec the reference config file and return its ``model`` dict."""
     ns: dict = {}
