@@ -140,6 +140,13 @@ def hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src, n_frames=None):
     t_gt = timed(lambda: pb.geom_targets())
     b_sc = 24.0 * p + 32.0 * v + 20.0 * (vm + vl)
     b_gt = 20.0 * vm + 28.0 * v + 24.0 * v
+    # the data step in front of the scatter: rotate / scale / flip / range-filter / compact, two
+    # passes over the 20-byte records: read 12 B (xyz) to count, read 20 B + write 20 B to move = 52 B per raw point
+    from geomae_b200.data import augment_filter, draw_augmentation
+    rs = np.random.RandomState(7)
+    augs = [draw_augmentation(rs) for _ in range(n_frames)]
+    t_au = timed(lambda: augment_filter(pb.points, pb.frame_offsets, augs, model.point_cloud_range))
+    b_au = 52.0 * p
     # DRAM traffic of the same stages from the committed ncu --set full capture (same batch size, 256 frames)
     traffic = {}
     try:
@@ -152,7 +159,8 @@ def hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src, n_frames=None):
         pass
     out = []
     for name, key, t, b in (("geomae_voxel_scatter (9 kernels)", "scatter", t_sc, b_sc),
-                            ("k_geom (geom_targets)", "geom", t_gt, b_gt)):
+                            ("k_geom (geom_targets)", "geom", t_gt, b_gt),
+                            ("geomae_augment_filter (3 kernels; data step N2)", "augment", t_au, b_au)):
         ach = b / (t * 1e-3) / 1e9
         out.append(dict(kernel=name, bound="hbm", frames=n_frames, points=p, pillars=v, ms=t, algorithmic_bytes=b,
                         achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, peak_source=peak_src,
@@ -333,6 +341,17 @@ def main():
         last["loss"] = trainer.train_step_from_host(host[i % len(host)])[0]
         last["loss_host"] = float(last["loss"])             # D2H read of the step's loss, every step
 
+    aug_rng = np.random.RandomState(1000 + rank)
+
+    def step_host_augmented(i):
+        """step_host with the train pipeline's GlobalRotScaleTrans / RandomFlip3D / PointsRangeFilter done on the
+        device in front of the scatter: fresh draws every step, as the reference's workers do."""
+        from geomae_b200.data import draw_augmentation
+        batch = host[i % len(host)]
+        augs = [draw_augmentation(aug_rng) for _ in batch]
+        last["loss"] = trainer.train_step_from_host(batch, augs=augs)[0]
+        last["loss_host"] = float(last["loss"])
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                           # before the warm-up: nvidia-smi's start-up (NVML init) stalls launches
@@ -392,11 +411,15 @@ def main():
         if out[args.sra_impl] is not None and out["tc3"]:
             loss_delta = dict(loss=out[args.sra_impl], loss_tc3=out["tc3"],
                               rel=abs(out[args.sra_impl] - out["tc3"]) / abs(out["tc3"]))
+    step_host_augmented(0)        # after the loss-delta block: that one re-uses the last un-augmented step's mask split
+    barrier()
+    ms_e2e_aug = timed_loop(step_host_augmented, K)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_e2e_aug], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_e2e_aug = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -479,6 +502,11 @@ def main():
                                "glue": "fp32 library GEMMs, TF32 off"}[args.sra_impl]),
         e2e=dict(value=frames / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / K),
+        # the same end-to-end step with the train pipeline's rotate / scale / flip / range filter done on the device
+        # in front of the scatter (geomae_augment_filter; fresh draws per step, one extra 20-byte offsets read)
+        e2e_with_device_augmentation=dict(value=frames / (ms_e2e_aug * 1e-3), unit="frames/s",
+                                          ms_per_step=ms_e2e_aug / K, h2d_bytes_per_step=h2d,
+                                          d2h_bytes_per_step=4 + 4 * (S + 1)),
         gpu_launches=launches, clocks=clocks, roofline=roof, kernel_families=fam_table, hbm_kernels=aux,
         kernel_ms_per_step={k: round(v[0] / K, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
         loss=last.get("loss_host"), loss_delta_vs_tc3=loss_delta)

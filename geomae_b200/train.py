@@ -132,10 +132,38 @@ class FlatTrainer:
         self.optimizer_step(lr)
         return total.detach(), losses
 
-    def train_step_from_host(self, host_points, ids=None, lr=None):
-        """host_points: list of pinned CPU tensors; H2D copies are issued on the compute stream."""
+    def train_step_from_host(self, host_points, ids=None, lr=None, augs=None, point_cloud_range=None):
+        """host_points: list of pinned CPU tensors; H2D copies are issued on the compute stream.
+
+        ``augs`` (one ``data.Augmentation`` per frame, e.g. from ``data.draw_augmentation``) runs the train pipeline's
+        GlobalRotScaleTrans / RandomFlip3D / PointsRangeFilter on the device first (``geomae_augment_filter``, one call
+        for the batch; configs/mae_sst/…6x_1e-5.py:180-190): the raw frames land in one buffer, are transformed,
+        filtered and compacted there, and the per-frame survivor counts come back in one small read (the scatter stage
+        sizes its buffers from the host-side point count)."""
         dev = self.flat_param.device
-        pts = [p.to(dev, non_blocking=True) for p in host_points]
+        if augs is None:
+            pts = [p.to(dev, non_blocking=True) for p in host_points]
+            return self.train_step(pts, ids=ids, lr=lr)
+        from .data import augment_filter
+        sizes = [p.shape[0] for p in host_points]
+        rng = point_cloud_range if point_cloud_range is not None else self.model.point_cloud_range
+        main = torch.cuda.current_stream(dev)
+        side = self.__dict__.get("_data_stream") or self.__dict__.setdefault("_data_stream", torch.cuda.Stream(dev))
+        # the data step runs on its own stream: the read of the survivor counts then waits for the copies and the
+        # three augmentation kernels only, not for the previous step's backward still draining on the compute stream
+        with torch.cuda.stream(side):
+            raw = torch.empty((sum(sizes), host_points[0].shape[1]), dtype=torch.float32, device=dev)
+            offs, at = [0], 0
+            for p, n in zip(host_points, sizes):
+                raw[at:at + n].copy_(p, non_blocking=True)
+                at += n
+                offs.append(at)
+            offsets = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+            out, out_off = augment_filter(raw, offsets, augs, rng)
+            o = out_off.tolist()
+        main.wait_stream(side)
+        out.record_stream(main)
+        pts = [out[o[b]:o[b + 1]] for b in range(len(sizes))]
         return self.train_step(pts, ids=ids, lr=lr)
 
 

@@ -64,3 +64,39 @@ def test_empty_batch():
     offs = torch.zeros(3, dtype=torch.int32, device=DEV)
     out, out_off = augment_filter(pts, offs, [Augmentation(), Augmentation()], cfg.pc_range)
     assert out.shape == (0, 5) and out_off.tolist() == [0, 0, 0]
+
+
+def test_train_step_from_host_with_device_augmentation_matches_preaugmented_frames():
+    """FlatTrainer.train_step_from_host(augs=...) == the same step on frames augmented + filtered by the oracle on the
+    host (same mask split, same weights): the device data step changes where the work happens, not the result."""
+    import os
+    import geomae_b200 as G
+    from geomae_b200.data import draw_augmentation, frame_params
+    from geomae_b200.registry import Config
+    from geomae_b200.synthetic import make_frame
+    from geomae_b200.train import FlatTrainer
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = Config.fromfile(os.path.join(root, "configs/mae_sst/geomae_nus_pretrain.py"))
+    frames = [make_frame(91, point_scale=0.5), make_frame(92, point_scale=0.3)]
+    rs = np.random.RandomState(5)
+    augs = [draw_augmentation(rs) for _ in frames]
+    pre = O.augment_filter(frames, frame_params(augs).numpy(), O.PathConfig().pc_range)
+    assert sum(f.shape[0] for f in pre) < sum(f.shape[0] for f in frames)
+
+    def run(feed):
+        torch.manual_seed(0)
+        model = G.build_detector(cfg.model).to(DEV)
+        model.set_impl("tc3")
+        model.train()
+        tr = FlatTrainer(model, lr=1e-4)
+        torch.manual_seed(3)                        # the mask split draws its seed from the CPU generator
+        loss = feed(tr)[0]
+        return float(loss), tr.flat_param.clone()
+
+    host = [torch.from_numpy(f).pin_memory() for f in frames]
+    la, pa = run(lambda tr: tr.train_step_from_host(host, augs=augs))
+    lb, pb = run(lambda tr: tr.train_step([torch.from_numpy(f).to(DEV) for f in pre]))
+    # same points in the same order; the scatter's float atomics make the last bits run-dependent
+    assert abs(la - lb) <= 1e-5 * abs(lb)
+    # one AdamW step moves every weight by about lr; a gradient that is pure rounding noise may flip its direction
+    assert (pa - pb).abs().max().item() <= 2.01e-4 and (pa - pb).abs().mean().item() <= 1e-7
