@@ -2,7 +2,7 @@
 mmdet3d/models/detectors/dynamic_voxelnet.py:10-83 up to and including ``extract_feat``
 (voxelize -> DynamicScatterVFE -> SSTInputLayer -> SSTSecondPretrainedv1 [-> neck]).
 
-The detection head (CenterHead), its losses and the SECONDFPN neck are outside SURVEY §8; a config that names them
+The detection head (Anchor3DHead in the pre_sst config), its losses and the SECONDFPN neck are outside SURVEY §8; a config that names them
 is accepted (so the reference's config file builds), the sub-configs are kept on the module, and ``forward_train`` /
 ``simple_test`` say so loudly instead of pretending.  ``load_pretrained`` is what ``load_from = …/epoch_72.pth`` does
 in the reference (configs/pre_sst/…6x_1e-5.py:280; mmcv load_checkpoint, strict=False): tensors whose keys and shapes

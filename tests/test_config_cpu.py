@@ -110,3 +110,48 @@ def test_flat_trainer_layout_buckets():
         assert p.data_ptr() == tr.flat_param.data_ptr() + 4 * off
         off += (p.numel() + 63) // 64 * 64
     assert off == tr.n
+
+
+REF_FT_CFG = ("/root/reference/configs/pre_sst/"
+              "m_sst_nus_second_pointpillar_fpn355_222_curv_07_ssl_data_wo_dbsampler_6x_1e-5.py")
+OWN_FT_CFG = os.path.join(os.path.dirname(OWN_CFG), "..", "pre_sst", "geomae_nus_finetune_features.py")
+
+
+def check_finetune_consumer(model, pre):
+    assert type(model).__name__ == "DynamicVoxelNet"
+    assert type(model.middle_encoder).__name__ == "SSTInputLayer" and model.middle_encoder.shuffle_voxels
+    assert type(model.backbone).__name__ == "SSTSecondPretrainedv1"
+    assert type(model.backbone.conv_blocks[0][1]).__name__ == "NaiveSyncBatchNorm2d"
+    assert [len(b) for b in model.backbone.conv_blocks] == [12, 18, 18]       # (1 + layer_num) x (conv, BN, ReLU)
+    # every VFE and encoder tensor of the pre-training checkpoint has a destination of the same shape (load by key)
+    own, sd = model.state_dict(), pre.state_dict()
+    shared = [k for k in sd if k in own]
+    assert len([k for k in shared if k.startswith("backbone.encoder_blocks.")]) == 6 * 2 * 12
+    assert len([k for k in shared if k.startswith("voxel_encoder.")]) == len([k for k in sd if k.startswith("voxel_encoder.")])
+    assert all(own[k].shape == sd[k].shape for k in shared)
+    loaded, untouched, unexpected = model.load_pretrained(dict(state_dict=sd))
+    assert sorted(loaded) == sorted(shared)
+    assert all(k.startswith("backbone.conv_blocks.") for k in untouched)
+    for k in loaded:
+        assert torch.equal(model.state_dict()[k], sd[k]), k
+
+
+def test_own_finetune_config_builds_and_takes_the_pretraining_checkpoint():
+    torch.manual_seed(0)
+    pre = build_model(Config.fromfile(OWN_CFG).model)
+    check_finetune_consumer(build_model(Config.fromfile(OWN_FT_CFG).model), pre)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FT_CFG), reason="reference tree not present")
+def test_reference_finetune_config_loads_unchanged():
+    cfg = Config.fromfile(REF_FT_CFG)
+    torch.manual_seed(0)
+    pre = build_model(Config.fromfile(OWN_CFG).model)
+    model = build_model(cfg.model, train_cfg=cfg.get("train_cfg"), test_cfg=cfg.get("test_cfg"))
+    check_finetune_consumer(model, pre)
+    assert model.bbox_head_cfg["type"] == "Anchor3DHead" and model.neck_cfg["type"] == "SECONDFPN"
+    own = Config.fromfile(OWN_FT_CFG).model
+    for part in ("voxel_layer", "voxel_encoder", "middle_encoder", "backbone"):
+        a, b = dict(own[part]), dict(cfg.model[part])
+        assert {k: (list(v) if isinstance(v, tuple) else v) for k, v in a.items()} == \
+               {k: (list(v) if isinstance(v, tuple) else v) for k, v in b.items()}, part

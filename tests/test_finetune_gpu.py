@@ -195,7 +195,7 @@ def test_dynamic_voxelnet_loads_pretraining_checkpoint_by_key(tmp_path):
                       dim_feedforward=[256] * 6, output_shape=[400, 400], conv_in_channels=128,
                       conv_out_channels=[32, 32, 64], layer_nums=[1, 1, 1], layer_strides=[2, 2, 2], debug=True,
                       drop_info=(di, di), pos_temperature=10000, normalize_pos=False, window_shape=win),
-        neck=dict(type="SECONDFPN"), bbox_head=dict(type="CenterHead"))
+        neck=dict(type="SECONDFPN"), bbox_head=dict(type="Anchor3DHead"))
     det = G.build_detector(model).to(DEV)
     loaded, untouched, unexpected = det.load_pretrained(str(ckpt))
     assert any(k.startswith("voxel_encoder.") for k in loaded)
