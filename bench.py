@@ -337,9 +337,26 @@ def main():
     def step_resident(i):
         last["loss"] = trainer.train_step(resident[i % len(resident)])[0]
 
+    loss_pinned = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_event = [None, None]
+
+    def read_back(i, loss, final):
+        """Device->host read of every step's loss inside the timed region, without draining the device each step: the
+        value goes to pinned memory asynchronously and the host consumes it one step later (the last one before the
+        closing synchronise), as a training loop's logger does."""
+        slot = i & 1
+        loss_pinned[slot:slot + 1].copy_(loss.reshape(1), non_blocking=True)
+        loss_event[slot] = torch.cuda.Event()
+        loss_event[slot].record()
+        for s_ in ((slot ^ 1, slot) if final else (slot ^ 1,)):
+            if loss_event[s_] is not None:
+                loss_event[s_].synchronize()
+                last["loss_host"] = float(loss_pinned[s_])
+                loss_event[s_] = None
+
     def step_host(i):
         last["loss"] = trainer.train_step_from_host(host[i % len(host)])[0]
-        last["loss_host"] = float(last["loss"])             # D2H read of the step's loss, every step
+        read_back(i, last["loss"], i == K - 1)
 
     aug_rng = np.random.RandomState(1000 + rank)
 
@@ -350,7 +367,7 @@ def main():
         batch = host[i % len(host)]
         augs = [draw_augmentation(aug_rng) for _ in batch]
         last["loss"] = trainer.train_step_from_host(batch, augs=augs)[0]
-        last["loss_host"] = float(last["loss"])
+        read_back(i, last["loss"], i == K - 1)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -500,13 +517,16 @@ def main():
                     precision={"tc1": "SRA GEMMs bf16 operands / fp32 TMEM accumulate; activations, LayerNorm, softmax, VFE, targets, losses fp32",
                                "tc3": "SRA GEMMs bf16x3 split on tensor cores (fp32-equivalent, loss parity <=1e-4); rest fp32",
                                "glue": "fp32 library GEMMs, TF32 off"}[args.sra_impl]),
-        e2e=dict(value=frames / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                 ms_per_step=ms_e2e / K),
+        e2e=dict(value=frames / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=h2d,
+                 d2h_bytes_per_step=4 + 4 * (5 + S), ms_per_step=ms_e2e / K,
+                 reads="every step: the scatter's pillar totals (blocking, on the input stream) and the loss (copied to "
+                       "pinned memory asynchronously, consumed by the host one step later, the last before the closing "
+                       "synchronise)"),
         # the same end-to-end step with the train pipeline's rotate / scale / flip / range filter done on the device
         # in front of the scatter (geomae_augment_filter; fresh draws per step, one extra 20-byte offsets read)
         e2e_with_device_augmentation=dict(value=frames / (ms_e2e_aug * 1e-3), unit="frames/s",
                                           ms_per_step=ms_e2e_aug / K, h2d_bytes_per_step=h2d,
-                                          d2h_bytes_per_step=4 + 4 * (S + 1)),
+                                          d2h_bytes_per_step=4 + 4 * (5 + S) + 4 * (S + 1)),
         gpu_launches=launches, clocks=clocks, roofline=roof, kernel_families=fam_table, hbm_kernels=aux,
         kernel_ms_per_step={k: round(v[0] / K, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
         loss=last.get("loss_host"), loss_delta_vs_tc3=loss_delta)

@@ -175,7 +175,7 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
     # ------------------------------------------------------------------ hot path
     def extract_feat(self, points, ids=None):
         batch_size = len(points)
-        pb = scatter_frames(self.geom, points)
+        pb = scatter_frames(self.geom, points, side=getattr(self, "scatter_stream", None))
         voxel_features, feature_coors = self.voxel_encoder(pb)
         ids_keep, ids_mask = ids if ids is not None else self.get_vanilla_mask_index(
             feature_coors, batch_size, pb.pillars_per_frame(), pb.counts[4:])

@@ -17,8 +17,9 @@ class FlatTrainer:
     EARLY_KEYS = ("backbone.decoder_", "backbone.cls_pred_")
 
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, max_grad_norm=10.0,
-                 no_decay_keys=("norm",)):
+                 no_decay_keys=("norm",), overlap_input=True):
         self.model = model
+        self.overlap_input = overlap_input      # run the input stage on its own stream (see input_stream())
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]     # frozen parameters stay outside
         is_nd = lambda k: any(s in k for s in no_decay_keys)                        # noqa: E731
         is_early = lambda k: k.startswith(self.EARLY_KEYS)                           # noqa: E731
@@ -95,10 +96,27 @@ class FlatTrainer:
             self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, L.ptr(self.stats),
             L.stream_ptr(self.flat_param.device))
 
-    def train_step(self, points, ids=None, lr=None):
-        """points: list of [N_i, C] CUDA tensors (one rank's samples).  Returns (total loss, loss dict)."""
+    def input_stream(self):
+        """The side stream of the input stage (H2D copies, device augmentation, voxel scatter and the read of its
+        totals).  Work queued here never waits for the compute stream, so the one host read a step needs (pillar
+        counts size every later buffer) blocks for the input stage only and the host keeps enqueueing ahead."""
+        st = self.__dict__.get("_input_stream")
+        if st is None:
+            st = self.__dict__["_input_stream"] = torch.cuda.Stream(self.flat_param.device)
+        return st
+
+    def train_step(self, points, ids=None, lr=None, ready=None):
+        """points: list of [N_i, C] CUDA tensors (one rank's samples).  Returns (total loss, loss dict).
+
+        The scatter runs on ``input_stream()``: ``points`` must be complete when this is called (synchronised, produced
+        on ``input_stream()``, or guarded by ``ready``, a torch.cuda.Event recorded after whatever produced them)."""
         if self.step_count == 0:
             self.check_bindings()
+        if hasattr(self.model, "extract_feat"):
+            side = self.input_stream() if self.overlap_input else None
+            if ready is not None:
+                (side or torch.cuda.current_stream(self.flat_param.device)).wait_event(ready)
+            self.model.scatter_stream = side
         prev = L.pin_stream(self.flat_param.device)
         try:
             return self._train_step(points, ids, lr)
@@ -133,37 +151,37 @@ class FlatTrainer:
         return total.detach(), losses
 
     def train_step_from_host(self, host_points, ids=None, lr=None, augs=None, point_cloud_range=None):
-        """host_points: list of pinned CPU tensors; H2D copies are issued on the compute stream.
+        """host_points: list of pinned CPU tensors; the H2D copies are issued on ``input_stream()``.
 
         ``augs`` (one ``data.Augmentation`` per frame, e.g. from ``data.draw_augmentation``) runs the train pipeline's
         GlobalRotScaleTrans / RandomFlip3D / PointsRangeFilter on the device first (``geomae_augment_filter``, one call
         for the batch; configs/mae_sst/…6x_1e-5.py:180-190): the raw frames land in one buffer, are transformed,
         filtered and compacted there, and the per-frame survivor counts come back in one small read (the scatter stage
-        sizes its buffers from the host-side point count)."""
+        sizes its buffers from the host-side point count).  Copies and the data step are queued on ``input_stream()``."""
         dev = self.flat_param.device
-        if augs is None:
-            pts = [p.to(dev, non_blocking=True) for p in host_points]
-            return self.train_step(pts, ids=ids, lr=lr)
-        from .data import augment_filter
-        sizes = [p.shape[0] for p in host_points]
-        rng = point_cloud_range if point_cloud_range is not None else self.model.point_cloud_range
         main = torch.cuda.current_stream(dev)
-        side = self.__dict__.get("_data_stream") or self.__dict__.setdefault("_data_stream", torch.cuda.Stream(dev))
-        # the data step runs on its own stream: the read of the survivor counts then waits for the copies and the
-        # three augmentation kernels only, not for the previous step's backward still draining on the compute stream
+        side = self.input_stream() if self.overlap_input else main
+        sizes = [p.shape[0] for p in host_points]
         with torch.cuda.stream(side):
-            raw = torch.empty((sum(sizes), host_points[0].shape[1]), dtype=torch.float32, device=dev)
-            offs, at = [0], 0
-            for p, n in zip(host_points, sizes):
-                raw[at:at + n].copy_(p, non_blocking=True)
-                at += n
-                offs.append(at)
-            offsets = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
-            out, out_off = augment_filter(raw, offsets, augs, rng)
-            o = out_off.tolist()
-        main.wait_stream(side)
-        out.record_stream(main)
-        pts = [out[o[b]:o[b + 1]] for b in range(len(sizes))]
+            if augs is None:
+                pts = [p.to(dev, non_blocking=True) for p in host_points]
+            else:
+                from .data import augment_filter
+                rng = point_cloud_range if point_cloud_range is not None else self.model.point_cloud_range
+                raw = torch.empty((sum(sizes), host_points[0].shape[1]), dtype=torch.float32, device=dev)
+                offs, at = [0], 0
+                for p, n in zip(host_points, sizes):
+                    raw[at:at + n].copy_(p, non_blocking=True)
+                    at += n
+                    offs.append(at)
+                offsets = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+                out, out_off = augment_filter(raw, offsets, augs, rng)
+                o = out_off.tolist()     # waits for the copies and three kernels on the input stream only
+                pts = [out[o[b]:o[b + 1]] for b in range(len(sizes))]
+        if side is not main and not hasattr(self.model, "extract_feat"):
+            main.wait_stream(side)
+        for t in pts:
+            t.record_stream(main)
         return self.train_step(pts, ids=ids, lr=lr)
 
 

@@ -119,11 +119,21 @@ class PillarBatch:
             L.ptr(self.low_mean), L.ptr(self.coors_top), L.ptr(self.coors_med), L.ptr(self.coors_low))
         self._n = None
 
-    def run(self):
+    def run(self, stream=None):
+        """stream: raw CUDA stream handle to launch on (default: the caller's current / pinned stream)."""
         L.run("voxel_scatter", C.byref(self.geom.cstruct), C.byref(self.io),
-                                             L.stream_ptr(self.points.device))
+              stream if stream is not None else L.stream_ptr(self.points.device))
         self._n = None
         return self
+
+    def hand_over(self, stream):
+        """The buffers were allocated (and filled) under another stream; tell the caching allocator that ``stream``
+        uses them from now on, so that a later free is not recycled under work still queued there."""
+        for t in (self.points, self.frame_offsets, self.bitmap, self.word_rank, self.scan_tmp, self.counts,
+                  self.pillar_coors, self.pillar_mean, self.point_pillar, self.med_mask, self.low_mask, self.med_ptr,
+                  self.low_ptr, self.med_mean, self.low_mean, self.coors_top, self.coors_med, self.coors_low):
+            if t is not None:
+                t.record_stream(stream)
 
     def sizes(self):
         """(n_pillars, n_med, n_low) — one device->host read of four ints."""
@@ -179,13 +189,29 @@ class PillarBatch:
         return low, low_m.bool(), med, med_m.bool(), top
 
 
-def scatter_frames(geom: VoxelGeometry, frames, want_coors=False) -> PillarBatch:
-    """frames: list of [N_i, C] float32 CUDA tensors (or one concatenated tensor + offsets)."""
+def scatter_frames(geom: VoxelGeometry, frames, want_coors=False, side=None) -> PillarBatch:
+    """frames: list of [N_i, C] float32 CUDA tensors (or one concatenated tensor + offsets).
+
+    ``side`` (a torch.cuda.Stream): concatenate, scatter and read the three totals back on that stream, then make the
+    caller's stream wait for it.  The read then blocks the host for the scatter alone instead of for everything
+    still queued on the compute stream (the previous step's backward and optimiser), which keeps the host enqueueing
+    ahead of the device.  The caller guarantees that ``frames`` are complete or were produced on ``side``."""
     for f in frames:
         L.require_cuda(f, "points")
-    points = torch.cat(frames, dim=0).contiguous()
     offs = [0]
     for f in frames:
         offs.append(offs[-1] + f.shape[0])
-    frame_offsets = torch.tensor(offs, dtype=torch.int32, device=points.device)
-    return PillarBatch(geom, points, frame_offsets, len(frames), want_coors).run()
+    if side is None:
+        points = torch.cat(frames, dim=0).contiguous()
+        frame_offsets = torch.tensor(offs, dtype=torch.int32, device=points.device)
+        return PillarBatch(geom, points, frame_offsets, len(frames), want_coors).run()
+    dev = frames[0].device
+    main = torch.cuda.current_stream(dev)
+    with torch.cuda.stream(side):
+        points = torch.cat(frames, dim=0).contiguous()
+        frame_offsets = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+        pb = PillarBatch(geom, points, frame_offsets, len(frames), want_coors).run(side.cuda_stream)
+        pb.sizes()
+    main.wait_stream(side)
+    pb.hand_over(main)
+    return pb
