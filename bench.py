@@ -15,6 +15,7 @@ FlatTrainer.train_step_from_host (pinned host frames, H2D inside the timed regio
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -299,24 +300,32 @@ def main():
     pool = make_batches(rank, min(K + W, 8), S, wl["frame"])
     host = [[torch.from_numpy(f).pin_memory() for f in b] for b in pool]
     resident = [[f.to(dev) for f in b] for b in host]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(step_fn, n):
-        evs = []
+    host_ms = {}
+
+    def timed_loop(step_fn, n, tag=None):
+        """ONE pair of events around the n steps (the L2 flushes sit inside the timed region: the input stage of step
+        i+1 overlaps the tail of step i, so per-step brackets would no longer add up to the job's time)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()            # no cyclic-GC pause in the middle of a step (collected between loops instead)
+        t0 = time.perf_counter()
+        e0.record()
         for i in range(n):
-            flush.zero_()                                   # evict L2 between steps (outside the timed events)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            flush.zero_()                                   # evict L2 between steps
             step_fn(i)
-            e1.record()
-            evs.append((e0, e1))
+        e1.record()
+        if tag:
+            host_ms[tag] = (time.perf_counter() - t0) * 1e3 / n      # how long the host needed to enqueue a step
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)
+        gc.enable()
+        return e0.elapsed_time(e1)
 
     last = {}
     model.keep_targets = True
@@ -373,8 +382,8 @@ def main():
     if rank == 0:
         sampler.start()                           # before the warm-up: nvidia-smi's start-up (NVML init) stalls launches
         sampler.wait_ready()
-    for i in range(len(resident)):                # allocator priming: every distinct synthetic batch once, so the timed
-        step_resident(i)                          # steps never call cudaMalloc for a first-seen tensor size (untimed setup)
+    for i in range(3 * len(resident)):            # allocator priming: every distinct synthetic batch, free-running (several
+        step_resident(i)                          # steps in flight), so the timed steps never call cudaMalloc (untimed setup)
     for i in range(W):
         step_resident(i)
     barrier()
@@ -394,7 +403,7 @@ def main():
         barrier()
     L.reset_call_counts()
     sampler.mark()
-    ms = timed_loop(step_resident, K)             # the headline number: no per-kernel instrumentation
+    ms = timed_loop(step_resident, K, "resident")  # the headline number: no per-kernel instrumentation
     sampler.mark()
     launches = L.launch_count()
     barrier()
@@ -405,11 +414,11 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    for i in range(min(W, 2)):
+    for i in range(max(W, len(host))):            # warm-up + allocator priming of the host-fed path (input-stream pool)
         step_host(i)
     barrier()
     sampler.mark()
-    ms_e2e = timed_loop(step_host, K)
+    ms_e2e = timed_loop(step_host, K, "e2e")
     sampler.mark()
     barrier()
     # bf16-mode vs parity-mode (bf16x3 + fp32 attention) loss on one identical batch, same weights, same mask split
@@ -428,7 +437,9 @@ def main():
         if out[args.sra_impl] is not None and out["tc3"]:
             loss_delta = dict(loss=out[args.sra_impl], loss_tc3=out["tc3"],
                               rel=abs(out[args.sra_impl] - out["tc3"]) / abs(out["tc3"]))
-    step_host_augmented(0)        # after the loss-delta block: that one re-uses the last un-augmented step's mask split
+    for i in range(len(host)):
+        step_host_augmented(i)
+    # ^ warm-up; placed after the loss-delta block: that one re-uses the last un-augmented step's mask split
     barrier()
     ms_e2e_aug = timed_loop(step_host_augmented, K)
     barrier()
@@ -512,7 +523,7 @@ def main():
         data="synthetic",
         config=dict(workload=WORKLOAD, workload_key=args.workload, samples_per_gpu=S, sweeps=wl["frame"].get("sweeps", 1),
                     points_per_frame=int(pool[0][0].shape[0]),
-                    parallelism=f"dp{world}", l2="flushed between steps (256 MiB write, outside the timed events)",
+                    parallelism=f"dp{world}", l2="flushed between steps (192 MiB write on the compute stream, inside the timed region)",
                     sra_impl=args.sra_impl,
                     precision={"tc1": "SRA GEMMs bf16 operands / fp32 TMEM accumulate; activations, LayerNorm, softmax, VFE, targets, losses fp32",
                                "tc3": "SRA GEMMs bf16x3 split on tensor cores (fp32-equivalent, loss parity <=1e-4); rest fp32",
@@ -527,7 +538,7 @@ def main():
         e2e_with_device_augmentation=dict(value=frames / (ms_e2e_aug * 1e-3), unit="frames/s",
                                           ms_per_step=ms_e2e_aug / K, h2d_bytes_per_step=h2d,
                                           d2h_bytes_per_step=4 + 4 * (5 + S) + 4 * (S + 1)),
-        gpu_launches=launches, clocks=clocks, roofline=roof, kernel_families=fam_table, hbm_kernels=aux,
+        host_enqueue_ms_per_step=host_ms, gpu_launches=launches, clocks=clocks, roofline=roof, kernel_families=fam_table, hbm_kernels=aux,
         kernel_ms_per_step={k: round(v[0] / K, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
         loss=last.get("loss_host"), loss_delta_vs_tc3=loss_delta)
     if (args.workload == "dense" or args.length_bins) and world == 1:

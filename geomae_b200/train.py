@@ -102,7 +102,8 @@ class FlatTrainer:
         counts size every later buffer) blocks for the input stage only and the host keeps enqueueing ahead."""
         st = self.__dict__.get("_input_stream")
         if st is None:
-            st = self.__dict__["_input_stream"] = torch.cuda.Stream(self.flat_param.device)
+            # high priority: its short kernels slot in at the next CTA boundary of the persistent compute kernels
+            st = self.__dict__["_input_stream"] = torch.cuda.Stream(self.flat_param.device, priority=-1)
         return st
 
     def train_step(self, points, ids=None, lr=None, ready=None):

@@ -15,3 +15,5 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(20): tr.train_step(frames)
 pr.disable(); torch.cuda.synchronize()
 st = pstats.Stats(pr); st.sort_stats("cumulative").print_stats("geomae_b200|built-in method torch|method .* of .torch", 60)
+print("=" * 30, "by self time")
+st.sort_stats("tottime").print_stats(45)
