@@ -2,6 +2,9 @@
 // One C-ABI call runs every kernel of every layer of the stack on the given stream, so the Python
 // host pays one call per stack and direction instead of one per kernel (the v1 path was CPU-bound).
 // Layer math: models/sst/sst_basic_block.py:26-61,85-102 (post-norm EncoderLayer with window attention).
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -193,12 +196,16 @@ extern "C" int geomae_sra_stack_forward(const geomae_sra_ctx* c, int32_t n_layer
 
 namespace {
 
-// Internal side streams / events (created once).  Weight-gradient GEMMs run on a side stream so they overlap
-// the latency-bound dX chain; the two decoder stacks run on separate streams.
+// Internal side streams / events, one set per device, created on first use.  Weight-gradient GEMMs run on a side
+// stream so they overlap the latency-bound dX chain; the two decoder stacks run on separate streams.  The set holds
+// no per-call state: every executor call re-synchronises the side streams with the caller's stream on entry
+// (hand_off) and hands back on exit, so any number of models / trainers / host threads can share it; the event ring
+// index is atomic, and an event is consumed (cudaStreamWaitEvent) right after it is recorded, before its slot can
+// come round again.
 struct Lanes {
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev[64];
-  int next_ev = 0;
+  std::atomic<unsigned> next_ev{0};
   bool ready = false;
   int init() {
     if (ready) return GEOMAE_OK;
@@ -207,13 +214,32 @@ struct Lanes {
     ready = true;
     return GEOMAE_OK;
   }
-  cudaEvent_t event() { cudaEvent_t e = ev[next_ev]; next_ev = (next_ev + 1) % 64; return e; }
+  cudaEvent_t event() { return ev[next_ev.fetch_add(1) % 64]; }
 };
-Lanes g_lanes;
+constexpr int MAX_DEVICES = 64;
+Lanes g_lanes_of[MAX_DEVICES];
+std::mutex g_lanes_mutex;
+
+// the lanes of the CURRENT device (the one the caller's stream lives on); nullptr + error text on failure
+Lanes* lanes() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) {
+    gm_set_error("sra_stack: cannot identify the current device");
+    return nullptr;
+  }
+  Lanes& l = g_lanes_of[dev];
+  if (!l.ready) {
+    std::lock_guard<std::mutex> lock(g_lanes_mutex);
+    if (l.init() != GEOMAE_OK) return nullptr;
+  }
+  return &l;
+}
 
 // signal on `from`, wait on `to`
 int hand_off(cudaStream_t from, cudaStream_t to) {
-  cudaEvent_t e = g_lanes.event();
+  Lanes* L_ = lanes();
+  if (!L_) return GEOMAE_ERR_CUDA;
+  cudaEvent_t e = L_->event();
   GM_CUDA(cudaEventRecord(e, from));
   GM_CUDA(cudaStreamWaitEvent(to, e, 0));
   return GEOMAE_OK;
@@ -295,7 +321,7 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
         Span span(1, 2.0 * n * (3.0 * dd_ * dd_ + dd_ * dd_ + 2.0 * dd_ * ff), side, n * 2.0 * (6.0 * dd_ + 2.0 * ff + 3.0 * dd_) + 4.0 * (4.0 * dd_ * dd_ + 2.0 * dd_ * ff));
         GM_TRY(geomae_sra_wgrad_layer(&g, side));
       }
-      side_done[l & 1] = g_lanes.event();
+      side_done[l & 1] = lanes()->event();
       GM_CUDA(cudaEventRecord(side_done[l & 1], side));
     }
     {
@@ -378,7 +404,7 @@ int stack_backward_on(cudaStream_t main, cudaStream_t side, const geomae_sra_ctx
     GM_TRY(wgrad(du, f, S.y, d, n, L.g_lin1_w, d, L.g_lin1_b, f, d, p, side, nullptr, nullptr, 0, 0, b16));
     GM_TRY(wgrad(ds1, d, S.attn, d, n, L.g_out_proj_w, d, nullptr, d, d, p, side));
     GM_TRY(wgrad(dqkv, 3 * d, x, d, n, L.g_in_proj_w, d, L.g_in_proj_b, 3 * d, d, p, side, c->pos_table, w.tok_cell, 2, 0, b16));
-    side_done[l & 1] = g_lanes.event();
+    side_done[l & 1] = lanes()->event();
     GM_CUDA(cudaEventRecord(side_done[l & 1], side));
   }
   GM_TRY(hand_off(side, main));   // join
@@ -396,10 +422,11 @@ extern "C" int geomae_sra_stack_backward(const geomae_sra_ctx* c, int32_t n_laye
                                          float* d_in, float* scratch, void* stream) {
   GM_REQUIRE(c && layers && saved && d_out && d_in && scratch, "sra_stack_backward: null argument");
   if (c->n_tokens == 0) return GEOMAE_OK;
-  GM_TRY(g_lanes.init());
+  Lanes* ln = lanes();
+  if (!ln) return GEOMAE_ERR_CUDA;
   cudaStream_t main = (cudaStream_t)stream;
-  GM_TRY(hand_off(main, g_lanes.side[0]));     // the side stream must see everything queued before this call
-  return stack_backward_on(main, g_lanes.side[0], c, n_layers, layers, saved, x_in, d_out, d_in, scratch);
+  GM_TRY(hand_off(main, ln->side[0]));     // the side stream must see everything queued before this call
+  return stack_backward_on(main, ln->side[0], c, n_layers, layers, saved, x_in, d_out, d_in, scratch);
 }
 
 // Two stacks that read the same input (the centroid and density decoders, backbones/…top_only.py:269-277)
@@ -407,8 +434,9 @@ extern "C" int geomae_sra_stack_backward(const geomae_sra_ctx* c, int32_t n_laye
 extern "C" int geomae_sra_stack2_forward(const geomae_sra_ctx* c, int32_t n_layers, const geomae_sra_layer* layers_a,
                                          const geomae_sra_saved* saved_a, const geomae_sra_layer* layers_b,
                                          const geomae_sra_saved* saved_b, const float* x_in, void* stream) {
-  GM_TRY(g_lanes.init());
-  cudaStream_t main = (cudaStream_t)stream, other = g_lanes.side[1];
+  Lanes* ln = lanes();
+  if (!ln) return GEOMAE_ERR_CUDA;
+  cudaStream_t main = (cudaStream_t)stream, other = ln->side[1];
   GM_TRY(hand_off(main, other));
   GM_TRY(geomae_sra_stack_forward(c, n_layers, layers_a, saved_a, x_in, main));
   GM_TRY(geomae_sra_stack_forward(c, n_layers, layers_b, saved_b, x_in, other));
@@ -423,13 +451,14 @@ extern "C" int geomae_sra_stack2_backward(const geomae_sra_ctx* c, int32_t n_lay
   GM_REQUIRE(c && layers_a && layers_b && saved_a && saved_b && d_out_a && d_out_b && d_in_a && d_in_b && scratch,
              "sra_stack2_backward: null argument");
   if (c->n_tokens == 0) return GEOMAE_OK;
-  GM_TRY(g_lanes.init());
+  Lanes* ln = lanes();
+  if (!ln) return GEOMAE_ERR_CUDA;
   cudaStream_t main = (cudaStream_t)stream;
-  for (int i = 0; i < 3; ++i) GM_TRY(hand_off(main, g_lanes.side[i]));
-  GM_TRY(stack_backward_on(main, g_lanes.side[0], c, n_layers, layers_a, saved_a, x_in, d_out_a, d_in_a, scratch));
-  GM_TRY(stack_backward_on(g_lanes.side[1], g_lanes.side[2], c, n_layers, layers_b, saved_b, x_in, d_out_b, d_in_b,
+  for (int i = 0; i < 3; ++i) GM_TRY(hand_off(main, ln->side[i]));
+  GM_TRY(stack_backward_on(main, ln->side[0], c, n_layers, layers_a, saved_a, x_in, d_out_a, d_in_a, scratch));
+  GM_TRY(stack_backward_on(ln->side[1], ln->side[2], c, n_layers, layers_b, saved_b, x_in, d_out_b, d_in_b,
                            scratch + 2 * scratch_floats(c)));
-  return hand_off(g_lanes.side[1], main);
+  return hand_off(ln->side[1], main);
 }
 
 // ---- per-family timing of the stack kernels (bench.py roofline leg)

@@ -71,3 +71,54 @@ def test_flat_trainer_checkpoint_resume_and_binding_check():
     mb[0].weight.grad = None
     with pytest.raises(RuntimeError, match="no longer lives"):
         tb.check_bindings()
+
+
+def test_two_trainers_in_one_process_do_not_interfere():
+    """Two models + FlatTrainers stepping alternately (sharing the library's per-device side streams, the input
+    streams and the pinned-stream cache) compute what each computes alone."""
+    import os
+    import geomae_b200 as G
+    from geomae_b200.registry import Config
+    from geomae_b200.synthetic import make_frame
+    from geomae_b200.train import FlatTrainer
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = Config.fromfile(os.path.join(root, "configs/mae_sst/geomae_nus_pretrain.py"))
+    dev = "cuda:0"
+    batches = {s: [torch.from_numpy(make_frame(s * 10 + b, point_scale=0.3)).to(dev) for b in range(2)] for s in (1, 2)}
+
+    def make(seed, impl):
+        torch.manual_seed(seed)
+        m = G.build_detector(cfg.model).to(dev)
+        m.set_impl(impl)
+        m.train()
+        return m, FlatTrainer(m, lr=1e-4)
+
+    def steps(tr, seed, n, out):
+        for i in range(n):
+            torch.manual_seed(100 * seed + i)            # the mask split draws its seed from the CPU generator
+            out.append(float(tr.train_step(batches[seed])[0]))
+
+    alone = {}
+    for seed, impl in ((1, "tc1"), (2, "tc3")):
+        _, tr = make(seed, impl)
+        losses = []
+        steps(tr, seed, 3, losses)
+        alone[seed] = (losses, tr.flat_param.clone())
+    (_, ta), (_, tb) = make(1, "tc1"), make(2, "tc3")
+    la, lb = [], []
+    for i in range(3):                                   # interleaved, no synchronisation in between
+        torch.manual_seed(100 + i)
+        la.append(ta.train_step(batches[1])[0])
+        torch.manual_seed(200 + i)
+        lb.append(tb.train_step(batches[2])[0])
+    for seed, got, tr in ((1, la, ta), (2, lb, tb)):
+        ref_losses, ref_param = alone[seed]
+        for i, (a, b) in enumerate(zip(got, ref_losses)):
+            # float atomics in the scatter make the last bits run-dependent; after an AdamW step (update ~ lr * sign for
+            # noise-level gradients) that grows to ~1e-4 relative on the next loss
+            # (bf16 operands amplify it: a flipped rounding is 2^-9 of one activation)
+            tol = (2e-5 if i == 0 else 5e-4) * (1 if seed == 2 else 15)
+            assert abs(float(a) - b) <= tol * abs(b), (seed, i)
+        d = (tr.flat_param - ref_param).abs()
+        assert d.max().item() <= 6.1e-4 and d.mean().item() <= (2e-6 if seed == 2 else 2e-5)   # 3 AdamW steps of lr 1e-4
+    assert abs(alone[1][0][0] - alone[2][0][0]) > 1e-2 * alone[1][0][0]     # the two runs are distinguishable
