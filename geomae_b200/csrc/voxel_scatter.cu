@@ -656,6 +656,18 @@ __global__ void __launch_bounds__(TPB) k_token_of_cell(VoxGeom g, const int32_t*
   tok_of_pillar[cell_rank(bitmap, word_rank, top_cell(g, c.x, c.z, c.w))] = (int32_t)i;
 }
 
+__global__ void __launch_bounds__(TPB) k_rank_of_row(VoxGeom g, const int32_t* __restrict__ coors, int64_t n,
+                                                     const uint32_t* __restrict__ bitmap,
+                                                     const int32_t* __restrict__ word_rank, int32_t* rank_of_row,
+                                                     int32_t* first_row) {
+  const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = __ldg(reinterpret_cast<const int4*>(coors) + i);
+  const int r = cell_rank(bitmap, word_rank, top_cell(g, c.x, c.z, c.w));
+  rank_of_row[i] = r;
+  if (first_row) atomicMin(first_row + r, (int32_t)i);
+}
+
 // ---------------------------------------------------------------- standalone dynamic_voxelize (a1)
 __global__ void __launch_bounds__(TPB) k_dynamic_voxelize(const float* __restrict__ pts, int64_t n, int stride, float lx,
                                                           float ly, float lz, float vx, float vy, float vz, int gx,
@@ -785,6 +797,33 @@ extern "C" int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* c
   k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, bitmap, n_words, scan_tmp, word_rank, counts, nullptr, nullptr,
                                                  nullptr, nullptr, n > 0 ? n : 1, 0, 0);
   if (n > 0) k_token_of_cell<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap, word_rank, tok_of_pillar);
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
+
+extern "C" int geomae_coors_rank(const geomae_voxel_cfg* cfg, const int32_t* coors, int64_t n, int32_t n_frames,
+                                 uint32_t* bitmap, int32_t* word_rank, int32_t* scan_tmp, int32_t* counts,
+                                 int32_t* rank_of_row, int32_t* first_row, void* stream_) {
+  GM_REQUIRE(cfg && bitmap && word_rank && scan_tmp && counts && rank_of_row && (coors || n == 0),
+             "coors_rank: null argument");
+  GM_REQUIRE(n_frames >= 1 && n >= 0 && n < ((int64_t)1 << 31), "coors_rank: bad sizes");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VoxGeom g;
+  int rc = gm_make_geom(cfg, n_frames, &g);
+  if (rc) return rc;
+  const int64_t n_cells = (int64_t)n_frames * g.grid[0][0] * g.grid[0][1];
+  GM_REQUIRE(n_cells < ((int64_t)1 << 31), "coors_rank: %lld cells, supported < 2^31", (long long)n_cells);
+  const int n_words = gm_div_up(n_cells, 32);
+  const int scan_blocks = gm_div_up(n_words, SCAN_CHUNK);
+  GM_REQUIRE(scan_blocks <= SCAN_MAX_BLOCKS, "coors_rank: grid too large (%d scan blocks)", scan_blocks);
+  GM_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)n_words * 4, stream));
+  if (first_row && n > 0) GM_CUDA(cudaMemsetAsync(first_row, 0x7f, (size_t)n * 4, stream));
+  if (n > 0) k_mark_coors<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap);
+  k_bitmap_sums<<<scan_blocks, TPB, 0, stream>>>(bitmap, n_words, scan_tmp);
+  k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, bitmap, n_words, scan_tmp, word_rank, counts, nullptr, nullptr,
+                                                 nullptr, nullptr, n > 0 ? n : 1, 0, 0);
+  if (n > 0)
+    k_rank_of_row<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap, word_rank, rank_of_row, first_row);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
 }

@@ -161,6 +161,7 @@ class _Sigs:
     geomae_window_candidates = [C.POINTER(VoxelCfg), C.POINTER(WindowCfg), _i32, C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     geomae_coors_bitmap = [C.POINTER(VoxelCfg), _p, _i64, _i32, _p, _p, _p, _p, _p, _p]
+    geomae_coors_rank = [C.POINTER(VoxelCfg), _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p]
     geomae_token_map = [_p, _i64, _p, _i64, _p]
     geomae_window_csr = [C.POINTER(VoxelCfg), C.POINTER(WindowCfg), C.POINTER(ScatterIO), _p, _i64,
                          C.POINTER(WindowIO), _p]
@@ -215,7 +216,7 @@ _timing = None      # list of (name, start_event, end_event) while bench.py meas
 _calls = {}         # name -> number of C-ABI calls (bench.py reports kernel launches from these)
 
 # kernels launched per C-ABI call (upper bound for the optional ones), for the gpu_launches claim
-LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=9, augment_filter=3, geom_targets=1, dense_targets=1, coors_bitmap=4,
+LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=9, augment_filter=3, geom_targets=1, dense_targets=1, coors_bitmap=4, coors_rank=4,
                          token_map=1, window_csr=3, window_drop=2, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
                          scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=2, sra_attention_tc_fwd=1,
                          sra_attention_tc_bwd=1, adamw_step=2,

@@ -50,6 +50,47 @@ class _ScatterRows(torch.autograd.Function):
         return d_feat, None, None, None
 
 
+_MAX_CELLS = (1 << 31) - 1
+
+
+def unique_rows(coors):
+    """``torch.unique(coors, return_inverse=True, return_counts=True, dim=0)`` for non-negative integer grid rows
+    [N, 3] (z,y,x) or [N, 4] (b,z,y,x) without the library's lexicographic sort: the rows set bits in an occupancy
+    bitmap over the bounding grid, a prefix sum ranks the set bits (= the sorted unique rows), every row looks its rank
+    up (geomae_coors_rank, csrc/voxel_scatter.cu).  Falls back to torch.unique only when the bounding grid has 2^31
+    cells or more, or a coordinate is negative (both on the device; the reference's -1 rows are filtered upstream)."""
+    import ctypes as C
+    from .voxel import VoxelGeometry
+    n, w = coors.shape
+    if n == 0 or w not in (3, 4) or not coors.is_cuda:
+        return torch.unique(coors, return_inverse=True, return_counts=True, dim=0)
+    lo = coors.min().item()
+    ext = (coors.max(dim=0)[0] + 1).tolist()
+    b_ext, (gz, gy, gx) = (ext[0], ext[1:]) if w == 4 else (1, ext)
+    if lo < 0 or b_ext * gz * gy * gx > _MAX_CELLS:
+        return torch.unique(coors, return_inverse=True, return_counts=True, dim=0)
+    dev = coors.device
+    c32 = coors.to(torch.int32)
+    folded = torch.zeros((n, 4), dtype=torch.int32, device=dev)          # (b, 0, z*Y + y, x)
+    if w == 4:
+        folded[:, 0] = c32[:, 0]
+    folded[:, 2] = c32[:, -3] * gy + c32[:, -2]
+    folded[:, 3] = c32[:, -1]
+    geom = VoxelGeometry((0.0, 0.0, 0.0, float(gx), float(gz * gy), 1.0), (1.0, 1.0, 1.0), (1.0, 1.0, 1.0),
+                         (1.0, 1.0, 1.0), (1, 1, 1), (1, 1, 1))
+    n_words = (b_ext * gz * gy * gx + 31) // 32
+    i32 = dict(dtype=torch.int32, device=dev)
+    bitmap, word_rank = torch.empty(n_words, **i32), torch.empty(n_words, **i32)
+    scan_tmp, counts = torch.empty(3 * 16384, **i32), torch.zeros(4, **i32)
+    rank, first = torch.empty(n, **i32), torch.empty(n, **i32)
+    L.run("coors_rank", C.byref(geom.cstruct), L.ptr(folded), n, b_ext, L.ptr(bitmap), L.ptr(word_rank), L.ptr(scan_tmp),
+          L.ptr(counts), L.ptr(rank), L.ptr(first), L.stream_ptr(dev))
+    n_unique = int(counts[0].item())
+    inv = rank.long()
+    new_coors = coors.index_select(0, first[:n_unique].long())
+    return new_coors, inv, torch.bincount(inv, minlength=n_unique)
+
+
 def scatter_v2(feat, coors, mode, return_inv=True, min_points=0, unq_inv=None, new_coors=None):
     """mmdet3d/ops/sst/sst_ops.py:8-39.  ``new_coors`` are the unique rows of ``coors`` in lexicographic order,
     ``unq_inv`` maps every point to its row, ``new_feat`` is the per-row 'sum' | 'mean' ('avg') | 'max' of ``feat``."""
@@ -58,7 +99,7 @@ def scatter_v2(feat, coors, mode, return_inv=True, min_points=0, unq_inv=None, n
         raise NotImplementedError(mode)
     counts = None
     if unq_inv is None:
-        new_coors, unq_inv, counts = torch.unique(coors, return_inverse=True, return_counts=True, dim=0)
+        new_coors, unq_inv, counts = unique_rows(coors)
     else:
         assert new_coors is not None, "please pass new_coors for interface consistency"
     if min_points > 0:
@@ -66,7 +107,7 @@ def scatter_v2(feat, coors, mode, return_inv=True, min_points=0, unq_inv=None, n
             counts = torch.bincount(unq_inv, minlength=new_coors.shape[0])
         valid = counts[unq_inv] >= min_points
         feat, coors = feat[valid], coors[valid]
-        new_coors, unq_inv = torch.unique(coors, return_inverse=True, dim=0)
+        new_coors, unq_inv, _ = unique_rows(coors)
     new_feat = _ScatterRows.apply(feat, unq_inv, new_coors.shape[0], _MODES[mode])
     return (new_feat, new_coors, unq_inv) if return_inv else (new_feat, new_coors)
 

@@ -161,6 +161,16 @@ int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* coors, int64
                         uint32_t* bitmap, int32_t* word_rank, int32_t* scan_tmp, int32_t* counts,
                         int32_t* tok_of_pillar, void* stream);
 
+/* Duplicate-tolerant variant for point-level rows: rank_of_row[i] = rank of coors[i]'s cell among the distinct cells
+ * (cells in (b, y, x) order, i.e. the row order of torch.unique(dim=0) for a grid with one z level), counts[0] =
+ * number of distinct cells, first_row[r] = smallest i with rank r (optional; [n] ints).  A (b, z, y, x) grid with Z
+ * levels is served by folding z into y (y' = z*Y + y, grid Z*Y rows).  Scratch buffers as for geomae_coors_bitmap.
+ * replaces: the torch.unique(coors, return_inverse, dim=0) of scatter_v2 (ops/sst/sst_ops.py:15-17) — a library
+ *           lexicographic sort — by one bitmap pass + a prefix sum. */
+int geomae_coors_rank(const geomae_voxel_cfg* cfg, const int32_t* coors, int64_t n, int32_t n_frames, uint32_t* bitmap,
+                      int32_t* word_rank, int32_t* scan_tmp, int32_t* counts, int32_t* rank_of_row,
+                      int32_t* first_row, void* stream);
+
 /* Random visible / masked split of each frame's pillars: frame f (pillars frame_starts[f] .. frame_starts[f+1])
  * keeps exactly k_f = (int)(L_f * keep_frac) pillars chosen uniformly at random (hash of (seed, f, index), k-th
  * smallest found by radix select — no sort); ids_keep [sum k_f] and ids_mask [sum (L_f - k_f)] receive the pillar

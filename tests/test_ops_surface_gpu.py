@@ -5,6 +5,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
 ARGS = ([0.32, 0.32, 6], [-74.88, -74.88, -2, 74.88, 74.88, 4])
 
 
@@ -80,3 +81,25 @@ def test_scatter_v2_modes_and_gradients():
     assert torch.equal(nc, uniq[cnt >= 5])
     out2, nc2, inv2 = scatter_v2(feat, coors, "sum", unq_inv=inv, new_coors=uniq)
     assert torch.equal(nc2, uniq) and torch.equal(inv2, inv)
+
+
+def test_unique_rows_matches_torch_unique():
+    """scatter_v2's row ranking (bitmap + prefix sum, geomae_coors_rank) == torch.unique(dim=0): same unique rows in
+    the same (lexicographic) order, same inverse map, same counts — for (z,y,x) and (b,z,y,x) rows with duplicates,
+    sub-voxel sized grids, a single row, and the fallback for negative rows."""
+    from geomae_b200.ops import unique_rows
+    g = torch.Generator().manual_seed(0)
+    cases = [torch.stack([torch.randint(0, hi, (n,), generator=g) for hi in his], dim=1)
+             for n, his in ((5000, (3, 8, 200, 200)), (20000, (8, 1600, 1600)), (1, (2, 1, 40, 40)),
+                            (3000, (4, 1, 400, 400)), (4000, (2, 4, 30, 17)))]
+    cases.append(torch.tensor([[0, 0, 5, 7]] * 9 + [[1, 0, 0, 0]]))
+    for dtype in (torch.int32, torch.int64):
+        for c in cases:
+            c = c.to(DEV).to(dtype)
+            uniq, inv, cnt = unique_rows(c)
+            ru, ri, rc = torch.unique(c, return_inverse=True, return_counts=True, dim=0)
+            assert uniq.dtype == c.dtype and torch.equal(uniq, ru)
+            assert torch.equal(inv, ri) and torch.equal(cnt, rc)
+    neg = torch.tensor([[0, -1, -1, -1], [0, 0, 2, 3], [0, 0, 2, 3]], device=DEV)
+    uniq, inv, cnt = unique_rows(neg)
+    assert torch.equal(uniq, torch.unique(neg, dim=0)) and cnt.tolist() == [1, 2]
