@@ -27,7 +27,30 @@ struct AugArgs {
   int n_frames;
   const float* params;   // [n_frames, 4]: cos, sin, scale, flip bits (1 horizontal, 2 vertical) as a float
   float lo[3], hi[3];
+  const double* seg;     // sweep-merge mode (non-null): [n_frames, 16] doubles per SEGMENT (= one sweep file):
+                         // R row-major (9), t (3), time lag, close radius (< 0: keep everything), 2 unused
 };
+
+// Sweep merge (LoadPointsFromMultiSweeps, datasets/pipelines/loading.py:160-181,218-226): a raw sweep point inside
+// the |x| < r, |y| < r box is dropped; the others move into the key frame: the float32 row times the float64
+// sensor->lidar rotation (numpy promotes to float64), rounded to float32 on assignment, then the float64 translation
+// added in place (computed in float64, rounded to float32 again); channel 4 becomes the sweep's time lag.
+__device__ __forceinline__ bool merge_point(const AugArgs& a, int64_t idx, int s, float& x, float& y, float& z) {
+  const float* rec = a.pts + idx * a.stride;
+  const float px = __ldg(rec), py = __ldg(rec + 1), pz = __ldg(rec + 2);
+  const double* q = a.seg + (int64_t)s * 16;
+  const double r = __ldg(q + 13);
+  if (r >= 0.0 && fabsf(px) < (float)r && fabsf(py) < (float)r) return false;
+  const double dx = px, dy = py, dz = pz;
+  // row . R^T: x' = p . R[0], in the operand order of a row-major dot product
+  const float rx = (float)__dadd_rn(__dadd_rn(__dmul_rn(dx, __ldg(q + 0)), __dmul_rn(dy, __ldg(q + 1))), __dmul_rn(dz, __ldg(q + 2)));
+  const float ry = (float)__dadd_rn(__dadd_rn(__dmul_rn(dx, __ldg(q + 3)), __dmul_rn(dy, __ldg(q + 4))), __dmul_rn(dz, __ldg(q + 5)));
+  const float rz = (float)__dadd_rn(__dadd_rn(__dmul_rn(dx, __ldg(q + 6)), __dmul_rn(dy, __ldg(q + 7))), __dmul_rn(dz, __ldg(q + 8)));
+  x = (float)__dadd_rn((double)rx, __ldg(q + 9));
+  y = (float)__dadd_rn((double)ry, __ldg(q + 10));
+  z = (float)__dadd_rn((double)rz, __ldg(q + 11));
+  return true;
+}
 
 // transformed xyz of point idx and whether it survives the range filter
 __device__ __forceinline__ bool aug_point(const AugArgs& a, int64_t idx, int b, float& x, float& y, float& z) {
@@ -49,10 +72,12 @@ __device__ __forceinline__ unsigned aug_flags(const AugArgs& a, int64_t p0, int 
 #pragma unroll
   for (int j = 0; j < APPT; ++j) {
     const int l = threadIdx.x + j * ATPB;
-    if (l < nvalid) {
+    if (l < nvalid && p0 + l < (int64_t)__ldg(a.off + a.n_frames)) {   // rows past the last frame's end are not points
       int b = b0;
       while (b + 1 < a.n_frames && (int64_t)__ldg(a.off + b + 1) <= p0 + l) ++b;
-      if (aug_point(a, p0 + l, b, xyz[j][0], xyz[j][1], xyz[j][2])) keep |= 1u << j;
+      const bool ok = a.seg ? merge_point(a, p0 + l, b, xyz[j][0], xyz[j][1], xyz[j][2])
+                            : aug_point(a, p0 + l, b, xyz[j][0], xyz[j][1], xyz[j][2]);
+      if (ok) keep |= 1u << j;
     }
   }
   return keep;
@@ -137,6 +162,10 @@ __global__ void __launch_bounds__(ATPB) k_aug_write(AugArgs a, const int32_t* __
       o[1] = xyz[j][1];
       o[2] = xyz[j][2];
       for (int c = 3; c < a.stride; ++c) o[c] = __ldg(rec + c);
+      if (a.seg && a.stride > 4) {       // the time channel of the sweep this point came from
+        int sg = frame_of(a.off, a.n_frames, p0 + l);
+        o[4] = (float)__ldg(a.seg + (int64_t)sg * 16 + 12);
+      }
     }
   }
   __syncthreads();
@@ -178,10 +207,35 @@ extern "C" int geomae_augment_filter(const float* points, int64_t n_points, int3
              (long long)scan_tmp_len, n_tiles + 1);
   AugArgs a;
   a.pts = points; a.n = n_points; a.stride = stride; a.off = frame_offsets; a.n_frames = n_frames; a.params = frame_params;
+  a.seg = nullptr;
   for (int i = 0; i < 3; ++i) { a.lo[i] = range_min[i]; a.hi[i] = range_max[i]; }
   k_aug_count<<<n_tiles, ATPB, 0, stream>>>(a, scan_tmp);
   k_aug_scan<<<1, 1024, 0, stream>>>(scan_tmp, n_tiles);
   k_aug_write<<<n_tiles, ATPB, 0, stream>>>(a, scan_tmp, out_points, out_frame_offsets);
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
+
+extern "C" int geomae_sweep_merge(const float* points, int64_t n_points, int32_t stride, const int32_t* seg_offsets,
+                                  int32_t n_segments, const double* seg_params, float* out_points,
+                                  int32_t* out_seg_offsets, int32_t* scan_tmp, int64_t scan_tmp_len, void* stream_) {
+  GM_REQUIRE(n_points >= 0 && n_segments >= 1 && stride >= 3 && stride <= 16, "sweep_merge: bad sizes (stride %d)", stride);
+  GM_REQUIRE(seg_offsets && seg_params && out_seg_offsets && scan_tmp, "sweep_merge: null argument");
+  GM_REQUIRE(n_points < ((int64_t)1 << 31), "sweep_merge: more than 2^31 points");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_points == 0) {
+    GM_CUDA(cudaMemsetAsync(out_seg_offsets, 0, sizeof(int32_t) * (size_t)(n_segments + 1), stream));
+    return GEOMAE_OK;
+  }
+  GM_REQUIRE(points && out_points, "sweep_merge: null point buffer");
+  const int n_tiles = gm_div_up(n_points, ATILE);
+  GM_REQUIRE(scan_tmp_len >= (int64_t)n_tiles + 1, "sweep_merge: scan_tmp holds %lld ints, %d needed",
+             (long long)scan_tmp_len, n_tiles + 1);
+  AugArgs a{};
+  a.pts = points; a.n = n_points; a.stride = stride; a.off = seg_offsets; a.n_frames = n_segments; a.seg = seg_params;
+  k_aug_count<<<n_tiles, ATPB, 0, stream>>>(a, scan_tmp);
+  k_aug_scan<<<1, 1024, 0, stream>>>(scan_tmp, n_tiles);
+  k_aug_write<<<n_tiles, ATPB, 0, stream>>>(a, scan_tmp, out_points, out_seg_offsets);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
 }

@@ -145,6 +145,70 @@ def load_multi_sweeps(points: np.ndarray, info: dict, sweeps_num: int = 9, load_
     return np.concatenate(parts, axis=0)[:, list(use_dim)]
 
 
+@dataclass
+class RawSweeps:
+    """One sample as it lies on disk: the raw [n_i, load_dim] float32 records of the key frame and of the chosen
+    earlier sweeps (``arrays``) and what moves each of them into the key frame (``params`` [S, 16] float64, the
+    layout of ``geomae_sweep_merge``).  ``FlatTrainer.train_step_from_host`` merges them on the device."""
+    arrays: list
+    params: np.ndarray
+
+    @property
+    def n_points(self):
+        return sum(a.shape[0] for a in self.arrays)
+
+
+def _segment_params(rotation=None, translation=None, time_lag=0.0, close_radius=-1.0):
+    p = np.zeros(16, np.float64)
+    p[:9] = (np.eye(3) if rotation is None else np.asarray(rotation, np.float64)).reshape(-1)
+    p[9:12] = 0.0 if translation is None else np.asarray(translation, np.float64)
+    p[12], p[13] = time_lag, close_radius
+    return p
+
+
+def load_multi_sweeps_raw(points: np.ndarray, info: dict, sweeps_num: int = 9, load_dim: int = 5,
+                          pad_empty_sweeps: bool = True, remove_close_points: bool = True, test_mode: bool = False,
+                          rng=np.random, read=None, close_radius: float = 1.0) -> RawSweeps:
+    """`load_multi_sweeps` without the arithmetic: same sweep choice (same draws from ``rng``), but the sweeps stay raw
+    and the per-sweep transform / close-point filter / time channel are described by ``params`` for the device."""
+    read = read or (lambda path: np.fromfile(path, dtype=np.float32))
+    key = np.ascontiguousarray(points, dtype=np.float32)
+    arrays, params = [key], [_segment_params()]
+    r = close_radius if remove_close_points else -1.0
+    sweeps = info["sweeps"]
+    if pad_empty_sweeps and not sweeps:
+        arrays += [key] * sweeps_num
+        params += [_segment_params(close_radius=r)] * sweeps_num
+    else:
+        for i in _pick_sweeps(len(sweeps), sweeps_num, test_mode, rng):
+            sw = sweeps[i]
+            arrays.append(np.ascontiguousarray(read(sw["data_path"]), dtype=np.float32).reshape(-1, load_dim))
+            params.append(_segment_params(sw["sensor2lidar_rotation"], sw["sensor2lidar_translation"],
+                                          info["timestamp"] - sw["timestamp"] / 1e6, r))
+    return RawSweeps(arrays, np.stack(params))
+
+
+def sweep_merge(points: torch.Tensor, seg_offsets: torch.Tensor, seg_params: torch.Tensor):
+    """points [N, C] float32 CUDA (raw segments back to back), seg_offsets [S+1] int32 CUDA, seg_params [S, 16] float64
+    CUDA -> (merged points [N, C], first ``out_off[-1]`` rows valid; out_off [S+1] int32 CUDA).  No host sync."""
+    L.require_cuda(points, "points")
+    if points.dtype != torch.float32 or seg_offsets.dtype != torch.int32 or seg_params.dtype != torch.float64:
+        raise RuntimeError("sweep_merge: points float32, seg_offsets int32, seg_params float64")
+    points, seg_params = points.contiguous(), seg_params.contiguous()
+    n, stride = points.shape
+    n_seg = seg_offsets.numel() - 1
+    if seg_params.shape != (n_seg, 16):
+        raise RuntimeError(f"sweep_merge: seg_params {tuple(seg_params.shape)} for {n_seg} segments")
+    dev = points.device
+    out = torch.empty_like(points)
+    out_off = torch.empty(n_seg + 1, dtype=torch.int32, device=dev)
+    n_tmp = (n + 1023) // 1024 + 1
+    tmp = torch.empty(n_tmp, dtype=torch.int32, device=dev)
+    L.run("sweep_merge", L.ptr(points), n, stride, L.ptr(seg_offsets), n_seg, L.ptr(seg_params), L.ptr(out),
+          L.ptr(out_off), L.ptr(tmp), C.c_int64(n_tmp), L.stream_ptr(dev))
+    return out, out_off
+
+
 class NuScenesSSLIndex:
     """The `nuscenes_ssl_infos_*.pkl` index as `NuScenesDatasetSSL` reads it (datasets/nuscenes_ssl_dataset.py:176-206,
     228-235): `{'infos': [...], 'metadata': {'version': ...}}`, entries sorted by timestamp, every `load_interval`-th
@@ -166,6 +230,12 @@ class NuScenesSSLIndex:
         info = self.data_infos[index]
         return dict(sample_idx=info["token"], pts_filename=info["lidar_path"], sweeps=info["sweeps"],
                     timestamp=info["timestamp"] / 1e6)
+
+    def load_frame_raw(self, index: int, sweeps_num: int = 9, test_mode: bool = False, rng=np.random) -> RawSweeps:
+        """The same sample as ``load_frame`` (same sweep draws), left raw for the device-side merge."""
+        info = self.get_data_info(index)
+        key = read_points_bin(info["pts_filename"], 5, 5)
+        return load_multi_sweeps_raw(key, info, sweeps_num=sweeps_num, test_mode=test_mode, rng=rng)
 
     def load_frame(self, index: int, sweeps_num: int = 9, test_mode: bool = False, rng=np.random) -> np.ndarray:
         """Raw multi-sweep frame [N, 5] float32 of entry `index` (the first two stages of the train pipeline)."""

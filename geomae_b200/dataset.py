@@ -22,7 +22,8 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import torch
 
-from .data import Augmentation, NuScenesSSLIndex, draw_augmentation, load_multi_sweeps, read_points_bin
+from .data import (Augmentation, NuScenesSSLIndex, RawSweeps, draw_augmentation, load_multi_sweeps, load_multi_sweeps_raw,
+                   read_points_bin)
 from .registry import Registry
 
 DATASETS = Registry("dataset")
@@ -36,8 +37,11 @@ class NuScenesDatasetSSL:
 
     def __init__(self, ann_file, pipeline=None, data_root=None, classes=None, load_interval=1, with_velocity=True,
                  modality=None, box_type_3d="LiDAR", filter_empty_gt=False, test_mode=False,
-                 eval_version="detection_cvpr_2019", use_valid_flag=False):
-        self.data_root, self.ann_file, self.test_mode = data_root, ann_file, test_mode
+                 eval_version="detection_cvpr_2019", use_valid_flag=False, device_merge=False):
+        """``device_merge`` (not a reference argument): leave the sweeps raw (``data.RawSweeps``) so that the sweep ->
+        key-frame transform, the close-point filter and the concatenation run on the device (geomae_sweep_merge)
+        instead of in numpy on the loader threads; same sweep choice, same result."""
+        self.data_root, self.ann_file, self.test_mode, self.device_merge = data_root, ann_file, test_mode, device_merge
         self.CLASSES = tuple(classes) if classes is not None else self.CLASSES
         self.modality = modality or dict(use_camera=False, use_lidar=True, use_radar=False, use_map=False,
                                          use_external=False)
@@ -92,6 +96,10 @@ class NuScenesDatasetSSL:
         """-> dict(points [N, C] float32 raw multi-sweep frame, aug = this sample's draws, sample_idx)."""
         info = self.get_data_info(index)
         pts = read_points_bin(info["pts_filename"], self.load["load_dim"], self.load["use_dim"])
+        if self.sweeps is not None and self.device_merge and tuple(self.sweeps["use_dim"]) == tuple(range(pts.shape[1])):
+            kw = {k: v for k, v in self.sweeps.items() if k != "use_dim"}
+            return dict(points=load_multi_sweeps_raw(pts, info, rng=rng, **kw), aug=self.draw(rng),
+                        sample_idx=info["sample_idx"])
         if self.sweeps is not None:
             pts = load_multi_sweeps(pts, info, rng=rng, **self.sweeps)
         return dict(points=np.ascontiguousarray(pts, dtype=np.float32), aug=self.draw(rng), sample_idx=info["sample_idx"])
@@ -138,8 +146,12 @@ class BatchLoader:
     def _sample(self, index, seed):
         rng = np.random.RandomState(seed)        # per-sample stream: the result does not depend on thread timing
         item = self.dataset.__getitem__(index, rng=rng)
-        t = torch.from_numpy(item["points"])
-        return (t.pin_memory() if self.pin and torch.cuda.is_available() else t), item["aug"]
+        pin = (lambda a: torch.from_numpy(a).pin_memory()) if self.pin and torch.cuda.is_available() else torch.from_numpy
+        pts = item["points"]
+        if isinstance(pts, RawSweeps):
+            seen = {}          # padded samples repeat the key frame: pin it once
+            return RawSweeps([seen.setdefault(id(a), pin(a)) for a in pts.arrays], pts.params), item["aug"]
+        return pin(pts), item["aug"]
 
     def __iter__(self):
         idx = epoch_indices(len(self.dataset), self.spg, self.rank, self.world, self.epoch, self.seed, self.shuffle)

@@ -208,6 +208,7 @@ class _Sigs:
     geomae_profile_enable = [_i32]
     geomae_profile_read = [_p, _p, _p, _p]
     geomae_augment_filter = [_p, _i64, _i32, _p, _i32, _p, _f3, _f3, _p, _p, _p, _i64, _p]
+    geomae_sweep_merge = [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _i64, _p]
     geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                          C.c_float, C.c_float, _i64, _p, _p]
 
@@ -216,7 +217,7 @@ _timing = None      # list of (name, start_event, end_event) while bench.py meas
 _calls = {}         # name -> number of C-ABI calls (bench.py reports kernel launches from these)
 
 # kernels launched per C-ABI call (upper bound for the optional ones), for the gpu_launches claim
-LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=9, augment_filter=3, geom_targets=1, dense_targets=1, coors_bitmap=4, coors_rank=4,
+LAUNCHES_PER_CALL = dict(dynamic_voxelize=1, voxel_scatter=9, augment_filter=3, sweep_merge=3, geom_targets=1, dense_targets=1, coors_bitmap=4, coors_rank=4,
                          token_map=1, window_csr=3, window_drop=2, pos_table=1, vfe_decorate=1, scatter_reduce_fwd=5,
                          scatter_reduce_bwd=1, sra_attention_fwd=1, sra_attention_bwd=2, sra_attention_tc_fwd=1,
                          sra_attention_tc_bwd=1, adamw_step=2,

@@ -152,7 +152,10 @@ class FlatTrainer:
         return total.detach(), losses
 
     def train_step_from_host(self, host_points, ids=None, lr=None, augs=None, point_cloud_range=None):
-        """host_points: list of pinned CPU tensors; the H2D copies are issued on ``input_stream()``.
+        """host_points: list of pinned CPU tensors (one frame each) or ``data.RawSweeps`` (a sample still split into its
+        key frame and raw earlier sweeps: merged on the device by ``geomae_sweep_merge``, which does what
+        LoadPointsFromMultiSweeps does on the reference's loader workers); the H2D copies are issued on
+        ``input_stream()``.
 
         ``augs`` (one ``data.Augmentation`` per frame, e.g. from ``data.draw_augmentation``) runs the train pipeline's
         GlobalRotScaleTrans / RandomFlip3D / PointsRangeFilter on the device first (``geomae_augment_filter``, one call
@@ -162,23 +165,43 @@ class FlatTrainer:
         dev = self.flat_param.device
         main = torch.cuda.current_stream(dev)
         side = self.input_stream() if self.overlap_input else main
-        sizes = [p.shape[0] for p in host_points]
+        from .data import RawSweeps, augment_filter, sweep_merge
+        raw_sweeps = any(isinstance(p, RawSweeps) for p in host_points)
         with torch.cuda.stream(side):
-            if augs is None:
+            if augs is None and not raw_sweeps:
                 pts = [p.to(dev, non_blocking=True) for p in host_points]
             else:
-                from .data import augment_filter
-                rng = point_cloud_range if point_cloud_range is not None else self.model.point_cloud_range
-                raw = torch.empty((sum(sizes), host_points[0].shape[1]), dtype=torch.float32, device=dev)
+                # every segment (a whole frame, or one sweep file of a RawSweeps sample) lands in ONE device buffer
+                segs, seg_par, first_seg = [], [], [0]
+                for p in host_points:
+                    if isinstance(p, RawSweeps):
+                        segs += [a if torch.is_tensor(a) else torch.from_numpy(a) for a in p.arrays]
+                        seg_par.append(torch.as_tensor(p.params))
+                    else:
+                        segs.append(p)
+                        seg_par.append(None)
+                    first_seg.append(len(segs))
+                raw = torch.empty((sum(t.shape[0] for t in segs), segs[0].shape[1]), dtype=torch.float32, device=dev)
                 offs, at = [0], 0
-                for p, n in zip(host_points, sizes):
-                    raw[at:at + n].copy_(p, non_blocking=True)
-                    at += n
+                for t in segs:
+                    raw[at:at + t.shape[0]].copy_(t, non_blocking=True)
+                    at += t.shape[0]
                     offs.append(at)
-                offsets = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
-                out, out_off = augment_filter(raw, offsets, augs, rng)
-                o = out_off.tolist()     # waits for the copies and three kernels on the input stream only
-                pts = [out[o[b]:o[b + 1]] for b in range(len(sizes))]
+                if raw_sweeps:
+                    ident = torch.zeros(1, 16, dtype=torch.float64)
+                    ident[0, 0] = ident[0, 4] = ident[0, 8] = 1.0
+                    ident[0, 13] = -1.0
+                    par = torch.cat([ident if q is None else q for q in seg_par]).to(dev, non_blocking=True)
+                    seg_off = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+                    raw, seg_off = sweep_merge(raw, seg_off, par)
+                    frame_off = seg_off[torch.tensor(first_seg, dtype=torch.int64)]      # a sample starts at its first segment
+                else:
+                    frame_off = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+                if augs is not None:
+                    rng = point_cloud_range if point_cloud_range is not None else self.model.point_cloud_range
+                    raw, frame_off = augment_filter(raw, frame_off.contiguous(), augs, rng)
+                o = frame_off.tolist()     # waits for the copies and the data-step kernels on the input stream only
+                pts = [raw[o[b]:o[b + 1]] for b in range(len(host_points))]
         if side is not main and not hasattr(self.model, "extract_feat"):
             main.wait_stream(side)
         for t in pts:

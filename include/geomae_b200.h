@@ -590,10 +590,25 @@ int geomae_adamw_step(float* params, const float* grads, float* exp_avg, float* 
  *           core/points/base_points.py:139-179,207-229,263-269; core/points/lidar_points.py:28-33), which the reference
  *           applies per sample on the data-loader workers.  PointShuffle (transforms_3d.py:771-790) is not reproduced:
  *           everything downstream is order-free. */
+/* (rows of `points` at or beyond frame_offsets[n_frames] are ignored: the buffer may be the over-sized output of an
+ * earlier compaction whose length only the device knows.) */
 int geomae_augment_filter(const float* points, int64_t n_points, int32_t stride, const int32_t* frame_offsets,
                           int32_t n_frames, const float* frame_params, const float range_min[3],
                           const float range_max[3], float* out_points, int32_t* out_frame_offsets,
                           int32_t* scan_tmp, int64_t scan_tmp_len, void* stream);
+
+/* Multi-sweep merge on the device: `points` holds the raw records of S segments back to back (segment = one
+ * `.pcd.bin` file: the key frame first, then its earlier sweeps; several samples may follow each other),
+ * seg_offsets [S+1].  seg_params [S,16] doubles per segment: sensor->key-frame rotation R row-major (9), translation
+ * (3), time lag in seconds, close radius (< 0: keep all points), 2 unused.  Per point: dropped when |x| < r and
+ * |y| < r; else xyz = f32(f32(row . R^T in float64) + t in float64), channel 4 = (float)time lag; survivors are
+ * compacted in input order, out_seg_offsets [S+1] are the segments' new starts (a sample's frame offsets are the
+ * entries of its first segment).  scan_tmp: int32 [ceil(n/1024)+1].
+ * replaces: LoadPointsFromMultiSweeps.__call__ / _remove_close (datasets/pipelines/loading.py:160-235), numpy on the
+ *           data-loader workers in the reference. */
+int geomae_sweep_merge(const float* points, int64_t n_points, int32_t stride, const int32_t* seg_offsets,
+                       int32_t n_segments, const double* seg_params, float* out_points, int32_t* out_seg_offsets,
+                       int32_t* scan_tmp, int64_t scan_tmp_len, void* stream);
 
 #ifdef __cplusplus
 }

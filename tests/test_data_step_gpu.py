@@ -100,3 +100,75 @@ def test_train_step_from_host_with_device_augmentation_matches_preaugmented_fram
     assert abs(la - lb) <= 1e-5 * abs(lb)
     # one AdamW step moves every weight by about lr; a gradient that is pure rounding noise may flip its direction
     assert (pa - pb).abs().max().item() <= 2.01e-4 and (pa - pb).abs().mean().item() <= 1e-7
+
+
+def _scene(tmp_path, n_sweeps, seed):
+    from tests.test_data_step_cpu import _write_scene
+    rng = np.random.default_rng(seed)
+    info, _ = _write_scene(tmp_path, rng, n_sweeps, tag=f"g{seed}")
+    return dict(pts_filename=info["lidar_path"], sweeps=info["sweeps"], timestamp=info["timestamp"] / 1e6)
+
+
+def test_sweep_merge_matches_host_loader(tmp_path):
+    """geomae_sweep_merge vs data.load_multi_sweeps (bit-exact vs the reference's LoadPointsFromMultiSweeps on CPU):
+    same sweeps, same survivors in the same order, same time channel; coordinates equal except where the BLAS dot
+    product of the host (fused multiply-adds) and the kernel's separately rounded float64 products round a float32
+    tie differently (<= 1 ulp, a vanishing fraction)."""
+    from geomae_b200.data import load_multi_sweeps, load_multi_sweeps_raw, read_points_bin, sweep_merge
+    samples, refs = [], []
+    for n_sweeps, seed in ((0, 1), (4, 2), (14, 3)):
+        info = _scene(tmp_path, n_sweeps, seed)
+        key = read_points_bin(info["pts_filename"], 5, 5)
+        refs.append(load_multi_sweeps(key, info, rng=np.random.RandomState(9)))
+        samples.append(load_multi_sweeps_raw(key, info, rng=np.random.RandomState(9)))
+    segs = [a for s in samples for a in s.arrays]
+    offs = np.concatenate([[0], np.cumsum([a.shape[0] for a in segs])]).astype(np.int32)
+    pts = torch.from_numpy(np.concatenate(segs)).to(DEV)
+    par = torch.from_numpy(np.concatenate([s.params for s in samples])).to(DEV)
+    out, out_off = sweep_merge(pts, torch.from_numpy(offs).to(DEV), par)
+    o = out_off.cpu().numpy()
+    first = np.concatenate([[0], np.cumsum([len(s.arrays) for s in samples])])
+    got_all = out.cpu().numpy()
+    for i, ref in enumerate(refs):
+        got = got_all[o[first[i]]:o[first[i + 1]]]
+        assert got.shape == ref.shape
+        assert np.array_equal(got[:, 3:], ref[:, 3:])                      # intensity, time channel: exact
+        diff = got[:, :3] != ref[:, :3]
+        assert diff.mean() < 1e-4
+        ulp = np.spacing(np.abs(ref[:, :3]).astype(np.float32))
+        assert (np.abs(got[:, :3] - ref[:, :3]) <= ulp).all()
+    assert o[-1] < pts.shape[0]                                            # close points were dropped
+
+
+def test_train_step_from_host_merges_raw_sweeps_on_the_device(tmp_path):
+    """RawSweeps samples through train_step_from_host (sweep merge -> augmentation -> scatter, all on the input
+    stream) == the same step fed with host-merged frames."""
+    import os
+    import geomae_b200 as G
+    from geomae_b200.data import draw_augmentation, load_multi_sweeps, load_multi_sweeps_raw, read_points_bin
+    from geomae_b200.registry import Config
+    from geomae_b200.train import FlatTrainer
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = Config.fromfile(os.path.join(root, "configs/mae_sst/geomae_nus_pretrain.py"))
+    raw, merged = [], []
+    for n_sweeps, seed in ((3, 5), (0, 6)):
+        info = _scene(tmp_path, n_sweeps, seed)
+        key = read_points_bin(info["pts_filename"], 5, 5)
+        merged.append(torch.from_numpy(load_multi_sweeps(key, info, rng=np.random.RandomState(4))).pin_memory())
+        raw.append(load_multi_sweeps_raw(key, info, rng=np.random.RandomState(4)))
+    rs = np.random.RandomState(8)
+    augs = [draw_augmentation(rs) for _ in raw]
+
+    def run(feed):
+        torch.manual_seed(0)
+        model = G.build_detector(cfg.model).to(DEV)
+        model.set_impl("tc3")
+        model.train()
+        tr = FlatTrainer(model, lr=1e-4)
+        torch.manual_seed(3)
+        return float(feed(tr)[0])
+
+    for a in (None, augs):
+        la = run(lambda tr: tr.train_step_from_host(raw, augs=a))
+        lb = run(lambda tr: tr.train_step_from_host(merged, augs=a))
+        assert abs(la - lb) <= 2e-5 * abs(lb), (a is None, la, lb)

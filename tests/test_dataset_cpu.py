@@ -87,3 +87,22 @@ def test_batch_loader_is_deterministic_and_covers_the_epoch(tmp_path):
             assert len(pts) == 2 == len(augs) and all(p.dtype.is_floating_point and p.shape[1] == 5 for p in pts)
         seen += epoch_indices(len(ds), 2, rank, 2, 4, seed=1)
     assert sorted(seen) == [0, 0, 1, 2, 3, 4, 5, 5] or set(seen) == set(range(6))
+
+
+def test_device_merge_mode_keeps_the_sweeps_raw_with_the_same_draws(tmp_path):
+    from geomae_b200.data import RawSweeps
+    ann = write_dataset(tmp_path)
+    host = NuScenesDatasetSSL(ann, pipeline=TRAIN_PIPELINE)
+    dev = NuScenesDatasetSSL(ann, pipeline=TRAIN_PIPELINE, device_merge=True)
+    for i in range(len(host)):
+        a = host.__getitem__(i, rng=np.random.RandomState(3))
+        b = dev.__getitem__(i, rng=np.random.RandomState(3))
+        raw = b["points"]
+        assert isinstance(raw, RawSweeps) and raw.params.shape == (len(raw.arrays), 16)
+        assert a["aug"] == b["aug"]                                   # the sweep choice consumed the same draws
+        assert raw.n_points >= a["points"].shape[0]                   # close points still inside
+        assert np.array_equal(raw.arrays[0][:, :4], a["points"][: raw.arrays[0].shape[0], :4])   # key frame first, untouched
+        assert raw.params[0, 13] == -1.0 and (raw.params[1:, 13] == 1.0).all()
+    loader = BatchLoader(dev, samples_per_gpu=2, workers=2, pin_memory=False)
+    pts, augs = next(iter(loader))
+    assert all(isinstance(p, RawSweeps) for p in pts) and len(augs) == 2

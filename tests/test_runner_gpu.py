@@ -29,10 +29,10 @@ def test_epochs_checkpoint_and_resume(tmp_path):
     ann = write_dataset(tmp_path, n_scenes=6)
     ds = NuScenesDatasetSSL(ann, pipeline=TRAIN_PIPELINE)
 
-    def run(work, epochs, resume=None, seed=11, until=None):
+    def run(work, epochs, resume=None, seed=11, until=None, dataset=None):
         torch.manual_seed(seed)                 # mask-split seeds come from the CPU generator
         model = build()
-        loader = BatchLoader(ds, samples_per_gpu=2, seed=1, workers=2)
+        loader = BatchLoader(dataset or ds, samples_per_gpu=2, seed=1, workers=2)
         lines = []
         trainer, hist = train(model, loader, str(work), epochs, base_lr=1e-4, resume_from=resume, log_interval=2,
                               log=lines.append, until_epoch=until)
@@ -44,6 +44,11 @@ def test_epochs_checkpoint_and_resume(tmp_path):
     ckpt = torch.load(tmp_path / "a" / "epoch_1.pth", map_location="cpu", weights_only=False)
     assert set(ckpt) == {"meta", "state_dict", "optimizer"} and ckpt["meta"]["epoch"] == 1 and ckpt["meta"]["iter"] == 3
     assert set(ckpt["state_dict"]) == set(m2.state_dict())
+
+    # the same first epoch with the sweeps merged on the device instead of on the loader threads
+    _, _, h_dev, _ = run(tmp_path / "c", 2, until=1, dataset=NuScenesDatasetSSL(ann, pipeline=TRAIN_PIPELINE, device_merge=True))
+    for a, b in zip(h_dev, h2[:3]):
+        assert abs(a - b) <= 2e-3 * abs(b)
 
     # one epoch, then resume for the second: same schedule position, same optimiser state
     torch.manual_seed(11)
