@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -441,7 +441,7 @@ def main():
         step_host_augmented(i)
     # ^ warm-up; placed after the loss-delta block: that one re-uses the last un-augmented step's mask split
     barrier()
-    ms_e2e_aug = timed_loop(step_host_augmented, K)
+    ms_e2e_aug = timed_loop(step_host_augmented, K, "e2e_aug")
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms, ms_e2e, ms_e2e_aug], dtype=torch.float64, device=dev)

@@ -174,12 +174,21 @@ class MultiMAESSTSPChoose(nn.Module):
             return WindowLayout.from_pillars(self.spec, pillar_batch, rows)
         return WindowLayout.from_coors(self.spec, self.geom, coors, batch_size)
 
-    def forward(self, voxel_feat, coors, coors_mask, batch_size, pillar_batch=None, rows_keep=None, rows_mask=None):
+    def build_layouts(self, pillar_batch: PillarBatch, rows_keep, rows_mask):
+        """(encoder layout over the visible pillars, decoder layout over visible + masked) — index work that depends on
+        the scatter result and the mask split only, so the detector runs it on the input stream under the VFE."""
+        return (WindowLayout.from_pillars(self.spec, pillar_batch, rows_keep),
+                WindowLayout.from_pillars(self.spec, pillar_batch, torch.cat([rows_keep, rows_mask])))
+
+    def forward(self, voxel_feat, coors, coors_mask, batch_size, pillar_batch=None, rows_keep=None, rows_mask=None,
+                layouts=None):
         """Reference call form ``backbone(voxel_feat, coors, coors_mask, batch_size)``; when the
-        caller also holds the scatter result it passes it (with the pillar rows) to reuse its bitmap."""
-        enc_layout = self._layout(coors, batch_size, pillar_batch, rows_keep)
+        caller also holds the scatter result it passes it (with the pillar rows) to reuse its bitmap, and possibly
+        the two window layouts it already built from it (``build_layouts``)."""
+        enc_layout = layouts[0] if layouts else self._layout(coors, batch_size, pillar_batch, rows_keep)
         x = self.forward_encoder(voxel_feat, enc_layout)
-        return self.forward_decoder(x, coors, coors_mask, batch_size, pillar_batch, rows_keep, rows_mask)
+        return self.forward_decoder(x, coors, coors_mask, batch_size, pillar_batch, rows_keep, rows_mask,
+                                    layout=layouts[1] if layouts else None)
 
     def forward_encoder(self, voxel_feat, layout):
         pos, table = self._pos(layout)
@@ -191,16 +200,17 @@ class MultiMAESSTSPChoose(nn.Module):
         return out
 
     def forward_decoder(self, visible_voxel_feat, coors, coors_mask, batch_size, pillar_batch=None, rows_keep=None,
-                        rows_mask=None):
+                        rows_mask=None, layout=None):
         n_vis = coors.shape[0]
         hook = getattr(self, "encoder_output_hook", None)
         if hook is not None and visible_voxel_feat.requires_grad:
             # fires in backward once every decoder / head gradient has been queued (FlatTrainer: early all-reduce bucket)
             visible_voxel_feat.register_hook(lambda g: (hook(g), None)[1])
         tokens = torch.cat([visible_voxel_feat, self.mask_token.repeat(coors_mask.shape[0], 1)], dim=0)
-        all_coors = torch.cat([coors, coors_mask], dim=0)
-        rows = torch.cat([rows_keep, rows_mask]) if pillar_batch is not None else None
-        layout = self._layout(all_coors, batch_size, pillar_batch, rows)
+        if layout is None:
+            all_coors = torch.cat([coors, coors_mask], dim=0)
+            rows = torch.cat([rows_keep, rows_mask]) if pillar_batch is not None else None
+            layout = self._layout(all_coors, batch_size, pillar_batch, rows)
         pos, table = self._pos(layout)
         cen = den = tokens
         if pos is None:

@@ -175,25 +175,48 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
     # ------------------------------------------------------------------ hot path
     def extract_feat(self, points, ids=None):
         batch_size = len(points)
-        pb = scatter_frames(self.geom, points, side=getattr(self, "scatter_stream", None))
-        voxel_features, feature_coors = self.voxel_encoder(pb)
-        ids_keep, ids_mask = ids if ids is not None else self.get_vanilla_mask_index(
-            feature_coors, batch_size, pb.pillars_per_frame(), pb.counts[4:])
+        side = getattr(self, "scatter_stream", None)
+        pb = scatter_frames(self.geom, points, side=side)
         fused = getattr(self, "fused_loss", True)
-        with torch.no_grad():
-            normal, curv = pb.geom_targets()
-            if fused:       # the fused loss reads the CSR sub-voxel lists directly: no dense targets at all
-                low = low_mask = med = med_mask = top = None
-                normal_m = normal
-            else:
-                low, low_mask, med, med_mask, top = pb.dense_targets(ids_mask)
-                normal_m = normal.index_select(0, ids_mask)
+        layouts = None
+        if side is not None and fused and getattr(self.backbone, "sra_impl", "tc3") != "glue":
+            # everything that depends on the scatter result and the mask split only — the split itself, both window
+            # layouts, the geometric targets — is queued on the input stream and runs under the VFE forward
+            main = torch.cuda.current_stream(pb.points.device)
+            v = pb.n_pillars
+            with torch.cuda.stream(side), L.stream_override(side), torch.no_grad():
+                ids_keep, ids_mask = ids if ids is not None else self.get_vanilla_mask_index(
+                    pb.pillar_coors[:v], batch_size, pb.pillars_per_frame(), pb.counts[4:])
+                layouts = self.backbone.build_layouts(pb, ids_keep, ids_mask)
+                normal, curv = pb.geom_targets()
+                ready = torch.cuda.Event()
+                ready.record(side)
+            voxel_features, feature_coors = self.voxel_encoder(pb)
+            main.wait_event(ready)
+            for t in (ids_keep, ids_mask, normal, curv):
+                t.record_stream(main)
+            for lay in layouts:
+                lay.hand_over(main)
+            low = low_mask = med = med_mask = top = None
+            normal_m = normal
+        else:
+            voxel_features, feature_coors = self.voxel_encoder(pb)
+            ids_keep, ids_mask = ids if ids is not None else self.get_vanilla_mask_index(
+                feature_coors, batch_size, pb.pillars_per_frame(), pb.counts[4:])
+            with torch.no_grad():
+                normal, curv = pb.geom_targets()
+                if fused:       # the fused loss reads the CSR sub-voxel lists directly: no dense targets at all
+                    low = low_mask = med = med_mask = top = None
+                    normal_m = normal
+                else:
+                    low, low_mask, med, med_mask, top = pb.dense_targets(ids_mask)
+                    normal_m = normal.index_select(0, ids_mask)
         if getattr(self, "keep_targets", False):   # parity harness: expose exactly what this step regressed against
             self.last_targets = dict(pillar_batch=pb, normal=normal, curvature=curv, ids_keep=ids_keep,
                                      ids_mask=ids_mask)
         x = self.backbone(voxel_features.index_select(0, ids_keep), feature_coors.index_select(0, ids_keep),
                           feature_coors.index_select(0, ids_mask), batch_size, pillar_batch=pb, rows_keep=ids_keep,
-                          rows_mask=ids_mask)
+                          rows_mask=ids_mask, layouts=layouts)
         if fused:
             return x, pb, ids_mask, normal_m
         return x, low, low_mask, med, med_mask, top, normal_m, None, None

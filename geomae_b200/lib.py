@@ -301,6 +301,25 @@ def unpin_stream(prev=None):
     _stream_cache = prev
 
 
+class stream_override:
+    """``with stream_override(torch_stream):`` — C-ABI calls made inside launch on that stream even while a step has its
+    compute stream pinned (the input-stage work FlatTrainer runs on its side stream)."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        global _stream_cache
+        self.prev = _stream_cache
+        _stream_cache = (self.stream.device.index, self.stream.cuda_stream)
+        return self
+
+    def __exit__(self, *exc):
+        global _stream_cache
+        _stream_cache = self.prev
+        return False
+
+
 def stream_ptr(device=None):
     c = _stream_cache
     if c is not None and (device is None or getattr(device, "index", None) == c[0]):

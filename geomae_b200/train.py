@@ -102,8 +102,9 @@ class FlatTrainer:
         counts size every later buffer) blocks for the input stage only and the host keeps enqueueing ahead."""
         st = self.__dict__.get("_input_stream")
         if st is None:
-            # high priority: its short kernels slot in at the next CTA boundary of the persistent compute kernels
-            st = self.__dict__["_input_stream"] = torch.cuda.Stream(self.flat_param.device, priority=-1)
+            # default priority on purpose: a high-priority input stream measured slightly better medians but rare
+            # 50-60 ms host stalls inside its allocations (tools/step_jitter_probe.py); at equal priority there are none
+            st = self.__dict__["_input_stream"] = torch.cuda.Stream(self.flat_param.device)
         return st
 
     def train_step(self, points, ids=None, lr=None, ready=None):

@@ -105,6 +105,12 @@ class WindowLayout:
         self._keep = keep
         return self
 
+    def hand_over(self, stream):
+        """Built under another stream: from now on ``stream`` uses these buffers (see PillarBatch.hand_over)."""
+        for t in (self._scratch, self.n_windows, self.win_ptr, self.win_id, self.win_tok, self.tok_cell, self.tok_win,
+                  self.tok_pos) + tuple(t for t in getattr(self, "_keep", ()) if torch.is_tensor(t)):
+            t.record_stream(stream)
+
     def shift(self, i: int):
         return dict(n_windows=self.n_windows[i:i + 1], win_ptr=self.win_ptr[i], win_tok=self.win_tok[i],
                     tok_cell=self.tok_cell[i], tok_win=self.tok_win[i], tok_pos=self.tok_pos[i],
