@@ -32,15 +32,25 @@ class FusedHeads:
         self.width_d = 128
 
     def cat_params(self, dev):
-        wc = torch.zeros((self.width_c, 128), dtype=torch.float32, device=dev)
-        bc = torch.zeros(self.width_c, dtype=torch.float32, device=dev)
+        """The fused weights / biases of this step.  The buffers persist (pad rows are zeroed once, at creation); only
+        the live rows are refreshed from the parameters."""
+        buf = self.__dict__.get("_param_buf")
+        if buf is None or buf[0].device != dev:
+            z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)     # noqa: E731
+            buf = self._param_buf = (z(self.width_c, 128), z(self.width_c), z(self.width_d, 128), z(self.width_d))
+        wc, bc, wd, bd = buf
         torch.cat([h.weight.detach() for h in self.heads_c], out=wc[:self.n_c])
         torch.cat([h.bias.detach() for h in self.heads_c], out=bc[:self.n_c])
-        wd = torch.zeros((self.width_d, 128), dtype=torch.float32, device=dev)
-        bd = torch.zeros(self.width_d, dtype=torch.float32, device=dev)
         wd[:self.head_d.out_features].copy_(self.head_d.weight.detach())
         bd[:self.head_d.out_features].copy_(self.head_d.bias.detach())
         return wc, bc, wd, bd
+
+    def grad_scratch(self, dev):
+        """(gw_c, gb_c, gw_d, gb_d) as views of ONE zeroed buffer: one fill per step instead of four."""
+        sizes = (self.width_c * 128, self.width_c, self.width_d * 128, self.width_d)
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        a, b, c, d = torch.split(flat, sizes)
+        return a.view(self.width_c, 128), b, c.view(self.width_d, 128), d
 
 
 class _FusedHeadsFn(torch.autograd.Function):
@@ -65,8 +75,7 @@ class _FusedHeadsFn(torch.autograd.Function):
         d_cen, d_den = torch.zeros_like(cen), torch.zeros_like(den)
         tc_linear(d_c, wc, n_out=128, w_mn_major=True, out=d_cen[n_vis:], precision=precision, packed=pc)
         tc_linear(d_d, wd, n_out=128, w_mn_major=True, out=d_den[n_vis:], precision=precision, packed=pd)
-        gw_c, gb_c = torch.zeros_like(wc), torch.zeros(fh.width_c, dtype=torch.float32, device=cen.device)
-        gw_d, gb_d = torch.zeros_like(wd), torch.zeros(fh.width_d, dtype=torch.float32, device=cen.device)
+        gw_c, gb_c, gw_d, gb_d = fh.grad_scratch(cen.device)
         tc_wgrad(d_c, cen[n_vis:], gw_c, gb_c, precision=precision)
         tc_wgrad(d_d, den[n_vis:], gw_d, gb_d, precision=precision)
         dst, src = [], []
@@ -84,6 +93,31 @@ class _FusedHeadsFn(torch.autograd.Function):
             src.append(g)
         torch._foreach_add_(dst, src)
         return d_cen, d_den, None, None, None
+
+
+class _DecoderTokensFn(torch.autograd.Function):
+    """[visible ; mask_token x n_mask] and its backward as one launch each (csrc/tokens.cu); the mask token's gradient
+    is accumulated straight into ``mask_token.grad`` like every other parameter gradient of the fused path."""
+
+    @staticmethod
+    def forward(ctx, vis, mask_token, n_mask):
+        from . import lib as L
+        vis = vis.contiguous()
+        n_vis, d = vis.shape
+        out = torch.empty((n_vis + n_mask, d), dtype=torch.float32, device=vis.device)
+        L.run("decoder_tokens", L.ptr(vis), n_vis, L.ptr(mask_token), n_mask, d, L.ptr(out), L.stream_ptr(vis.device))
+        ctx.mask_token, ctx.shape = mask_token, (n_vis, n_mask, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_tokens):
+        from . import lib as L
+        from .sst import _grad_of
+        n_vis, n_mask, d = ctx.shape
+        d_tokens = d_tokens.contiguous()
+        L.run("mask_token_grad", L.ptr(d_tokens), n_vis, n_mask, d, L.ptr(_grad_of(ctx.mask_token)),
+              L.stream_ptr(d_tokens.device))
+        return d_tokens[:n_vis], None, None
 
 
 @BACKBONES.register_module()
@@ -201,12 +235,16 @@ class MultiMAESSTSPChoose(nn.Module):
 
     def forward_decoder(self, visible_voxel_feat, coors, coors_mask, batch_size, pillar_batch=None, rows_keep=None,
                         rows_mask=None, layout=None):
-        n_vis = coors.shape[0]
+        n_vis = visible_voxel_feat.shape[0]
+        n_mask = coors_mask.shape[0] if coors_mask is not None else rows_mask.shape[0]
         hook = getattr(self, "encoder_output_hook", None)
         if hook is not None and visible_voxel_feat.requires_grad:
             # fires in backward once every decoder / head gradient has been queued (FlatTrainer: early all-reduce bucket)
             visible_voxel_feat.register_hook(lambda g: (hook(g), None)[1])
-        tokens = torch.cat([visible_voxel_feat, self.mask_token.repeat(coors_mask.shape[0], 1)], dim=0)
+        if getattr(self, "sra_impl", "tc3") != "glue" and self.d_model[0] == 128 and visible_voxel_feat.is_cuda:
+            tokens = _DecoderTokensFn.apply(visible_voxel_feat, self.mask_token, n_mask)
+        else:
+            tokens = torch.cat([visible_voxel_feat, self.mask_token.repeat(n_mask, 1)], dim=0)
         if layout is None:
             all_coors = torch.cat([coors, coors_mask], dim=0)
             rows = torch.cat([rows_keep, rows_mask]) if pillar_batch is not None else None

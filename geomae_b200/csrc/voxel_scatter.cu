@@ -742,6 +742,7 @@ extern "C" int geomae_voxel_scatter(const geomae_voxel_cfg* cfg, const geomae_sc
   const int pblocks = gm_div_up(n > 0 ? n : 1, TILE);
   const size_t tile_bytes = (size_t)TILE * io->stride * sizeof(float);
   GM_CUDA(cudaMemsetAsync(io->bitmap, 0, (size_t)n_words * 4, stream));
+  GM_CUDA(cudaMemsetAsync(io->counts, 0, sizeof(int32_t) * (size_t)(4 + io->n_frames + 1), stream));
   if (n > 0)
     (g.fast ? k_mark<true> : k_mark<false>)<<<pblocks, TPB, tile_bytes, stream>>>(
         g, io->points, n, io->stride, io->frame_offsets, io->bitmap, io->coors_top, io->coors_med, io->coors_low);
@@ -792,6 +793,7 @@ extern "C" int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* c
   const int scan_blocks = gm_div_up(n_words, SCAN_CHUNK);
   GM_REQUIRE(scan_blocks <= SCAN_MAX_BLOCKS, "coors_bitmap: grid too large (%d scan blocks)", scan_blocks);
   GM_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)n_words * 4, stream));
+  GM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4, stream));
   if (n > 0) k_mark_coors<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap);
   k_bitmap_sums<<<scan_blocks, TPB, 0, stream>>>(bitmap, n_words, scan_tmp);
   k_bitmap_rank<<<scan_blocks, TPB, 0, stream>>>(g, bitmap, n_words, scan_tmp, word_rank, counts, nullptr, nullptr,
@@ -817,6 +819,7 @@ extern "C" int geomae_coors_rank(const geomae_voxel_cfg* cfg, const int32_t* coo
   const int scan_blocks = gm_div_up(n_words, SCAN_CHUNK);
   GM_REQUIRE(scan_blocks <= SCAN_MAX_BLOCKS, "coors_rank: grid too large (%d scan blocks)", scan_blocks);
   GM_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)n_words * 4, stream));
+  GM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 4, stream));
   if (first_row && n > 0) GM_CUDA(cudaMemsetAsync(first_row, 0x7f, (size_t)n * 4, stream));
   if (n > 0) k_mark_coors<<<gm_div_up(n, TPB), TPB, 0, stream>>>(g, coors, n, bitmap);
   k_bitmap_sums<<<scan_blocks, TPB, 0, stream>>>(bitmap, n_words, scan_tmp);

@@ -214,9 +214,13 @@ class MultiSubVoxelDynamicVoxelNetSSL(nn.Module):
         if getattr(self, "keep_targets", False):   # parity harness: expose exactly what this step regressed against
             self.last_targets = dict(pillar_batch=pb, normal=normal, curvature=curv, ids_keep=ids_keep,
                                      ids_mask=ids_mask)
-        x = self.backbone(voxel_features.index_select(0, ids_keep), feature_coors.index_select(0, ids_keep),
-                          feature_coors.index_select(0, ids_mask), batch_size, pillar_batch=pb, rows_keep=ids_keep,
-                          rows_mask=ids_mask, layouts=layouts)
+        if layouts is not None:     # the layouts are built: the backbone needs no coordinates, only the pillar rows
+            x = self.backbone(voxel_features.index_select(0, ids_keep), None, None, batch_size, pillar_batch=pb,
+                              rows_keep=ids_keep, rows_mask=ids_mask, layouts=layouts)
+        else:
+            x = self.backbone(voxel_features.index_select(0, ids_keep), feature_coors.index_select(0, ids_keep),
+                              feature_coors.index_select(0, ids_mask), batch_size, pillar_batch=pb, rows_keep=ids_keep,
+                              rows_mask=ids_mask)
         if fused:
             return x, pb, ids_mask, normal_m
         return x, low, low_mask, med, med_mask, top, normal_m, None, None

@@ -208,6 +208,8 @@ class _Sigs:
     geomae_profile_enable = [_i32]
     geomae_profile_read = [_p, _p, _p, _p]
     geomae_augment_filter = [_p, _i64, _i32, _p, _i32, _p, _f3, _f3, _p, _p, _p, _i64, _p]
+    geomae_decoder_tokens = [_p, _i64, _p, _i64, _i32, _p, _p]
+    geomae_mask_token_grad = [_p, _i64, _i64, _i32, _p, _p]
     geomae_sweep_merge = [_p, _i64, _i32, _p, _i32, _p, _p, _p, _p, _i64, _p]
     geomae_adamw_step = [_p, _p, _p, _p, _i64, _i64, _p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                          C.c_float, C.c_float, _i64, _p, _p]

@@ -81,7 +81,7 @@ def unique_rows(coors):
     n_words = (b_ext * gz * gy * gx + 31) // 32
     i32 = dict(dtype=torch.int32, device=dev)
     bitmap, word_rank = torch.empty(n_words, **i32), torch.empty(n_words, **i32)
-    scan_tmp, counts = torch.empty(3 * 16384, **i32), torch.zeros(4, **i32)
+    scan_tmp, counts = torch.empty(3 * 16384, **i32), torch.empty(4, **i32)
     rank, first = torch.empty(n, **i32), torch.empty(n, **i32)
     L.run("coors_rank", C.byref(geom.cstruct), L.ptr(folded), n, b_ext, L.ptr(bitmap), L.ptr(word_rank), L.ptr(scan_tmp),
           L.ptr(counts), L.ptr(rank), L.ptr(first), L.stream_ptr(dev))

@@ -96,7 +96,7 @@ class PillarBatch:
         self.bitmap = torch.empty(n_words, **i32)
         self.word_rank = torch.empty(n_words, **i32)
         self.scan_tmp = torch.empty(3 * 16384, **i32)
-        self.counts = torch.zeros(4 + n_frames + 1, **i32)
+        self.counts = torch.empty(4 + n_frames + 1, **i32)       # cleared by geomae_voxel_scatter
         self.pillar_coors = torch.empty((cap, 4), **i32)
         self.pillar_mean = torch.empty((cap, 4), **f32)
         self.point_pillar = torch.empty(cap, **i32)

@@ -103,8 +103,7 @@ class _FusedVFEFn(torch.autograd.Function):
         out = torch.empty((v, 128), **f32)
         L.run("vmax_decode", L.ptr(vmax2), v * 128, L.ptr(out), s)
         if not sync:
-            for layer in (l0, l1):
-                layer.norm.num_batches_tracked += 1
+            torch._foreach_add_([l0.norm.num_batches_tracked, l1.norm.num_batches_tracked], 1)
         ctx.keep = (vfe, pb, precision, world, x1, feat1, x2, mom0, mom1, vmax1, vmax2, vox, off)
         return out
 

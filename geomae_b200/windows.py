@@ -26,7 +26,7 @@ def coors_bitmap(geom: VoxelGeometry, coors: torch.Tensor, batch_size: int):
     n_words = (batch_size * gx * gy + 31) // 32
     i32 = dict(dtype=torch.int32, device=dev)
     bitmap, word_rank = torch.empty(n_words, **i32), torch.empty(n_words, **i32)
-    scan_tmp, counts = torch.empty(3 * 16384, **i32), torch.zeros(4, **i32)
+    scan_tmp, counts = torch.empty(3 * 16384, **i32), torch.empty(4, **i32)     # counts: cleared by the C call
     tok_of_pillar = torch.empty(max(n, 1), **i32)
     L.run("coors_bitmap", C.byref(geom.cstruct), L.ptr(coors), n, batch_size, L.ptr(bitmap), L.ptr(word_rank),
           L.ptr(scan_tmp), L.ptr(counts), L.ptr(tok_of_pillar), L.stream_ptr(dev))
@@ -67,7 +67,7 @@ class WindowLayout:
         self.ptr_stride = self.n_cand + 1
         nt = max(n_tokens, 1)
         self._scratch = torch.empty((3, ns, self.n_cand), **i32)
-        self.n_windows = torch.zeros(ns, **i32)
+        self.n_windows = torch.empty(ns, **i32)        # written by k_win_scan for every shift
         self.win_ptr = torch.empty((ns, self.ptr_stride), **i32)
         self.win_id = torch.empty((ns, self.ptr_stride), **i32)
         self.win_tok = torch.empty((ns, nt), **i32)

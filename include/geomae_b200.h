@@ -156,7 +156,7 @@ int geomae_window_candidates(const geomae_voxel_cfg* cfg, const geomae_window_cf
  * tok_of_pillar[rank(cell_i)] = i.  Lets geomae_window_csr serve callers that only hold coordinates,
  * i.e. the reference signature backbone.forward(voxel_feat, coors, coors_mask, batch_size)
  * (…top_only.py:136-141) and SSTInputLayer.forward (middle_encoders/sst_input_layer.py:51-103).
- * bitmap/word_rank: [ceil(n_frames*gy*gx/32)], scan_tmp [3*16384], counts [4], tok_of_pillar [n]. */
+ * bitmap/word_rank: [ceil(n_frames*gy*gx/32)], scan_tmp [3*16384], counts [4] (cleared here), tok_of_pillar [n]. */
 int geomae_coors_bitmap(const geomae_voxel_cfg* cfg, const int32_t* coors, int64_t n, int32_t n_frames,
                         uint32_t* bitmap, int32_t* word_rank, int32_t* scan_tmp, int32_t* counts,
                         int32_t* tok_of_pillar, void* stream);
@@ -596,6 +596,15 @@ int geomae_augment_filter(const float* points, int64_t n_points, int32_t stride,
                           int32_t n_frames, const float* frame_params, const float range_min[3],
                           const float range_max[3], float* out_points, int32_t* out_frame_offsets,
                           int32_t* scan_tmp, int64_t scan_tmp_len, void* stream);
+
+/* tokens [n_vis + n_mask, d_model] = [visible rows ; mask_token repeated n_mask times].
+ * replaces: torch.cat([visible_voxel_feat, self.mask_token.repeat(n_mask, 1)]) (…top_only.py:204-210). */
+int geomae_decoder_tokens(const float* visible, int64_t n_vis, const float* mask_token, int64_t n_mask, int32_t d_model,
+                          float* tokens, void* stream);
+/* g_mask_token[c] += sum over the n_mask trailing rows of d_tokens[:, c] (the gradient of the repeat); the visible
+ * rows' gradient is the leading slice of d_tokens itself.  d_model must be 128. */
+int geomae_mask_token_grad(const float* d_tokens, int64_t n_vis, int64_t n_mask, int32_t d_model, float* g_mask_token,
+                           void* stream);
 
 /* Multi-sweep merge on the device: `points` holds the raw records of S segments back to back (segment = one
  * `.pcd.bin` file: the key frame first, then its earlier sweeps; several samples may follow each other),
