@@ -275,6 +275,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if os.environ.get("GEOMAE_ALLOC_CONF"):          # experiment switch for the caching allocator
+        torch.cuda.memory._set_allocator_settings(os.environ["GEOMAE_ALLOC_CONF"])
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a hang must not eat the box

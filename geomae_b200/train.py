@@ -5,6 +5,8 @@ process per GPU, all parameters and gradients live in ONE flat fp32 buffer each,
 exchange is a single NCCL all-reduce over NVLink and the optimiser is a single fused kernel."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -17,8 +19,15 @@ class FlatTrainer:
     EARLY_KEYS = ("backbone.decoder_", "backbone.cls_pred_")
 
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, max_grad_norm=10.0,
-                 no_decay_keys=("norm",), overlap_input=True):
+                 no_decay_keys=("norm",), overlap_input=True, allocator_rounding=True):
         self.model = model
+        if allocator_rounding and torch.cuda.is_available() and not os.environ.get("PYTORCH_CUDA_ALLOC_CONF"):
+            # pillar / token counts differ from step to step, so nearly every buffer of a step has a size never seen
+            # before; with exact sizes the caching allocator keeps splitting blocks and falls back to cudaMalloc inside
+            # the loop (measured: host time per step jumping from 3.3 to 4-20 ms on fresh augmentations).  Rounding
+            # request sizes to 1/16 steps of a power of two makes them repeat (<= 6 % more memory).  Process-wide
+            # PyTorch setting; an explicit PYTORCH_CUDA_ALLOC_CONF wins.
+            torch.cuda.memory._set_allocator_settings("roundup_power2_divisions:16")
         self.overlap_input = overlap_input      # run the input stage on its own stream (see input_stream())
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]     # frozen parameters stay outside
         is_nd = lambda k: any(s in k for s in no_decay_keys)                        # noqa: E731
