@@ -146,13 +146,24 @@ def lib():
                 fn.restype = C.c_int
         _lib.geomae_sra_scratch_floats.argtypes = [C.POINTER(SRACtx), C.c_int32]
         _lib.geomae_sra_scratch_floats.restype = C.c_int64
+        _lib.geomae_peer_mailbox_doubles.argtypes = [C.c_int32]
+        _lib.geomae_peer_mailbox_doubles.restype = C.c_int64
     return _lib
 
 
 _p, _i64, _i32, _f3 = C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_float)
 
 
+class PeerCtx(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("mailbox", C.c_void_p * 8), ("timeout_flag", C.c_void_p)]
+
+
 class _Sigs:
+    geomae_peer_enable_access = [_i32]
+    geomae_peer_mailbox_create = [_i32, C.POINTER(C.c_void_p), _p]
+    geomae_peer_mailbox_open = [_p, C.POINTER(C.c_void_p)]
+    geomae_peer_mailbox_close = [_p, _i32]
+    geomae_peer_allreduce_f64 = [C.POINTER(PeerCtx), _p, _i32, C.c_double, C.c_double, C.c_uint64, _p]
     geomae_grid_size = [_f3, _f3, _f3, C.POINTER(C.c_int32)]
     geomae_dynamic_voxelize = [_p, _i64, _i32, _f3, _f3, _f3, _p, _p]
     geomae_voxel_scatter = [C.POINTER(VoxelCfg), C.POINTER(ScatterIO), _p]

@@ -52,12 +52,31 @@ def scatter_reduce(feat, pb: PillarBatch, mode: str):
 
 def _bn_moments(stats, n, world):
     """[sum | sum of squares] (fp64) of this rank's n rows -> [E x | E x^2] averaged over ranks with EQUAL weight per
-    rank (the rule of naiveSyncBN1d, mmdet3d/ops/norm.py:66-73): one 2C-double all-reduce."""
+    rank (the rule of naiveSyncBN1d, mmdet3d/ops/norm.py:66-73), in place.  One launch: the normalisation by n and —
+    with several ranks on one node — the exchange itself over peer memory (csrc/peer.cu); ``torch.distributed`` only
+    when the peer mailboxes could not be set up."""
+    from . import peer
+    if world == 1:
+        return peer.scale_(stats, 1.0 / float(max(n, 1)))
+    px = peer.PeerExchange.get(stats.device)
+    if px is not None:
+        return px.allreduce_(stats, pre_scale=1.0 / float(max(n, 1)), post_scale=1.0 / world)
     mom = stats / float(max(n, 1))
-    if world > 1:
-        dist.all_reduce(mom)
-        mom /= world
+    dist.all_reduce(mom)
+    mom /= world
     return mom
+
+
+def _sum_over_ranks(buf, world):
+    """In-place sum of a small fp64 vector over the ranks (BatchNorm backward coefficients)."""
+    if world > 1:
+        from . import peer
+        px = peer.PeerExchange.get(buf.device)
+        if px is not None:
+            px.allreduce_(buf)
+        else:
+            dist.all_reduce(buf)
+    return buf
 
 
 class _FusedVFEFn(torch.autograd.Function):
@@ -133,9 +152,7 @@ class _FusedVFEFn(torch.autograd.Function):
             nm = layer.norm
             L.run("bn_backward_coeffs", c, L.ptr(sums), L.ptr(mom), L.ptr(nm.weight), float(nm.eps), L.ptr(ab),
                   L.ptr(grad(nm.weight)), L.ptr(grad(nm.bias)), s)
-            if world > 1:
-                dist.all_reduce(ab)
-            return ab
+            return _sum_over_ranks(ab, world)
 
         # ---- layer 1
         sums1 = torch.empty(256, **f64)

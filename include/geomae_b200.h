@@ -597,6 +597,36 @@ int geomae_augment_filter(const float* points, int64_t n_points, int32_t stride,
                           const float range_max[3], float* out_points, int32_t* out_frame_offsets,
                           int32_t* scan_tmp, int64_t scan_tmp_len, void* stream);
 
+/* ------------------------------------------------------ peer-memory exchange (multi-GPU, one node) */
+
+/* mailbox[r] = rank r's mailbox as mapped into THIS process (own allocation for r == rank, CUDA-IPC mapping of the
+ * peer's allocation otherwise), geomae_peer_mailbox_doubles(world) doubles each, zero-initialised once.
+ * timeout_flag: optional device int32 set to 1 when a peer did not arrive within ~10 s. */
+typedef struct geomae_peer_ctx {
+  int32_t rank, world;
+  void* mailbox[8];
+  void* timeout_flag;
+} geomae_peer_ctx;
+
+int64_t geomae_peer_mailbox_doubles(int32_t world);
+/* Own mailbox: device memory of the current device, zeroed, with its 64-byte CUDA IPC handle (send it to the other
+ * ranks of the node by any means).  _open maps a peer's mailbox from the CURRENT device (peer access is enabled
+ * lazily by the driver); _close unmaps (owned = 0) or frees (owned = 1). */
+int geomae_peer_mailbox_create(int32_t world, void** mailbox, void* ipc_handle_64);
+int geomae_peer_mailbox_open(const void* ipc_handle_64, void** mapped);
+int geomae_peer_mailbox_close(void* ptr, int32_t owned);
+/* Kernels of the CURRENT device may dereference memory of peer_device from now on (cudaDeviceEnablePeerAccess). */
+int geomae_peer_enable_access(int32_t peer_device);
+
+/* In place: buf[i] = post_scale * sum over ranks of (pre_scale_r * buf_r[i]), count <= 512 doubles, ONE single-CTA
+ * kernel per rank: peer stores into every rank's mailbox over NVLink, a system-scope release flag, acquire-spin on the
+ * own mailbox, sum in rank order.  Every rank must issue the same sequence of calls with epoch = 1, 2, 3, ...
+ * world == 1: just the scaling (no mailbox needed).
+ * replaces: the four dist.all_reduce / all_gather calls per step of naiveSyncBN1d (mmdet3d/ops/norm.py:28-86) and the
+ *           stats / n normalisation in front of them. */
+int geomae_peer_allreduce_f64(const geomae_peer_ctx* ctx, double* buf, int32_t count, double pre_scale,
+                              double post_scale, uint64_t epoch, void* stream);
+
 /* tokens [n_vis + n_mask, d_model] = [visible rows ; mask_token repeated n_mask times].
  * replaces: torch.cat([visible_voxel_feat, self.mask_token.repeat(n_mask, 1)]) (…top_only.py:204-210). */
 int geomae_decoder_tokens(const float* visible, int64_t n_vis, const float* mask_token, int64_t n_mask, int32_t d_model,

@@ -1,0 +1,73 @@
+"""Peer-memory exchange (csrc/peer.cu, geomae_b200/peer.py) on two GPUs of one node: the single-kernel all-reduce
+against torch.distributed, and a synchronised-BatchNorm training step with and without it."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+    try:
+        from geomae_b200.peer import PeerExchange
+        px = PeerExchange.get(dev)
+        assert px is not None, "peer exchange could not be set up on this box"
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        worst = 0.0
+        for it in range(200):                      # many epochs back to back: exercises both parities and slot reuse
+            n = (1, 7, 128, 256, 512)[it % 5]
+            x = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+            ref = x * (0.5 + rank)
+            dist.all_reduce(ref)
+            ref *= 0.25
+            got = px.allreduce_(x.clone(), pre_scale=0.5 + rank, post_scale=0.25)
+            worst = max(worst, (got - ref).abs().max().item())
+        assert int(px.timeout.item()) == 0
+        assert worst <= 1e-15, worst                # two ranks: the sum has one order
+
+        # a full training step: synchronised BatchNorm statistics through the mailboxes vs through NCCL
+        import geomae_b200 as G
+        from geomae_b200 import peer
+        from geomae_b200.registry import Config
+        from geomae_b200.synthetic import make_frame
+        from geomae_b200.train import FlatTrainer
+        cfg = Config.fromfile(os.path.join(ROOT, "configs/mae_sst/geomae_nus_pretrain.py"))
+        frames = [torch.from_numpy(make_frame(50 + 10 * rank + s, point_scale=0.3)).to(dev) for s in range(2)]
+        losses = []
+        for use_peer in (True, False):
+            peer._INSTANCE[dev.index] = px if use_peer else None
+            torch.manual_seed(0)
+            model = G.build_detector(cfg.model).to(dev)
+            model.set_impl("tc3")
+            model.train()
+            tr = FlatTrainer(model, lr=1e-4)
+            run = []
+            for i in range(2):
+                torch.manual_seed(7 + i)
+                run.append(float(tr.train_step(frames)[0]))
+            losses.append(run)
+        for a, b in zip(*losses):
+            assert abs(a - b) <= 2e-5 * abs(b), losses
+        if rank == 0:
+            np.save(out, np.array(losses))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one node")
+def test_peer_allreduce_and_sync_bn_step(tmp_path):
+    import numpy as np
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "losses.npy")
+    mp.spawn(_worker, args=(2, 29541, out), nprocs=2, join=True)
+    losses = np.load(out)
+    assert losses.shape == (2, 2) and np.isfinite(losses).all()
