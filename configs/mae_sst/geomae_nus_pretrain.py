@@ -52,3 +52,23 @@ data = dict(samples_per_gpu=4, workers_per_gpu=4)
 optimizer = dict(type='AdamW', lr=1e-5, betas=(0.9, 0.999), weight_decay=0.05,
                  paramwise_cfg=dict(custom_keys={'norm': dict(decay_mult=0.)}))
 optimizer_config = dict(grad_clip=dict(max_norm=10, norm_type=2))
+# data / schedule of the reference config (…6x_1e-5.py:164-197,257-291); `tools/train.py` reads these
+dataset_type, data_root = 'NuScenesDatasetSSL', 'data/nuscenes/'
+class_names = ['car', 'truck', 'construction_vehicle', 'bus', 'trailer', 'barrier', 'motorcycle', 'bicycle',
+               'pedestrian', 'traffic_cone']
+train_pipeline = [
+    dict(type='LoadPointsFromFile', coord_type='LIDAR', load_dim=5, use_dim=5),
+    dict(type='LoadPointsFromMultiSweeps', sweeps_num=9, use_dim=[0, 1, 2, 3, 4], pad_empty_sweeps=True,
+         remove_close=True),
+    dict(type='GlobalRotScaleTrans', rot_range=[-0.3925, 0.3925], scale_ratio_range=[0.95, 1.05],
+         translation_std=[0, 0, 0]),
+    dict(type='RandomFlip3D', sync_2d=False, flip_ratio_bev_horizontal=0.5, flip_ratio_bev_vertical=0.5),
+    dict(type='PointsRangeFilter', point_cloud_range=pc_range),
+    dict(type='PointShuffle'),
+    dict(type='DefaultFormatBundle3D', class_names=class_names),
+    dict(type='Collect3D', keys=['points']),
+]
+data.update(train=dict(type=dataset_type, data_root=data_root, ann_file=data_root + 'nuscenes_ssl_infos_train.pkl',
+                       pipeline=train_pipeline, classes=class_names, test_mode=False, box_type_3d='LiDAR',
+                       device_merge=True))
+runner = dict(type='EpochBasedRunner', max_epochs=72)
