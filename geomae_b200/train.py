@@ -27,7 +27,8 @@ class FlatTrainer:
             # the loop (measured: host time per step jumping from 3.3 to 4-20 ms on fresh augmentations).  Rounding
             # request sizes to 1/16 steps of a power of two makes them repeat (<= 6 % more memory).  Process-wide
             # PyTorch setting; an explicit PYTORCH_CUDA_ALLOC_CONF wins.
-            torch.cuda.memory._set_allocator_settings("roundup_power2_divisions:16")
+            setter = getattr(torch._C, "_accelerator_setAllocatorSettings", None) or torch.cuda.memory._set_allocator_settings
+            setter("roundup_power2_divisions:16")
         self.overlap_input = overlap_input      # run the input stage on its own stream (see input_stream())
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]     # frozen parameters stay outside
         is_nd = lambda k: any(s in k for s in no_decay_keys)                        # noqa: E731

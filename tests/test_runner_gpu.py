@@ -70,3 +70,25 @@ def test_epochs_checkpoint_and_resume(tmp_path):
     assert d.max().item() <= 2.5e-2 and d.mean().item() <= 2e-4, (d.max().item(), d.mean().item())
     meta = load_checkpoint(str(tmp_path / "b" / "epoch_2.pth"), build())
     assert meta["epoch"] == 2 and meta["iter"] == 6
+
+
+def test_train_cli_from_a_config_file(tmp_path):
+    """tools/train.py: config file -> dataset -> loader -> runner, two tiny epochs, then resume for a third."""
+    import subprocess
+    import sys
+    ann = write_dataset(tmp_path, n_scenes=4)
+    own = os.path.join(ROOT, "configs/mae_sst/geomae_nus_pretrain.py")
+    cfg = tmp_path / "cfg.py"
+    cfg.write_text(f"_base_ = [{own!r}]\n"
+                   f"data = dict(samples_per_gpu=2, workers_per_gpu=2, train=dict(data_root={str(tmp_path) + '/'!r}, "
+                   f"ann_file={ann!r}))\n"
+                   "runner = dict(max_epochs=2)\n")
+    work = tmp_path / "work"
+    cmd = [sys.executable, os.path.join(ROOT, "tools/train.py"), str(cfg), "--work-dir", str(work), "--impl", "tc1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Epoch [2][2/2]" in out.stdout and sorted(os.listdir(work)) == ["epoch_1.pth", "epoch_2.pth"]
+    out = subprocess.run(cmd + ["--max-epochs", "3", "--resume-from", str(work / "epoch_2.pth")], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Epoch [3][2/2]" in out.stdout and "Epoch [1]" not in out.stdout and os.path.exists(work / "epoch_3.pth")
