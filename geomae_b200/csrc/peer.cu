@@ -70,9 +70,47 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerArgs a, double* buf)
   }
 }
 
+// Gradient exchange as reduce-scatter + all-gather in ONE kernel over peer memory: this rank owns the slice
+// [lo + (hi-lo)*rank/world, lo + (hi-lo)*(rank+1)/world) of every rank's gradient buffer, reads the slice from all
+// ranks (peer loads), sums in rank order and stores the sum back into all ranks' buffers (peer stores).  Every element
+// is summed by exactly one rank, so all ranks end up with bit-identical gradients.  The caller brackets it with two
+// geomae_peer_allreduce_f64 calls acting as barriers ("every rank's gradients are complete" before, "every slice has
+// been written everywhere" after).
+struct ShardArgs {
+  float* g[8];
+  int world;
+  int64_t begin4, end4;     // my slice in float4 units
+};
+
+__global__ void __launch_bounds__(256) k_peer_reduce_shard(ShardArgs a) {
+  for (int64_t i = a.begin4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.end4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < a.world; ++r) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(a.g[r]) + i);      // L2 / peer, never a stale L1 line
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    for (int r = 0; r < a.world; ++r) reinterpret_cast<float4*>(a.g[r])[i] = acc;
+  }
+}
+
 }  // namespace
 
 extern "C" int64_t geomae_peer_mailbox_doubles(int32_t world) { return (int64_t)2 * world * PEER_SLOT; }
+
+extern "C" int geomae_peer_buffer_create(int64_t bytes_, void** buffer, void* ipc_handle_64) {
+  GM_REQUIRE(bytes_ > 0 && buffer && ipc_handle_64, "peer_buffer_create: bad argument");
+  const size_t bytes = (size_t)bytes_;
+  void* p = nullptr;
+  GM_CUDA(cudaMalloc(&p, bytes));
+  GM_CUDA(cudaMemset(p, 0, bytes));
+  GM_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  GM_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(ipc_handle_64, &h, 64);
+  *buffer = p;
+  return GEOMAE_OK;
+}
 
 extern "C" int geomae_peer_mailbox_create(int32_t world, void** mailbox, void* ipc_handle_64) {
   GM_REQUIRE(world >= 1 && world <= 8 && mailbox && ipc_handle_64, "peer_mailbox_create: bad argument");
@@ -135,6 +173,26 @@ extern "C" int geomae_peer_allreduce_f64(const geomae_peer_ctx* ctx, double* buf
   a.rank = ctx->rank; a.world = ctx->world; a.count = count; a.pre = pre_scale; a.post = post_scale; a.epoch = epoch;
   a.timeout_flag = (int32_t*)ctx->timeout_flag;
   k_peer_allreduce<<<1, 256, 0, (cudaStream_t)stream>>>(a, buf);
+  GM_LAUNCH_CHECK();
+  return GEOMAE_OK;
+}
+
+extern "C" int geomae_peer_reduce_shard(const geomae_peer_ctx* ctx, void* const* grads, int64_t lo, int64_t hi,
+                                        void* stream) {
+  GM_REQUIRE(ctx && grads, "peer_reduce_shard: null argument");
+  GM_REQUIRE(ctx->world >= 2 && ctx->world <= 8 && ctx->rank >= 0 && ctx->rank < ctx->world, "peer_reduce_shard: bad ranks");
+  GM_REQUIRE(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, "peer_reduce_shard: range [%lld, %lld) must be float4-aligned",
+             (long long)lo, (long long)hi);
+  ShardArgs a;
+  for (int r = 0; r < 8; ++r) a.g[r] = r < ctx->world ? (float*)grads[r] : nullptr;
+  for (int r = 0; r < ctx->world; ++r) GM_REQUIRE(a.g[r], "peer_reduce_shard: buffer of rank %d missing", r);
+  a.world = ctx->world;
+  const int64_t n4 = (hi - lo) / 4;
+  a.begin4 = lo / 4 + n4 * ctx->rank / ctx->world;
+  a.end4 = lo / 4 + n4 * (ctx->rank + 1) / ctx->world;
+  if (a.end4 <= a.begin4) return GEOMAE_OK;
+  const int blocks = (int)min((int64_t)GM_NUM_SMS * 4, (a.end4 - a.begin4 + 255) / 256);
+  k_peer_reduce_shard<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
   GM_LAUNCH_CHECK();
   return GEOMAE_OK;
 }

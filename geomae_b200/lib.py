@@ -161,6 +161,8 @@ class PeerCtx(C.Structure):
 class _Sigs:
     geomae_peer_enable_access = [_i32]
     geomae_peer_mailbox_create = [_i32, C.POINTER(C.c_void_p), _p]
+    geomae_peer_buffer_create = [_i64, C.POINTER(C.c_void_p), _p]
+    geomae_peer_reduce_shard = [C.POINTER(PeerCtx), C.POINTER(C.c_void_p), _i64, _i64, _p]
     geomae_peer_mailbox_open = [_p, C.POINTER(C.c_void_p)]
     geomae_peer_mailbox_close = [_p, _i32]
     geomae_peer_allreduce_f64 = [C.POINTER(PeerCtx), _p, _i32, C.c_double, C.c_double, C.c_uint64, _p]

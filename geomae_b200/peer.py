@@ -72,11 +72,13 @@ class PeerExchange:
         return buf
 
     @classmethod
-    def get(cls, device):
-        """The process-wide exchange for ``device`` (every rank must call at the same point the first time)."""
+    def get(cls, device, name="bn"):
+        """The process-wide exchange ``name`` for ``device`` (every rank must call at the same point the first time).
+        Exchanges that may be in flight at the same time (different streams) need different names: one mailbox serves
+        ONE ordered sequence of calls."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return None
-        key = torch.device(device).index
+        key = (torch.device(device).index, name)
         if key not in _INSTANCE:
             inst = None
             if not os.environ.get("GEOMAE_NO_PEER_EXCHANGE"):       # (set on every rank or on none)
@@ -87,6 +89,57 @@ class PeerExchange:
                                   f"through torch.distributed")
             _INSTANCE[key] = inst
         return _INSTANCE[key]
+
+
+class _RawCuda:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(ptr, False), version=3)
+
+
+class SharedGradients:
+    """The flat gradient buffer of every rank, mapped everywhere, and the peer-memory form of the DDP gradient exchange
+    (csrc/peer.cu: k_peer_reduce_shard between two barrier exchanges).  Collective constructor; raises when the node
+    cannot do it (the trainer then keeps NCCL)."""
+
+    def __init__(self, device, n_floats):
+        dev = torch.device(device)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.early, self.late = PeerExchange.get(dev, "grad_early"), PeerExchange.get(dev, "grad_late")
+        if self.early is None or self.late is None:
+            raise RuntimeError("peer mailboxes unavailable")
+        ptrs, problem = [None] * self.world, None
+        with torch.cuda.device(dev):
+            own, handle = C.c_void_p(), C.create_string_buffer(64)
+            L.run("peer_buffer_create", 4 * n_floats, C.byref(own), handle)
+            ptrs[self.rank] = own.value
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, handle.raw)
+            try:
+                for r, raw in enumerate(everyone):
+                    if r != self.rank:
+                        mapped = C.c_void_p()
+                        L.run("peer_mailbox_open", C.create_string_buffer(raw, 64), C.byref(mapped))
+                        ptrs[r] = mapped.value
+            except Exception as e:      # noqa: BLE001
+                problem = e
+        flag = torch.tensor([0 if problem else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            raise RuntimeError(str(problem) if problem else "another rank could not map the gradient buffers")
+        self.ptrs = (C.c_void_p * 8)(*ptrs)
+        self.flat_grad = torch.as_tensor(_RawCuda(own.value, n_floats, "<f4"), device=dev)
+        self.token = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.stream = torch.cuda.Stream(dev)
+
+    def exchange(self, px: PeerExchange, ranges):
+        """Sum the element ranges over the ranks, in place in every rank's buffer, on the CURRENT stream."""
+        tok = self.token[:1] if px is self.early else self.token[1:]
+        px.allreduce_(tok)                          # barrier: every rank's gradients of these ranges are complete
+        s = L.stream_ptr(self.flat_grad.device)
+        for a, b in ranges:
+            if b > a:
+                L.run("peer_reduce_shard", C.byref(px.ctx), self.ptrs, a, b, s)
+        px.allreduce_(tok)                          # barrier: every slice has been written into every buffer
 
 
 def scale_(buf: torch.Tensor, scale: float):

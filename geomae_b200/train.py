@@ -19,7 +19,7 @@ class FlatTrainer:
     EARLY_KEYS = ("backbone.decoder_", "backbone.cls_pred_")
 
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, max_grad_norm=10.0,
-                 no_decay_keys=("norm",), overlap_input=True, allocator_rounding=True):
+                 no_decay_keys=("norm",), overlap_input=True, allocator_rounding=True, peer_gradients=True):
         self.model = model
         if allocator_rounding and torch.cuda.is_available() and not os.environ.get("PYTORCH_CUDA_ALLOC_CONF"):
             # pillar / token counts differ from step to step, so nearly every buffer of a step has a size never seen
@@ -51,8 +51,20 @@ class FlatTrainer:
         self.late_range = (sizes[0], self.n - sizes[3])
         self.n_params = sum(p.numel() for _, p in self.order)
         dev = named[0][1].device
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.flat_param = torch.zeros(self.n, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.shared_grads = None
+        if self.world > 1 and peer_gradients and dev.type == "cuda" and not os.environ.get("GEOMAE_NO_PEER_EXCHANGE"):
+            # the gradient buffer of every rank mapped on every rank: the DDP exchange becomes one reduce-scatter +
+            # all-gather kernel over NVLink peer memory per bucket (peer.SharedGradients) instead of NCCL all-reduces
+            from .peer import SharedGradients
+            try:
+                self.shared_grads = SharedGradients(dev, self.n)
+            except Exception as e:      # noqa: BLE001
+                import warnings
+                warnings.warn(f"geomae_b200: peer-memory gradient exchange unavailable ({e}); using NCCL all-reduce")
+        self.flat_grad = self.shared_grads.flat_grad if self.shared_grads is not None else \
+            torch.zeros(self.n, dtype=torch.float32, device=dev)
         off = 0
         for _, p in self.order:
             n = p.numel()
@@ -66,7 +78,6 @@ class FlatTrainer:
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)
         self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
         self.step_count = 0
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -142,10 +153,18 @@ class FlatTrainer:
         vec = getattr(self.model, "last_loss_vector", None)
         total = vec.sum() if vec is not None else sum(losses.values())     # one reduction instead of six adds
         pending = []
+        sg = self.shared_grads
         if self.world > 1:
-            # bucket 1 (decoders + heads) starts its all-reduce from inside backward, as soon as the gradient reaching the
-            # encoder output exists: NCCL runs it on its own stream under the encoder / VFE backward
+            # bucket 1 (decoders + heads) starts its exchange from inside backward, as soon as the gradient reaching the
+            # encoder output exists, and runs on its own stream under the encoder / VFE backward
             def early(_grad):
+                if sg is not None:
+                    here = torch.cuda.current_stream(self.flat_grad.device)
+                    sg.stream.wait_stream(here)
+                    with torch.cuda.stream(sg.stream), L.stream_override(sg.stream):
+                        sg.exchange(sg.early, self.early_ranges)
+                    pending.append(None)
+                    return
                 for a, b in self.early_ranges:
                     if b > a:
                         pending.append(dist.all_reduce(self.flat_grad[a:b], async_op=True))
@@ -155,10 +174,14 @@ class FlatTrainer:
             self.model.backbone.encoder_output_hook = None
             if not pending:                          # the hook never fired (model without the backbone hook point)
                 early(None)
-            a, b = self.late_range
-            pending.append(dist.all_reduce(self.flat_grad[a:b], async_op=True))
-            for w in pending:
-                w.wait()                             # stream-level wait: the optimiser kernel is ordered after NCCL
+            if sg is not None:
+                sg.exchange(sg.late, [self.late_range])
+                torch.cuda.current_stream(self.flat_grad.device).wait_stream(sg.stream)
+            else:
+                a, b = self.late_range
+                pending.append(dist.all_reduce(self.flat_grad[a:b], async_op=True))
+                for w in pending:
+                    w.wait()                         # stream-level wait: the optimiser kernel is ordered after NCCL
         self.optimizer_step(lr)
         return total.detach(), losses
 

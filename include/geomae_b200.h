@@ -613,6 +613,9 @@ int64_t geomae_peer_mailbox_doubles(int32_t world);
  * ranks of the node by any means).  _open maps a peer's mailbox from the CURRENT device (peer access is enabled
  * lazily by the driver); _close unmaps (owned = 0) or frees (owned = 1). */
 int geomae_peer_mailbox_create(int32_t world, void** mailbox, void* ipc_handle_64);
+/* Any buffer meant to be mapped by the other ranks (the flat gradient buffer): zeroed device memory + IPC handle;
+ * map with geomae_peer_mailbox_open, release with geomae_peer_mailbox_close. */
+int geomae_peer_buffer_create(int64_t bytes, void** buffer, void* ipc_handle_64);
 int geomae_peer_mailbox_open(const void* ipc_handle_64, void** mapped);
 int geomae_peer_mailbox_close(void* ptr, int32_t owned);
 /* Kernels of the CURRENT device may dereference memory of peer_device from now on (cudaDeviceEnablePeerAccess). */
@@ -626,6 +629,14 @@ int geomae_peer_enable_access(int32_t peer_device);
  *           stats / n normalisation in front of them. */
 int geomae_peer_allreduce_f64(const geomae_peer_ctx* ctx, double* buf, int32_t count, double pre_scale,
                               double post_scale, uint64_t epoch, void* stream);
+
+/* Gradient exchange over peer memory: grads[r] = rank r's gradient buffer as mapped here (float32).  This rank sums
+ * its 1/world slice of the element range [lo, hi) (multiples of 4) over all ranks, in rank order, and stores the sum
+ * into every rank's buffer — reduce-scatter + all-gather in one launch, bit-identical results on all ranks.  The
+ * caller orders it between two geomae_peer_allreduce_f64 calls used as barriers (all gradients complete / all slices
+ * written).
+ * replaces: the DDP gradient all-reduce (MMDistributedDataParallel; reference apis/train.py:117-127). */
+int geomae_peer_reduce_shard(const geomae_peer_ctx* ctx, void* const* grads, int64_t lo, int64_t hi, void* stream);
 
 /* tokens [n_vis + n_mask, d_model] = [visible rows ; mask_token repeated n_mask times].
  * replaces: torch.cat([visible_voxel_feat, self.mask_token.repeat(n_mask, 1)]) (…top_only.py:204-210). */

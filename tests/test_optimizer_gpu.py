@@ -117,7 +117,8 @@ def test_two_trainers_in_one_process_do_not_interfere():
             # float atomics in the scatter make the last bits run-dependent; after an AdamW step (update ~ lr * sign for
             # noise-level gradients) that grows to ~1e-4 relative on the next loss
             # (bf16 operands amplify it: a flipped rounding is 2^-9 of one activation)
-            tol = (2e-5 if i == 0 else 5e-4) * (1 if seed == 2 else 15)
+            # (and the normal-regression term moves in quanta of up to 1.2e-4 on its own: golden_util.assert_same_step)
+            tol = (1e-4 if i == 0 else 5e-4) * (1 if seed == 2 else 15)
             assert abs(float(a) - b) <= tol * abs(b), (seed, i)
         d = (tr.flat_param - ref_param).abs()
         assert d.max().item() <= 6.1e-4 and d.mean().item() <= (2e-6 if seed == 2 else 2e-5)   # 3 AdamW steps of lr 1e-4

@@ -42,21 +42,33 @@ def _worker(rank, world, port, out):
         from geomae_b200.train import FlatTrainer
         cfg = Config.fromfile(os.path.join(ROOT, "configs/mae_sst/geomae_nus_pretrain.py"))
         frames = [torch.from_numpy(make_frame(50 + 10 * rank + s, point_scale=0.3)).to(dev) for s in range(2)]
-        losses = []
+        losses, params = [], []
         for use_peer in (True, False):
-            peer._INSTANCE[dev.index] = px if use_peer else None
+            peer._INSTANCE[(dev.index, "bn")] = px if use_peer else None
             torch.manual_seed(0)
             model = G.build_detector(cfg.model).to(dev)
             model.set_impl("tc3")
             model.train()
-            tr = FlatTrainer(model, lr=1e-4)
+            tr = FlatTrainer(model, lr=1e-4, peer_gradients=use_peer)
+            assert (tr.shared_grads is not None) == use_peer
             run = []
-            for i in range(2):
+            for i in range(3):
                 torch.manual_seed(7 + i)
                 run.append(float(tr.train_step(frames)[0]))
             losses.append(run)
-        for a, b in zip(*losses):
-            assert abs(a - b) <= 2e-5 * abs(b), losses
+            params.append(tr.flat_param.clone())
+            # every rank holds the same weights after the exchange + update
+            mine = tr.flat_param.double().sum().reshape(1)
+            both = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(both, mine)
+            assert both[0].item() == both[1].item(), (use_peer, both)
+        d = (params[0] - params[1]).abs()
+        assert d.max().item() <= 6.1e-4 and d.mean().item() <= 2e-6, (d.max().item(), d.mean().item())
+        for i, (a, b) in enumerate(zip(*losses)):
+            # step 0: same weights, the exchange only touches statistics; later steps also carry the run-to-run noise
+            # of the scatter's float atomics through AdamW updates
+            # (step 0 still carries the quantised noise of the normal-regression term: golden_util.assert_same_step)
+            assert abs(a - b) <= (1e-4 if i == 0 else 5e-4) * abs(b), losses
         if rank == 0:
             np.save(out, np.array(losses))
     finally:
@@ -70,4 +82,4 @@ def test_peer_allreduce_and_sync_bn_step(tmp_path):
     out = str(tmp_path / "losses.npy")
     mp.spawn(_worker, args=(2, 29541, out), nprocs=2, join=True)
     losses = np.load(out)
-    assert losses.shape == (2, 2) and np.isfinite(losses).all()
+    assert losses.shape == (2, 3) and np.isfinite(losses).all()
