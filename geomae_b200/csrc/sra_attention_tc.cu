@@ -20,6 +20,7 @@
 // warp-level MMA keeps S and P in registers.  The K = 128/256 projections around it are on tcgen05
 // (sra_layer.cu).  fp32 parity mode (precision 3) keeps the SIMT kernel of sra_attention.cu.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -225,8 +226,8 @@ __device__ __forceinline__ void put_frag(float* sO, int r0, int h, const float (
   *reinterpret_cast<float2*>(b + 8) = make_float2(o1[2] * s1, o1[3] * s1);
 }
 
-template <int TQ, int KC>
-__global__ void __launch_bounds__(256, 2) k_sra_tc_fwd(const float* __restrict__ qkv, int n,
+template <int TQ, int KC, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) k_sra_tc_fwd(const float* __restrict__ qkv, int n,
                                                        const int32_t* __restrict__ win_ptr,
                                                        const int32_t* __restrict__ win_tok,
                                                        const int32_t* __restrict__ tok_win, float* out, float* lse,
@@ -522,6 +523,20 @@ template <int TQ> constexpr int smem_fwd() { return (TQ + 2 * KC_FWD) * RSB; }
 template <int TQ> constexpr int smem_bwd() { return (2 * TQ + 2 * KC_BWD) * RSB + 2 * KC_BWD * NH * 4; }
 static_assert(64 * OS * 4 <= 2 * KC_FWD * RSB && 64 * OS * 4 <= 2 * KC_BWD * RSB, "output staging tile must fit");
 
+// 32-query tiles, 112-key chunks, three CTAs per SM (<= 85 registers, 70 KB of shared memory)
+int launch_fwd_occ3(const float* qkv, int n, const int32_t* win_ptr, const int32_t* win_tok, const int32_t* tok_win,
+                    float* out, float* lse, int io_flags, cudaStream_t st) {
+  constexpr int TQ = 32, KC = 112, SM = (TQ + 2 * KC) * RSB;
+  static bool configured = false;
+  if (!configured) {
+    GM_CUDA(cudaFuncSetAttribute(k_sra_tc_fwd<TQ, KC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+    configured = true;
+  }
+  GM_CUDA(gm_launch_pdl(k_sra_tc_fwd<TQ, KC, 3>, dim3(gm_div_up(n, TQ)), dim3(256), (size_t)SM, st, qkv, n, win_ptr,
+                        win_tok, tok_win, out, lse, io_flags));
+  return GEOMAE_OK;
+}
+
 template <int TQ>
 int launch_fwd(const float* qkv, int n, const int32_t* win_ptr, const int32_t* win_tok, const int32_t* tok_win, float* out,
                float* lse, int io_flags, cudaStream_t st) {
@@ -559,10 +574,16 @@ extern "C" int geomae_sra_attention_tc_fwd(const float* qkv, int64_t n_tokens, i
   GM_REQUIRE(qkv && win_ptr && win_tok && tok_win && out && lse, "sra_attention_tc_fwd: null argument");
   GM_REQUIRE(n_tokens < (int64_t)1 << 31, "sra_attention_tc: too many tokens");
   const int n = (int)n_tokens;
-  // small token sets (the encoder sees 30 % of the pillars): 32-query CTAs so the grid still covers the SMs
-  if (gm_div_up(n, 64) < 2 * GM_NUM_SMS)
+  static const int force_tq = getenv("GEOMAE_ATTN_TQ") ? atoi(getenv("GEOMAE_ATTN_TQ")) : 0;   // tuning switch
+  // small token sets (the encoder sees 30 % of the pillars): 32-query CTAs so the grid still covers the SMs (one
+  // wave: bound by the per-CTA latency chain).  Large sets are throughput-bound and gain from a third resident CTA
+  // per SM (32 queries, 112-key chunks, <= 85 registers): 38.9 -> 34 us on 24.7 k decoder tokens
+  // (tools/bench_attention.py); GEOMAE_ATTN_TQ = 32 | 64 forces the older tilings.
+  if (force_tq == 32 || (force_tq != 64 && gm_div_up(n, 64) < 2 * GM_NUM_SMS))
     return launch_fwd<32>(qkv, n, win_ptr, win_tok, tok_win, out, lse, io_flags, (cudaStream_t)stream);
-  return launch_fwd<64>(qkv, n, win_ptr, win_tok, tok_win, out, lse, io_flags, (cudaStream_t)stream);
+  if (force_tq == 64)
+    return launch_fwd<64>(qkv, n, win_ptr, win_tok, tok_win, out, lse, io_flags, (cudaStream_t)stream);
+  return launch_fwd_occ3(qkv, n, win_ptr, win_tok, tok_win, out, lse, io_flags, (cudaStream_t)stream);
 }
 
 extern "C" int geomae_sra_attention_tc_bwd(const float* qkv, const float* out, const float* lse, const float* d_out,
@@ -575,7 +596,8 @@ extern "C" int geomae_sra_attention_tc_bwd(const float* qkv, const float* out, c
   GM_REQUIRE(!(io_flags & 2) || dd, "sra_attention_tc_bwd: a bf16 d_out needs the precomputed D = dO.O (dd)");
   GM_REQUIRE(n_tokens < (int64_t)1 << 31, "sra_attention_tc: too many tokens");
   const int n = (int)n_tokens;
-  if (gm_div_up(n, 64) < GM_NUM_SMS)
+  static const int force_tq = getenv("GEOMAE_ATTN_TQ") ? atoi(getenv("GEOMAE_ATTN_TQ")) : 0;   // tuning switch
+  if (force_tq == 32 || (force_tq != 64 && gm_div_up(n, 64) < GM_NUM_SMS))
     return launch_bwd<32>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags, (cudaStream_t)stream);
   return launch_bwd<64>(qkv, out, lse, d_out, n, win_ptr, win_tok, tok_win, d_qkv, dd, io_flags, (cudaStream_t)stream);
 }
