@@ -19,10 +19,13 @@ torch.manual_seed(1)
 tr.train_step(frames)
 ids = (model.last_targets["ids_keep"].clone(), model.last_targets["ids_mask"].clone())
 torch.cuda.synchronize()
-rows = []
+rows, grads = [], []
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+names = [k for k, _ in tr.order]
 for i in range(N):
     loss, parts = tr.train_step(frames, ids=ids)
+    if i < 12:
+        grads.append(tr.flat_grad.clone())          # lr = 0: the gradient of the same step, again and again
     rows.append([float(v) for v in model.last_loss_vector.tolist()] if getattr(model, "last_loss_vector", None) is not None else [float(loss)])
 rows = np.array(rows)
 med = np.median(rows, axis=0)
@@ -31,3 +34,17 @@ print("loss terms (median):", np.round(med, 5))
 print("max relative deviation per term:", rel.max(axis=0))
 bad = np.where(rel.max(axis=1) > 2e-6)[0]
 print("steps deviating by more than 2e-6:", bad.tolist(), [rel[j].max() for j in bad])
+
+# gradients: relative deviation of every parameter's gradient from the first repeat (normal-regression noise reaches the
+# density decoder and, through the shared encoder, everything upstream at a much smaller level)
+off, worst = 0, []
+ref = grads[0]
+for k, p in tr.order:
+    n = p.numel()
+    a = ref[off:off + n]
+    dev_ = max(float((g[off:off + n] - a).norm() / (a.norm() + 1e-20)) for g in grads[1:])
+    worst.append((dev_, k))
+    off += (n + 63) // 64 * 64
+worst.sort(reverse=True)
+print("largest relative gradient deviation between repeats:", [(f"{d:.2e}", k) for d, k in worst[:5]])
+print("median over parameters:", f"{np.median([d for d, _ in worst]):.2e}")
