@@ -396,7 +396,8 @@ def main():
         # timed loop of a fresh process measured up to 15 % slow on this host-launch-bound step).
         L.start_timing()
         L.run("profile_enable", 1)
-        ms_prof = timed_loop(step_resident, K)
+        Kp = min(K, 64)                                # the C side keeps 8192 spans (~106 per step)
+        ms_prof = timed_loop(step_resident, Kp)
         per_call = L.stop_timing()
         prof_ms, prof_n, prof_fl, prof_by = (C.c_double * 5)(), (C.c_int64 * 5)(), (C.c_double * 5)(), (C.c_double * 5)()
         L.run("profile_read", prof_ms, prof_n, prof_fl, prof_by)
@@ -486,18 +487,18 @@ def main():
         sq = attention_pair_counts()
         bb = model.backbone
         n_enc, n_dec = len(bb.encoder_blocks), len(bb.decoder_centroid_blocks) + len(bb.decoder_density_blocks)
-        pairs = (n_enc * (sq["enc", 0] + sq["enc", 1]) + n_dec * (sq["dec", 0] + sq["dec", 1])) * K   # all layers, K steps
+        pairs = (n_enc * (sq["enc", 0] + sq["enc", 1]) + n_dec * (sq["dec", 0] + sq["dec", 1])) * Kp   # all layers, Kp steps
         prof_fl[2] = pairs * bb.nhead[0] * 64.0     # fwd: QK^T + PV = 2 products x 16 x 2 flop per (i,j,head)
         prof_fl[3] = pairs * bb.nhead[0] * 160.0    # bwd: 5 products
         for f, nm in enumerate(fam_names):
             if prof_n[f]:
                 sec = prof_ms[f] * 1e-3
-                fam_table[nm] = dict(ms_per_step=prof_ms[f] / K, launches_per_step=prof_n[f] / K,
+                fam_table[nm] = dict(ms_per_step=prof_ms[f] / Kp, launches_per_step=prof_n[f] / Kp,
                                      avg_launch_us=1e3 * prof_ms[f] / prof_n[f],
-                                     algorithmic_gflop_per_step=prof_fl[f] / K / 1e9,
+                                     algorithmic_gflop_per_step=prof_fl[f] / Kp / 1e9,
                                      tflops=prof_fl[f] / sec / 1e12 if prof_fl[f] else None,
                                      tensor_frac=prof_fl[f] / sec / 1e12 / tens_peak if prof_fl[f] else None,
-                                     algorithmic_gb_per_step=prof_by[f] / K / 1e9, gbs=prof_by[f] / sec / 1e9,
+                                     algorithmic_gb_per_step=prof_by[f] / Kp / 1e9, gbs=prof_by[f] / sec / 1e9,
                                      hbm_frac=prof_by[f] / sec / 1e9 / hbm_peak)
         # the SRA layer (projections + attention + FFN) is bounded by the TENSOR pipe:
         # achieved = algorithmic flops of the family's launches / their CUDA-event time, peak = the measured sustained
@@ -513,13 +514,13 @@ def main():
                     hbm_view=dict(algorithmic_bytes_per_launch=prof_by[top] / prof_n[top],
                                   achieved_gbs=prof_by[top] / (prof_ms[top] * 1e-3) / 1e9, peak_gbs=hbm_peak,
                                   frac=prof_by[top] / (prof_ms[top] * 1e-3) / 1e9 / hbm_peak),
-                    whole_step=dict(algorithmic_gflop=sum(prof_fl[:4]) / K / 1e9,
-                                    tflops=sum(prof_fl[:4]) / K / (ms / K * 1e-3) / 1e12,
-                                    tensor_frac=sum(prof_fl[:4]) / K / (ms / K * 1e-3) / 1e12 / tens_peak),
+                    whole_step=dict(algorithmic_gflop=sum(prof_fl[:4]) / Kp / 1e9,
+                                    tflops=sum(prof_fl[:4]) / Kp / (ms / K * 1e-3) / 1e12,
+                                    tensor_frac=sum(prof_fl[:4]) / Kp / (ms / K * 1e-3) / 1e12 / tens_peak),
                     note="timed with CUDA events on the launching stream around every launch of the family in a separate "
                          "instrumented pass over the same K steps; launches of concurrent streams overlap, so family "
                          "shares can add up to more than 1; the ncu launch list of the same command is under profiles/",
-                    share_of_step=prof_ms[top] / ms_prof, instrumented_ms_per_step=ms_prof / K)
+                    share_of_step=prof_ms[top] / ms_prof, instrumented_ms_per_step=ms_prof / Kp)
     aux = hbm_kernel_rooflines(model, pool, dev, hbm_peak, peak_src)
     line = dict(
         metric=METRIC, value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=K, warmup=W,
@@ -544,7 +545,7 @@ def main():
                                           ms_per_step=ms_e2e_aug / K, h2d_bytes_per_step=h2d,
                                           d2h_bytes_per_step=4 + 4 * (5 + S) + 4 * (S + 1)),
         host_enqueue_ms_per_step=host_ms, gpu_launches=launches, clocks=clocks, roofline=roof, kernel_families=fam_table, hbm_kernels=aux,
-        kernel_ms_per_step={k: round(v[0] / K, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
+        kernel_ms_per_step={k: round(v[0] / Kp, 4) for k, v in sorted(per_call.items(), key=lambda kv: -kv[1][0])},
         loss=last.get("loss_host"), loss_delta_vs_tc3=loss_delta)
     if (args.workload == "dense" or args.length_bins) and world == 1:
         line["sra_length_bins"] = sra_length_bin_sweep(dev, tens_peak)
