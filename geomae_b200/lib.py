@@ -270,9 +270,14 @@ def launch_count():
     return sum((1 if k == "__extra__" else LAUNCHES_PER_CALL.get(k, 1)) * v for k, v in _calls.items())
 
 
+_fn_cache = {}
+
+
 def run(what: str, *args):
     """Call geomae_<what>(*args); raise RuntimeError on a non-zero status."""
-    fn = getattr(lib(), "geomae_" + what)
+    fn = _fn_cache.get(what)
+    if fn is None:
+        fn = _fn_cache[what] = getattr(lib(), "geomae_" + what)
     _calls[what] = _calls.get(what, 0) + 1
     if _timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
